@@ -1,0 +1,557 @@
+"""Host-side mirror of the reference's Julia interface for the solve path, on top of the C ABI.
+
+Same names, argument order and error behaviour as JuliaInv/Helmholtz.jl (no Julia runtime exists in
+this image, so the mirror is Python; the Julia shim with identical structure is in
+`julia/HelmholtzB200.jl`):
+
+  HelmholtzParam                      src/Helmholtz.jl:13-20
+  getShiftedHelmholtzParam            src/Helmholtz.jl:32-34
+  GetHelmholtzOperator (3 methods)    src/GetHelmholtz.jl:14-16, 22-31, 33-50
+  GetHelmholtzShiftOP                 src/GetHelmholtz.jl:81-83
+  getABL / getMaximalFrequency        src/GetHelmholtz.jl:97-220 / 75-79
+  getAcousticPointSource, loc2cs, ... src/getPointSource.jl:63-112
+  getMGparam (Multigrid.jl)           call sites test/ShiftedLaplacianTest.jl:63-64,127-128,137
+  getShiftedLaplacianMultigridSolver  src/ShiftedLaplacianMultigridSolver.jl:24-30
+  solveLinearSystem / copySolver / clear!   src/ShiftedLaplacianMultigridSolver.jl:33-102, 18-22, 105-109
+
+All arithmetic happens in libhelmholtz_b200.so on the GPU; nothing here computes a solve on the CPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+import time
+
+import numpy as np
+
+from . import _lib as L
+
+ComplexF64 = np.complex128
+ComplexF32 = np.complex64
+Int64 = np.int64
+
+
+def _ptr(a, ctype):
+    return a.ctypes.data_as(C.POINTER(ctype))
+
+
+# ------------------------------------------------------------------ jInv.Mesh.RegularMesh (boundary type)
+class RegularMesh:
+    """Only what crosses the ABI: domain, n (cells), h, dim (jInv.Mesh.RegularMesh)."""
+
+    def __init__(self, domain, n):
+        self.domain = np.asarray(domain, dtype=np.float64).ravel()
+        self.n = np.asarray(n, dtype=np.int64).ravel()
+        self.dim = len(self.n)
+        self.h = (self.domain[1::2] - self.domain[0::2]) / self.n.astype(np.float64)
+
+
+def getRegularMesh(domain, n):
+    return RegularMesh(domain, n)
+
+
+# ------------------------------------------------------------------ HelmholtzParam
+class HelmholtzParam:
+    """src/Helmholtz.jl:13-20.  gamma already contains the absorbing layer."""
+
+    def __init__(self, Mesh, gamma, m, omega, NeumannOnTop, Sommerfeld):
+        self.Mesh = Mesh
+        self.gamma = np.asarray(gamma, dtype=np.float64)
+        self.m = np.asarray(m, dtype=np.float64)
+        self.omega = complex(omega) if np.iscomplexobj(omega) else float(omega)
+        self.NeumannOnTop = bool(NeumannOnTop)
+        self.Sommerfeld = bool(Sommerfeld)
+
+
+def getShiftedHelmholtzParam(p, s):
+    """src/Helmholtz.jl:32-34"""
+    return HelmholtzParam(p.Mesh, p.gamma + s * np.real(p.omega), p.m, p.omega, p.NeumannOnTop, p.Sommerfeld)
+
+
+# ------------------------------------------------------------------ device handle
+class _Handle:
+    """Owns an hh_handle_t (HelmholtzParam + device state)."""
+
+    def __init__(self, Mesh, m, omega, gamma, NeumannOnTop, Sommerfeld, orderNeumannBC=2, precision=ComplexF64,
+                 devices=None):
+        lib = L.load()
+        nodes = (np.asarray(Mesh.n, dtype=np.int64) + 1).copy()
+        N = int(np.prod(nodes))
+        mm = np.ascontiguousarray(np.asarray(m, dtype=np.float64).ravel(order="F"))
+        gg = np.ascontiguousarray(np.asarray(gamma, dtype=np.float64).ravel(order="F"))
+        if mm.size != N or gg.size != N:
+            raise ValueError(f"m and gamma must have prod(n+1) = {N} entries (got {mm.size}, {gg.size})")
+        h = np.ascontiguousarray(np.asarray(Mesh.h, dtype=np.float64))
+        self.dim = int(Mesh.dim)
+        self.nodes = nodes
+        self.N = N
+        self.dtype = np.dtype(precision)
+        prec = L.HH_C64 if self.dtype == np.complex128 else L.HH_C32
+        if self.dtype not in (np.dtype(np.complex128), np.dtype(np.complex64)):
+            raise ValueError("precision must be ComplexF64 or ComplexF32")
+        w = complex(omega)
+        out = C.c_void_p()
+        if devices is None:
+            devices = [_current_device()]
+        devs = np.asarray(devices, dtype=np.int32)
+        rc = lib.hh_create_multi(self.dim, _ptr(nodes, C.c_int64), _ptr(h, C.c_double), _ptr(mm, C.c_double),
+                                 _ptr(gg, C.c_double), w.real, w.imag, int(bool(NeumannOnTop)), int(bool(Sommerfeld)),
+                                 int(orderNeumannBC), prec, _ptr(devs, C.c_int), len(devs), C.byref(out))
+        L.check(rc, None)
+        self.h = out
+        self.devices = [int(d) for d in devs]
+        self.lib = lib
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.hh_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def _current_device():
+    try:
+        import torch
+
+        if torch.cuda.is_available():
+            return torch.cuda.current_device()
+    except Exception:
+        pass
+    return 0
+
+
+def _is_torch_cuda(x):
+    try:
+        import torch
+
+        return isinstance(x, torch.Tensor) and x.is_cuda
+    except Exception:
+        return False
+
+
+# ------------------------------------------------------------------ operator objects
+class HelmholtzShiftOP:
+    """What GetHelmholtzShiftOP returns: i*shift*omega^2*diag(m) (src/GetHelmholtz.jl:81-83), kept symbolic."""
+
+    def __init__(self, shift, omega):
+        self.shift = float(shift)
+        self.omega = float(omega)
+
+
+def GetHelmholtzShiftOP(mNodal, omega, shift):
+    if np.iscomplexobj(omega):
+        # the reference's method is typed omega::Float64 (GetHelmholtz.jl:81)
+        raise TypeError("GetHelmholtzShiftOP: omega must be real (Float64)")
+    return HelmholtzShiftOP(shift, omega)
+
+
+class HelmholtzOperator:
+    """Matrix-free counterpart of the sparse matrix GetHelmholtzOperator returns: `H @ x`, `H * x`,
+    `H + GetHelmholtzShiftOP(...)`, `H.H` / `H.T.conj()` (adjoint view)."""
+
+    def __init__(self, handle, shift=0.0, adjoint=False):
+        self._hd = handle
+        self.shift = float(shift)
+        self.adjoint = bool(adjoint)
+        self.shape = (handle.N, handle.N)
+        self.dtype = handle.dtype
+
+    def __add__(self, other):
+        if isinstance(other, HelmholtzShiftOP):
+            return HelmholtzOperator(self._hd, self.shift + other.shift, self.adjoint)
+        return NotImplemented
+
+    __radd__ = __add__
+
+    @property
+    def H(self):
+        return HelmholtzOperator(self._hd, self.shift, not self.adjoint)
+
+    def adjoint_view(self):
+        return self.H
+
+    def matvec(self, x):
+        hd = self._hd
+        if _is_torch_cuda(x):
+            import torch
+
+            want = torch.complex128 if hd.dtype == np.complex128 else torch.complex64
+            xx = x.to(want).reshape(-1, hd.N) if x.dim() > 1 else x.to(want).reshape(1, hd.N)
+            xx = xx.contiguous()
+            y = torch.empty_like(xx)
+            L.check(hd.lib.hh_apply_device(hd.h, xx.data_ptr(), y.data_ptr(), xx.shape[0], int(self.shift != 0.0),
+                                           self.shift, int(self.adjoint)), hd.h)
+            return y.reshape(x.shape)
+        x = np.asarray(x)
+        vec = x.ndim == 1
+        X = np.asfortranarray(x.reshape(hd.N, -1), dtype=hd.dtype)
+        Y = np.empty_like(X, order="F")
+        L.check(hd.lib.hh_apply(hd.h, X.ctypes.data, Y.ctypes.data, X.shape[1], int(self.shift != 0.0), self.shift,
+                                int(self.adjoint)), hd.h)
+        return Y[:, 0] if vec else Y
+
+    __matmul__ = matvec
+    __mul__ = matvec
+
+    def diagonal_mass(self):
+        """The complex diagonal added to the Laplacian (mass + Sommerfeld [+ shift]), ComplexF64."""
+        hd = self._hd
+        out = np.empty(hd.N, dtype=np.complex128)
+        L.check(hd.lib.hh_get_diagonal(hd.h, int(self.shift != 0.0), self.shift, _ptr(out.view(np.float64), C.c_double)),
+                hd.h)
+        return out
+
+
+def getABL(n, NeumannAtFirstDim, ABLpad, ABLamp):
+    """src/GetHelmholtz.jl:97-220 (host-side Float64 set-up, computed by the library)."""
+    lib = L.load()
+    n = np.ascontiguousarray(np.asarray(n, dtype=np.int64).ravel())
+    pad = np.ascontiguousarray(np.asarray(ABLpad, dtype=np.int64).ravel())
+    if pad.size == 1:
+        pad = np.repeat(pad, n.size)
+    out = np.empty(int(np.prod(n)), dtype=np.float64)
+    L.check(lib.hh_get_abl(len(n), _ptr(n, C.c_int64), int(bool(NeumannAtFirstDim)), _ptr(pad, C.c_int64), float(ABLamp),
+                           _ptr(out, C.c_double)))
+    return out.reshape(tuple(int(v) for v in n), order="F")
+
+
+def getMaximalFrequency(m, M):
+    """src/GetHelmholtz.jl:75-79"""
+    lib = L.load()
+    mm = np.ascontiguousarray(np.atleast_1d(np.asarray(m, dtype=np.float64)).ravel())
+    h = np.ascontiguousarray(np.asarray(M.h, dtype=np.float64))
+    out = C.c_double()
+    L.check(lib.hh_get_maximal_frequency(_ptr(mm, C.c_double), mm.size, int(M.dim), _ptr(h, C.c_double), C.byref(out)))
+    return out.value
+
+
+def GetHelmholtzOperator(*args, precision=ComplexF64, devices=None):
+    """The three methods of src/GetHelmholtz.jl:14-16, 22-31, 33-50, dispatched on the argument list:
+
+      GetHelmholtzOperator(Hparam[, orderNeumannBC])                                             -> H
+      GetHelmholtzOperator(Msh, m, omega, gamma, NeumannAtFirstDim, ABLpad, ABLamp, Sommerfeld[, order]) -> (H, gamma)
+      GetHelmholtzOperator(Msh, m, omega, gamma, NeumannAtFirstDim, Sommerfeld[, order])        -> H
+    """
+    if isinstance(args[0], HelmholtzParam):
+        hp = args[0]
+        order = args[1] if len(args) > 1 else 2
+        hd = _Handle(hp.Mesh, hp.m, hp.omega, hp.gamma, hp.NeumannOnTop, hp.Sommerfeld, order, precision, devices)
+        return HelmholtzOperator(hd)
+    Msh, m, omega, gamma, neumann = args[:5]
+    if len(args) >= 8:
+        pad, amp, somm = args[5:8]
+        order = args[8] if len(args) > 8 else 2
+        abl = getABL(np.asarray(Msh.n) + 1, neumann, pad, amp)
+        if gamma is None or np.size(gamma) == 0:
+            gamma = abl
+        else:
+            gamma = np.asarray(gamma, dtype=np.float64).reshape(abl.shape, order="F") + abl
+        hd = _Handle(Msh, m, omega, gamma, neumann, somm, order, precision, devices)
+        return HelmholtzOperator(hd), gamma
+    somm = args[5]
+    order = args[6] if len(args) > 6 else 2
+    hd = _Handle(Msh, m, omega, gamma, neumann, somm, order, precision, devices)
+    return HelmholtzOperator(hd)
+
+
+# ------------------------------------------------------------------ point sources
+def loc2cs(n, sub):
+    """src/getPointSource.jl:82-102 (1-based in and out)."""
+    lib = L.load()
+    n = np.ascontiguousarray(np.asarray(n, dtype=np.int64).ravel())
+    sub = np.ascontiguousarray(np.asarray(sub, dtype=np.int64).ravel())
+    return int(lib.hh_point_source_index(len(sub), _ptr(n, C.c_int64), _ptr(sub, C.c_int64)))
+
+
+def getTopPointSrc(Minv):
+    n = Minv.n
+    if Minv.dim == 3:
+        return [(int(n[0]) + 1) // 2, (int(n[1]) + 1) // 2, 1]
+    return [(int(n[0]) + 1) // 2, 1]
+
+
+def getMidPointSrc(Minv):
+    n = Minv.n
+    return [(int(v) + 1) // 2 for v in n]
+
+
+def getAcousticPointSource(Minv, TYPE=ComplexF64, src=None):
+    """src/getPointSource.jl:105-112"""
+    if src is None:
+        src = getTopPointSrc(Minv)
+    nodes = np.asarray(Minv.n, dtype=np.int64) + 1
+    q = np.zeros(tuple(int(v) for v in nodes), dtype=TYPE, order="F")
+    q.reshape(-1, order="F")[loc2cs(nodes, src) - 1] = 1.0 / (np.linalg.norm(Minv.h) ** 2)
+    return q, src
+
+
+# ------------------------------------------------------------------ MGparam (Multigrid.jl boundary type)
+class MGparam:
+    """The Multigrid.MGparam fields the reference reads or mutates.  The hierarchy itself lives on the
+    device behind `_hd`."""
+
+    def __init__(self, VAL, levels, numCores, maxOuterIter, relativeTol, relaxType, relaxParam, relaxPre, relaxPost,
+                 cycleType, coarseSolveType, strongConnParam=0.5, FilteringParam=0.0, transferOperatorType="FullWeighting",
+                 coarseIters=10):
+        self.VAL = np.dtype(VAL)
+        self.levels = int(levels)
+        self.numCores = int(numCores)
+        self.maxOuterIter = int(maxOuterIter)
+        self.relativeTol = float(relativeTol)
+        self.relaxType = relaxType
+        self.relaxParam = float(relaxParam)
+        self.relaxPre = relaxPre
+        self.relaxPost = relaxPost
+        self.cycleType = cycleType
+        self.coarseSolveType = coarseSolveType
+        self.strongConnParam = strongConnParam
+        self.FilteringParam = FilteringParam
+        self.transferOperatorType = transferOperatorType
+        self.coarseIters = int(coarseIters)
+        self.doTranspose = 0
+        self._hd = None
+        self._built_for = None
+
+    def _options(self, shift, doTranspose):
+        o = L.hh_mg_options()
+        o.levels = self.levels
+        try:
+            o.relax_type = {"Jac": L.HH_RELAX_JAC, "Jac-GMRES": L.HH_RELAX_JAC_GMRES}[self.relaxType]
+        except KeyError:
+            raise ValueError(f"relaxType {self.relaxType!r} is not supported on the acoustic path (Jac, Jac-GMRES)")
+        try:
+            o.cycle_type = {"V": L.HH_CYCLE_V, "W": L.HH_CYCLE_W, "K": L.HH_CYCLE_K}[str(self.cycleType)]
+        except KeyError:
+            raise ValueError(f"cycleType {self.cycleType!r} is not supported (V, W, K)")
+        try:
+            o.coarse_type = {"NoMUMPS": L.HH_COARSE_LU, "Julia": L.HH_COARSE_LU, "GMRES": L.HH_COARSE_GMRES}[
+                self.coarseSolveType]
+        except KeyError:
+            raise ValueError(f"coarseSolveType {self.coarseSolveType!r} is not supported (NoMUMPS, Julia, GMRES)")
+        o.coarse_iters = self.coarseIters
+        o.do_transpose = int(doTranspose)
+        o.relax_param = self.relaxParam
+        for l in range(L.HH_MAX_LEVELS):
+            o.relax_pre[l] = int(self.relaxPre(l + 1)) if callable(self.relaxPre) else int(self.relaxPre)
+            o.relax_post[l] = int(self.relaxPost(l + 1)) if callable(self.relaxPost) else int(self.relaxPost)
+            o.shift[l] = float(shift[min(l, len(shift) - 1)])
+        return o
+
+    def _signature(self, shift, doTranspose):
+        pre = tuple(int(self.relaxPre(l + 1)) if callable(self.relaxPre) else int(self.relaxPre) for l in range(self.levels))
+        post = tuple(int(self.relaxPost(l + 1)) if callable(self.relaxPost) else int(self.relaxPost) for l in range(self.levels))
+        return (self.levels, self.relaxType, self.relaxParam, pre, post, str(self.cycleType), self.coarseSolveType,
+                self.coarseIters, float(shift[0]), int(doTranspose))
+
+
+def getMGparam(*args, **kw):
+    """Multigrid.getMGparam.  Accepts both call forms seen in the reference:
+      getMGparam(VAL, IND, levels, numCores, maxIter, relativeTol, relaxType, relaxParam, relaxPre, relaxPost,
+                 cycleType, coarseSolveType[, strongConnParam, FilteringParam, transferOperatorType])   (tests)
+      getMGparam(levels, numCores, ...)                                                                  (examples)
+    """
+    args = list(args)
+    VAL = ComplexF64
+    if isinstance(args[0], type) or isinstance(args[0], np.dtype):
+        VAL = args[0]
+        args = args[2:]
+    return MGparam(VAL, *args, **kw)
+
+
+def hierarchyExists(MG):
+    return MG._hd is not None and bool(MG._hd.lib.hh_hierarchy_exists(MG._hd.h))
+
+
+def clear(obj):
+    """clear!(MG) / clear!(solver) / clear!(HelmholtzParam)."""
+    if isinstance(obj, MGparam):
+        if obj._hd is not None:
+            L.check(obj._hd.lib.hh_clear(obj._hd.h), obj._hd.h)
+            obj._hd.close()
+        obj._hd = None
+        obj._built_for = None
+    elif isinstance(obj, ShiftedLaplacianMultigridSolver):
+        clear(obj.MG)  # src/ShiftedLaplacianMultigridSolver.jl:105-109
+        clear(obj.helmParam)
+        obj.doClear = 0
+    elif isinstance(obj, HelmholtzParam):
+        pass  # src/Helmholtz.jl:25-30 only clears the mesh's cached operators
+    else:
+        raise TypeError("clear!: unsupported object")
+
+
+# ------------------------------------------------------------------ the solver plugin
+class ShiftedLaplacianMultigridSolver:
+    """src/ShiftedLaplacianMultigridSolver.jl:4-15"""
+
+    def __init__(self, helmParam, MG, shift, Krylov="BiCGSTAB", inner=5, doClear=0, verbose=False, setupTime=0.0,
+                 nPrec=0, solveTime=0.0):
+        self.helmParam = helmParam
+        self.MG = MG
+        self.shift = np.asarray(shift, dtype=np.float64)
+        self.Krylov = Krylov
+        self.inner = int(inner)
+        self.doClear = doClear
+        self.verbose = verbose
+        self.setupTime = setupTime
+        self.nPrec = nPrec
+        self.solveTime = solveTime
+        # extras the reference only prints
+        self.iterations = None
+        self.relres = None
+        self.devices = None
+
+
+def getShiftedLaplacianMultigridSolver(helmParam, MG, shift, Krylov="BiCGSTAB", inner=5, verbose=False):
+    """src/ShiftedLaplacianMultigridSolver.jl:24-30"""
+    if np.isscalar(shift):
+        shift = np.ones(MG.levels) * float(shift)
+    return ShiftedLaplacianMultigridSolver(helmParam, MG, shift, Krylov, inner, 0, verbose, 0.0, 0, 0.0)
+
+
+def copySolver(s):
+    """src/ShiftedLaplacianMultigridSolver.jl:18-22: clone the settings, not the hierarchy."""
+    MG = s.MG
+    MG2 = MGparam(MG.VAL, MG.levels, MG.numCores, MG.maxOuterIter, MG.relativeTol, MG.relaxType, MG.relaxParam,
+                  MG.relaxPre, MG.relaxPost, MG.cycleType, MG.coarseSolveType, MG.strongConnParam, MG.FilteringParam,
+                  MG.transferOperatorType, MG.coarseIters)
+    s2 = getShiftedLaplacianMultigridSolver(s.helmParam, MG2, s.shift, s.Krylov, s.inner, s.verbose)
+    s2.devices = s.devices
+    return s2
+
+
+def _ensure_hierarchy(param, doTranspose):
+    MG = param.MG
+    hp = param.helmParam
+    sig = MG._signature(param.shift, doTranspose)
+    if MG._hd is None:
+        MG._hd = _Handle(hp.Mesh, hp.m, hp.omega, hp.gamma, hp.NeumannOnTop, hp.Sommerfeld, 2, MG.VAL, param.devices)
+    hd = MG._hd
+    if (not hd.lib.hh_hierarchy_exists(hd.h)) or MG._built_for != sig:
+        # first call (hierarchyExists == false, :50-66), a flipped doTranspose (transposeHierarchy, :68-70) or
+        # settings mutated since the last solve (the tests mutate MG.relaxType / MG.cycleType, test :86-87,138-139)
+        o = MG._options(param.shift, doTranspose)
+        L.check(hd.lib.hh_setup(hd.h, C.byref(o)), hd.h)
+        MG._built_for = sig
+        MG.doTranspose = int(doTranspose)
+    return hd
+
+
+def solveLinearSystem_(ShiftedHT, B, X, param, doTranspose=0):
+    """In-place variant (jInv.LinearSolvers.solveLinearSystem!): X is overwritten.  Returns (X, param)."""
+    if np.iscomplexobj(param.helmParam.omega) and complex(param.helmParam.omega).imag != 0.0:
+        # GetHelmholtzShiftOP(m, omega::Float64, shift) has no method for a complex omega
+        # (src/ShiftedLaplacianMultigridSolver.jl:77)
+        raise TypeError("solveLinearSystem: complex omega is not supported by the shifted-Laplacian solver")
+    if param.Krylov not in ("GMRES", "BiCGSTAB"):
+        raise ValueError(f"Krylov {param.Krylov!r} is not supported (GMRES, BiCGSTAB)")
+    if isinstance(ShiftedHT, HelmholtzOperator) and abs(ShiftedHT.shift - float(param.shift[0])) > 0:
+        raise ValueError("the shifted operator passed in does not carry solver.shift[1]")
+    MG = param.MG
+    if param.doClear == 1:
+        clear(MG)
+    torch_in = _is_torch_cuda(B)
+    if torch_in:
+        import torch
+
+        if float(torch.linalg.vector_norm(B)) == 0.0:  # :40-43
+            X.zero_()
+            return X, param
+    else:
+        if np.linalg.norm(B) == 0.0:
+            X[...] = 0
+            return X, param
+    t0 = time.perf_counter()
+    hd = _ensure_hierarchy(param, doTranspose)
+    param.setupTime += time.perf_counter() - t0
+    so = L.hh_solve_options()
+    so.krylov = L.HH_KRYLOV_GMRES if param.Krylov == "GMRES" else L.HH_KRYLOV_BICGSTAB
+    so.inner = max(int(param.inner), 1)
+    so.max_iter = MG.maxOuterIter
+    so.do_transpose = int(doTranspose)
+    so.rel_tol = MG.relativeTol
+    t0 = time.perf_counter()
+    if torch_in:
+        import torch
+
+        want = torch.complex128 if hd.dtype == np.complex128 else torch.complex64
+        Bt = B.to(want).reshape(-1, hd.N).contiguous()  # rows = right-hand sides (column-major N x nrhs)
+        Xt = X.reshape(-1, hd.N)
+        assert Xt.dtype == want and Xt.is_contiguous()
+        nrhs = Bt.shape[0]
+        iters = np.zeros(nrhs, dtype=np.int32)
+        relres = np.zeros(nrhs, dtype=np.float64)
+        rc = L.check(hd.lib.hh_solve_device(hd.h, Bt.data_ptr(), Xt.data_ptr(), nrhs, C.byref(so),
+                                            _ptr(iters, C.c_int32), _ptr(relres, C.c_double)), hd.h)
+    else:
+        Bm = np.asfortranarray(np.asarray(B).reshape(hd.N, -1), dtype=hd.dtype)
+        nrhs = Bm.shape[1]
+        Xm = np.empty_like(Bm, order="F")
+        iters = np.zeros(nrhs, dtype=np.int32)
+        relres = np.zeros(nrhs, dtype=np.float64)
+        rc = L.check(hd.lib.hh_solve(hd.h, Bm.ctypes.data, Xm.ctypes.data, nrhs, C.byref(so), _ptr(iters, C.c_int32),
+                                     _ptr(relres, C.c_double)), hd.h)
+        X[...] = Xm.reshape(X.shape, order="F")
+    param.solveTime += time.perf_counter() - t0
+    param.nPrec += int(iters.sum())
+    param.iterations = iters
+    param.relres = relres
+    if rc == L.HH_NOT_CONVERGED:
+        print("WARNING: MG solver reached maximum iterations without convergence")  # :97-99
+    return X, param
+
+
+def solveLinearSystem(ShiftedHT, B, param, doTranspose=0):
+    """src/ShiftedLaplacianMultigridSolver.jl:33-102.  The first argument (the adjoint of the shifted
+    matrix in the reference) is accepted for signature compatibility; the hierarchy is built matrix-free
+    from param.helmParam and param.shift[1].  Returns (X, param); X has the shape of B."""
+    if _is_torch_cuda(B):
+        import torch
+
+        dt = torch.complex128 if np.dtype(param.MG.VAL) == np.complex128 else torch.complex64
+        X = torch.empty(B.shape, dtype=dt, device=B.device)
+    else:
+        B = np.asarray(B)
+        if B.ndim == 2 and B.shape[1] == 1:
+            B = B[:, 0]  # :34-36
+        X = np.empty(B.shape, dtype=np.dtype(param.MG.VAL), order="F")
+    return solveLinearSystem_(ShiftedHT, B, X, param, doTranspose)
+
+
+def solvePointSources(param, srcs, amplitudes=None, doTranspose=0):
+    """Solve for point sources without materialising a dense B on the host (hh_solve_point_sources).
+    srcs: list of 1-based subscripts; amplitude default 1/||h||^2 as getAcousticPointSource."""
+    hd = _ensure_hierarchy(param, doTranspose)
+    MG = param.MG
+    Mesh = param.helmParam.Mesh
+    nodes = np.asarray(Mesh.n, dtype=np.int64) + 1
+    idx = np.array([loc2cs(nodes, s) for s in srcs], dtype=np.int64)
+    nrhs = len(idx)
+    if amplitudes is None:
+        amplitudes = np.full(nrhs, 1.0 / (np.linalg.norm(Mesh.h) ** 2))
+    val = np.ascontiguousarray(np.asarray(amplitudes, dtype=np.complex128))
+    so = L.hh_solve_options()
+    so.krylov = L.HH_KRYLOV_GMRES if param.Krylov == "GMRES" else L.HH_KRYLOV_BICGSTAB
+    so.inner = max(int(param.inner), 1)
+    so.max_iter = MG.maxOuterIter
+    so.do_transpose = int(doTranspose)
+    so.rel_tol = MG.relativeTol
+    X = np.empty((hd.N, nrhs), dtype=hd.dtype, order="F")
+    iters = np.zeros(nrhs, dtype=np.int32)
+    relres = np.zeros(nrhs, dtype=np.float64)
+    t0 = time.perf_counter()
+    rc = L.check(hd.lib.hh_solve_point_sources(hd.h, _ptr(idx, C.c_int64), _ptr(val.view(np.float64), C.c_double), nrhs,
+                                               X.ctypes.data, C.byref(so), _ptr(iters, C.c_int32),
+                                               _ptr(relres, C.c_double)), hd.h)
+    param.solveTime += time.perf_counter() - t0
+    param.nPrec += int(iters.sum())
+    param.iterations = iters
+    param.relres = relres
+    if rc == L.HH_NOT_CONVERGED:
+        print("WARNING: MG solver reached maximum iterations without convergence")
+    return X, param

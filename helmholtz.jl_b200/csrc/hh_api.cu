@@ -1,0 +1,577 @@
+// hh_api.cu -- the extern "C" boundary of libhelmholtz_b200.so (see include/helmholtz_b200.h).
+// Catches every C++ exception, maps it to a status code + message, shards right-hand sides over
+// devices for multi-GPU handles, and implements the host-side set-up helpers of the reference
+// (getABL, getMaximalFrequency, loc2cs) that stay Float64 host work.
+#include <memory>
+#include <mutex>
+#include <thread>
+
+#include "hh_solver.cuh"
+
+using namespace hh;
+
+struct hh_handle_s {
+    std::vector<std::unique_ptr<SolverBase>> subs;  // one per device
+    int precision = HH_C64;
+    Problem pb;
+    std::string err;
+    bool have_opts = false;
+    hh_mg_options opts{};
+};
+
+static thread_local std::string g_err;
+
+template <class F>
+static int guarded(hh_handle_t h, F&& f) {
+    try {
+        return f();
+    } catch (const hh::Error& e) {
+        g_err = e.what();
+        if (h) h->err = g_err;
+        return e.code;
+    } catch (const std::bad_alloc&) {
+        g_err = "host allocation failed";
+        if (h) h->err = g_err;
+        return HH_ERR_ALLOC;
+    } catch (const std::exception& e) {
+        g_err = e.what();
+        if (h) h->err = g_err;
+        return HH_ERR_STATE;
+    } catch (...) {
+        g_err = "unknown error";
+        if (h) h->err = g_err;
+        return HH_ERR_STATE;
+    }
+}
+
+// run f(sub_index) on every device replica concurrently; rethrow the first failure
+template <class F>
+static void for_each_sub(hh_handle_t h, F&& f) {
+    const int n = (int)h->subs.size();
+    if (n == 1) {
+        f(0);
+        return;
+    }
+    std::vector<std::thread> th;
+    std::vector<std::string> msg(n);
+    std::vector<int> code(n, 0);
+    for (int i = 0; i < n; ++i) {
+        th.emplace_back([&, i] {
+            try {
+                f(i);
+            } catch (const hh::Error& e) {
+                code[i] = e.code;
+                msg[i] = e.what();
+            } catch (const std::exception& e) {
+                code[i] = HH_ERR_STATE;
+                msg[i] = e.what();
+            }
+        });
+    }
+    for (auto& t : th) t.join();
+    for (int i = 0; i < n; ++i)
+        if (code[i] != 0) throw hh::Error(code[i], "device replica " + std::to_string(i) + ": " + msg[i]);
+}
+
+extern "C" {
+
+int hh_version(void) { return HH_VERSION; }
+
+const char* hh_last_error(hh_handle_t h) { return h ? h->err.c_str() : g_err.c_str(); }
+
+int hh_device_count(int* count) {
+    if (!count) return HH_ERR_ARG;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        n = 0;
+    }
+    *count = n;
+    return HH_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// getABL (src/GetHelmholtz.jl:97-220), live branches only: 2-D impl == 1 (:141-163), 3-D (:164-218)
+// ---------------------------------------------------------------------------------------------
+int hh_get_abl(int dim, const int64_t* n, int neumann_on_top, const int64_t* pad, double amp, double* gamma) {
+    return guarded(nullptr, [&]() -> int {
+        HH_REQUIRE((dim == 2 || dim == 3) && n && pad && gamma, HH_ERR_ARG, "hh_get_abl: bad arguments");
+        for (int d = 0; d < dim; ++d)
+            HH_REQUIRE(n[d] >= 2 && pad[d] >= 1 && pad[d] <= n[d], HH_ERR_ARG, "hh_get_abl: pad must be in 1..n");
+        if (dim == 2) {
+            const int64_t n1 = n[0], n2 = n[1], p1 = pad[0], p2 = pad[1];
+            std::vector<double> a1(n1, 0.0), a2(n2, 0.0);
+            // a1: ramp ((p1..1)/p1)^2 on the first p1 nodes, ((1..p1)/p1)^2 on the last p1; later writes add
+            for (int64_t t = 0; t < p1; ++t) {
+                const double bwd = (double)((p1 - t) * (p1 - t)) / (double)(p1 * p1);
+                const double fwd = (double)((t + 1) * (t + 1)) / (double)(p1 * p1);
+                a1[t] += bwd;
+                a1[n1 - p1 + t] += fwd;
+            }
+            std::vector<double> top(n2, 0.0), bot(n2, 0.0);
+            for (int64_t t = 0; t < p2; ++t) {
+                top[t] = (double)((p2 - t) * (p2 - t)) / (double)(p2 * p2);
+                bot[n2 - p2 + t] = (double)((t + 1) * (t + 1)) / (double)(p2 * p2);
+            }
+            // the reference adds the side ramps over all columns and subtracts the corner products only where
+            // the side ramp meets the dim-2 ramp (first p1 / last p1 rows separately, GetHelmholtz.jl:152-161)
+            std::vector<double> l1(n1, 0.0), r1(n1, 0.0);
+            for (int64_t t = 0; t < p1; ++t) {
+                l1[t] = (double)((p1 - t) * (p1 - t)) / (double)(p1 * p1);
+                r1[n1 - p1 + t] = (double)((t + 1) * (t + 1)) / (double)(p1 * p1);
+            }
+            for (int64_t j = 0; j < n2; ++j) {
+                for (int64_t i = 0; i < n1; ++i) {
+                    double g = 0.0;
+                    if (!neumann_on_top) g += top[j] - l1[i] * top[j] - r1[i] * top[j];
+                    g += bot[j];
+                    g += l1[i];
+                    g += r1[i];
+                    g -= l1[i] * bot[j];
+                    g -= r1[i] * bot[j];
+                    gamma[i + n1 * j] = g * amp;
+                }
+            }
+            (void)a1;
+            (void)a2;
+            return HH_OK;
+        }
+        const int64_t nn[3] = {n[0], n[1], n[2]};
+        std::vector<double> g[3];
+        for (int d = 0; d < 3; ++d) {
+            const int64_t nd = nn[d], p = pad[d];
+            const double x0 = d < 2 ? -1.0 : 0.0, x1 = 1.0;
+            std::vector<double> x(nd);
+            // Julia range(a, stop=b, length=n): a + i*(b-a)/(n-1) (evaluated like LinRange: lerp)
+            for (int64_t i = 0; i < nd; ++i) {
+                const double t = nd > 1 ? (double)i / (double)(nd - 1) : 0.0;
+                x[i] = (1.0 - t) * x0 + t * x1;
+            }
+            g[d].assign(nd, 0.0);
+            const bool left = !(d == 2 && neumann_on_top);
+            if (left)
+                for (int64_t i = 0; i < p; ++i) g[d][i] += (x[i] - x[p - 1]) * (x[i] - x[p - 1]);
+            for (int64_t i = nd - p; i < nd; ++i) g[d][i] += (x[i] - x[nd - p]) * (x[i] - x[nd - p]);
+            double mx = 0.0;
+            for (int64_t i = 0; i < nd; ++i) mx = std::max(mx, g[d][i]);
+            for (int64_t i = 0; i < nd; ++i) g[d][i] /= (mx + 1e-5);
+        }
+        for (int64_t k = 0; k < nn[2]; ++k)
+            for (int64_t j = 0; j < nn[1]; ++j)
+                for (int64_t i = 0; i < nn[0]; ++i) {
+                    double v = (g[0][i] + g[1][j] + g[2][k]) * amp;
+                    if (v >= amp) v = amp;
+                    gamma[i + nn[0] * (j + nn[1] * k)] = v;
+                }
+        return HH_OK;
+    });
+}
+
+// getMaximalFrequency (src/GetHelmholtz.jl:75-79)
+int hh_get_maximal_frequency(const double* m, int64_t n, int dim, const double* h, double* omega_max) {
+    return guarded(nullptr, [&]() -> int {
+        HH_REQUIRE(m && h && omega_max && n > 0 && dim >= 1 && dim <= 3, HH_ERR_ARG, "hh_get_maximal_frequency: bad arguments");
+        double mm = m[0], hm = h[0];
+        for (int64_t i = 1; i < n; ++i) mm = std::max(mm, m[i]);
+        for (int d = 1; d < dim; ++d) hm = std::max(hm, h[d]);
+        *omega_max = (0.1 * 2 * M_PI) / (hm * std::sqrt(mm));
+        return HH_OK;
+    });
+}
+
+// loc2cs / loc2cs3D (src/getPointSource.jl:82-102): 1-based in, 1-based out
+int64_t hh_point_source_index(int dim, const int64_t* n, const int64_t* sub) {
+    if (!n || !sub) return -1;
+    if (dim == 2) return sub[0] + (sub[1] - 1) * n[0];
+    if (dim == 3) return sub[0] + (sub[1] - 1) * n[0] + (sub[2] - 1) * n[0] * n[1];
+    return -1;
+}
+
+// ---------------------------------------------------------------------------------------------
+static int create_impl(int dim, const int64_t* n_nodes, const double* hsp, const double* m, const double* gamma,
+                       double wre, double wim, int neumann_on_top, int sommerfeld, int order_bc, int precision,
+                       const int* devices, int ndev, hh_handle_t* out) {
+    return guarded(nullptr, [&]() -> int {
+        HH_REQUIRE(out != nullptr, HH_ERR_ARG, "hh_create: out is NULL");
+        *out = nullptr;
+        HH_REQUIRE(dim == 2 || dim == 3, HH_ERR_ARG, "hh_create: dim must be 2 or 3");
+        HH_REQUIRE(n_nodes && hsp && m && gamma, HH_ERR_ARG, "hh_create: NULL array");
+        HH_REQUIRE(precision == HH_C64 || precision == HH_C32, HH_ERR_ARG, "hh_create: bad precision");
+        HH_REQUIRE(order_bc == 1 || order_bc == 2, HH_ERR_ARG, "getNodalLaplacianMatrix: BC not supported");
+        HH_REQUIRE(wre != 0.0, HH_ERR_ARG, "hh_create: Re(omega) must be non-zero");
+        HH_REQUIRE(ndev >= 1 && devices, HH_ERR_ARG, "hh_create: no devices");
+        Problem pb;
+        pb.dim = dim;
+        for (int d = 0; d < dim; ++d) {
+            HH_REQUIRE(n_nodes[d] >= 2 && n_nodes[d] < (1 << 30), HH_ERR_ARG, "hh_create: node counts must be >= 2");
+            HH_REQUIRE(hsp[d] > 0.0, HH_ERR_ARG, "hh_create: mesh spacing must be positive");
+            pb.n[d] = (int)n_nodes[d];
+            pb.h[d] = hsp[d];
+        }
+        pb.neumann_top = neumann_on_top ? 1 : 0;
+        pb.sommerfeld = sommerfeld ? 1 : 0;
+        pb.order_bc = order_bc;
+        int ndevices = 0;
+        cudaError_t e = cudaGetDeviceCount(&ndevices);
+        if (e != cudaSuccess || ndevices == 0) {
+            cudaGetLastError();
+            throw hh::Error(HH_ERR_CUDA, "no CUDA device available (this library has no CPU fallback)");
+        }
+        std::unique_ptr<hh_handle_s> h(new hh_handle_s);
+        h->precision = precision;
+        h->pb = pb;
+        for (int i = 0; i < ndev; ++i) {
+            HH_REQUIRE(devices[i] >= 0 && devices[i] < ndevices, HH_ERR_ARG, "hh_create: bad device ordinal");
+            if (precision == HH_C64) h->subs.emplace_back(new Solver<double>(pb, devices[i]));
+            else h->subs.emplace_back(new Solver<float>(pb, devices[i]));
+        }
+        for_each_sub(h.get(), [&](int i) { h->subs[i]->set_model(m, gamma, wre, wim); });
+        h->pb.w_re = wre;
+        h->pb.w_im = wim;
+        *out = h.release();
+        return HH_OK;
+    });
+}
+
+int hh_create(int dim, const int64_t* n_nodes, const double* h, const double* m, const double* gamma, double omega_re,
+              double omega_im, int neumann_on_top, int sommerfeld, int order_neumann_bc, int precision, int device,
+              hh_handle_t* out) {
+    return create_impl(dim, n_nodes, h, m, gamma, omega_re, omega_im, neumann_on_top, sommerfeld, order_neumann_bc,
+                       precision, &device, 1, out);
+}
+
+int hh_create_multi(int dim, const int64_t* n_nodes, const double* h, const double* m, const double* gamma,
+                    double omega_re, double omega_im, int neumann_on_top, int sommerfeld, int order_neumann_bc,
+                    int precision, const int* devices, int n_devices, hh_handle_t* out) {
+    return create_impl(dim, n_nodes, h, m, gamma, omega_re, omega_im, neumann_on_top, sommerfeld, order_neumann_bc,
+                       precision, devices, n_devices, out);
+}
+
+int hh_destroy(hh_handle_t h) {
+    if (!h) return HH_OK;
+    return guarded(nullptr, [&]() -> int {
+        for (auto& s : h->subs) {
+            cudaSetDevice(s->device);
+            s.reset();
+        }
+        delete h;
+        return HH_OK;
+    });
+}
+
+int hh_set_stream(hh_handle_t h, void* cuda_stream) {
+    if (!h) return HH_ERR_ARG;
+    return guarded(h, [&]() -> int {
+        HH_REQUIRE(h->subs.size() == 1 || cuda_stream == nullptr, HH_ERR_ARG,
+                   "hh_set_stream: a multi-device handle runs on per-device default streams");
+        h->subs[0]->stream = (cudaStream_t)cuda_stream;
+        return HH_OK;
+    });
+}
+
+int hh_update_model(hh_handle_t h, const double* m, const double* gamma, double omega_re, double omega_im) {
+    if (!h) return HH_ERR_ARG;
+    return guarded(h, [&]() -> int {
+        HH_REQUIRE(m && gamma && omega_re != 0.0, HH_ERR_ARG, "hh_update_model: bad arguments");
+        for_each_sub(h, [&](int i) { h->subs[i]->set_model(m, gamma, omega_re, omega_im); });
+        h->pb.w_re = omega_re;
+        h->pb.w_im = omega_im;
+        return HH_OK;
+    });
+}
+
+int hh_setup(hh_handle_t h, const hh_mg_options* opts) {
+    if (!h) return HH_ERR_ARG;
+    return guarded(h, [&]() -> int {
+        HH_REQUIRE(opts != nullptr, HH_ERR_ARG, "hh_setup: opts is NULL");
+        for_each_sub(h, [&](int i) { h->subs[i]->setup(*opts); });
+        h->opts = *opts;
+        h->have_opts = true;
+        return HH_OK;
+    });
+}
+
+int hh_clear(hh_handle_t h) {
+    if (!h) return HH_ERR_ARG;
+    return guarded(h, [&]() -> int {
+        for_each_sub(h, [&](int i) {
+            cudaSetDevice(h->subs[i]->device);
+            h->subs[i]->clear();
+        });
+        return HH_OK;
+    });
+}
+
+int hh_hierarchy_exists(hh_handle_t h) { return (h && h->subs[0]->hierarchy_exists()) ? 1 : 0; }
+
+int hh_level_nodes(hh_handle_t h, int level, int64_t* out) {
+    if (!h || !out) return HH_ERR_ARG;
+    return guarded(h, [&]() -> int {
+        h->subs[0]->level_nodes(level, out);
+        return HH_OK;
+    });
+}
+
+int hh_get_level_stencil(hh_handle_t h, int level, void* coef_out) {
+    if (!h || !coef_out) return HH_ERR_ARG;
+    return guarded(h, [&]() -> int {
+        h->subs[0]->get_level_stencil(level, coef_out);
+        return HH_OK;
+    });
+}
+
+int hh_get_diagonal(hh_handle_t h, int shifted, double shift, double* diag_out) {
+    if (!h || !diag_out) return HH_ERR_ARG;
+    return guarded(h, [&]() -> int {
+        h->subs[0]->get_diagonal(shifted, shift, diag_out);
+        return HH_OK;
+    });
+}
+
+// ---------------------------------------------------------------------------------------------
+int hh_apply_device(hh_handle_t h, const void* dX, void* dY, int64_t nrhs, int shifted, double shift, int transpose) {
+    if (!h) return HH_ERR_ARG;
+    return guarded(h, [&]() -> int {
+        HH_REQUIRE(dX && dY && nrhs >= 1 && dX != dY, HH_ERR_ARG, "hh_apply_device: bad arguments");
+        HH_REQUIRE(h->subs.size() == 1, HH_ERR_UNSUPPORTED, "device-pointer entry points need a single-device handle");
+        h->subs[0]->apply_device(dX, dY, nrhs, shifted, shift, transpose);
+        return HH_OK;
+    });
+}
+
+// split [0,nrhs) into contiguous column ranges, one per replica
+static void column_range(int64_t nrhs, int nparts, int part, int64_t& c0, int64_t& c1) {
+    const int64_t base = nrhs / nparts, rem = nrhs % nparts;
+    c0 = part * base + std::min<int64_t>(part, rem);
+    c1 = c0 + base + (part < rem ? 1 : 0);
+}
+
+int hh_apply(hh_handle_t h, const void* X, void* Y, int64_t nrhs, int shifted, double shift, int transpose) {
+    if (!h) return HH_ERR_ARG;
+    return guarded(h, [&]() -> int {
+        HH_REQUIRE(X && Y && nrhs >= 1, HH_ERR_ARG, "hh_apply: bad arguments");
+        const int64_t N = h->pb.N();
+        for_each_sub(h, [&](int i) {
+            SolverBase* s = h->subs[i].get();
+            int64_t c0, c1;
+            column_range(nrhs, (int)h->subs.size(), i, c0, c1);
+            if (c1 <= c0) return;
+            HH_CUDA(cudaSetDevice(s->device));
+            const size_t es = s->elem_size();
+            // chunk so that two N x k buffers fit comfortably
+            size_t fr = 0, tot = 0;
+            HH_CUDA(cudaMemGetInfo(&fr, &tot));
+            int64_t kmax = std::max<int64_t>(1, (int64_t)(0.4 * (double)fr / ((double)N * es)));
+            for (int64_t c = c0; c < c1; c += kmax) {
+                const int64_t k = std::min(kmax, c1 - c);
+                DevBuf<char> dx, dy;
+                dx.alloc((size_t)N * k * es);
+                dy.alloc((size_t)N * k * es);
+                HH_CUDA(cudaMemcpyAsync(dx.p, (const char*)X + (size_t)c * N * es, (size_t)N * k * es, cudaMemcpyHostToDevice, s->stream));
+                s->apply_device(dx.p, dy.p, k, shifted, shift, transpose);
+                HH_CUDA(cudaMemcpyAsync((char*)Y + (size_t)c * N * es, dy.p, (size_t)N * k * es, cudaMemcpyDeviceToHost, s->stream));
+                HH_CUDA(cudaStreamSynchronize(s->stream));
+            }
+        });
+        return HH_OK;
+    });
+}
+
+int hh_cycle_device(hh_handle_t h, const void* dB, void* dZ, int64_t nrhs) {
+    if (!h) return HH_ERR_ARG;
+    return guarded(h, [&]() -> int {
+        HH_REQUIRE(dB && dZ && nrhs >= 1 && dB != dZ, HH_ERR_ARG, "hh_cycle_device: bad arguments");
+        HH_REQUIRE(h->subs.size() == 1, HH_ERR_UNSUPPORTED, "device-pointer entry points need a single-device handle");
+        h->subs[0]->cycle_device(dB, dZ, nrhs);
+        return HH_OK;
+    });
+}
+
+int hh_cycle(hh_handle_t h, const void* B, void* Z, int64_t nrhs) {
+    if (!h) return HH_ERR_ARG;
+    return guarded(h, [&]() -> int {
+        HH_REQUIRE(B && Z && nrhs >= 1, HH_ERR_ARG, "hh_cycle: bad arguments");
+        SolverBase* s = h->subs[0].get();
+        HH_CUDA(cudaSetDevice(s->device));
+        const int64_t N = h->pb.N();
+        const size_t es = s->elem_size();
+        DevBuf<char> db, dz;
+        db.alloc((size_t)N * nrhs * es);
+        dz.alloc((size_t)N * nrhs * es);
+        HH_CUDA(cudaMemcpy(db.p, B, (size_t)N * nrhs * es, cudaMemcpyHostToDevice));
+        s->cycle_device(db.p, dz.p, nrhs);
+        HH_CUDA(cudaMemcpy(Z, dz.p, (size_t)N * nrhs * es, cudaMemcpyDeviceToHost));
+        return HH_OK;
+    });
+}
+
+// ---------------------------------------------------------------------------------------------
+static void check_solve_opts(const hh_solve_options* o) {
+    HH_REQUIRE(o != nullptr, HH_ERR_ARG, "solve options are NULL");
+    HH_REQUIRE(o->rel_tol >= 0.0, HH_ERR_ARG, "rel_tol must be >= 0");
+}
+
+int hh_solve_device(hh_handle_t h, const void* dB, void* dX, int64_t nrhs, const hh_solve_options* opts,
+                    int32_t* iters_out, double* relres_out) {
+    if (!h) return HH_ERR_ARG;
+    return guarded(h, [&]() -> int {
+        HH_REQUIRE(dB && dX && nrhs >= 1 && dB != dX, HH_ERR_ARG, "hh_solve_device: bad arguments");
+        check_solve_opts(opts);
+        HH_REQUIRE(h->subs.size() == 1, HH_ERR_UNSUPPORTED, "device-pointer entry points need a single-device handle");
+        SolverBase* s = h->subs[0].get();
+        const int64_t kmax = s->max_rhs_per_batch(*opts);
+        HH_REQUIRE(kmax >= 1, HH_ERR_ALLOC, "not enough device memory for one right-hand side");
+        const int64_t N = h->pb.N();
+        const size_t es = s->elem_size();
+        int rc = HH_OK;
+        for (int64_t c = 0; c < nrhs; c += kmax) {
+            const int64_t k = std::min(kmax, nrhs - c);
+            int r = s->solve_device((const char*)dB + (size_t)c * N * es, (char*)dX + (size_t)c * N * es, k, *opts,
+                                    iters_out ? iters_out + c : nullptr, relres_out ? relres_out + c : nullptr);
+            rc = std::max(rc, r);
+        }
+        return rc;
+    });
+}
+
+// host-pointer solve; `idx`/`val` non-NULL selects point-source right-hand sides instead of B
+static int solve_host(hh_handle_t h, const void* B, const int64_t* idx, const double* val, void* X, int64_t nrhs,
+                      const hh_solve_options* opts, int32_t* iters_out, double* relres_out) {
+    check_solve_opts(opts);
+    const int64_t N = h->pb.N();
+    const int nsub = (int)h->subs.size();
+    std::vector<int> rcs(nsub, HH_OK);
+    if (idx)
+        for (int64_t r = 0; r < nrhs; ++r)
+            HH_REQUIRE(idx[r] >= 1 && idx[r] <= N, HH_ERR_ARG, "point source index out of range (1-based)");
+    for_each_sub(h, [&](int i) {
+        SolverBase* s = h->subs[i].get();
+        int64_t c0, c1;
+        column_range(nrhs, nsub, i, c0, c1);
+        if (c1 <= c0) return;
+        HH_CUDA(cudaSetDevice(s->device));
+        const size_t es = s->elem_size();
+        // B and X chunks live on the device next to the Krylov vectors: reserve them first
+        size_t fr = 0, tot = 0;
+        HH_CUDA(cudaMemGetInfo(&fr, &tot));
+        int64_t kmax = s->max_rhs_per_batch(*opts);
+        // two more vectors per RHS (B, X)
+        const double per_now = (double)N * es;
+        {
+            // shrink so that B and X fit as well (max_rhs_per_batch assumed they were caller memory)
+            const int kv = opts->krylov == HH_KRYLOV_GMRES ? 2 * opts->inner + 1 : 7;
+            kmax = (int64_t)((double)kmax * (double)(kv + 2) / (double)(kv + 4));
+        }
+        (void)per_now;
+        kmax = std::min<int64_t>(std::max<int64_t>(kmax, 1), c1 - c0);
+        DevBuf<char> db, dx;
+        db.alloc((size_t)N * kmax * es);
+        dx.alloc((size_t)N * kmax * es);
+        std::vector<int64_t> idx0;
+        for (int64_t c = c0; c < c1; c += kmax) {
+            const int64_t k = std::min(kmax, c1 - c);
+            if (idx) {
+                idx0.resize(k);
+                for (int64_t r = 0; r < k; ++r) idx0[r] = idx[c + r] - 1;
+                s->scatter_point_sources(db.p, idx0.data(), val + 2 * c, k);
+            } else {
+                HH_CUDA(cudaMemcpyAsync(db.p, (const char*)B + (size_t)c * N * es, (size_t)N * k * es, cudaMemcpyHostToDevice, s->stream));
+            }
+            int r = s->solve_device(db.p, dx.p, k, *opts, iters_out ? iters_out + c : nullptr,
+                                    relres_out ? relres_out + c : nullptr);
+            rcs[i] = std::max(rcs[i], r);
+            HH_CUDA(cudaMemcpyAsync((char*)X + (size_t)c * N * es, dx.p, (size_t)N * k * es, cudaMemcpyDeviceToHost, s->stream));
+            HH_CUDA(cudaStreamSynchronize(s->stream));
+        }
+    });
+    int rc = HH_OK;
+    for (int r : rcs) rc = std::max(rc, r);
+    return rc;
+}
+
+int hh_solve(hh_handle_t h, const void* B, void* X, int64_t nrhs, const hh_solve_options* opts, int32_t* iters_out,
+             double* relres_out) {
+    if (!h) return HH_ERR_ARG;
+    return guarded(h, [&]() -> int {
+        HH_REQUIRE(B && X && nrhs >= 1, HH_ERR_ARG, "hh_solve: bad arguments");
+        return solve_host(h, B, nullptr, nullptr, X, nrhs, opts, iters_out, relres_out);
+    });
+}
+
+int hh_solve_point_sources(hh_handle_t h, const int64_t* idx, const double* val, int64_t nrhs, void* X,
+                           const hh_solve_options* opts, int32_t* iters_out, double* relres_out) {
+    if (!h) return HH_ERR_ARG;
+    return guarded(h, [&]() -> int {
+        HH_REQUIRE(idx && val && X && nrhs >= 1, HH_ERR_ARG, "hh_solve_point_sources: bad arguments");
+        return solve_host(h, nullptr, idx, val, X, nrhs, opts, iters_out, relres_out);
+    });
+}
+
+// ---------------------------------------------------------------------------------------------
+int hh_get_counters(hh_handle_t h, double* setup_seconds, double* solve_seconds, int64_t* n_prec,
+                    int64_t* kernel_launches) {
+    if (!h) return HH_ERR_ARG;
+    double a = 0, b = 0;
+    int64_t c = 0, d = 0;
+    for (auto& s : h->subs) {
+        a = std::max(a, s->setup_seconds);
+        b = std::max(b, s->solve_seconds);
+        c += s->n_prec;
+        d += s->launches;
+    }
+    if (setup_seconds) *setup_seconds = a;
+    if (solve_seconds) *solve_seconds = b;
+    if (n_prec) *n_prec = c;
+    if (kernel_launches) *kernel_launches = d;
+    return HH_OK;
+}
+
+int hh_profile_enable(hh_handle_t h, int on) {
+    if (!h) return HH_ERR_ARG;
+    return guarded(h, [&]() -> int {
+        for (auto& s : h->subs) {
+            HH_CUDA(cudaSetDevice(s->device));
+            if (!on) s->prof.flush(s->stream);
+            s->prof.on = on != 0;
+        }
+        return HH_OK;
+    });
+}
+
+int hh_profile_reset(hh_handle_t h) {
+    if (!h) return HH_ERR_ARG;
+    return guarded(h, [&]() -> int {
+        for (auto& s : h->subs) {
+            HH_CUDA(cudaSetDevice(s->device));
+            s->prof.flush(s->stream);
+            s->prof.reset();
+        }
+        return HH_OK;
+    });
+}
+
+int hh_profile_num_tags(void) { return T_NTAGS; }
+
+const char* hh_profile_tag_name(int tag) { return (tag >= 0 && tag < T_NTAGS) ? kTagNames[tag] : ""; }
+
+int hh_profile_get(hh_handle_t h, int tag, int64_t* launches, double* milliseconds, double* algorithmic_bytes) {
+    if (!h || tag < 0 || tag >= T_NTAGS) return HH_ERR_ARG;
+    return guarded(h, [&]() -> int {
+        int64_t n = 0;
+        double ms = 0, by = 0;
+        for (auto& s : h->subs) {
+            HH_CUDA(cudaSetDevice(s->device));
+            s->prof.flush(s->stream);
+            n += s->prof.count[tag];
+            ms += s->prof.ms[tag];
+            by += s->prof.bytes[tag];
+        }
+        if (launches) *launches = n;
+        if (milliseconds) *milliseconds = ms;
+        if (algorithmic_bytes) *algorithmic_bytes = by;
+        return HH_OK;
+    });
+}
+
+}  // extern "C"

@@ -1,0 +1,902 @@
+// hh_kernels.cuh -- sm_100a kernels of the shifted-Laplacian multigrid Helmholtz solve.
+//
+// Operator (reference src/GetHelmholtz.jl:33-50,81-83,222-247 and
+// src/PlainNodalLaplacian.jl:18-46):
+//   (H u)_p = sum_d L_d(u)_p + c_p u_p,   L = -laplacian with ghost-eliminated Neumann rows,
+//   c_p = -w^2 m_p (1 - i g_p / Re w) + i Re(w) sqrt(m_p) sum_faces 2/h_d  [+ i shift Re(w)^2 m_p]
+// The fine level is matrix-free (m, gamma are the only arrays read besides the vectors); coarse
+// levels hold the Galerkin 3^dim-point stencil as structure-of-arrays coef[s][node].
+#pragma once
+#include "hh_common.cuh"
+
+namespace hh {
+
+enum { MODE_APPLY = 0, MODE_RESID = 1, MODE_JACOBI = 2 };
+
+template <typename T>
+struct FineOp {
+    const T* m;   // slowness squared, N reals
+    const T* g;   // gamma (attenuation incl. absorbing layer), N reals
+    T a, b;       // omega^2 = a + i b
+    T inv_wr;     // 1 / Re(omega)
+    T shift_w2;   // shift * Re(omega)^2   (0 for the un-shifted operator)
+    T somm[3];    // Re(omega) * 2/h_d when Sommerfeld, else 0
+    T ih2[3];     // 1/h_d^2
+    T BC;         // 2 (second-order Neumann ghost) or 1
+    int n[3];     // node counts (n[2] == 1 in 2-D)
+    int neumann_top;
+    int adj;      // 1: conjugate transpose
+};
+
+template <typename T>
+struct CoarseOp {
+    const cx<T>* coef;  // [3^dim][N] stencil coefficients
+    const cx<T>* dinv;  // [N] damping / diagonal
+    int n[3];
+};
+
+// ---------------------------------------------------------------------------------------------
+// fine-level coefficient evaluation
+// ---------------------------------------------------------------------------------------------
+template <typename T, int DIM>
+__device__ __forceinline__ cx<T> fine_center(const FineOp<T>& op, int64_t p, int i, int j, int k) {
+    const T mv = op.m[p];
+    const T gv = op.g[p] * op.inv_wr;
+    T re = -mv * (op.a + op.b * gv);
+    T im = -mv * (op.b - op.a * gv) + op.shift_w2 * mv;
+    T sf = T(0);
+    const bool bi = (i == 0) | (i == op.n[0] - 1);
+    const bool bj = (j == 0) | (j == op.n[1] - 1);
+    if (DIM == 2) {
+        if (bi) sf += op.somm[0];
+        if ((j == 0 && !op.neumann_top) || j == op.n[1] - 1) sf += op.somm[1];
+    } else {
+        if (bi) sf += op.somm[0];
+        if (bj) sf += op.somm[1];
+        if ((k == 0 && !op.neumann_top) || k == op.n[2] - 1) sf += op.somm[2];
+    }
+    if (sf != T(0)) im += sf * sqrt(mv);
+    re += (bi ? op.BC : T(2)) * op.ih2[0];
+    re += (bj ? op.BC : T(2)) * op.ih2[1];
+    if (DIM == 3) re += ((k == 0 || k == op.n[2] - 1) ? op.BC : T(2)) * op.ih2[2];
+    if (op.adj) im = -im;
+    return mk<T>(re, im);
+}
+
+// weight w such that the row of node `idx` (along dimension d, n nodes) holds -w on the neighbour at
+// idx-1 (side 0) / idx+1 (side 1); 0 when that neighbour does not exist.
+template <typename T>
+__device__ __forceinline__ T fine_w(const FineOp<T>& op, int d, int side, int idx, int n) {
+    if (side == 0) {
+        if (idx == 0) return T(0);
+        const bool bc = op.adj ? (idx - 1 == 0) : (idx == n - 1);
+        return (bc ? op.BC : T(1)) * op.ih2[d];
+    } else {
+        if (idx == n - 1) return T(0);
+        const bool bc = op.adj ? (idx + 1 == n - 1) : (idx == 0);
+        return (bc ? op.BC : T(1)) * op.ih2[d];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K1/K2 (baseline form): fine-level stencil, one thread per node, KB right-hand sides per pass so
+// that m/gamma and the index arithmetic are amortised.  MODE selects the fused epilogue:
+//   APPLY : out = A x        RESID : out = b - A x        JACOBI : out = x + damp/diag (b - A x)
+// ---------------------------------------------------------------------------------------------
+template <typename T, int DIM, int MODE, int KB>
+__global__ void __launch_bounds__(256) k_fine_stencil(FineOp<T> op, const cx<T>* __restrict__ x,
+                                                      const cx<T>* __restrict__ b, cx<T>* __restrict__ out,
+                                                      int64_t ld, int nrhs, T damp) {
+    const int n0 = op.n[0], n1 = op.n[1], n2 = op.n[2];
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = blockIdx.y * blockDim.y + threadIdx.y;
+    const int k = (DIM == 3) ? blockIdx.z * blockDim.z + threadIdx.z : 0;
+    if (i >= n0 || j >= n1 || k >= n2) return;
+    const int64_t sy = n0, sz = (int64_t)n0 * n1;
+    const int64_t p = i + sy * j + sz * k;
+    const cx<T> c = fine_center<T, DIM>(op, p, i, j, k);
+    const T wxm = fine_w(op, 0, 0, i, n0), wxp = fine_w(op, 0, 1, i, n0);
+    const T wym = fine_w(op, 1, 0, j, n1), wyp = fine_w(op, 1, 1, j, n1);
+    const T wzm = (DIM == 3) ? fine_w(op, 2, 0, k, n2) : T(0);
+    const T wzp = (DIM == 3) ? fine_w(op, 2, 1, k, n2) : T(0);
+    // clamp neighbour offsets so that absent neighbours (weight 0) read the centre
+    const int64_t oxm = wxm != T(0) ? -1 : 0, oxp = wxp != T(0) ? 1 : 0;
+    const int64_t oym = wym != T(0) ? -sy : 0, oyp = wyp != T(0) ? sy : 0;
+    const int64_t ozm = wzm != T(0) ? -sz : 0, ozp = wzp != T(0) ? sz : 0;
+    cx<T> dinv = mk<T>(T(0), T(0));
+    if (MODE == MODE_JACOBI) dinv = rdiv(damp, c);
+    for (int r0 = 0; r0 < nrhs; r0 += KB) {
+        cx<T> acc[KB], xc[KB];
+#pragma unroll
+        for (int q = 0; q < KB; ++q) {
+            if (r0 + q < nrhs) {
+                const cx<T>* xr = x + (int64_t)(r0 + q) * ld + p;
+                xc[q] = xr[0];
+                cx<T> a = c * xc[q];
+                rfma(a, -wxm, xr[oxm]);
+                rfma(a, -wxp, xr[oxp]);
+                rfma(a, -wym, xr[oym]);
+                rfma(a, -wyp, xr[oyp]);
+                if (DIM == 3) {
+                    rfma(a, -wzm, xr[ozm]);
+                    rfma(a, -wzp, xr[ozp]);
+                }
+                acc[q] = a;
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < KB; ++q) {
+            if (r0 + q < nrhs) {
+                const int64_t o = (int64_t)(r0 + q) * ld + p;
+                if (MODE == MODE_APPLY) {
+                    out[o] = acc[q];
+                } else if (MODE == MODE_RESID) {
+                    out[o] = b[o] - acc[q];
+                } else {
+                    out[o] = xc[q] + dinv * (b[o] - acc[q]);
+                }
+            }
+        }
+    }
+}
+
+// first Jacobi sweep from a zero guess on the fine level: out = damp/diag * b
+template <typename T, int DIM>
+__global__ void __launch_bounds__(256) k_fine_jacobi0(FineOp<T> op, const cx<T>* __restrict__ b,
+                                                      cx<T>* __restrict__ out, int64_t ld, int nrhs, T damp) {
+    const int n0 = op.n[0], n1 = op.n[1], n2 = op.n[2];
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = blockIdx.y * blockDim.y + threadIdx.y;
+    const int k = (DIM == 3) ? blockIdx.z * blockDim.z + threadIdx.z : 0;
+    if (i >= n0 || j >= n1 || k >= n2) return;
+    const int64_t p = i + (int64_t)n0 * j + (int64_t)n0 * n1 * k;
+    const cx<T> dinv = rdiv(damp, fine_center<T, DIM>(op, p, i, j, k));
+    for (int r = 0; r < nrhs; ++r) out[(int64_t)r * ld + p] = dinv * b[(int64_t)r * ld + p];
+}
+
+// complex diagonal c_p (without the Laplacian part) in double, for hh_get_diagonal
+template <typename T, int DIM>
+__global__ void k_fine_diag(FineOp<T> op, zc* __restrict__ out) {
+    const int n0 = op.n[0], n1 = op.n[1], n2 = op.n[2];
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = blockIdx.y * blockDim.y + threadIdx.y;
+    const int k = (DIM == 3) ? blockIdx.z * blockDim.z + threadIdx.z : 0;
+    if (i >= n0 || j >= n1 || k >= n2) return;
+    const int64_t p = i + (int64_t)n0 * j + (int64_t)n0 * n1 * k;
+    cx<T> c = fine_center<T, DIM>(op, p, i, j, k);
+    const bool bi = (i == 0) | (i == n0 - 1), bj = (j == 0) | (j == n1 - 1);
+    T lap = (bi ? op.BC : T(2)) * op.ih2[0] + (bj ? op.BC : T(2)) * op.ih2[1];
+    if (DIM == 3) lap += ((k == 0 || k == n2 - 1) ? op.BC : T(2)) * op.ih2[2];
+    out[p] = mk<double>((double)(c.x - lap), (double)c.y);
+}
+
+// ---------------------------------------------------------------------------------------------
+// coarse levels (baseline form): stored 3^DIM-point stencil, one thread per node, KB RHS per pass
+// so that every coefficient is loaded once per KB right-hand sides.
+// ---------------------------------------------------------------------------------------------
+template <typename T, int DIM, int MODE, int KB>
+__global__ void __launch_bounds__(256) k_coarse_stencil(CoarseOp<T> op, const cx<T>* __restrict__ x,
+                                                        const cx<T>* __restrict__ b, cx<T>* __restrict__ out,
+                                                        int64_t ld, int nrhs) {
+    const int n0 = op.n[0], n1 = op.n[1], n2 = op.n[2];
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = blockIdx.y * blockDim.y + threadIdx.y;
+    const int k = (DIM == 3) ? blockIdx.z * blockDim.z + threadIdx.z : 0;
+    if (i >= n0 || j >= n1 || k >= n2) return;
+    const int64_t sy = n0, sz = (int64_t)n0 * n1;
+    const int64_t N = sz * n2;
+    const int64_t p = i + sy * j + sz * k;
+    for (int r0 = 0; r0 < nrhs; r0 += KB) {
+        cx<T> acc[KB];
+#pragma unroll
+        for (int q = 0; q < KB; ++q) acc[q] = mk<T>(T(0), T(0));
+#pragma unroll
+        for (int dk = (DIM == 3 ? -1 : 0); dk <= (DIM == 3 ? 1 : 0); ++dk) {
+            const bool okk = (unsigned)(k + dk) < (unsigned)n2;
+#pragma unroll
+            for (int dj = -1; dj <= 1; ++dj) {
+                const bool okj = (unsigned)(j + dj) < (unsigned)n1;
+#pragma unroll
+                for (int di = -1; di <= 1; ++di) {
+                    const bool ok = okk && okj && ((unsigned)(i + di) < (unsigned)n0);
+                    if (ok) {
+                        const int s = (di + 1) + 3 * (dj + 1) + (DIM == 3 ? 9 * (dk + 1) : 0);
+                        const cx<T> cf = op.coef[(int64_t)s * N + p];
+                        const int64_t off = p + di + sy * dj + sz * dk;
+#pragma unroll
+                        for (int q = 0; q < KB; ++q)
+                            if (r0 + q < nrhs) cfma(acc[q], cf, x[(int64_t)(r0 + q) * ld + off]);
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < KB; ++q) {
+            if (r0 + q < nrhs) {
+                const int64_t o = (int64_t)(r0 + q) * ld + p;
+                if (MODE == MODE_APPLY) {
+                    out[o] = acc[q];
+                } else if (MODE == MODE_RESID) {
+                    out[o] = b[o] - acc[q];
+                } else {
+                    out[o] = x[o] + op.dinv[p] * (b[o] - acc[q]);
+                }
+            }
+        }
+    }
+}
+
+// out = dinv .* b   (first Jacobi sweep from zero on a coarse level; also the Jacobi right
+// preconditioner of the inexact coarsest GMRES and the Jac-GMRES smoother)
+template <typename T>
+__global__ void __launch_bounds__(256) k_diag_scale(const cx<T>* __restrict__ dinv, const cx<T>* __restrict__ b,
+                                                    cx<T>* __restrict__ out, int64_t N, int64_t ld, int nrhs) {
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= N) return;
+    const cx<T> d = dinv[p];
+    for (int r = 0; r < nrhs; ++r) out[(int64_t)r * ld + p] = d * b[(int64_t)r * ld + p];
+}
+
+// fine-level damp/diag as an explicit array (used by Jac-GMRES on the fine level)
+template <typename T, int DIM>
+__global__ void __launch_bounds__(256) k_fine_dinv(FineOp<T> op, cx<T>* __restrict__ dinv, T damp) {
+    const int n0 = op.n[0], n1 = op.n[1], n2 = op.n[2];
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = blockIdx.y * blockDim.y + threadIdx.y;
+    const int k = (DIM == 3) ? blockIdx.z * blockDim.z + threadIdx.z : 0;
+    if (i >= n0 || j >= n1 || k >= n2) return;
+    const int64_t p = i + (int64_t)n0 * j + (int64_t)n0 * n1 * k;
+    dinv[p] = rdiv(damp, fine_center<T, DIM>(op, p, i, j, k));
+}
+
+// ---------------------------------------------------------------------------------------------
+// K3 (baseline form): full-weighting restriction  bc = R r,  R = 2^-DIM P^T  (1-D weights 1/4 1/2 1/4,
+// truncated at the boundary).  One thread per coarse node.
+// ---------------------------------------------------------------------------------------------
+template <typename T, int DIM>
+__global__ void __launch_bounds__(256) k_restrict(const cx<T>* __restrict__ r, cx<T>* __restrict__ bc, int nf0, int nf1,
+                                                  int nf2, int nc0, int nc1, int nc2, int64_t ldf, int64_t ldc,
+                                                  int nrhs) {
+    const int I = blockIdx.x * blockDim.x + threadIdx.x;
+    const int J = blockIdx.y * blockDim.y + threadIdx.y;
+    const int K = (DIM == 3) ? blockIdx.z * blockDim.z + threadIdx.z : 0;
+    if (I >= nc0 || J >= nc1 || K >= nc2) return;
+    const int64_t sy = nf0, sz = (int64_t)nf0 * nf1;
+    const int64_t pc = I + (int64_t)nc0 * J + (int64_t)nc0 * nc1 * K;
+    const int fi = 2 * I, fj = 2 * J, fk = (DIM == 3) ? 2 * K : 0;
+    for (int q = 0; q < nrhs; ++q) {
+        const cx<T>* rr = r + (int64_t)q * ldf;
+        cx<T> acc = mk<T>(T(0), T(0));
+#pragma unroll
+        for (int dk = (DIM == 3 ? -1 : 0); dk <= (DIM == 3 ? 1 : 0); ++dk) {
+            if ((unsigned)(fk + dk) >= (unsigned)nf2) continue;
+            const T wk = (DIM == 3) ? (dk == 0 ? T(0.5) : T(0.25)) : T(1);
+#pragma unroll
+            for (int dj = -1; dj <= 1; ++dj) {
+                if ((unsigned)(fj + dj) >= (unsigned)nf1) continue;
+                const T wj = wk * (dj == 0 ? T(0.5) : T(0.25));
+#pragma unroll
+                for (int di = -1; di <= 1; ++di) {
+                    if ((unsigned)(fi + di) >= (unsigned)nf0) continue;
+                    const T w = wj * (di == 0 ? T(0.5) : T(0.25));
+                    rfma(acc, w, rr[(fi + di) + sy * (fj + dj) + sz * (fk + dk)]);
+                }
+            }
+        }
+        bc[(int64_t)q * ldc + pc] = acc;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K4: prolongation + correction  x += P xc  (bi/tri-linear).  One thread per fine node.
+// ---------------------------------------------------------------------------------------------
+template <typename T, int DIM>
+__global__ void __launch_bounds__(256) k_prolong_add(cx<T>* __restrict__ x, const cx<T>* __restrict__ xc, int nf0,
+                                                     int nf1, int nf2, int nc0, int nc1, int64_t ldf, int64_t ldc,
+                                                     int nrhs) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = blockIdx.y * blockDim.y + threadIdx.y;
+    const int k = (DIM == 3) ? blockIdx.z * blockDim.z + threadIdx.z : 0;
+    if (i >= nf0 || j >= nf1 || k >= nf2) return;
+    const int64_t p = i + (int64_t)nf0 * j + (int64_t)nf0 * nf1 * k;
+    const int64_t cy = nc0, cz = (int64_t)nc0 * nc1;
+    const int I0 = i >> 1, J0 = j >> 1, K0 = k >> 1;
+    const int oi = i & 1, oj = j & 1, ok = (DIM == 3) ? (k & 1) : 0;
+    const T w = T(1) / T((1 << oi) * (1 << oj) * (1 << ok));
+    const int64_t base = I0 + cy * J0 + cz * K0;
+    for (int q = 0; q < nrhs; ++q) {
+        const cx<T>* c = xc + (int64_t)q * ldc + base;
+        cx<T> acc = mk<T>(T(0), T(0));
+#pragma unroll
+        for (int dk = 0; dk <= 1; ++dk) {
+            if (dk > ok) continue;
+#pragma unroll
+            for (int dj = 0; dj <= 1; ++dj) {
+                if (dj > oj) continue;
+#pragma unroll
+                for (int di = 0; di <= 1; ++di) {
+                    if (di > oi) continue;
+                    acc = acc + c[di + cy * dj + cz * dk];
+                }
+            }
+        }
+        const int64_t o = (int64_t)q * ldf + p;
+        cx<T> v = x[o];
+        rfma(v, w, acc);
+        x[o] = v;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K5: Galerkin coarse operator  A_c = R A P  as a 3^DIM-point stencil (set-up, once per model/omega).
+// One thread per (coarse node, coarse offset).  A(i, t) is supplied by the functor `Coef`.
+// ---------------------------------------------------------------------------------------------
+template <typename T, int DIM>
+struct FineCoef {
+    FineOp<T> op;
+    __device__ __forceinline__ bool sparse7() const { return true; }
+    __device__ __forceinline__ cx<double> get(int i, int j, int k, int di, int dj, int dk) const {
+        const int nz = (di != 0) + (dj != 0) + (dk != 0);
+        if (nz == 0) {
+            const int64_t p = i + (int64_t)op.n[0] * j + (int64_t)op.n[0] * op.n[1] * k;
+            cx<T> c = fine_center<T, DIM>(op, p, i, j, k);
+            return mk<double>((double)c.x, (double)c.y);
+        }
+        if (nz > 1) return mk<double>(0.0, 0.0);
+        T w;
+        if (di != 0) w = fine_w(op, 0, di > 0, i, op.n[0]);
+        else if (dj != 0) w = fine_w(op, 1, dj > 0, j, op.n[1]);
+        else w = fine_w(op, 2, dk > 0, k, op.n[2]);
+        return mk<double>(-(double)w, 0.0);
+    }
+};
+
+template <typename T, int DIM>
+struct StoredCoef {
+    CoarseOp<T> op;
+    __device__ __forceinline__ bool sparse7() const { return false; }
+    __device__ __forceinline__ cx<double> get(int i, int j, int k, int di, int dj, int dk) const {
+        const int64_t N = (int64_t)op.n[0] * op.n[1] * op.n[2];
+        const int64_t p = i + (int64_t)op.n[0] * j + (int64_t)op.n[0] * op.n[1] * k;
+        const int s = (di + 1) + 3 * (dj + 1) + (DIM == 3 ? 9 * (dk + 1) : 0);
+        cx<T> c = op.coef[(int64_t)s * N + p];
+        return mk<double>((double)c.x, (double)c.y);
+    }
+};
+
+template <typename T, int DIM, typename Coef>
+__global__ void __launch_bounds__(128) k_galerkin(Coef A, int nf0, int nf1, int nf2, int nc0, int nc1, int nc2,
+                                                  cx<T>* __restrict__ coefc) {
+    const int64_t Nc = (int64_t)nc0 * nc1 * nc2;
+    const int NS = (DIM == 3) ? 27 : 9;
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= Nc * NS) return;
+    const int s = (int)(t / Nc);
+    int64_t pc = t - (int64_t)s * Nc;
+    const int I = (int)(pc % nc0);
+    const int J = (int)((pc / nc0) % nc1);
+    const int K = (int)(pc / ((int64_t)nc0 * nc1));
+    const int dI = s % 3 - 1, dJ = (s / 3) % 3 - 1, dK = (DIM == 3) ? (s / 9 - 1) : 0;
+    const int JI = I + dI, JJ = J + dJ, JK = K + dK;  // coarse column node
+    cx<double> acc = mk<double>(0.0, 0.0);
+    if ((unsigned)JI < (unsigned)nc0 && (unsigned)JJ < (unsigned)nc1 && (unsigned)JK < (unsigned)nc2) {
+        const double rscale = (DIM == 3) ? 0.125 : 0.25;
+        for (int ek = (DIM == 3 ? -1 : 0); ek <= (DIM == 3 ? 1 : 0); ++ek) {
+            const int fk = 2 * K + ek;
+            if ((unsigned)fk >= (unsigned)nf2) continue;
+            for (int ej = -1; ej <= 1; ++ej) {
+                const int fj = 2 * J + ej;
+                if ((unsigned)fj >= (unsigned)nf1) continue;
+                for (int ei = -1; ei <= 1; ++ei) {
+                    const int fi = 2 * I + ei;
+                    if ((unsigned)fi >= (unsigned)nf0) continue;
+                    const double wR = rscale * (ei ? 0.5 : 1.0) * (ej ? 0.5 : 1.0) * (ek ? 0.5 : 1.0);
+                    // columns j = i + t of A that interpolate from coarse node (JI,JJ,JK)
+                    for (int tk = (DIM == 3 ? -1 : 0); tk <= (DIM == 3 ? 1 : 0); ++tk) {
+                        const int gk = fk + tk;
+                        if ((unsigned)gk >= (unsigned)nf2) continue;
+                        const int qk = (DIM == 3) ? gk - 2 * JK : 0;
+                        if (qk < -1 || qk > 1) continue;
+                        for (int tj = -1; tj <= 1; ++tj) {
+                            const int gj = fj + tj;
+                            if ((unsigned)gj >= (unsigned)nf1) continue;
+                            const int qj = gj - 2 * JJ;
+                            if (qj < -1 || qj > 1) continue;
+                            for (int ti = -1; ti <= 1; ++ti) {
+                                const int gi = fi + ti;
+                                if ((unsigned)gi >= (unsigned)nf0) continue;
+                                const int qi = gi - 2 * JI;
+                                if (qi < -1 || qi > 1) continue;
+                                if (A.sparse7() && ((ti != 0) + (tj != 0) + (tk != 0)) > 1) continue;
+                                const double wP = (qi ? 0.5 : 1.0) * (qj ? 0.5 : 1.0) * (qk ? 0.5 : 1.0);
+                                const cx<double> a = A.get(fi, fj, fk, ti, tj, tk);
+                                const double w = wR * wP;
+                                acc.x += w * a.x;
+                                acc.y += w * a.y;
+                            }
+                        }
+                    }
+                }
+            }
+        }
+    }
+    coefc[t] = mk<T>((T)acc.x, (T)acc.y);
+}
+
+template <typename T>
+__global__ void k_coarse_dinv(const cx<T>* __restrict__ center, cx<T>* __restrict__ dinv, int64_t N, T damp) {
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < N) dinv[p] = rdiv(damp, center[p]);
+}
+
+// ---------------------------------------------------------------------------------------------
+// coarsest level, exact: banded LU without pivoting (the shifted operator has its numerical range in
+// a half plane, so every leading minor is non-singular), then an explicit inverse so that the
+// per-cycle coarsest solve is one dense, HBM-streaming matrix product instead of a serial
+// triangular solve.
+// band[row*W + (col-row+bw)], W = 2 bw + 1, in double.
+// ---------------------------------------------------------------------------------------------
+template <typename T, int DIM>
+__global__ void k_band_fill(CoarseOp<T> op, zc* __restrict__ band, int bw) {
+    const int64_t N = (int64_t)op.n[0] * op.n[1] * op.n[2];
+    const int NS = (DIM == 3) ? 27 : 9;
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= N * NS) return;
+    const int s = (int)(t / N);
+    const int64_t p = t - (int64_t)s * N;
+    const int i = (int)(p % op.n[0]), j = (int)((p / op.n[0]) % op.n[1]), k = (int)(p / ((int64_t)op.n[0] * op.n[1]));
+    const int di = s % 3 - 1, dj = (s / 3) % 3 - 1, dk = (DIM == 3) ? (s / 9 - 1) : 0;
+    if ((unsigned)(i + di) >= (unsigned)op.n[0] || (unsigned)(j + dj) >= (unsigned)op.n[1] ||
+        (unsigned)(k + dk) >= (unsigned)op.n[2])
+        return;
+    const int64_t off = di + (int64_t)op.n[0] * dj + (int64_t)op.n[0] * op.n[1] * dk;
+    const cx<T> c = op.coef[t];
+    band[p * (2 * (int64_t)bw + 1) + (off + bw)] = mk<double>((double)c.x, (double)c.y);
+}
+
+// right-looking banded LU, one CTA (set-up only).  L (unit lower) and U overwrite the band.
+__global__ void __launch_bounds__(1024) k_band_lu(zc* __restrict__ band, int64_t N, int bw) {
+    const int64_t W = 2 * (int64_t)bw + 1;
+    for (int64_t k = 0; k < N; ++k) {
+        const int nrow = (int)min((int64_t)bw, N - 1 - k);
+        const zc piv = band[k * W + bw];
+        for (int t = threadIdx.x; t < nrow; t += blockDim.x) {
+            const int64_t i = k + 1 + t;
+            zc* e = &band[i * W + (k - i + bw)];
+            *e = cdiv(*e, piv);
+        }
+        __syncthreads();
+        const int64_t tot = (int64_t)nrow * nrow;
+        for (int64_t t = threadIdx.x; t < tot; t += blockDim.x) {
+            const int ri = (int)(t / nrow), cj = (int)(t % nrow);
+            const int64_t i = k + 1 + ri, j = k + 1 + cj;
+            const zc l = band[i * W + (k - i + bw)];
+            const zc u = band[k * W + (j - k + bw)];
+            zc* e = &band[i * W + (j - i + bw)];
+            zc v = *e;
+            v.x -= l.x * u.x - l.y * u.y;
+            v.y -= l.x * u.y + l.y * u.x;
+            *e = v;
+        }
+        __syncthreads();
+    }
+}
+
+// Columns [c0, c0+gridDim.x) of the inverse: solve L U x = e_c with the band factors.  One CTA per
+// column; x lives in global memory (column c of `inv`, column-major N x N, double).
+__global__ void __launch_bounds__(256) k_band_inverse(const zc* __restrict__ band, int64_t N, int bw, int64_t c0,
+                                                      zc* __restrict__ inv) {
+    const int64_t W = 2 * (int64_t)bw + 1;
+    const int64_t c = c0 + blockIdx.x;
+    if (c >= N) return;
+    zc* x = inv + c * N;
+    for (int64_t p = threadIdx.x; p < N; p += blockDim.x) x[p] = mk<double>(p == c ? 1.0 : 0.0, 0.0);
+    __syncthreads();
+    // forward substitution (unit lower); entries before row c stay zero
+    for (int64_t k = c; k < N; ++k) {
+        const zc yk = x[k];
+        const int nrow = (int)min((int64_t)bw, N - 1 - k);
+        if (yk.x != 0.0 || yk.y != 0.0) {
+            for (int t = threadIdx.x; t < nrow; t += blockDim.x) {
+                const int64_t i = k + 1 + t;
+                const zc l = band[i * W + (k - i + bw)];
+                zc v = x[i];
+                v.x -= l.x * yk.x - l.y * yk.y;
+                v.y -= l.x * yk.y + l.y * yk.x;
+                x[i] = v;
+            }
+        }
+        __syncthreads();
+    }
+    // backward substitution
+    for (int64_t k = N - 1; k >= 0; --k) {
+        if (threadIdx.x == 0) x[k] = cdiv(x[k], band[k * W + bw]);
+        __syncthreads();
+        const zc xk = x[k];
+        const int nrow = (int)min((int64_t)bw, k);
+        for (int t = threadIdx.x; t < nrow; t += blockDim.x) {
+            const int64_t i = k - 1 - t;
+            const zc u = band[i * W + (k - i + bw)];
+            zc v = x[i];
+            v.x -= u.x * xk.x - u.y * xk.y;
+            v.y -= u.x * xk.y + u.y * xk.x;
+            x[i] = v;
+        }
+        __syncthreads();
+    }
+}
+
+// inverse (column-major, double) -> row-major copy in the solve precision
+template <typename T>
+__global__ void k_inverse_pack(const zc* __restrict__ inv, cx<T>* __restrict__ invT, int64_t N) {
+    __shared__ zc tile[32][33];
+    const int64_t bx = (int64_t)blockIdx.x * 32, by = (int64_t)blockIdx.y * 32;
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        const int64_t row = bx + threadIdx.x, col = by + r;  // inv[row + col*N]
+        if (row < N && col < N) tile[r][threadIdx.x] = inv[row + col * N];
+    }
+    __syncthreads();
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        const int64_t row = bx + r, col = by + threadIdx.x;  // invT[row*N + col]
+        if (row < N && col < N) {
+            const zc v = tile[threadIdx.x][r];
+            invT[row * N + col] = mk<T>((T)v.x, (T)v.y);
+        }
+    }
+}
+
+// K6 (exact): xc = Ainv * bc.  One warp per output row, KB right-hand sides per pass; the row of
+// the inverse is streamed once from HBM and reused for KB right-hand sides.
+template <typename T, int KB>
+__global__ void __launch_bounds__(256) k_dense_apply(const cx<T>* __restrict__ invT, const cx<T>* __restrict__ b,
+                                                     cx<T>* __restrict__ x, int64_t N, int64_t ld, int nrhs) {
+    const int lane = threadIdx.x & 31;
+    const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= N) return;
+    const cx<T>* a = invT + row * N;
+    for (int r0 = 0; r0 < nrhs; r0 += KB) {
+        double ax[KB], ay[KB];
+#pragma unroll
+        for (int q = 0; q < KB; ++q) ax[q] = ay[q] = 0.0;
+        for (int64_t c = lane; c < N; c += 32) {
+            const cx<T> av = a[c];
+#pragma unroll
+            for (int q = 0; q < KB; ++q) {
+                if (r0 + q < nrhs) {
+                    const cx<T> bv = b[(int64_t)(r0 + q) * ld + c];
+                    ax[q] += (double)av.x * bv.x - (double)av.y * bv.y;
+                    ay[q] += (double)av.x * bv.y + (double)av.y * bv.x;
+                }
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < KB; ++q) {
+            const double sx = warp_sum(ax[q]), sy = warp_sum(ay[q]);
+            if (lane == 0 && r0 + q < nrhs) x[(int64_t)(r0 + q) * ld + row] = mk<T>((T)sx, (T)sy);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K7: batched Krylov vector kernels.  Vectors are N x nrhs (leading dimension ld); every
+// right-hand side has its own scalars (batched, not block, Krylov).
+// ---------------------------------------------------------------------------------------------
+#define HH_MAXV 8
+template <typename T>
+struct VecList {
+    const cx<T>* v[HH_MAXV];
+};
+
+// partial[(i*nrhs + r)*nblk + blk] = sum over the block's slice of conj(V_i) .* w  for i < NV, and, if
+// WITH_NORM, entry i = NV holds sum |w|^2.  Grid (nblk, nrhs).  Accumulation in double.
+template <typename T, int NV, bool WITH_NORM>
+__global__ void __launch_bounds__(256) k_multidot(VecList<T> V, const cx<T>* __restrict__ w, int64_t N, int64_t ld,
+                                                  zc* __restrict__ partial) {
+    __shared__ double sm[32];
+    const int r = blockIdx.y, nrhs = gridDim.y, nblk = gridDim.x;
+    const int64_t base = (int64_t)r * ld;
+    double ax[NV + 1], ay[NV + 1];
+#pragma unroll
+    for (int i = 0; i <= NV; ++i) ax[i] = ay[i] = 0.0;
+    for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < N; p += (int64_t)nblk * blockDim.x) {
+        const cx<T> wv = w[base + p];
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            const cx<T> vv = V.v[i][base + p];
+            ax[i] += (double)vv.x * wv.x + (double)vv.y * wv.y;
+            ay[i] += (double)vv.x * wv.y - (double)vv.y * wv.x;
+        }
+        if (WITH_NORM) ax[NV] += (double)wv.x * wv.x + (double)wv.y * wv.y;
+    }
+    const int nout = WITH_NORM ? NV + 1 : NV;
+#pragma unroll
+    for (int i = 0; i < nout; ++i) {
+        const double sx = block_sum(ax[i], sm);
+        const double sy = (i < NV) ? block_sum(ay[i], sm) : 0.0;
+        if (threadIdx.x == 0) partial[((int64_t)i * nrhs + r) * nblk + blockIdx.x] = mk<double>(sx, sy);
+    }
+}
+
+// w <- w + sum_i coef[r*cstride + i] * V_i   (i < NV), optionally accumulating |w_new|^2 partials
+// into partial[r*nblk + blk].  `negate` subtracts instead (Gram-Schmidt).
+template <typename T, int NV, bool WITH_NORM>
+__global__ void __launch_bounds__(256) k_multiaxpy(VecList<T> V, cx<T>* __restrict__ w, int64_t N, int64_t ld,
+                                                   const zc* __restrict__ coef, int cstride, int negate,
+                                                   zc* __restrict__ partial) {
+    __shared__ double sm[32];
+    const int r = blockIdx.y, nblk = gridDim.x;
+    const int64_t base = (int64_t)r * ld;
+    cx<T> c[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        const zc cc = coef[(int64_t)r * cstride + i];
+        c[i] = negate ? mk<T>((T)-cc.x, (T)-cc.y) : mk<T>((T)cc.x, (T)cc.y);
+    }
+    double nrm = 0.0;
+    for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < N; p += (int64_t)nblk * blockDim.x) {
+        cx<T> wv = w[base + p];
+#pragma unroll
+        for (int i = 0; i < NV; ++i) cfma(wv, c[i], V.v[i][base + p]);
+        w[base + p] = wv;
+        if (WITH_NORM) nrm += (double)wv.x * wv.x + (double)wv.y * wv.y;
+    }
+    if (WITH_NORM) {
+        const double s = block_sum(nrm, sm);
+        if (threadIdx.x == 0) partial[(int64_t)r * nblk + blockIdx.x] = mk<double>(s, 0.0);
+    }
+}
+
+// out = alpha[r] * in  (per-RHS complex scalar; used for v = w / ||w||)
+template <typename T>
+__global__ void __launch_bounds__(256) k_scale(const cx<T>* __restrict__ in, cx<T>* __restrict__ out, int64_t N,
+                                               int64_t ld_in, int64_t ld_out, const zc* __restrict__ alpha, int astride) {
+    const int r = blockIdx.y;
+    const zc a = alpha[(int64_t)r * astride];
+    const cx<T> s = mk<T>((T)a.x, (T)a.y);
+    for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < N; p += (int64_t)gridDim.x * blockDim.x)
+        out[(int64_t)r * ld_out + p] = s * in[(int64_t)r * ld_in + p];
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) k_copy(const cx<T>* __restrict__ in, cx<T>* __restrict__ out, int64_t N,
+                                              int64_t ld_in, int64_t ld_out) {
+    const int r = blockIdx.y;
+    for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < N; p += (int64_t)gridDim.x * blockDim.x)
+        out[(int64_t)r * ld_out + p] = in[(int64_t)r * ld_in + p];
+}
+
+// scatter point sources: B[idx[r] + r*ld] = val[r]  (B zeroed beforehand)
+template <typename T>
+__global__ void k_point_sources(cx<T>* __restrict__ B, int64_t ld, const int64_t* __restrict__ idx,
+                                const zc* __restrict__ val, int nrhs) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < nrhs) B[(int64_t)r * ld + idx[r]] = mk<T>((T)val[r].x, (T)val[r].y);
+}
+
+// ---- small per-RHS scalar kernels (one warp per right-hand side; all state in double) ----------
+
+// sum `nblk` partials for quantity (i, r):  partial[(i*nrhs + r)*nblk + .]
+__device__ __forceinline__ zc reduce_partials(const zc* partial, int64_t idx, int nblk) {
+    const int lane = threadIdx.x & 31;
+    double sx = 0.0, sy = 0.0;
+    for (int t = lane; t < nblk; t += 32) {
+        const zc v = partial[idx * nblk + t];
+        sx += v.x;
+        sy += v.y;
+    }
+    return mk<double>(warp_sum(sx), warp_sum(sy));
+}
+
+struct GmresState {
+    // per RHS r:  H[r][(m+1)*m] column-major (ldh = m+1), cs[r][m] (real in .x), sn[r][m], s[r][m+1],
+    // hcol[r][m+1] (raw Gram-Schmidt coefficients of the current column), y[r][m]
+    zc *H, *cs, *sn, *s, *hcol, *y;
+    double *bnorm, *err;  // per RHS
+    zc* scale;            // per RHS: 1/h_{j+1,j} (or 1/beta), 0 when frozen
+    int *done, *jdone, *nprec;
+    int m;  // restart length
+};
+
+// after the multidot: hcol[r][i] = <v_i, w>, i <= j
+__global__ void k_gmres_hcol(GmresState st, const zc* __restrict__ partial, int nblk, int j, int i0, int nv) {
+    const int r = blockIdx.x, nrhs = gridDim.x;
+    for (int i = 0; i < nv; ++i) {
+        const zc h = reduce_partials(partial, (int64_t)i * nrhs + r, nblk);
+        if ((threadIdx.x & 31) == 0) st.hcol[(int64_t)r * (st.m + 1) + i0 + i] = st.done[r] ? mk<double>(0.0, 0.0) : h;
+    }
+}
+
+// after the orthogonalisation: h_{j+1,j} = ||w||, apply/compute Givens rotations, residual estimate
+__global__ void k_gmres_givens(GmresState st, const zc* __restrict__ partial, int nblk, int j, double tol) {
+    const int r = blockIdx.x;
+    const zc nn = reduce_partials(partial, r, nblk);
+    if ((threadIdx.x & 31) != 0) return;
+    const int m = st.m, ldh = m + 1;
+    if (st.done[r]) {
+        st.scale[r] = mk<double>(0.0, 0.0);
+        return;
+    }
+    zc* Hc = st.H + (int64_t)r * ldh * m + (int64_t)j * ldh;
+    zc* hc = st.hcol + (int64_t)r * ldh;
+    zc* cs = st.cs + (int64_t)r * m;
+    zc* sn = st.sn + (int64_t)r * m;
+    zc* s = st.s + (int64_t)r * ldh;
+    const double hn = sqrt(nn.x);
+    for (int i = 0; i <= j; ++i) Hc[i] = hc[i];
+    Hc[j + 1] = mk<double>(hn, 0.0);
+    for (int k = 0; k < j; ++k) {
+        const zc t = cs[k].x * Hc[k] + sn[k] * Hc[k + 1];
+        Hc[k + 1] = cs[k].x * Hc[k + 1] - conj(sn[k]) * Hc[k];
+        Hc[k] = t;
+    }
+    const zc a = Hc[j];
+    const double aa = sqrt(a.x * a.x + a.y * a.y);
+    const double den = sqrt(aa * aa + hn * hn);
+    double c;
+    zc sgn;
+    if (den == 0.0) {
+        c = 1.0;
+        sgn = mk<double>(0.0, 0.0);
+    } else if (aa == 0.0) {
+        c = 0.0;
+        sgn = mk<double>(1.0, 0.0);
+    } else {
+        c = aa / den;
+        sgn = (hn / (den * aa)) * a;  // (a/|a|) * conj(b)/den with b = hn real
+    }
+    cs[j] = mk<double>(c, 0.0);
+    sn[j] = sgn;
+    Hc[j] = c * a + hn * sgn;
+    Hc[j + 1] = mk<double>(0.0, 0.0);
+    const zc sj = s[j];
+    s[j + 1] = mk<double>(0.0, 0.0) - conj(sgn) * sj;
+    s[j] = c * sj;
+    const zc sn1 = s[j + 1];
+    const double err = sqrt(sn1.x * sn1.x + sn1.y * sn1.y) / st.bnorm[r];
+    st.err[r] = err;
+    st.jdone[r] = j + 1;
+    st.nprec[r] += 1;
+    st.scale[r] = mk<double>(hn > 0.0 ? 1.0 / hn : 0.0, 0.0);
+    if (!(err > tol)) st.done[r] = 1;  // also catches NaN -> stops; host checks for NaN separately
+    if (err != err) st.done[r] = 2;
+}
+
+// y = H(1:jd,1:jd) \ s(1:jd), zero beyond jd  (jd = jdone[r]; 0 if the RHS took no step this cycle)
+__global__ void k_gmres_solve_y(GmresState st, int nrhs) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= nrhs) return;
+    const int m = st.m, ldh = m + 1;
+    const int jd = st.jdone[r];
+    const zc* H = st.H + (int64_t)r * ldh * m;
+    const zc* s = st.s + (int64_t)r * ldh;
+    zc* y = st.y + (int64_t)r * m;
+    for (int i = 0; i < m; ++i) y[i] = mk<double>(0.0, 0.0);
+    for (int i = jd - 1; i >= 0; --i) {
+        zc acc = s[i];
+        for (int k = i + 1; k < jd; ++k) acc = acc - H[(int64_t)k * ldh + i] * y[k];
+        y[i] = cdiv(acc, H[(int64_t)i * ldh + i]);
+    }
+    st.jdone[r] = 0;
+}
+
+// start of a cycle: beta = ||r|| from norm partials; s = beta e1; scale = 1/beta; err = beta/bnorm.
+// first != 0: this is ||b||: record bnorm, mark zero right-hand sides done.
+__global__ void k_gmres_begin(GmresState st, const zc* __restrict__ partial, int nblk, int first, double tol) {
+    const int r = blockIdx.x;
+    const zc nn = reduce_partials(partial, r, nblk);
+    if ((threadIdx.x & 31) != 0) return;
+    const int ldh = st.m + 1;
+    const double beta = sqrt(nn.x);
+    if (first) {
+        st.bnorm[r] = beta;
+        st.nprec[r] = 0;
+        st.jdone[r] = 0;
+        st.done[r] = (beta == 0.0) ? 1 : 0;
+        st.err[r] = (beta == 0.0) ? 0.0 : 1.0;
+        if (beta != beta) st.done[r] = 2;
+    } else if (!st.done[r]) {
+        const double err = beta / st.bnorm[r];
+        st.err[r] = err;
+        if (!(err > tol)) st.done[r] = 1;
+        if (err != err) st.done[r] = 2;
+    }
+    zc* s = st.s + (int64_t)r * ldh;
+    for (int i = 0; i < ldh; ++i) s[i] = mk<double>(0.0, 0.0);
+    s[0] = mk<double>(beta, 0.0);
+    st.scale[r] = mk<double>((st.done[r] || beta == 0.0) ? 0.0 : 1.0 / beta, 0.0);
+}
+
+// ---- BiCGSTAB: per-RHS scalars and the p-update -------------------------------------------------
+struct BicgState {
+    zc *rho, *rho_old, *alpha, *omega, *beta;  // per RHS
+    zc *neg_alpha, *neg_omega, *ao;            // helper coefficient slots; ao[r][2] = (alpha, omega)
+    double *bnorm, *err;
+    int *done, *half, *nprec, *iters;
+};
+
+enum { BICG_INIT = 0, BICG_RHO = 1, BICG_ALPHA = 2, BICG_HALF = 3, BICG_OMEGA = 4, BICG_END = 5 };
+
+// stage machine of preconditioned BiCGSTAB; `partial` holds the reductions the stage needs
+// (layout of k_multidot: quantity i, RHS r -> partial[(i*nrhs + r)*nblk + .]).
+__global__ void k_bicg_scalars(BicgState st, const zc* __restrict__ partial, int nblk, int stage, double tol) {
+    const int r = blockIdx.x, nrhs = gridDim.x;
+    const zc q0 = reduce_partials(partial, r, nblk);
+    zc q1 = mk<double>(0.0, 0.0);
+    if (stage == BICG_OMEGA) q1 = reduce_partials(partial, (int64_t)nrhs + r, nblk);
+    if ((threadIdx.x & 31) != 0) return;
+    const zc zero = mk<double>(0.0, 0.0);
+    if (stage == BICG_INIT) {  // q0 = |b|^2
+        const double bn = sqrt(q0.x);
+        st.bnorm[r] = bn;
+        st.err[r] = bn == 0.0 ? 0.0 : 1.0;
+        st.done[r] = bn == 0.0 ? 1 : (bn != bn ? 2 : 0);
+        st.half[r] = 0;
+        st.nprec[r] = 0;
+        st.iters[r] = 0;
+        st.rho_old[r] = st.alpha[r] = st.omega[r] = mk<double>(1.0, 0.0);
+        st.beta[r] = zero;
+        return;
+    }
+    if (st.done[r]) {
+        st.beta[r] = zero;
+        st.neg_alpha[r] = zero;
+        st.neg_omega[r] = zero;
+        st.ao[2 * r] = zero;
+        st.ao[2 * r + 1] = zero;
+        return;
+    }
+    if (stage == BICG_RHO) {  // q0 = <rt, r>
+        st.rho[r] = q0;
+        if (st.iters[r] == 0) {
+            st.beta[r] = zero;
+        } else {
+            st.beta[r] = cdiv(q0, st.rho_old[r]) * cdiv(st.alpha[r], st.omega[r]);
+        }
+        st.nprec[r] += 1;  // the p-hat preconditioner application that follows
+    } else if (stage == BICG_ALPHA) {  // q0 = <rt, v>
+        const zc a = cdiv(st.rho[r], q0);
+        st.alpha[r] = a;
+        st.neg_alpha[r] = zero - a;
+    } else if (stage == BICG_HALF) {  // q0 = |s|^2
+        const double err = sqrt(q0.x) / st.bnorm[r];
+        st.err[r] = err;
+        if (!(err > tol)) st.half[r] = 1;
+        if (err != err) st.done[r] = 2;
+        if (!st.half[r]) st.nprec[r] += 1;  // the s-hat application is only counted when needed
+    } else if (stage == BICG_OMEGA) {  // q0 = <s, t>, q1 = |t|^2
+        zc w = zero;
+        if (!st.half[r] && q1.x > 0.0) w = (1.0 / q1.x) * conj(q0);
+        st.omega[r] = w;
+        st.neg_omega[r] = zero - w;
+        st.ao[2 * r] = st.alpha[r];
+        st.ao[2 * r + 1] = w;
+    } else if (stage == BICG_END) {  // q0 = |r|^2
+        st.iters[r] += 1;
+        if (st.half[r]) {
+            st.done[r] = 1;
+        } else {
+            const double err = sqrt(q0.x) / st.bnorm[r];
+            st.err[r] = err;
+            if (!(err > tol)) st.done[r] = 1;
+            if (err != err) st.done[r] = 2;
+        }
+        st.rho_old[r] = st.rho[r];
+    }
+}
+
+// p = r + beta (p - omega v)
+template <typename T>
+__global__ void __launch_bounds__(256) k_bicg_p(cx<T>* __restrict__ p, const cx<T>* __restrict__ r,
+                                                const cx<T>* __restrict__ v, int64_t N, int64_t ld,
+                                                const zc* __restrict__ beta, const zc* __restrict__ omega) {
+    const int c = blockIdx.y;
+    const cx<T> be = mk<T>((T)beta[c].x, (T)beta[c].y);
+    const cx<T> om = mk<T>((T)omega[c].x, (T)omega[c].y);
+    for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < N; q += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t o = (int64_t)c * ld + q;
+        const cx<T> t = p[o] - om * v[o];
+        p[o] = r[o] + be * t;
+    }
+}
+
+}  // namespace hh

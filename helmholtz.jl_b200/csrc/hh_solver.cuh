@@ -1,0 +1,1074 @@
+// hh_solver.cuh -- host-side orchestration of the device-resident solve: hierarchy set-up
+// (MGsetup), multigrid cycle (recursiveCycle), batched FGMRES / BiCGSTAB (solveGMRES_MG /
+// solveBiCGSTAB_MG).  Mirrors the control flow of src/ShiftedLaplacianMultigridSolver.jl:33-102;
+// the arithmetic of the un-vendored Multigrid.jl / KrylovMethods.jl is restated from the published
+// algorithms.
+#pragma once
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/helmholtz_b200.h"
+#include "hh_kernels.cuh"
+
+namespace hh {
+
+struct Error : std::runtime_error {
+    int code;
+    Error(int c, const std::string& m) : std::runtime_error(m), code(c) {}
+};
+
+#define HH_CUDA(call)                                                                                   \
+    do {                                                                                                \
+        cudaError_t e__ = (call);                                                                       \
+        if (e__ != cudaSuccess)                                                                         \
+            throw hh::Error(HH_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__) + " (" +    \
+                                             __FILE__ + ":" + std::to_string(__LINE__) + ")");          \
+    } while (0)
+
+#define HH_REQUIRE(cond, code, msg)                      \
+    do {                                                 \
+        if (!(cond)) throw hh::Error((code), (msg));     \
+    } while (0)
+
+// kernel classes for the per-kernel device timing (hh_profile_*)
+enum Tag {
+    T_FINE_APPLY = 0,
+    T_FINE_RESID,
+    T_FINE_JACOBI,
+    T_FINE_JACOBI0,
+    T_COARSE_APPLY,
+    T_COARSE_RESID,
+    T_COARSE_JACOBI,
+    T_COARSE_JACOBI0,
+    T_RESTRICT,
+    T_PROLONG,
+    T_COARSEST_DENSE,
+    T_DOT,
+    T_AXPY,
+    T_SCALE,
+    T_COPY,
+    T_SCALAR,
+    T_SETUP,
+    T_NTAGS
+};
+static const char* const kTagNames[T_NTAGS] = {
+    "fine_apply",   "fine_resid",   "fine_jacobi",    "fine_jacobi0", "coarse_apply", "coarse_resid",
+    "coarse_jacobi", "coarse_jacobi0", "restrict",    "prolong",      "coarsest_dense", "krylov_dot",
+    "krylov_axpy",  "krylov_scale", "copy",           "scalar",       "setup"};
+
+struct Profiler {
+    struct Rec {
+        int tag;
+        cudaEvent_t a, b;
+        double bytes;
+    };
+    bool on = false;
+    std::vector<Rec> recs;
+    std::vector<cudaEvent_t> pool;
+    int64_t count[T_NTAGS] = {0};
+    double ms[T_NTAGS] = {0};
+    double bytes[T_NTAGS] = {0};
+    cudaEvent_t get() {
+        if (!pool.empty()) {
+            cudaEvent_t e = pool.back();
+            pool.pop_back();
+            return e;
+        }
+        cudaEvent_t e;
+        HH_CUDA(cudaEventCreate(&e));
+        return e;
+    }
+    void flush(cudaStream_t st) {
+        if (recs.empty()) return;
+        HH_CUDA(cudaStreamSynchronize(st));
+        for (auto& r : recs) {
+            float t = 0.f;
+            HH_CUDA(cudaEventElapsedTime(&t, r.a, r.b));
+            count[r.tag] += 1;
+            ms[r.tag] += t;
+            bytes[r.tag] += r.bytes;
+            pool.push_back(r.a);
+            pool.push_back(r.b);
+        }
+        recs.clear();
+    }
+    void reset() {
+        recs.clear();
+        for (int i = 0; i < T_NTAGS; ++i) count[i] = 0, ms[i] = 0, bytes[i] = 0;
+    }
+    ~Profiler() {
+        for (auto& r : recs) {
+            cudaEventDestroy(r.a);
+            cudaEventDestroy(r.b);
+        }
+        for (auto e : pool) cudaEventDestroy(e);
+    }
+};
+
+template <typename U>
+struct DevBuf {
+    U* p = nullptr;
+    size_t n = 0;
+    void alloc(size_t count) {
+        release();
+        if (count == 0) return;
+        cudaError_t e = cudaMalloc((void**)&p, count * sizeof(U));
+        if (e != cudaSuccess) {
+            p = nullptr;
+            throw Error(HH_ERR_ALLOC, std::string("cudaMalloc of ") + std::to_string(count * sizeof(U)) +
+                                          " bytes failed: " + cudaGetErrorString(e));
+        }
+        n = count;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        n = 0;
+    }
+    ~DevBuf() { release(); }
+    DevBuf() = default;
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    DevBuf(DevBuf&& o) noexcept : p(o.p), n(o.n) {
+        o.p = nullptr;
+        o.n = 0;
+    }
+    DevBuf& operator=(DevBuf&& o) noexcept {
+        if (this != &o) {
+            release();
+            p = o.p;
+            n = o.n;
+            o.p = nullptr;
+            o.n = 0;
+        }
+        return *this;
+    }
+};
+
+// Problem description shared by both precisions (HelmholtzParam, src/Helmholtz.jl:13-20)
+struct Problem {
+    int dim = 0;
+    int n[3] = {1, 1, 1};
+    double h[3] = {1, 1, 1};
+    double w_re = 0, w_im = 0;
+    int neumann_top = 0, sommerfeld = 0, order_bc = 2;
+    int64_t N() const { return (int64_t)n[0] * n[1] * n[2]; }
+};
+
+struct SolverBase {
+    virtual ~SolverBase() {}
+    virtual void set_model(const double* m, const double* gamma, double wre, double wim) = 0;
+    virtual void setup(const hh_mg_options& o) = 0;
+    virtual void clear() = 0;
+    virtual bool hierarchy_exists() const = 0;
+    virtual void level_nodes(int level, int64_t* out) const = 0;
+    virtual void get_level_stencil(int level, void* out) = 0;
+    virtual void get_diagonal(int shifted, double shift, double* out) = 0;
+    virtual void apply_device(const void* dX, void* dY, int64_t nrhs, int shifted, double shift, int transpose) = 0;
+    virtual void cycle_device(const void* dB, void* dZ, int64_t nrhs) = 0;
+    virtual int solve_device(const void* dB, void* dX, int64_t nrhs, const hh_solve_options& o, int32_t* iters,
+                             double* relres) = 0;
+    virtual int64_t max_rhs_per_batch(const hh_solve_options& o) = 0;
+    virtual size_t elem_size() const = 0;
+    virtual void scatter_point_sources(void* dB, const int64_t* idx0, const double* val, int64_t nrhs) = 0;
+    Problem pb;
+    int device = 0;
+    cudaStream_t stream = 0;
+    Profiler prof;
+    int64_t launches = 0;
+    double setup_seconds = 0, solve_seconds = 0;
+    int64_t n_prec = 0;
+};
+
+template <typename T>
+class Solver : public SolverBase {
+   public:
+    typedef cx<T> C;
+    static constexpr double S = sizeof(C);  // bytes per complex entry
+    static constexpr double CR = sizeof(T); // bytes per real coefficient
+
+    struct GmresMem {
+        DevBuf<zc> H, cs, sn, s, hcol, y, scale;
+        DevBuf<double> bnorm, err;
+        DevBuf<int> done, jdone, nprec;
+        GmresState st{};
+    };
+    // workspace of a fixed-length GMRES nested inside the cycle
+    struct SmallWs {
+        DevBuf<C> v, z;  // (steps+1) basis vectors; `steps` preconditioned vectors when flexible
+        int steps = 0;
+        GmresMem g;
+    };
+    struct Level {
+        int n[3] = {1, 1, 1};
+        int64_t N = 0;
+        DevBuf<C> coef, dinv;       // l >= 1 (dinv also on l = 0 when Jac-GMRES is used)
+        DevBuf<C> x, b, t;          // work vectors N x kcap (l >= 1); l = 0 owns only t
+        SmallWs gs;                 // Jac-GMRES smoother / inexact coarsest solve (Jacobi-preconditioned)
+        SmallWs ks;                 // K-cycle: 2 steps of FGMRES preconditioned by the recursive cycle
+        C *px = nullptr, *pb = nullptr, *pt = nullptr;
+    };
+
+    Solver(const Problem& p, int dev) {
+        pb = p;
+        device = dev;
+    }
+    ~Solver() override {}
+
+    size_t elem_size() const override { return sizeof(C); }
+
+    // ------------------------------------------------------------------ model
+    void set_model(const double* m, const double* gamma, double wre, double wim) override {
+        HH_CUDA(cudaSetDevice(device));
+        const int64_t N = pb.N();
+        pb.w_re = wre;
+        pb.w_im = wim;
+        std::vector<T> hm(N), hg(N);
+        for (int64_t i = 0; i < N; ++i) {
+            hm[i] = (T)m[i];
+            hg[i] = (T)gamma[i];
+        }
+        if (d_m.n != (size_t)N) {
+            d_m.alloc(N);
+            d_g.alloc(N);
+        }
+        HH_CUDA(cudaMemcpy(d_m.p, hm.data(), N * sizeof(T), cudaMemcpyHostToDevice));
+        HH_CUDA(cudaMemcpy(d_g.p, hg.data(), N * sizeof(T), cudaMemcpyHostToDevice));
+        clear();
+    }
+
+    FineOp<T> fine_op(double shift, int adj) const {
+        FineOp<T> op;
+        op.m = d_m.p;
+        op.g = d_g.p;
+        const double wr = pb.w_re, wi = pb.w_im;
+        op.a = (T)(wr * wr - wi * wi);
+        op.b = (T)(2.0 * wr * wi);
+        op.inv_wr = (T)(1.0 / wr);
+        op.shift_w2 = (T)(shift * wr * wr);
+        for (int d = 0; d < 3; ++d) {
+            op.ih2[d] = d < pb.dim ? (T)(1.0 / (pb.h[d] * pb.h[d])) : T(0);
+            // getSommerfeldBC is always called with its default orderNeumannBC = 2 (GetHelmholtz.jl:45)
+            op.somm[d] = (pb.sommerfeld && d < pb.dim) ? (T)(wr * 2.0 / pb.h[d]) : T(0);
+            op.n[d] = pb.n[d];
+        }
+        op.BC = (T)(pb.order_bc == 2 ? 2.0 : 1.0);
+        op.neumann_top = pb.neumann_top;
+        op.adj = adj;
+        return op;
+    }
+
+    // ------------------------------------------------------------------ launch plumbing
+    template <class F>
+    void launch(int tag, double bytes, F&& f) {
+        ++launches;
+        if (prof.on) {
+            cudaEvent_t a = prof.get(), b = prof.get();
+            HH_CUDA(cudaEventRecord(a, stream));
+            f();
+            HH_CUDA(cudaEventRecord(b, stream));
+            prof.recs.push_back({tag, a, b, bytes});
+            if (prof.recs.size() >= 8192) prof.flush(stream);
+        } else {
+            f();
+        }
+#ifdef HH_DEBUG_SYNC
+        HH_CUDA(cudaStreamSynchronize(stream));
+#endif
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess)
+            throw Error(HH_ERR_CUDA, std::string("kernel launch (") + kTagNames[tag] + "): " + cudaGetErrorString(e));
+    }
+
+    static void grid3(const int n[3], int dim, dim3& g, dim3& b) {
+        if (dim == 3) {
+            b = dim3(32, 4, 2);
+            g = dim3((n[0] + 31) / 32, (n[1] + 3) / 4, (n[2] + 1) / 2);
+        } else {
+            b = dim3(32, 8, 1);
+            g = dim3((n[0] + 31) / 32, (n[1] + 7) / 8, 1);
+        }
+    }
+    static int vec_blocks(int64_t N, int nrhs) {
+        int64_t nb = (N + 2047) / 2048;  // 8 elements per thread
+        int64_t cap = std::max<int64_t>(1, (148 * 8 + nrhs - 1) / nrhs);
+        return (int)std::max<int64_t>(1, std::min<int64_t>(nb, cap));
+    }
+
+    // ------------------------------------------------------------------ operator kernels
+    // out = op(x) with MODE epilogue on the fine level
+    void fine_stencil(int mode, const FineOp<T>& op, const C* x, const C* b, C* out, int64_t ld, int nrhs, T damp) {
+        dim3 g, blk;
+        grid3(pb.n, pb.dim, g, blk);
+        const double N = (double)pb.N();
+        const double coefb = 2.0 * CR * N;
+        double bytes;
+        int tag;
+        if (mode == MODE_APPLY) bytes = 2 * S * N * nrhs + coefb, tag = T_FINE_APPLY;
+        else if (mode == MODE_RESID) bytes = 3 * S * N * nrhs + coefb, tag = T_FINE_RESID;
+        else bytes = 3 * S * N * nrhs + coefb, tag = T_FINE_JACOBI;
+        launch(tag, bytes, [&] {
+            if (pb.dim == 3) {
+                if (mode == MODE_APPLY) k_fine_stencil<T, 3, MODE_APPLY, 2><<<g, blk, 0, stream>>>(op, x, b, out, ld, nrhs, damp);
+                else if (mode == MODE_RESID) k_fine_stencil<T, 3, MODE_RESID, 2><<<g, blk, 0, stream>>>(op, x, b, out, ld, nrhs, damp);
+                else k_fine_stencil<T, 3, MODE_JACOBI, 2><<<g, blk, 0, stream>>>(op, x, b, out, ld, nrhs, damp);
+            } else {
+                if (mode == MODE_APPLY) k_fine_stencil<T, 2, MODE_APPLY, 2><<<g, blk, 0, stream>>>(op, x, b, out, ld, nrhs, damp);
+                else if (mode == MODE_RESID) k_fine_stencil<T, 2, MODE_RESID, 2><<<g, blk, 0, stream>>>(op, x, b, out, ld, nrhs, damp);
+                else k_fine_stencil<T, 2, MODE_JACOBI, 2><<<g, blk, 0, stream>>>(op, x, b, out, ld, nrhs, damp);
+            }
+        });
+    }
+    void fine_jacobi0(const FineOp<T>& op, const C* b, C* out, int64_t ld, int nrhs, T damp) {
+        dim3 g, blk;
+        grid3(pb.n, pb.dim, g, blk);
+        const double N = (double)pb.N();
+        launch(T_FINE_JACOBI0, 2 * S * N * nrhs + 2.0 * CR * N, [&] {
+            if (pb.dim == 3) k_fine_jacobi0<T, 3><<<g, blk, 0, stream>>>(op, b, out, ld, nrhs, damp);
+            else k_fine_jacobi0<T, 2><<<g, blk, 0, stream>>>(op, b, out, ld, nrhs, damp);
+        });
+    }
+    CoarseOp<T> coarse_op(const Level& L) const {
+        CoarseOp<T> op;
+        op.coef = L.coef.p;
+        op.dinv = L.dinv.p;
+        for (int d = 0; d < 3; ++d) op.n[d] = L.n[d];
+        return op;
+    }
+    void coarse_stencil(int mode, const Level& L, const C* x, const C* b, C* out, int nrhs) {
+        dim3 g, blk;
+        grid3(L.n, pb.dim, g, blk);
+        const double N = (double)L.N;
+        const int NS = pb.dim == 3 ? 27 : 9;
+        const int KB = 4;
+        const double coefb = NS * S * N * ((nrhs + KB - 1) / KB);
+        double bytes;
+        int tag;
+        if (mode == MODE_APPLY) bytes = 2 * S * N * nrhs + coefb, tag = T_COARSE_APPLY;
+        else if (mode == MODE_RESID) bytes = 3 * S * N * nrhs + coefb, tag = T_COARSE_RESID;
+        else bytes = 3 * S * N * nrhs + coefb + S * N, tag = T_COARSE_JACOBI;
+        CoarseOp<T> op = coarse_op(L);
+        const int64_t ld = L.N;
+        launch(tag, bytes, [&] {
+            if (pb.dim == 3) {
+                if (mode == MODE_APPLY) k_coarse_stencil<T, 3, MODE_APPLY, 4><<<g, blk, 0, stream>>>(op, x, b, out, ld, nrhs);
+                else if (mode == MODE_RESID) k_coarse_stencil<T, 3, MODE_RESID, 4><<<g, blk, 0, stream>>>(op, x, b, out, ld, nrhs);
+                else k_coarse_stencil<T, 3, MODE_JACOBI, 4><<<g, blk, 0, stream>>>(op, x, b, out, ld, nrhs);
+            } else {
+                if (mode == MODE_APPLY) k_coarse_stencil<T, 2, MODE_APPLY, 4><<<g, blk, 0, stream>>>(op, x, b, out, ld, nrhs);
+                else if (mode == MODE_RESID) k_coarse_stencil<T, 2, MODE_RESID, 4><<<g, blk, 0, stream>>>(op, x, b, out, ld, nrhs);
+                else k_coarse_stencil<T, 2, MODE_JACOBI, 4><<<g, blk, 0, stream>>>(op, x, b, out, ld, nrhs);
+            }
+        });
+    }
+    void diag_scale(int tag, const C* dinv, const C* b, C* out, int64_t N, int nrhs) {
+        launch(tag, 2 * S * (double)N * nrhs + S * (double)N, [&] {
+            k_diag_scale<T><<<(unsigned)((N + 255) / 256), 256, 0, stream>>>(dinv, b, out, N, N, nrhs);
+        });
+    }
+    void restrict_to(const Level& F, const Level& Cc, const C* r, C* bc, int nrhs) {
+        dim3 g, blk;
+        grid3(Cc.n, pb.dim, g, blk);
+        launch(T_RESTRICT, S * ((double)F.N + (double)Cc.N) * nrhs, [&] {
+            if (pb.dim == 3)
+                k_restrict<T, 3><<<g, blk, 0, stream>>>(r, bc, F.n[0], F.n[1], F.n[2], Cc.n[0], Cc.n[1], Cc.n[2], F.N, Cc.N, nrhs);
+            else
+                k_restrict<T, 2><<<g, blk, 0, stream>>>(r, bc, F.n[0], F.n[1], 1, Cc.n[0], Cc.n[1], 1, F.N, Cc.N, nrhs);
+        });
+    }
+    void prolong_add(const Level& F, const Level& Cc, C* x, const C* xc, int nrhs) {
+        dim3 g, blk;
+        grid3(F.n, pb.dim, g, blk);
+        launch(T_PROLONG, S * (2.0 * (double)F.N + (double)Cc.N) * nrhs, [&] {
+            if (pb.dim == 3)
+                k_prolong_add<T, 3><<<g, blk, 0, stream>>>(x, xc, F.n[0], F.n[1], F.n[2], Cc.n[0], Cc.n[1], F.N, Cc.N, nrhs);
+            else
+                k_prolong_add<T, 2><<<g, blk, 0, stream>>>(x, xc, F.n[0], F.n[1], 1, Cc.n[0], Cc.n[1], F.N, Cc.N, nrhs);
+        });
+    }
+
+    // ------------------------------------------------------------------ vector kernels
+    void copy_vec(const C* in, C* out, int64_t N, int nrhs) {
+        if (in == out) return;
+        launch(T_COPY, 2 * S * (double)N * nrhs, [&] {
+            HH_CUDA(cudaMemcpyAsync(out, in, (size_t)N * nrhs * sizeof(C), cudaMemcpyDeviceToDevice, stream));
+        });
+    }
+    void zero_vec(C* v, int64_t N, int nrhs) {
+        launch(T_COPY, S * (double)N * nrhs, [&] { HH_CUDA(cudaMemsetAsync(v, 0, (size_t)N * nrhs * sizeof(C), stream)); });
+    }
+    // partial sums of conj(V_i).w (i<nv) [+ |w|^2 if with_norm]; returns nblk
+    int multidot(const C* const* V, int nv, const C* w, int64_t N, int nrhs, bool with_norm, zc* partial) {
+        HH_REQUIRE(nv >= 0 && nv <= HH_MAXV, HH_ERR_ARG, "multidot: too many vectors");
+        const int nblk = vec_blocks(N, nrhs);
+        HH_REQUIRE((size_t)(nv + 1) * nrhs * nblk <= d_partial.n, HH_ERR_STATE, "multidot: partial buffer too small");
+        VecList<T> L;
+        for (int i = 0; i < HH_MAXV; ++i) L.v[i] = i < nv ? V[i] : nullptr;
+        dim3 g(nblk, nrhs);
+        launch(T_DOT, S * (double)N * nrhs * (nv + 1), [&] {
+#define HH_MD(NV)                                                                              \
+    case NV:                                                                                   \
+        if (with_norm) k_multidot<T, NV, true><<<g, 256, 0, stream>>>(L, w, N, N, partial);    \
+        else k_multidot<T, NV, false><<<g, 256, 0, stream>>>(L, w, N, N, partial);             \
+        break;
+            switch (nv) {
+                HH_MD(0) HH_MD(1) HH_MD(2) HH_MD(3) HH_MD(4) HH_MD(5) HH_MD(6) HH_MD(7) HH_MD(8)
+            }
+#undef HH_MD
+        });
+        return nblk;
+    }
+    int multiaxpy(const C* const* V, int nv, C* w, int64_t N, int nrhs, const zc* coef, int cstride, bool negate,
+                  bool with_norm, zc* partial) {
+        HH_REQUIRE(nv >= 1 && nv <= HH_MAXV, HH_ERR_ARG, "multiaxpy: bad vector count");
+        const int nblk = vec_blocks(N, nrhs);
+        VecList<T> L;
+        for (int i = 0; i < HH_MAXV; ++i) L.v[i] = i < nv ? V[i] : nullptr;
+        dim3 g(nblk, nrhs);
+        launch(T_AXPY, S * (double)N * nrhs * (nv + 2), [&] {
+#define HH_MA(NV)                                                                                                 \
+    case NV:                                                                                                      \
+        if (with_norm) k_multiaxpy<T, NV, true><<<g, 256, 0, stream>>>(L, w, N, N, coef, cstride, negate, partial); \
+        else k_multiaxpy<T, NV, false><<<g, 256, 0, stream>>>(L, w, N, N, coef, cstride, negate, partial);          \
+        break;
+            switch (nv) { HH_MA(1) HH_MA(2) HH_MA(3) HH_MA(4) HH_MA(5) HH_MA(6) HH_MA(7) HH_MA(8) }
+#undef HH_MA
+        });
+        return nblk;
+    }
+    void scale_vec(const C* in, C* out, int64_t N, int nrhs, const zc* alpha, int astride) {
+        dim3 g(vec_blocks(N, nrhs), nrhs);
+        launch(T_SCALE, 2 * S * (double)N * nrhs,
+               [&] { k_scale<T><<<g, 256, 0, stream>>>(in, out, N, N, N, alpha, astride); });
+    }
+
+    // ------------------------------------------------------------------ hierarchy (MGsetup)
+    void clear() override {
+        levels.clear();
+        have_hierarchy = false;
+        inv_dense.release();
+        kcap = 0;
+        kry.release();
+        kry_cap = 0;
+    }
+    bool hierarchy_exists() const override { return have_hierarchy; }
+    void level_nodes(int level, int64_t* out) const override {
+        HH_REQUIRE(have_hierarchy && level >= 0 && level < (int)levels.size(), HH_ERR_ARG, "bad level");
+        for (int d = 0; d < pb.dim; ++d) out[d] = levels[level].n[d];
+    }
+
+    void setup(const hh_mg_options& o) override {
+        HH_CUDA(cudaSetDevice(device));
+        auto t0 = std::chrono::steady_clock::now();
+        HH_REQUIRE(o.levels >= 1 && o.levels <= HH_MAX_LEVELS, HH_ERR_ARG, "levels out of range");
+        HH_REQUIRE(d_m.p != nullptr, HH_ERR_STATE, "no model set");
+        HH_REQUIRE(o.relax_type == HH_RELAX_JAC || o.relax_type == HH_RELAX_JAC_GMRES, HH_ERR_ARG, "bad relax_type");
+        HH_REQUIRE(o.cycle_type >= HH_CYCLE_V && o.cycle_type <= HH_CYCLE_K, HH_ERR_ARG, "bad cycle_type");
+        HH_REQUIRE(o.coarse_type == HH_COARSE_LU || o.coarse_type == HH_COARSE_GMRES, HH_ERR_ARG, "bad coarse_type");
+        clear();
+        opt = o;
+        levels.resize(o.levels);
+        for (int d = 0; d < 3; ++d) levels[0].n[d] = pb.n[d];
+        levels[0].N = pb.N();
+        for (int l = 1; l < o.levels; ++l) {
+            for (int d = 0; d < 3; ++d) {
+                const int nf = levels[l - 1].n[d];
+                if (d < pb.dim) {
+                    HH_REQUIRE(nf >= 3 && (nf % 2) == 1, HH_ERR_ARG,
+                               "cannot coarsen: every level needs an odd node count >= 3 in each dimension (cells "
+                               "divisible by 2^(levels-1))");
+                    levels[l].n[d] = (nf + 1) / 2;
+                } else {
+                    levels[l].n[d] = 1;
+                }
+            }
+            levels[l].N = (int64_t)levels[l].n[0] * levels[l].n[1] * levels[l].n[2];
+        }
+        mg_fine = fine_op(o.shift[0], o.do_transpose);
+        const int NS = pb.dim == 3 ? 27 : 9;
+        const int center = pb.dim == 3 ? 13 : 4;
+        for (int l = 1; l < o.levels; ++l) {
+            Level& Lc = levels[l];
+            Level& Lf = levels[l - 1];
+            Lc.coef.alloc((size_t)NS * Lc.N);
+            Lc.dinv.alloc(Lc.N);
+            const int64_t tot = Lc.N * NS;
+            const unsigned nb = (unsigned)((tot + 127) / 128);
+            launch(T_SETUP, 0, [&] {
+                if (l == 1) {
+                    if (pb.dim == 3) {
+                        FineCoef<T, 3> A{mg_fine};
+                        k_galerkin<T, 3, FineCoef<T, 3>><<<nb, 128, 0, stream>>>(A, Lf.n[0], Lf.n[1], Lf.n[2], Lc.n[0], Lc.n[1], Lc.n[2], Lc.coef.p);
+                    } else {
+                        FineCoef<T, 2> A{mg_fine};
+                        k_galerkin<T, 2, FineCoef<T, 2>><<<nb, 128, 0, stream>>>(A, Lf.n[0], Lf.n[1], 1, Lc.n[0], Lc.n[1], 1, Lc.coef.p);
+                    }
+                } else {
+                    if (pb.dim == 3) {
+                        StoredCoef<T, 3> A{coarse_op(Lf)};
+                        k_galerkin<T, 3, StoredCoef<T, 3>><<<nb, 128, 0, stream>>>(A, Lf.n[0], Lf.n[1], Lf.n[2], Lc.n[0], Lc.n[1], Lc.n[2], Lc.coef.p);
+                    } else {
+                        StoredCoef<T, 2> A{coarse_op(Lf)};
+                        k_galerkin<T, 2, StoredCoef<T, 2>><<<nb, 128, 0, stream>>>(A, Lf.n[0], Lf.n[1], 1, Lc.n[0], Lc.n[1], 1, Lc.coef.p);
+                    }
+                }
+            });
+            launch(T_SETUP, 0, [&] {
+                k_coarse_dinv<T><<<(unsigned)((Lc.N + 255) / 256), 256, 0, stream>>>(Lc.coef.p + (int64_t)center * Lc.N, Lc.dinv.p, Lc.N, (T)o.relax_param);
+            });
+        }
+        if (o.relax_type == HH_RELAX_JAC_GMRES || (o.levels == 1 && o.coarse_type == HH_COARSE_GMRES)) {
+            Level& L0 = levels[0];
+            L0.dinv.alloc(L0.N);
+            dim3 g, blk;
+            grid3(pb.n, pb.dim, g, blk);
+            launch(T_SETUP, 0, [&] {
+                if (pb.dim == 3) k_fine_dinv<T, 3><<<g, blk, 0, stream>>>(mg_fine, L0.dinv.p, (T)o.relax_param);
+                else k_fine_dinv<T, 2><<<g, blk, 0, stream>>>(mg_fine, L0.dinv.p, (T)o.relax_param);
+            });
+        }
+        if (o.coarse_type == HH_COARSE_LU) build_dense_inverse();
+        HH_CUDA(cudaStreamSynchronize(stream));
+        have_hierarchy = true;
+        setup_seconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    }
+
+    // exact coarsest solve: banded LU (device) -> explicit inverse (device), row-major in precision T
+    void build_dense_inverse() {
+        const int Lc = opt.levels - 1;
+        HH_REQUIRE(Lc >= 1, HH_ERR_UNSUPPORTED,
+                   "coarse_type LU needs levels >= 2 (the fine level is matrix-free; use GMRES for a 1-level solve)");
+        Level& L = levels[Lc];
+        const int64_t N = L.N;
+        const int bw = pb.dim == 3 ? (1 + L.n[0] + L.n[0] * L.n[1]) : (1 + L.n[0]);
+        const double need = (double)N * N * (16.0 + sizeof(C)) + (double)N * (2.0 * bw + 1) * 16.0;
+        size_t fr = 0, tot = 0;
+        HH_CUDA(cudaMemGetInfo(&fr, &tot));
+        HH_REQUIRE(need < 0.5 * (double)fr && N <= 46000, HH_ERR_UNSUPPORTED,
+                   "coarsest grid too large for the exact (LU) coarsest solve; use more levels or coarse_type GMRES");
+        const int64_t W = 2 * (int64_t)bw + 1;
+        DevBuf<zc> band, inv;
+        band.alloc((size_t)N * W);
+        inv.alloc((size_t)N * N);
+        HH_CUDA(cudaMemsetAsync(band.p, 0, (size_t)N * W * sizeof(zc), stream));
+        const int NS = pb.dim == 3 ? 27 : 9;
+        const unsigned nb = (unsigned)((N * NS + 255) / 256);
+        CoarseOp<T> op = coarse_op(L);
+        launch(T_SETUP, 0, [&] {
+            if (pb.dim == 3) k_band_fill<T, 3><<<nb, 256, 0, stream>>>(op, band.p, bw);
+            else k_band_fill<T, 2><<<nb, 256, 0, stream>>>(op, band.p, bw);
+        });
+        launch(T_SETUP, 0, [&] { k_band_lu<<<1, 1024, 0, stream>>>(band.p, N, bw); });
+        for (int64_t c0 = 0; c0 < N; c0 += 32768) {
+            const unsigned nc = (unsigned)std::min<int64_t>(32768, N - c0);
+            launch(T_SETUP, 0, [&] { k_band_inverse<<<nc, 256, 0, stream>>>(band.p, N, bw, c0, inv.p); });
+        }
+        inv_dense.alloc((size_t)N * N);
+        dim3 g((unsigned)((N + 31) / 32), (unsigned)((N + 31) / 32)), blk(32, 8);
+        launch(T_SETUP, 0, [&] { k_inverse_pack<T><<<g, blk, 0, stream>>>(inv.p, inv_dense.p, N); });
+        HH_CUDA(cudaStreamSynchronize(stream));
+    }
+
+    void get_level_stencil(int level, void* out) override {
+        HH_REQUIRE(have_hierarchy && level >= 1 && level < (int)levels.size(), HH_ERR_ARG, "bad level");
+        HH_CUDA(cudaSetDevice(device));
+        HH_CUDA(cudaStreamSynchronize(stream));
+        HH_CUDA(cudaMemcpy(out, levels[level].coef.p, levels[level].coef.n * sizeof(C), cudaMemcpyDeviceToHost));
+    }
+    void get_diagonal(int shifted, double shift, double* out) override {
+        HH_CUDA(cudaSetDevice(device));
+        DevBuf<zc> d;
+        d.alloc(pb.N());
+        FineOp<T> op = fine_op(shifted ? shift : 0.0, 0);
+        dim3 g, blk;
+        grid3(pb.n, pb.dim, g, blk);
+        launch(T_SETUP, 0, [&] {
+            if (pb.dim == 3) k_fine_diag<T, 3><<<g, blk, 0, stream>>>(op, d.p);
+            else k_fine_diag<T, 2><<<g, blk, 0, stream>>>(op, d.p);
+        });
+        HH_CUDA(cudaStreamSynchronize(stream));
+        HH_CUDA(cudaMemcpy(out, d.p, pb.N() * sizeof(zc), cudaMemcpyDeviceToHost));
+    }
+
+    // ------------------------------------------------------------------ work memory (adjustMemoryForNumRHS)
+    int gmres_small_steps(int l) const {
+        int s = 0;
+        const int L = opt.levels;
+        if (opt.relax_type == HH_RELAX_JAC_GMRES && l < L - 1) s = std::max(s, std::max(opt.relax_pre[l], opt.relax_post[l]));
+        if (l == L - 1 && opt.coarse_type == HH_COARSE_GMRES) s = std::max(s, opt.coarse_iters);
+        return s;
+    }
+    bool kcycle_level(int l) const { return opt.cycle_type == HH_CYCLE_K && l >= 1 && l < opt.levels - 1; }
+    double level_bytes_per_rhs() const {
+        double b = 0;
+        for (int l = 0; l < (int)levels.size(); ++l) {
+            const double N = (double)levels[l].N;
+            b += (l == 0 ? 1.0 : 3.0) * N * S;
+            const int gs = gmres_small_steps(l);
+            if (gs > 0) b += (gs + 1) * N * S;
+            if (kcycle_level(l)) b += 5 * N * S;
+        }
+        return b;
+    }
+    void ensure_level_memory(int nrhs) {
+        if (nrhs <= kcap) return;
+        for (int l = 0; l < (int)levels.size(); ++l) {
+            Level& L = levels[l];
+            L.t.alloc((size_t)L.N * nrhs);
+            if (l >= 1) {
+                L.x.alloc((size_t)L.N * nrhs);
+                L.b.alloc((size_t)L.N * nrhs);
+            }
+            L.px = L.x.p;
+            L.pb = L.b.p;
+            L.pt = L.t.p;
+            const int gs = gmres_small_steps(l);
+            L.gs.steps = gs;
+            if (gs > 0) {
+                L.gs.v.alloc((size_t)(gs + 1) * L.N * nrhs);
+                alloc_gmres_state(L.gs.g, gs, nrhs);
+            }
+            L.ks.steps = kcycle_level(l) ? 2 : 0;
+            if (L.ks.steps) {
+                L.ks.v.alloc((size_t)3 * L.N * nrhs);
+                L.ks.z.alloc((size_t)2 * L.N * nrhs);
+                alloc_gmres_state(L.ks.g, 2, nrhs);
+            }
+        }
+        kcap = nrhs;
+        const int nblk_max = 148 * 8 + 8;
+        d_partial.alloc((size_t)(HH_MAXV + 1) * std::max(nrhs, 1) * nblk_max);
+    }
+
+    void alloc_gmres_state(GmresMem& g, int m, int nrhs) {
+        g.H.alloc((size_t)nrhs * (m + 1) * m);
+        g.cs.alloc((size_t)nrhs * m);
+        g.sn.alloc((size_t)nrhs * m);
+        g.s.alloc((size_t)nrhs * (m + 1));
+        g.hcol.alloc((size_t)nrhs * (m + 1));
+        g.y.alloc((size_t)nrhs * m);
+        g.scale.alloc(nrhs);
+        g.bnorm.alloc(nrhs);
+        g.err.alloc(nrhs);
+        g.done.alloc(nrhs);
+        g.jdone.alloc(nrhs);
+        g.nprec.alloc(nrhs);
+        g.st = GmresState{g.H.p, g.cs.p, g.sn.p, g.s.p, g.hcol.p, g.y.p, g.bnorm.p, g.err.p, g.scale.p, g.done.p, g.jdone.p, g.nprec.p, m};
+    }
+
+    // ------------------------------------------------------------------ generic operator access per level
+    void level_apply(int l, int mode, const C* x, const C* b, C* out, int nrhs) {
+        if (l == 0) fine_stencil(mode, mg_fine, x, b, out, levels[0].N, nrhs, (T)opt.relax_param);
+        else coarse_stencil(mode, levels[l], x, b, out, nrhs);
+    }
+    void level_jacobi0(int l, const C* b, C* out, int nrhs) {
+        if (l == 0) fine_jacobi0(mg_fine, b, out, levels[0].N, nrhs, (T)opt.relax_param);
+        else diag_scale(T_COARSE_JACOBI0, levels[l].dinv.p, b, out, levels[l].N, nrhs);
+    }
+
+    // Orthogonalise w against V_0..V_j (classical Gram-Schmidt in one fused pass over the vectors),
+    // then the Givens update.  Leaves 1/||w|| in st.scale.
+    void gmres_orthogonalise(GmresMem& g, C* const* V, int j, C* w, int64_t N, int nrhs, double tol) {
+        const C* vv[HH_MAXV];
+        for (int i0 = 0; i0 <= j; i0 += HH_MAXV) {
+            const int nv = std::min(HH_MAXV, j + 1 - i0);
+            for (int i = 0; i < nv; ++i) vv[i] = V[i0 + i];
+            const int nblk = multidot(vv, nv, w, N, nrhs, false, d_partial.p);
+            launch(T_SCALAR, 0, [&] { k_gmres_hcol<<<nrhs, 32, 0, stream>>>(g.st, d_partial.p, nblk, j, i0, nv); });
+        }
+        int nblk = 0;
+        for (int i0 = 0; i0 <= j; i0 += HH_MAXV) {
+            const int nv = std::min(HH_MAXV, j + 1 - i0);
+            for (int i = 0; i < nv; ++i) vv[i] = V[i0 + i];
+            const bool last = (i0 + HH_MAXV > j);
+            nblk = multiaxpy(vv, nv, w, N, nrhs, g.hcol.p + i0, g.st.m + 1, true, last, d_partial.p);
+        }
+        launch(T_SCALAR, 0, [&] { k_gmres_givens<<<nrhs, 32, 0, stream>>>(g.st, d_partial.p, nblk, j, tol); });
+    }
+    void gmres_begin(GmresMem& g, const C* r, int64_t N, int nrhs, bool first, double tol) {
+        const int nblk = multidot(nullptr, 0, r, N, nrhs, true, d_partial.p);
+        launch(T_SCALAR, 0, [&] { k_gmres_begin<<<nrhs, 32, 0, stream>>>(g.st, d_partial.p, nblk, first ? 1 : 0, tol); });
+    }
+    void gmres_solve_y(GmresMem& g, int nrhs) {
+        launch(T_SCALAR, 0, [&] { k_gmres_solve_y<<<(nrhs + 63) / 64, 64, 0, stream>>>(g.st, nrhs); });
+    }
+
+    // `nsteps` steps of GMRES on level l (one cycle, no convergence test), right-preconditioned by
+    //   prec = 0: damped-Jacobi diagonal (Jac-GMRES smoother, inexact coarsest solve)
+    //   prec = 1: one recursive multigrid cycle on level l (K-cycle)
+    // x is updated in place (x_is_zero: x need not be initialised).
+    void small_gmres(int l, int nsteps, int prec, const C* b, C* x, bool x_is_zero, int nrhs) {
+        Level& L = levels[l];
+        SmallWs& ws = prec == 0 ? L.gs : L.ks;
+        GmresMem& g = ws.g;
+        HH_REQUIRE(nsteps >= 1 && nsteps <= ws.steps, HH_ERR_STATE, "small_gmres workspace");
+        const int64_t N = L.N;
+        const int64_t vs = N * kcap;
+        std::vector<C*> V(nsteps + 1);
+        for (int i = 0; i <= nsteps; ++i) V[i] = ws.v.p + (int64_t)i * vs;
+        if (x_is_zero) copy_vec(b, V[0], N, nrhs);
+        else level_apply(l, MODE_RESID, x, b, V[0], nrhs);
+        gmres_begin(g, V[0], N, nrhs, true, 0.0);
+        scale_vec(V[0], V[0], N, nrhs, g.scale.p, 1);
+        for (int j = 0; j < nsteps; ++j) {
+            C* z;
+            if (prec == 0) {
+                z = L.pt;  // Jacobi: z = dinv .* v_j (not stored: x += dinv .* (V y) at the end)
+                diag_scale(l == 0 ? T_FINE_JACOBI0 : T_COARSE_JACOBI0, L.dinv.p, V[j], z, N, nrhs);
+            } else {
+                z = ws.z.p + (int64_t)j * vs;
+                cycle(l, V[j], z, true, nrhs);
+            }
+            level_apply(l, MODE_APPLY, z, nullptr, V[j + 1], nrhs);
+            gmres_orthogonalise(g, V.data(), j, V[j + 1], N, nrhs, 0.0);
+            if (j + 1 < nsteps) scale_vec(V[j + 1], V[j + 1], N, nrhs, g.scale.p, 1);
+        }
+        gmres_solve_y(g, nrhs);
+        const C* vv[HH_MAXV];
+        if (prec == 0) {
+            // t = sum_j y_j v_j  (accumulated into V[nsteps], free now), then x (+)= dinv .* t
+            C* t = V[nsteps];
+            zero_vec(t, N, nrhs);
+            for (int i0 = 0; i0 < nsteps; i0 += HH_MAXV) {
+                const int nv = std::min(HH_MAXV, nsteps - i0);
+                for (int i = 0; i < nv; ++i) vv[i] = V[i0 + i];
+                multiaxpy(vv, nv, t, N, nrhs, g.y.p + i0, g.st.m, false, false, d_partial.p);
+            }
+            if (x_is_zero) {
+                diag_scale(l == 0 ? T_FINE_JACOBI0 : T_COARSE_JACOBI0, L.dinv.p, t, x, N, nrhs);
+            } else {
+                diag_scale(l == 0 ? T_FINE_JACOBI0 : T_COARSE_JACOBI0, L.dinv.p, t, t, N, nrhs);
+                const C* one[1] = {t};
+                multiaxpy(one, 1, x, N, nrhs, d_one.p, 0, false, false, d_partial.p);
+            }
+        } else {
+            if (x_is_zero) zero_vec(x, N, nrhs);
+            for (int i = 0; i < nsteps; ++i) vv[i] = ws.z.p + (int64_t)i * vs;
+            multiaxpy(vv, nsteps, x, N, nrhs, g.y.p, g.st.m, false, false, d_partial.p);
+        }
+    }
+
+    // ------------------------------------------------------------------ multigrid cycle (recursiveCycle)
+    // Jacobi sweeps on level l: result ends in `x`.  `t` is scratch of the same size.
+    void smooth(int l, int nsweeps, const C* b, C*& x, C*& t, bool x_is_zero, bool can_swap, int nrhs) {
+        if (nsweeps <= 0) {
+            if (x_is_zero) zero_vec(x, levels[l].N, nrhs);
+            return;
+        }
+        if (opt.relax_type == HH_RELAX_JAC_GMRES) {
+            small_gmres(l, nsweeps, 0, b, x, x_is_zero, nrhs);
+            return;
+        }
+        // ping-pong so that the final sweep writes x
+        C* cur = x;  // holds the current iterate (if !x_is_zero)
+        C* oth = t;
+        for (int s = 0; s < nsweeps; ++s) {
+            const int remaining = nsweeps - s;  // including this sweep
+            if (s == 0 && x_is_zero) {
+                // writes either buffer: choose so that parity ends in x
+                C* dst = (remaining % 2 == 1) ? x : t;
+                level_jacobi0(l, b, dst, nrhs);
+                cur = dst;
+                oth = (dst == x) ? t : x;
+            } else {
+                level_apply(l, MODE_JACOBI, cur, b, oth, nrhs);
+                std::swap(cur, oth);
+            }
+        }
+        if (cur != x) {
+            if (can_swap) std::swap(x, t);
+            else copy_vec(cur, x, levels[l].N, nrhs);
+        }
+    }
+
+    void coarsest_solve(int l, const C* b, C* x, int nrhs) {
+        Level& L = levels[l];
+        if (opt.coarse_type == HH_COARSE_LU) {
+            const int wpb = 8;
+            launch(T_COARSEST_DENSE, S * ((double)L.N * L.N * ((nrhs + 3) / 4) + 2.0 * L.N * nrhs), [&] {
+                k_dense_apply<T, 4><<<(unsigned)((L.N + wpb - 1) / wpb), wpb * 32, 0, stream>>>(inv_dense.p, b, x, L.N, L.N, nrhs);
+            });
+        } else {
+            small_gmres(l, opt.coarse_iters, 0, b, x, true, nrhs);
+        }
+    }
+
+    // one cycle on level l for A_l x = b; x is caller storage (level-owned for l >= 1).
+    void cycle(int l, const C* b, C* x, bool x_is_zero, int nrhs) {
+        const int Lmax = opt.levels - 1;
+        if (l == Lmax) {
+            coarsest_solve(l, b, x, nrhs);
+            return;
+        }
+        Level& F = levels[l];
+        Level& Cc = levels[l + 1];
+        C* xx = x;
+        C* tt = F.pt;
+        smooth(l, opt.relax_pre[l], b, xx, tt, x_is_zero, false, nrhs);
+        level_apply(l, MODE_RESID, xx, b, tt, nrhs);
+        restrict_to(F, Cc, tt, Cc.pb, nrhs);
+        if (l + 1 == Lmax) {
+            coarsest_solve(l + 1, Cc.pb, Cc.px, nrhs);
+        } else if (opt.cycle_type == HH_CYCLE_V) {
+            cycle(l + 1, Cc.pb, Cc.px, true, nrhs);
+        } else if (opt.cycle_type == HH_CYCLE_W) {
+            cycle(l + 1, Cc.pb, Cc.px, true, nrhs);
+            cycle(l + 1, Cc.pb, Cc.px, false, nrhs);
+        } else {
+            small_gmres(l + 1, 2, 1, Cc.pb, Cc.px, true, nrhs);
+        }
+        prolong_add(F, Cc, xx, Cc.px, nrhs);
+        smooth(l, opt.relax_post[l], b, xx, tt, false, false, nrhs);
+    }
+
+    void precondition(const C* b, C* z, int nrhs) {
+        cycle(0, b, z, true, nrhs);
+        ++n_prec;
+    }
+
+    void cycle_device(const void* dB, void* dZ, int64_t nrhs) override {
+        HH_CUDA(cudaSetDevice(device));
+        HH_REQUIRE(have_hierarchy, HH_ERR_STATE, "hh_setup has not been called");
+        ensure_level_memory((int)nrhs);
+        ensure_const();
+        precondition((const C*)dB, (C*)dZ, (int)nrhs);
+        HH_CUDA(cudaStreamSynchronize(stream));
+    }
+
+    void apply_device(const void* dX, void* dY, int64_t nrhs, int shifted, double shift, int transpose) override {
+        HH_CUDA(cudaSetDevice(device));
+        HH_REQUIRE(d_m.p != nullptr, HH_ERR_STATE, "no model set");
+        FineOp<T> op = fine_op(shifted ? shift : 0.0, transpose);
+        fine_stencil(MODE_APPLY, op, (const C*)dX, nullptr, (C*)dY, pb.N(), (int)nrhs, T(0));
+    }
+
+    void scatter_point_sources(void* dB, const int64_t* idx0, const double* val, int64_t nrhs) override {
+        HH_CUDA(cudaSetDevice(device));
+        DevBuf<int64_t> di;
+        DevBuf<zc> dv;
+        di.alloc(nrhs);
+        dv.alloc(nrhs);
+        HH_CUDA(cudaMemcpyAsync(di.p, idx0, nrhs * sizeof(int64_t), cudaMemcpyHostToDevice, stream));
+        HH_CUDA(cudaMemcpyAsync(dv.p, val, nrhs * sizeof(zc), cudaMemcpyHostToDevice, stream));
+        HH_CUDA(cudaMemsetAsync(dB, 0, (size_t)pb.N() * nrhs * sizeof(C), stream));
+        launch(T_COPY, 0, [&] { k_point_sources<T><<<(unsigned)((nrhs + 127) / 128), 128, 0, stream>>>((C*)dB, pb.N(), di.p, dv.p, (int)nrhs); });
+        HH_CUDA(cudaStreamSynchronize(stream));
+    }
+
+    void ensure_const() {
+        if (d_one.p) return;
+        d_one.alloc(1);
+        zc one = mk<double>(1.0, 0.0);
+        HH_CUDA(cudaMemcpy(d_one.p, &one, sizeof(zc), cudaMemcpyHostToDevice));
+    }
+
+    // ------------------------------------------------------------------ outer Krylov
+    int krylov_vectors(const hh_solve_options& o) const {
+        return o.krylov == HH_KRYLOV_GMRES ? (2 * o.inner + 1) : 7;
+    }
+    int64_t max_rhs_per_batch(const hh_solve_options& o) override {
+        HH_CUDA(cudaSetDevice(device));
+        size_t fr = 0, tot = 0;
+        HH_CUDA(cudaMemGetInfo(&fr, &tot));
+        double avail = (double)fr;
+        // memory we already hold for work vectors counts as available for re-use
+        avail += (double)kcap * level_bytes_per_rhs() + (double)kry.n * sizeof(C);
+        const double per = level_bytes_per_rhs() + (double)krylov_vectors(o) * pb.N() * S;
+        int64_t k = (int64_t)std::floor(0.90 * avail / per);
+        return std::max<int64_t>(k, 0);
+    }
+    void ensure_krylov_memory(const hh_solve_options& o, int nrhs) {
+        const size_t need = (size_t)krylov_vectors(o) * pb.N() * nrhs;
+        if (need > kry.n || nrhs > kry_cap) {
+            kry.release();
+            kry.alloc(need);
+            kry_cap = nrhs;
+        }
+    }
+
+    int solve_device(const void* dB, void* dX, int64_t nrhs64, const hh_solve_options& o, int32_t* iters,
+                     double* relres) override {
+        HH_CUDA(cudaSetDevice(device));
+        HH_REQUIRE(have_hierarchy, HH_ERR_STATE, "hh_setup has not been called");
+        HH_REQUIRE(o.krylov == HH_KRYLOV_GMRES || o.krylov == HH_KRYLOV_BICGSTAB, HH_ERR_ARG, "bad krylov");
+        HH_REQUIRE(o.krylov != HH_KRYLOV_GMRES || (o.inner >= 1 && o.inner <= 64), HH_ERR_ARG, "inner must be in 1..64");
+        HH_REQUIRE(o.max_iter >= 1, HH_ERR_ARG, "max_iter must be >= 1");
+        HH_REQUIRE((o.do_transpose != 0) == (opt.do_transpose != 0), HH_ERR_STATE,
+                   "hierarchy was built for the other transpose state; call hh_setup with do_transpose");
+        const int nrhs = (int)nrhs64;
+        auto t0 = std::chrono::steady_clock::now();
+        ensure_level_memory(nrhs);
+        ensure_krylov_memory(o, nrhs);
+        ensure_const();
+        int rc;
+        if (o.krylov == HH_KRYLOV_GMRES) rc = fgmres((const C*)dB, (C*)dX, nrhs, o, iters, relres);
+        else rc = bicgstab((const C*)dB, (C*)dX, nrhs, o, iters, relres);
+        solve_seconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        return rc;
+    }
+
+    // returns true when every RHS is done; throws on NaN
+    bool fetch_done(const int* d_done, int nrhs) {
+        h_done.resize(nrhs);
+        HH_CUDA(cudaMemcpyAsync(h_done.data(), d_done, nrhs * sizeof(int), cudaMemcpyDeviceToHost, stream));
+        HH_CUDA(cudaStreamSynchronize(stream));
+        bool all = true;
+        for (int r = 0; r < nrhs; ++r) {
+            if (h_done[r] == 2) throw Error(HH_ERR_NAN, "NaN in the residual norm of right-hand side " + std::to_string(r));
+            all = all && (h_done[r] != 0);
+        }
+        return all;
+    }
+
+    // Right-preconditioned restarted flexible GMRES, batched over the RHS block (each RHS keeps its own
+    // Hessenberg / Givens scalars).  Counterpart of KrylovMethods.fgmres as called by solveGMRES_MG
+    // (ShiftedLaplacianMultigridSolver.jl:89).
+    int fgmres(const C* B, C* X, int nrhs, const hh_solve_options& o, int32_t* iters, double* relres) {
+        const int m = o.inner;
+        const int64_t N = pb.N();
+        const int64_t vs = N * kry_cap;
+        if (outer.st.m != m || outer_cap < nrhs) {
+            alloc_gmres_state(outer, m, nrhs);
+            outer_cap = nrhs;
+        }
+        std::vector<C*> V(m + 1), Z(m);
+        for (int i = 0; i <= m; ++i) V[i] = kry.p + (int64_t)i * vs;
+        for (int i = 0; i < m; ++i) Z[i] = kry.p + (int64_t)(m + 1 + i) * vs;
+        const FineOp<T> Hop = fine_op(0.0, o.do_transpose);  // Afun: the un-shifted operator (GetHelmholtz.jl:85-95)
+        zero_vec(X, N, nrhs);
+        // r0 = b (x0 = 0); bnorm
+        gmres_begin(outer, B, N, nrhs, true, o.rel_tol);
+        scale_vec(B, V[0], N, nrhs, outer.scale.p, 1);
+        bool all_done = fetch_done(outer.done.p, nrhs);
+        for (int cyc = 0; cyc < o.max_iter && !all_done; ++cyc) {
+            for (int j = 0; j < m; ++j) {
+                precondition(V[j], Z[j], nrhs);
+                fine_stencil(MODE_APPLY, Hop, Z[j], nullptr, V[j + 1], N, nrhs, T(0));
+                gmres_orthogonalise(outer, V.data(), j, V[j + 1], N, nrhs, o.rel_tol);
+                scale_vec(V[j + 1], V[j + 1], N, nrhs, outer.scale.p, 1);
+                all_done = fetch_done(outer.done.p, nrhs);
+                if (all_done) break;
+            }
+            gmres_solve_y(outer, nrhs);
+            const C* zz[HH_MAXV];
+            for (int i0 = 0; i0 < m; i0 += HH_MAXV) {
+                const int nv = std::min(HH_MAXV, m - i0);
+                for (int i = 0; i < nv; ++i) zz[i] = Z[i0 + i];
+                multiaxpy(zz, nv, X, N, nrhs, outer.y.p + i0, m, false, false, d_partial.p);
+            }
+            if (all_done || cyc + 1 == o.max_iter) break;
+            // restart: r = b - H x
+            fine_stencil(MODE_RESID, Hop, X, B, V[0], N, nrhs, T(0));
+            gmres_begin(outer, V[0], N, nrhs, false, o.rel_tol);
+            scale_vec(V[0], V[0], N, nrhs, outer.scale.p, 1);
+            all_done = fetch_done(outer.done.p, nrhs);
+        }
+        return finish(outer.nprec.p, outer.err.p, nrhs, iters, relres, all_done);
+    }
+
+    int finish(const int* d_nprec, const double* d_err, int nrhs, int32_t* iters, double* relres, bool all_done) {
+        std::vector<int> np(nrhs);
+        std::vector<double> er(nrhs);
+        HH_CUDA(cudaMemcpyAsync(np.data(), d_nprec, nrhs * sizeof(int), cudaMemcpyDeviceToHost, stream));
+        HH_CUDA(cudaMemcpyAsync(er.data(), d_err, nrhs * sizeof(double), cudaMemcpyDeviceToHost, stream));
+        HH_CUDA(cudaStreamSynchronize(stream));
+        for (int r = 0; r < nrhs; ++r) {
+            if (iters) iters[r] = np[r];
+            if (relres) relres[r] = er[r];
+        }
+        if (prof.on) prof.flush(stream);
+        return all_done ? HH_OK : HH_NOT_CONVERGED;
+    }
+
+    // Preconditioned BiCGSTAB, batched (KrylovMethods.bicgstb as called by solveBiCGSTAB_MG,
+    // ShiftedLaplacianMultigridSolver.jl:92); two preconditioner applications per iteration.
+    struct BicgMem {
+        DevBuf<zc> rho, rho_old, alpha, omega, beta, neg_alpha, neg_omega, ao;
+        DevBuf<double> bnorm, err;
+        DevBuf<int> done, half, nprec, iters;
+        BicgState st;
+        int cap = 0;
+    };
+    int bicgstab(const C* B, C* X, int nrhs, const hh_solve_options& o, int32_t* iters, double* relres) {
+        const int64_t N = pb.N();
+        const int64_t vs = N * kry_cap;
+        if (bicg.cap < nrhs) {
+            BicgMem& g = bicg;
+            g.rho.alloc(nrhs); g.rho_old.alloc(nrhs); g.alpha.alloc(nrhs); g.omega.alloc(nrhs); g.beta.alloc(nrhs);
+            g.neg_alpha.alloc(nrhs); g.neg_omega.alloc(nrhs); g.ao.alloc(2 * (size_t)nrhs);
+            g.bnorm.alloc(nrhs); g.err.alloc(nrhs); g.done.alloc(nrhs); g.half.alloc(nrhs); g.nprec.alloc(nrhs); g.iters.alloc(nrhs);
+            g.st = BicgState{g.rho.p, g.rho_old.p, g.alpha.p, g.omega.p, g.beta.p, g.neg_alpha.p, g.neg_omega.p, g.ao.p,
+                             g.bnorm.p, g.err.p, g.done.p, g.half.p, g.nprec.p, g.iters.p};
+            g.cap = nrhs;
+        }
+        C* r = kry.p;
+        C* rt = kry.p + vs;
+        C* p = kry.p + 2 * vs;
+        C* v = kry.p + 3 * vs;
+        C* t = kry.p + 4 * vs;
+        C* ph = kry.p + 5 * vs;
+        C* sh = kry.p + 6 * vs;
+        const FineOp<T> Hop = fine_op(0.0, o.do_transpose);
+        auto scalars = [&](int nblk, int stage) {
+            launch(T_SCALAR, 0, [&] { k_bicg_scalars<<<nrhs, 32, 0, stream>>>(bicg.st, d_partial.p, nblk, stage, o.rel_tol); });
+        };
+        zero_vec(X, N, nrhs);
+        copy_vec(B, r, N, nrhs);
+        copy_vec(B, rt, N, nrhs);
+        zero_vec(p, N, nrhs);
+        zero_vec(v, N, nrhs);
+        scalars(multidot(nullptr, 0, B, N, nrhs, true, d_partial.p), BICG_INIT);
+        bool all_done = fetch_done(bicg.done.p, nrhs);
+        const C* one[2];
+        for (int it = 0; it < o.max_iter && !all_done; ++it) {
+            one[0] = rt;
+            scalars(multidot(one, 1, r, N, nrhs, false, d_partial.p), BICG_RHO);
+            {
+                dim3 g(vec_blocks(N, nrhs), nrhs);
+                launch(T_AXPY, 4 * S * (double)N * nrhs,
+                       [&] { k_bicg_p<T><<<g, 256, 0, stream>>>(p, r, v, N, N, bicg.beta.p, bicg.omega.p); });
+            }
+            precondition(p, ph, nrhs);
+            fine_stencil(MODE_APPLY, Hop, ph, nullptr, v, N, nrhs, T(0));
+            one[0] = rt;
+            scalars(multidot(one, 1, v, N, nrhs, false, d_partial.p), BICG_ALPHA);
+            one[0] = v;  // s = r - alpha v  (in place in r)
+            scalars(multiaxpy(one, 1, r, N, nrhs, bicg.neg_alpha.p, 1, false, true, d_partial.p), BICG_HALF);
+            precondition(r, sh, nrhs);
+            fine_stencil(MODE_APPLY, Hop, sh, nullptr, t, N, nrhs, T(0));
+            one[0] = r;  // <s,t> and |t|^2
+            scalars(multidot(one, 1, t, N, nrhs, true, d_partial.p), BICG_OMEGA);
+            one[0] = ph;
+            one[1] = sh;
+            multiaxpy(one, 2, X, N, nrhs, bicg.ao.p, 2, false, false, d_partial.p);
+            one[0] = t;  // r = s - omega t
+            scalars(multiaxpy(one, 1, r, N, nrhs, bicg.neg_omega.p, 1, false, true, d_partial.p), BICG_END);
+            all_done = fetch_done(bicg.done.p, nrhs);
+        }
+        return finish(bicg.nprec.p, bicg.err.p, nrhs, iters, relres, all_done);
+    }
+
+   private:
+    DevBuf<T> d_m, d_g;
+    std::vector<Level> levels;
+    bool have_hierarchy = false;
+    hh_mg_options opt{};
+    FineOp<T> mg_fine{};
+    DevBuf<C> inv_dense;
+    int kcap = 0;
+    DevBuf<C> kry;
+    int kry_cap = 0;
+    DevBuf<zc> d_partial, d_one;
+    GmresMem outer;
+    int outer_cap = 0;
+    BicgMem bicg;
+    std::vector<int> h_done;
+};
+
+}  // namespace hh
