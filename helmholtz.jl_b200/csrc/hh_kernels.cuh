@@ -26,6 +26,10 @@ struct FineOp {
     int n[3];     // node counts (n[2] == 1 in 2-D)
     int neumann_top;
     int adj;      // 1: conjugate transpose
+    // optional precomputed diagonal arrays (k_fine_precompute): centre coefficient incl. the Laplacian
+    // diagonal, and damp/centre.  Used by the TMA-staged production kernels.
+    const cx<T>* cdiag;
+    const cx<T>* dinv;
 };
 
 template <typename T>
@@ -138,6 +142,383 @@ __global__ void __launch_bounds__(256) k_fine_stencil(FineOp<T> op, const cx<T>*
             }
         }
     }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K1/K2 (3-D production form): z-marching 7-point stencil.  A CTA owns a 32 x TY tile of (i,j)
+// columns and walks a chunk of z planes; each thread keeps the z-1 / z / z+1 values of its column
+// in registers, so every x value is fetched from L2/HBM once per sweep (the four in-plane
+// neighbours were fetched as centres one step earlier by this warp or its neighbours and hit L1).
+// KB right-hand sides share one evaluation of the coefficients (m, gamma, Sommerfeld, weights).
+// blockIdx.x enumerates (RHS group, x tile) with the group fastest, so that the CTAs that share a tile's
+// m/gamma are co-scheduled and those coefficients come from HBM once per sweep.
+// ---------------------------------------------------------------------------------------------
+template <typename T, int MODE, int KB, int TY, int MINB>
+__global__ void __launch_bounds__(32 * TY, MINB) k_fine3d_zmarch(FineOp<T> op, const cx<T>* __restrict__ x,
+                                                                 const cx<T>* __restrict__ b, cx<T>* __restrict__ out,
+                                                                 int64_t ld, int nrhs, T damp, int zchunk, int groups) {
+    const int n0 = op.n[0], n1 = op.n[1], n2 = op.n[2];
+    const int i = (blockIdx.x / groups) * blockDim.x + threadIdx.x;  // CTA shape (blockDim.x, 32*TY/blockDim.x)
+    const int j = blockIdx.y * blockDim.y + threadIdx.y;
+    if (i >= n0 || j >= n1) return;
+    const int zc = blockIdx.z;
+    const int r0 = (blockIdx.x % groups) * KB;
+    const int z0 = zc * zchunk;
+    const int z1 = min(n2, z0 + zchunk);
+    const int64_t sy = n0, sz = (int64_t)n0 * n1;
+    const int64_t pxy = i + sy * j;
+    const T wxm = fine_w(op, 0, 0, i, n0), wxp = fine_w(op, 0, 1, i, n0);
+    const T wym = fine_w(op, 1, 0, j, n1), wyp = fine_w(op, 1, 1, j, n1);
+    const int64_t oxm = wxm != T(0) ? -1 : 0, oxp = wxp != T(0) ? 1 : 0;
+    const int64_t oym = wym != T(0) ? -sy : 0, oyp = wyp != T(0) ? sy : 0;
+    const bool bi = (i == 0) | (i == n0 - 1), bj = (j == 0) | (j == n1 - 1);
+    const T lapxy = (bi ? op.BC : T(2)) * op.ih2[0] + (bj ? op.BC : T(2)) * op.ih2[1];
+    const T sfxy = (bi ? op.somm[0] : T(0)) + (bj ? op.somm[1] : T(0));
+    const cx<T>* xr[KB];
+    cx<T> xm[KB], xc[KB], xp[KB];
+#pragma unroll
+    for (int q = 0; q < KB; ++q) {
+        const int r = min(r0 + q, nrhs - 1);  // clamped: surplus slots recompute the last RHS, never stored
+        xr[q] = x + (int64_t)r * ld + pxy;
+        xc[q] = xr[q][(int64_t)z0 * sz];
+        xm[q] = z0 > 0 ? xr[q][(int64_t)(z0 - 1) * sz] : mk<T>(T(0), T(0));
+    }
+#pragma unroll 1
+    for (int z = z0; z < z1; ++z) {
+        const int64_t zo = (int64_t)z * sz;
+        const int64_t p = pxy + zo;
+        const bool zlast = (z == n2 - 1);
+#pragma unroll
+        for (int q = 0; q < KB; ++q) xp[q] = zlast ? mk<T>(T(0), T(0)) : xr[q][zo + sz];
+        // centre coefficient (fine_center, with the z-independent parts hoisted)
+        const T mv = op.m[p];
+        const T gv = op.g[p] * op.inv_wr;
+        T re = -mv * (op.a + op.b * gv);
+        T im = -mv * (op.b - op.a * gv) + op.shift_w2 * mv;
+        T sf = sfxy;
+        if ((z == 0 && !op.neumann_top) || zlast) sf += op.somm[2];
+        if (sf != T(0)) im += sf * sqrt(mv);
+        re += lapxy + ((z == 0 || zlast) ? op.BC : T(2)) * op.ih2[2];
+        if (op.adj) im = -im;
+        const cx<T> c = mk<T>(re, im);
+        const T wzm = fine_w(op, 2, 0, z, n2), wzp = fine_w(op, 2, 1, z, n2);
+        cx<T> dinv = mk<T>(T(0), T(0));
+        if (MODE == MODE_JACOBI) dinv = rdiv(damp, c);
+#pragma unroll
+        for (int q = 0; q < KB; ++q) {
+            const cx<T>* xq = xr[q] + zo;
+            cx<T> a = c * xc[q];
+            rfma(a, -wxm, xq[oxm]);
+            rfma(a, -wxp, xq[oxp]);
+            rfma(a, -wym, xq[oym]);
+            rfma(a, -wyp, xq[oyp]);
+            rfma(a, -wzm, xm[q]);
+            rfma(a, -wzp, xp[q]);
+            if (r0 + q < nrhs) {
+                const int64_t o = (int64_t)(r0 + q) * ld + p;
+                if (MODE == MODE_APPLY) {
+                    out[o] = a;
+                } else if (MODE == MODE_RESID) {
+                    out[o] = b[o] - a;
+                } else {
+                    out[o] = xc[q] + dinv * (b[o] - a);
+                }
+            }
+            xm[q] = xc[q];
+            xc[q] = xp[q];
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// coarse levels, 3-D production form: z-marching 27-point stencil with stored coefficients.  For
+// every input plane a thread reads its 3 x 3 in-plane neighbourhood once and scatters it into three
+// rolling accumulators (outputs z-1, z, z+1), so x is read 9 (not 27) times per node through L1 and
+// once from L2/HBM; the 27 coefficients of a node are read once per KB right-hand sides.
+// ---------------------------------------------------------------------------------------------
+template <typename T, int MODE, int KB, int TY, int MINB>
+__global__ void __launch_bounds__(32 * TY, MINB) k_coarse3d_zmarch(CoarseOp<T> op, const cx<T>* __restrict__ x,
+                                                                   const cx<T>* __restrict__ b, cx<T>* __restrict__ out,
+                                                                   int64_t ld, int nrhs, int zchunk, int groups) {
+    const int n0 = op.n[0], n1 = op.n[1], n2 = op.n[2];
+    const int i = (blockIdx.x / groups) * blockDim.x + threadIdx.x;  // CTA shape (blockDim.x, 32*TY/blockDim.x)
+    const int j = blockIdx.y * blockDim.y + threadIdx.y;
+    if (i >= n0 || j >= n1) return;
+    const int zc = blockIdx.z;
+    const int r0 = (blockIdx.x % groups) * KB;
+    const int z0 = zc * zchunk;
+    const int z1 = min(n2, z0 + zchunk);
+    const int64_t sy = n0, sz = (int64_t)n0 * n1;
+    const int64_t N = sz * n2;
+    const int64_t pxy = i + sy * j;
+    const cx<T> zero = mk<T>(T(0), T(0));
+    // acc[0]: output plane zi-1, acc[1]: zi, acc[2]: zi+1 while input plane zi is processed
+    cx<T> acc[3][KB];
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+        for (int q = 0; q < KB; ++q) acc[a][q] = zero;
+    const cx<T>* xr[KB];
+#pragma unroll
+    for (int q = 0; q < KB; ++q) xr[q] = x + (int64_t)min(r0 + q, nrhs - 1) * ld + pxy;
+    const int zi0 = max(z0 - 1, 0), zi1 = min(z1, n2 - 1);  // input planes zi0..zi1 inclusive
+    for (int zi = zi0; zi <= zi1; ++zi) {
+        const int64_t zo = (int64_t)zi * sz;
+        // which outputs receive this plane
+        const bool om = (zi - 1 >= z0) && (zi - 1 < z1);  // output zi-1 via dk = +1
+        const bool oc = (zi >= z0) && (zi < z1);          // output zi   via dk =  0
+        const bool op_ = (zi + 1 >= z0) && (zi + 1 < z1); // output zi+1 via dk = -1
+#pragma unroll
+        for (int dj = -1; dj <= 1; ++dj) {
+            const bool okj = (unsigned)(j + dj) < (unsigned)n1;
+#pragma unroll
+            for (int di = -1; di <= 1; ++di) {
+                const bool ok = okj && ((unsigned)(i + di) < (unsigned)n0);
+                if (!ok) continue;
+                const int sxy = (di + 1) + 3 * (dj + 1);
+                const int64_t off = zo + di + sy * dj;
+                cx<T> xv[KB];
+#pragma unroll
+                for (int q = 0; q < KB; ++q) xv[q] = xr[q][off];
+                if (om) {
+                    const cx<T> cf = op.coef[(int64_t)(sxy + 18) * N + pxy + zo - sz];
+#pragma unroll
+                    for (int q = 0; q < KB; ++q) cfma(acc[0][q], cf, xv[q]);
+                }
+                if (oc) {
+                    const cx<T> cf = op.coef[(int64_t)(sxy + 9) * N + pxy + zo];
+#pragma unroll
+                    for (int q = 0; q < KB; ++q) cfma(acc[1][q], cf, xv[q]);
+                }
+                if (op_) {
+                    const cx<T> cf = op.coef[(int64_t)sxy * N + pxy + zo + sz];
+#pragma unroll
+                    for (int q = 0; q < KB; ++q) cfma(acc[2][q], cf, xv[q]);
+                }
+            }
+        }
+        // output plane zi-1 is complete (or, at the top of the grid, output zi when zi is the last plane)
+        if (om) {
+            const int64_t p = pxy + zo - sz;
+#pragma unroll
+            for (int q = 0; q < KB; ++q) {
+                if (r0 + q < nrhs) {
+                    const int64_t o = (int64_t)(r0 + q) * ld + p;
+                    if (MODE == MODE_APPLY) out[o] = acc[0][q];
+                    else if (MODE == MODE_RESID) out[o] = b[o] - acc[0][q];
+                    else out[o] = x[o] + op.dinv[p] * (b[o] - acc[0][q]);
+                }
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < KB; ++q) {
+            acc[0][q] = acc[1][q];
+            acc[1][q] = acc[2][q];
+            acc[2][q] = zero;
+        }
+    }
+    // the chunk's last output plane (z1-1) has no further input plane when z1 == n2
+    if (z1 == n2) {
+        const int64_t p = pxy + (int64_t)(n2 - 1) * sz;
+#pragma unroll
+        for (int q = 0; q < KB; ++q) {
+            if (r0 + q < nrhs) {
+                const int64_t o = (int64_t)(r0 + q) * ld + p;
+                if (MODE == MODE_APPLY) out[o] = acc[0][q];
+                else if (MODE == MODE_RESID) out[o] = b[o] - acc[0][q];
+                else out[o] = x[o] + op.dinv[p] * (b[o] - acc[0][q]);
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// mbarrier / TMA plumbing of the TMA-staged production kernels
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WAIT_DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+// 4-D / 3-D tiled TMA loads (cp.async.bulk.tensor, SASS UTMALDG): one instruction moves a whole box,
+// out-of-range coordinates are zero-filled by the hardware (that is how tile halos at the domain
+// boundary and surplus RHS slots are handled).
+__device__ __forceinline__ void tma_load_4d(void* dst, const void* tmap, int c0, int c1, int c2, int c3, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];" ::"r"(
+            smem_u32(dst)),
+        "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const void* tmap, int c0, int c1, int c2, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
+            smem_u32(dst)),
+        "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
+        : "memory");
+}
+
+// 128-byte tensor-map descriptor (CUtensorMap), passed by value as a __grid_constant__ parameter
+struct alignas(64) TmaDesc {
+    unsigned char bytes[128];
+};
+
+template <typename T, int MODE, int KB>
+struct FineTmaCfg {
+    static constexpr int TX = 32, TY = 8;
+    static constexpr int PX = TX + 2;  // row pitch of the halo tile (elements)
+    static constexpr int XT = (TY + 2) * PX;
+    static constexpr int BT = TY * TX;
+    static constexpr int ES = (int)sizeof(cx<T>);
+    static constexpr int al(int b) { return (b + 127) / 128 * 128; }
+    // byte offsets inside a stage (every TMA destination 128-byte aligned)
+    static constexpr int OFF_X = 0;
+    static constexpr int OFF_B = al(KB * XT * ES);
+    static constexpr int OFF_C = OFF_B + (MODE != MODE_APPLY ? al(KB * BT * ES) : 0);
+    static constexpr int OFF_D = OFF_C + al(BT * ES);
+    static constexpr int STAGE_BYTES = OFF_D + (MODE == MODE_JACOBI ? al(BT * ES) : 0);
+    static constexpr uint32_t TX_BYTES = KB * XT * ES + (MODE != MODE_APPLY ? KB * BT * ES : 0) + BT * ES +
+                                         (MODE == MODE_JACOBI ? BT * ES : 0);
+};
+
+// K1/K2 (3-D, TMA production form).  Same z-marching decomposition as k_fine3d_zmarch, but every operand
+// plane is staged into shared memory by the TMA engine with an NS-deep mbarrier ring: the x tile with a
+// one-node halo (all KB right-hand sides in one box), the b tile and the precomputed diagonal tiles of
+// planes z+1 .. z+NS-1 are in flight while plane z is computed, so memory-level parallelism no longer
+// depends on occupancy or registers.  In-plane neighbours are read from the staged tile.
+template <typename T, int MODE, int KB, int NS>
+__global__ void __launch_bounds__(256) k_fine3d_tma(FineOp<T> op, const __grid_constant__ TmaDesc tm_x,
+                                                    const __grid_constant__ TmaDesc tm_b,
+                                                    const __grid_constant__ TmaDesc tm_c,
+                                                    const __grid_constant__ TmaDesc tm_d, const cx<T>* __restrict__ x,
+                                                    cx<T>* __restrict__ out, int64_t ld, int nrhs, int zchunk,
+                                                    int groups) {
+    typedef FineTmaCfg<T, MODE, KB> Cfg;
+    constexpr int TX = Cfg::TX, TY = Cfg::TY, PX = Cfg::PX;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + (size_t)NS * Cfg::STAGE_BYTES);
+    const int n0 = op.n[0], n1 = op.n[1], n2 = op.n[2];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int i0 = (blockIdx.x / groups) * TX, j0 = blockIdx.y * TY;
+    const int i = i0 + tx, j = j0 + ty;
+    const int r0 = (blockIdx.x % groups) * KB;
+    const int z0 = blockIdx.z * zchunk;
+    const int z1 = min(n2, z0 + zchunk);
+    const int zl = min(z1, n2 - 1);  // last plane that must be staged (z+1 halo of the chunk)
+    const int64_t sy = n0, sz = (int64_t)n0 * n1;
+    const bool active = (i < n0) && (j < n1);
+    auto issue = [&](int s, int z) {
+        unsigned char* st = smem_raw + (size_t)s * Cfg::STAGE_BYTES;
+        mbar_expect_tx(&bars[s], Cfg::TX_BYTES);
+        tma_load_4d(st + Cfg::OFF_X, &tm_x, 2 * (i0 - 1), j0 - 1, z, r0, &bars[s]);
+        if (MODE != MODE_APPLY) tma_load_4d(st + Cfg::OFF_B, &tm_b, 2 * i0, j0, z, r0, &bars[s]);
+        tma_load_3d(st + Cfg::OFF_C, &tm_c, 2 * i0, j0, z, &bars[s]);
+        if (MODE == MODE_JACOBI) tma_load_3d(st + Cfg::OFF_D, &tm_d, 2 * i0, j0, z, &bars[s]);
+    };
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < NS; ++s) mbar_init(&bars[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        for (int s = 0; s < NS && z0 + s <= zl; ++s) issue(s, z0 + s);
+    }
+    __syncthreads();
+    // z-invariant pieces
+    const int ic = active ? i : 0, jc = active ? j : 0;
+    const T wxm = fine_w(op, 0, 0, ic, n0), wxp = fine_w(op, 0, 1, ic, n0);
+    const T wym = fine_w(op, 1, 0, jc, n1), wyp = fine_w(op, 1, 1, jc, n1);
+    const int64_t pxy = ic + sy * jc;
+    const int cidx = (ty + 1) * PX + (tx + 1);  // centre of this thread inside an x tile
+    const int bidx = ty * TX + tx;              // inside a b / diagonal tile
+    cx<T> xm[KB], xc[KB], xp[KB];
+    mbar_wait(&bars[0], 0);
+#pragma unroll
+    for (int q = 0; q < KB; ++q) {
+        xc[q] = reinterpret_cast<const cx<T>*>(smem_raw + Cfg::OFF_X)[q * Cfg::XT + cidx];
+        const int r = min(r0 + q, nrhs - 1);
+        xm[q] = (z0 > 0 && active) ? x[(int64_t)r * ld + pxy + (int64_t)(z0 - 1) * sz] : mk<T>(T(0), T(0));
+    }
+#pragma unroll 1
+    for (int z = z0; z < z1; ++z) {
+        const int s = (z - z0) % NS;
+        const unsigned char* st = smem_raw + (size_t)s * Cfg::STAGE_BYTES;
+        const bool zlast = (z == n2 - 1);
+        if (!zlast) {
+            const int s1 = (z + 1 - z0) % NS;
+            mbar_wait(&bars[s1], (uint32_t)(((z + 1 - z0) / NS) & 1));
+            const cx<T>* x1 = reinterpret_cast<const cx<T>*>(smem_raw + (size_t)s1 * Cfg::STAGE_BYTES + Cfg::OFF_X);
+#pragma unroll
+            for (int q = 0; q < KB; ++q) xp[q] = x1[q * Cfg::XT + cidx];
+        } else {
+#pragma unroll
+            for (int q = 0; q < KB; ++q) xp[q] = mk<T>(T(0), T(0));
+        }
+        if (active) {
+            const cx<T>* sx = reinterpret_cast<const cx<T>*>(st + Cfg::OFF_X);
+            const cx<T>* sb = reinterpret_cast<const cx<T>*>(st + Cfg::OFF_B);
+            const cx<T> c = reinterpret_cast<const cx<T>*>(st + Cfg::OFF_C)[bidx];
+            cx<T> dinv = mk<T>(T(0), T(0));
+            if (MODE == MODE_JACOBI) dinv = reinterpret_cast<const cx<T>*>(st + Cfg::OFF_D)[bidx];
+            const T wzm = fine_w(op, 2, 0, z, n2), wzp = fine_w(op, 2, 1, z, n2);
+            const int64_t p = pxy + (int64_t)z * sz;
+#pragma unroll
+            for (int q = 0; q < KB; ++q) {
+                const cx<T>* xt = sx + q * Cfg::XT + cidx;
+                cx<T> a = c * xc[q];
+                rfma(a, -wxm, xt[-1]);  // halo cells outside the grid were zero-filled by the TMA unit
+                rfma(a, -wxp, xt[1]);
+                rfma(a, -wym, xt[-PX]);
+                rfma(a, -wyp, xt[PX]);
+                rfma(a, -wzm, xm[q]);
+                rfma(a, -wzp, xp[q]);
+                if (r0 + q < nrhs) {
+                    const int64_t o = (int64_t)(r0 + q) * ld + p;
+                    if (MODE == MODE_APPLY) {
+                        out[o] = a;
+                    } else {
+                        const cx<T> bv = sb[q * Cfg::BT + bidx];
+                        if (MODE == MODE_RESID) out[o] = bv - a;
+                        else out[o] = xc[q] + dinv * (bv - a);
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < KB; ++q) {
+            xm[q] = xc[q];
+            xc[q] = xp[q];
+        }
+        __syncthreads();  // every thread is done with stage s: refill it with plane z + NS
+        if (threadIdx.x == 0 && z + NS <= zl) issue(s, z + NS);
+    }
+}
+
+// centre coefficient (incl. Laplacian diagonal) and damp/centre as arrays, for the TMA-staged kernels
+template <typename T, int DIM>
+__global__ void __launch_bounds__(256) k_fine_precompute(FineOp<T> op, cx<T>* __restrict__ cdiag, cx<T>* __restrict__ dinv,
+                                                         T damp) {
+    const int n0 = op.n[0], n1 = op.n[1], n2 = op.n[2];
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = blockIdx.y * blockDim.y + threadIdx.y;
+    const int k = (DIM == 3) ? blockIdx.z * blockDim.z + threadIdx.z : 0;
+    if (i >= n0 || j >= n1 || k >= n2) return;
+    const int64_t p = i + (int64_t)n0 * j + (int64_t)n0 * n1 * k;
+    const cx<T> c = fine_center<T, DIM>(op, p, i, j, k);
+    cdiag[p] = c;
+    if (dinv) dinv[p] = rdiv(damp, c);
 }
 
 // first Jacobi sweep from a zero guess on the fine level: out = damp/diag * b

@@ -13,6 +13,8 @@
 #include <string>
 #include <vector>
 
+#include <cuda.h>  // CUtensorMap types only; the encode function is fetched through the runtime
+
 #include "../../include/helmholtz_b200.h"
 #include "hh_kernels.cuh"
 
@@ -192,6 +194,8 @@ class Solver : public SolverBase {
     typedef cx<T> C;
     static constexpr double S = sizeof(C);  // bytes per complex entry
     static constexpr double CR = sizeof(T); // bytes per real coefficient
+    static constexpr int FINE_MINB = 4;     // resident CTAs per SM the z-marching kernels are compiled for
+    static constexpr int COARSE_MINB = 2;
 
     struct GmresMem {
         DevBuf<zc> H, cs, sn, s, hcol, y, scale;
@@ -218,6 +222,12 @@ class Solver : public SolverBase {
     Solver(const Problem& p, int dev) {
         pb = p;
         device = dev;
+        // A/B switch for the 3-D stencil kernels: tma (TMA-staged, default) | zmarch (register z-marching) |
+        // simple (baseline one thread per node)
+        const char* e = getenv("HH_FINE_KERNEL");
+        fine_kernel = FK_TMA;
+        if (e && !strcmp(e, "zmarch")) fine_kernel = FK_ZMARCH;
+        if (e && !strcmp(e, "simple")) fine_kernel = FK_SIMPLE;
     }
     ~Solver() override {}
 
@@ -240,6 +250,7 @@ class Solver : public SolverBase {
         }
         HH_CUDA(cudaMemcpy(d_m.p, hm.data(), N * sizeof(T), cudaMemcpyHostToDevice));
         HH_CUDA(cudaMemcpy(d_g.p, hg.data(), N * sizeof(T), cudaMemcpyHostToDevice));
+        h_op_valid[0] = h_op_valid[1] = false;
         clear();
     }
 
@@ -261,7 +272,31 @@ class Solver : public SolverBase {
         op.BC = (T)(pb.order_bc == 2 ? 2.0 : 1.0);
         op.neumann_top = pb.neumann_top;
         op.adj = adj;
+        op.cdiag = nullptr;
+        op.dinv = nullptr;
         return op;
+    }
+    // diagonal arrays for the bulk-async kernels (3-D only)
+    void precompute_diag(FineOp<T>& op, DevBuf<C>& cd, DevBuf<C>* dv, T damp) {
+        if (!tma_ok(pb.N())) return;
+        cd.alloc(pb.N());
+        if (dv) dv->alloc(pb.N());
+        dim3 g, blk;
+        grid3(pb.n, pb.dim, g, blk);
+        FineOp<T> o = op;
+        launch(T_SETUP, 0, [&] { k_fine_precompute<T, 3><<<g, blk, 0, stream>>>(o, cd.p, dv ? dv->p : nullptr, damp); });
+        op.cdiag = cd.p;
+        op.dinv = dv ? dv->p : nullptr;
+    }
+    // the un-shifted operator H of the outer Krylov method (GetHelmholtz.jl:85-95), with cached diagonal
+    const FineOp<T>& krylov_op(int transpose) {
+        const int t = transpose ? 1 : 0;
+        if (!h_op_valid[t]) {
+            h_op[t] = fine_op(0.0, t);
+            precompute_diag(h_op[t], h_cdiag[t], nullptr, T(0));
+            h_op_valid[t] = true;
+        }
+        return h_op[t];
     }
 
     // ------------------------------------------------------------------ launch plumbing
@@ -313,6 +348,16 @@ class Solver : public SolverBase {
         if (mode == MODE_APPLY) bytes = 2 * S * N * nrhs + coefb, tag = T_FINE_APPLY;
         else if (mode == MODE_RESID) bytes = 3 * S * N * nrhs + coefb, tag = T_FINE_RESID;
         else bytes = 3 * S * N * nrhs + coefb, tag = T_FINE_JACOBI;
+        if (op.cdiag != nullptr && (mode != MODE_JACOBI || op.dinv != nullptr) && tma_ok(ld) &&
+            ((uintptr_t)x % 16 == 0) && (mode == MODE_APPLY || (uintptr_t)b % 16 == 0)) {
+            launch(tag, bytes + S * N * (mode == MODE_JACOBI ? 2.0 : 1.0) - coefb,
+                   [&] { tma3d_dispatch(mode, op, x, b, out, ld, nrhs); });
+            return;
+        }
+        if (pb.dim == 3 && fine_kernel != FK_SIMPLE) {
+            launch(tag, bytes, [&] { fine3d_dispatch(mode, op, x, b, out, ld, nrhs, damp); });
+            return;
+        }
         launch(tag, bytes, [&] {
             if (pb.dim == 3) {
                 if (mode == MODE_APPLY) k_fine_stencil<T, 3, MODE_APPLY, 2><<<g, blk, 0, stream>>>(op, x, b, out, ld, nrhs, damp);
@@ -324,6 +369,130 @@ class Solver : public SolverBase {
                 else k_fine_stencil<T, 2, MODE_JACOBI, 2><<<g, blk, 0, stream>>>(op, x, b, out, ld, nrhs, damp);
             }
         });
+    }
+    // choose the z-chunking so that the grid has a few CTAs per SM
+    static void zchunks(int n2, int tiles, int groups, int pref, int& zchunk, int& nzc) {
+        int want = (592 + tiles * groups - 1) / (tiles * groups);
+        nzc = std::max((n2 + pref - 1) / pref, want);
+        nzc = std::max(1, std::min(nzc, n2));
+        zchunk = (n2 + nzc - 1) / nzc;
+        nzc = (n2 + zchunk - 1) / zchunk;
+    }
+    template <int MODE, int KB>
+    void fine3d_launch(const FineOp<T>& op, const C* x, const C* b, C* out, int64_t ld, int nrhs, T damp) {
+        constexpr int TY = 8;
+        const int groups = (nrhs + KB - 1) / KB;
+        const int tx = (pb.n[0] + 31) / 32, ty = (pb.n[1] + TY - 1) / TY;
+        int zchunk, nzc;
+        zchunks(pb.n[2], tx * ty, groups, 32, zchunk, nzc);
+        dim3 g(tx * groups, ty, nzc), blk(32, TY, 1);
+        k_fine3d_zmarch<T, MODE, KB, TY, FINE_MINB><<<g, blk, 0, stream>>>(op, x, b, out, ld, nrhs, damp, zchunk, groups);
+    }
+    template <int MODE>
+    void fine3d_mode(const FineOp<T>& op, const C* x, const C* b, C* out, int64_t ld, int nrhs, T damp) {
+        const int pref = sizeof(T) == 8 ? 2 : 4;
+        const int kb = std::min(pref, nrhs >= 4 ? 4 : (nrhs >= 2 ? 2 : 1));
+        if (kb == 4) fine3d_launch<MODE, 4>(op, x, b, out, ld, nrhs, damp);
+        else if (kb == 2) fine3d_launch<MODE, 2>(op, x, b, out, ld, nrhs, damp);
+        else fine3d_launch<MODE, 1>(op, x, b, out, ld, nrhs, damp);
+    }
+    void fine3d_dispatch(int mode, const FineOp<T>& op, const C* x, const C* b, C* out, int64_t ld, int nrhs, T damp) {
+        if (mode == MODE_APPLY) fine3d_mode<MODE_APPLY>(op, x, b, out, ld, nrhs, damp);
+        else if (mode == MODE_RESID) fine3d_mode<MODE_RESID>(op, x, b, out, ld, nrhs, damp);
+        else fine3d_mode<MODE_JACOBI>(op, x, b, out, ld, nrhs, damp);
+    }
+    // ---- TMA tensor maps (driver entry point fetched through the runtime; libcuda is not linked) ----
+    typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                      const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                      CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static EncodeTiledFn encode_fn() {
+        static EncodeTiledFn fn = nullptr;
+        if (!fn) {
+            void* p = nullptr;
+            cudaDriverEntryPointQueryResult q;
+            HH_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q));
+            HH_REQUIRE(p != nullptr && q == cudaDriverEntryPointSuccess, HH_ERR_CUDA, "cuTensorMapEncodeTiled is unavailable");
+            fn = (EncodeTiledFn)p;
+        }
+        return fn;
+    }
+    // TMA needs 16-byte aligned global strides: always true for ComplexF64, for ComplexF32 only on even grids
+    bool tma_ok(int64_t ld) const {
+        if (pb.dim != 3 || fine_kernel != FK_TMA) return false;
+        const int64_t es = 2 * sizeof(T);
+        return (es * pb.n[0]) % 16 == 0 && (es * pb.n[0] * pb.n[1]) % 16 == 0 && (es * ld) % 16 == 0;
+    }
+    template <int MODE, int KB>
+    void tma3d_launch(const FineOp<T>& op, const C* x, const C* b, C* out, int64_t ld, int nrhs) {
+        typedef FineTmaCfg<T, MODE, KB> Cfg;
+        constexpr int NS = 4;
+        constexpr size_t smem = (size_t)NS * Cfg::STAGE_BYTES + NS * sizeof(uint64_t);
+        static bool attr_set = false;  // per instantiation
+        if (!attr_set) {
+            HH_CUDA(cudaFuncSetAttribute(k_fine3d_tma<T, MODE, KB, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            attr_set = true;
+        }
+        const int groups = (nrhs + KB - 1) / KB;
+        const int tx = (pb.n[0] + Cfg::TX - 1) / Cfg::TX, ty = (pb.n[1] + Cfg::TY - 1) / Cfg::TY;
+        int zchunk, nzc;
+        zchunks(pb.n[2], tx * ty, groups, 64, zchunk, nzc);
+        dim3 g(tx * groups, ty, nzc);
+        // the RHS extent of the x / b maps is the true nrhs so that surplus slots of the last group are zero-filled
+        TmaDesc tx_ = make_tmap_n(x, ld, Cfg::TX + 2, Cfg::TY + 2, KB, nrhs);
+        TmaDesc tb_ = (MODE != MODE_APPLY) ? make_tmap_n(b, ld, Cfg::TX, Cfg::TY, KB, nrhs) : tx_;
+        TmaDesc tc_ = make_tmap_n(op.cdiag, ld, Cfg::TX, Cfg::TY, 1, 0);
+        TmaDesc td_ = (MODE == MODE_JACOBI) ? make_tmap_n(op.dinv, ld, Cfg::TX, Cfg::TY, 1, 0) : tc_;
+        k_fine3d_tma<T, MODE, KB, NS><<<g, 256, smem, stream>>>(op, tx_, tb_, tc_, td_, x, out, ld, nrhs, zchunk, groups);
+    }
+    TmaDesc make_tmap_n(const void* base, int64_t ld, int bx, int by, int kb, int nrhs) const {
+        static_assert(sizeof(TmaDesc) == sizeof(CUtensorMap), "CUtensorMap is 128 bytes");
+        TmaDesc d;
+        const cuuint64_t es = sizeof(T);
+        const int rank = nrhs > 0 ? 4 : 3;
+        cuuint64_t dims[4] = {(cuuint64_t)2 * pb.n[0], (cuuint64_t)pb.n[1], (cuuint64_t)pb.n[2], (cuuint64_t)std::max(nrhs, 1)};
+        cuuint64_t strides[3] = {2 * es * pb.n[0], 2 * es * (cuuint64_t)pb.n[0] * pb.n[1], 2 * es * (cuuint64_t)ld};
+        cuuint32_t box[4] = {(cuuint32_t)(2 * bx), (cuuint32_t)by, 1, (cuuint32_t)kb};
+        cuuint32_t estr[4] = {1, 1, 1, 1};
+        CUresult r = encode_fn()((CUtensorMap*)&d, sizeof(T) == 8 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32,
+                                 (cuuint32_t)rank, const_cast<void*>(base), dims, strides, box, estr,
+                                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        HH_REQUIRE(r == CUDA_SUCCESS, HH_ERR_CUDA, "cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")");
+        return d;
+    }
+    template <int MODE>
+    void tma3d_mode(const FineOp<T>& op, const C* x, const C* b, C* out, int64_t ld, int nrhs) {
+        if (nrhs >= 2) tma3d_launch<MODE, 2>(op, x, b, out, ld, nrhs);
+        else tma3d_launch<MODE, 1>(op, x, b, out, ld, nrhs);
+    }
+    void tma3d_dispatch(int mode, const FineOp<T>& op, const C* x, const C* b, C* out, int64_t ld, int nrhs) {
+        if (mode == MODE_APPLY) tma3d_mode<MODE_APPLY>(op, x, b, out, ld, nrhs);
+        else if (mode == MODE_RESID) tma3d_mode<MODE_RESID>(op, x, b, out, ld, nrhs);
+        else tma3d_mode<MODE_JACOBI>(op, x, b, out, ld, nrhs);
+    }
+    static int coarse_kb(int nrhs) {
+        const int pref = sizeof(T) == 8 ? 4 : 8;
+        int kb = 1;
+        while (kb * 2 <= nrhs && kb * 2 <= pref) kb *= 2;
+        return kb;
+    }
+    template <int MODE, int KB>
+    void coarse3d_launch(const Level& L, const C* x, const C* b, C* out, int nrhs) {
+        constexpr int TY = 8;
+        const int groups = (nrhs + KB - 1) / KB;
+        const int tx = (L.n[0] + 31) / 32, ty = (L.n[1] + TY - 1) / TY;
+        int zchunk, nzc;
+        zchunks(L.n[2], tx * ty, groups, 16, zchunk, nzc);
+        dim3 g(tx * groups, ty, nzc), blk(32, TY, 1);
+        k_coarse3d_zmarch<T, MODE, KB, TY, COARSE_MINB><<<g, blk, 0, stream>>>(coarse_op(L), x, b, out, L.N, nrhs, zchunk, groups);
+    }
+    template <int MODE>
+    void coarse3d_mode(const Level& L, const C* x, const C* b, C* out, int nrhs) {
+        const int kb = coarse_kb(nrhs);
+        if (kb == 8) coarse3d_launch<MODE, 8>(L, x, b, out, nrhs);
+        else if (kb == 4) coarse3d_launch<MODE, 4>(L, x, b, out, nrhs);
+        else if (kb == 2) coarse3d_launch<MODE, 2>(L, x, b, out, nrhs);
+        else coarse3d_launch<MODE, 1>(L, x, b, out, nrhs);
     }
     void fine_jacobi0(const FineOp<T>& op, const C* b, C* out, int64_t ld, int nrhs, T damp) {
         dim3 g, blk;
@@ -346,7 +515,7 @@ class Solver : public SolverBase {
         grid3(L.n, pb.dim, g, blk);
         const double N = (double)L.N;
         const int NS = pb.dim == 3 ? 27 : 9;
-        const int KB = 4;
+        const int KB = (pb.dim == 3 && fine_kernel != FK_SIMPLE) ? coarse_kb(nrhs) : 4;
         const double coefb = NS * S * N * ((nrhs + KB - 1) / KB);
         double bytes;
         int tag;
@@ -355,6 +524,14 @@ class Solver : public SolverBase {
         else bytes = 3 * S * N * nrhs + coefb + S * N, tag = T_COARSE_JACOBI;
         CoarseOp<T> op = coarse_op(L);
         const int64_t ld = L.N;
+        if (pb.dim == 3 && fine_kernel != FK_SIMPLE) {
+            launch(tag, bytes, [&] {
+                if (mode == MODE_APPLY) coarse3d_mode<MODE_APPLY>(L, x, b, out, nrhs);
+                else if (mode == MODE_RESID) coarse3d_mode<MODE_RESID>(L, x, b, out, nrhs);
+                else coarse3d_mode<MODE_JACOBI>(L, x, b, out, nrhs);
+            });
+            return;
+        }
         launch(tag, bytes, [&] {
             if (pb.dim == 3) {
                 if (mode == MODE_APPLY) k_coarse_stencil<T, 3, MODE_APPLY, 4><<<g, blk, 0, stream>>>(op, x, b, out, ld, nrhs);
@@ -491,6 +668,7 @@ class Solver : public SolverBase {
             levels[l].N = (int64_t)levels[l].n[0] * levels[l].n[1] * levels[l].n[2];
         }
         mg_fine = fine_op(o.shift[0], o.do_transpose);
+        if (o.levels > 1) precompute_diag(mg_fine, mg_cdiag, &mg_dinv, (T)o.relax_param);
         const int NS = pb.dim == 3 ? 27 : 9;
         const int center = pb.dim == 3 ? 13 : 4;
         for (int l = 1; l < o.levels; ++l) {
@@ -940,7 +1118,7 @@ class Solver : public SolverBase {
         std::vector<C*> V(m + 1), Z(m);
         for (int i = 0; i <= m; ++i) V[i] = kry.p + (int64_t)i * vs;
         for (int i = 0; i < m; ++i) Z[i] = kry.p + (int64_t)(m + 1 + i) * vs;
-        const FineOp<T> Hop = fine_op(0.0, o.do_transpose);  // Afun: the un-shifted operator (GetHelmholtz.jl:85-95)
+        const FineOp<T> Hop = krylov_op(o.do_transpose);  // Afun: the un-shifted operator (GetHelmholtz.jl:85-95)
         zero_vec(X, N, nrhs);
         // r0 = b (x0 = 0); bnorm
         gmres_begin(outer, B, N, nrhs, true, o.rel_tol);
@@ -1014,7 +1192,7 @@ class Solver : public SolverBase {
         C* t = kry.p + 4 * vs;
         C* ph = kry.p + 5 * vs;
         C* sh = kry.p + 6 * vs;
-        const FineOp<T> Hop = fine_op(0.0, o.do_transpose);
+        const FineOp<T> Hop = krylov_op(o.do_transpose);
         auto scalars = [&](int nblk, int stage) {
             launch(T_SCALAR, 0, [&] { k_bicg_scalars<<<nrhs, 32, 0, stream>>>(bicg.st, d_partial.p, nblk, stage, o.rel_tol); });
         };
@@ -1055,6 +1233,11 @@ class Solver : public SolverBase {
     }
 
    private:
+    enum { FK_TMA = 0, FK_ZMARCH = 1, FK_SIMPLE = 2 };
+    int fine_kernel = FK_TMA;
+    DevBuf<C> mg_cdiag, mg_dinv, h_cdiag[2];
+    FineOp<T> h_op[2];
+    bool h_op_valid[2] = {false, false};
     DevBuf<T> d_m, d_g;
     std::vector<Level> levels;
     bool have_hierarchy = false;
