@@ -491,12 +491,15 @@ def solveLinearSystem_(ShiftedHT, B, X, param, doTranspose=0):
     else:
         Bm = np.asfortranarray(np.asarray(B).reshape(hd.N, -1), dtype=hd.dtype)
         nrhs = Bm.shape[1]
-        Xm = np.empty_like(Bm, order="F")
+        # write straight into the caller's X when it already is an N x nrhs column-major block of the right type
+        direct = isinstance(X, np.ndarray) and X.dtype == hd.dtype and X.size == Bm.size and X.flags.f_contiguous
+        Xm = X if direct else np.empty_like(Bm, order="F")
         iters = np.zeros(nrhs, dtype=np.int32)
         relres = np.zeros(nrhs, dtype=np.float64)
         rc = L.check(hd.lib.hh_solve(hd.h, Bm.ctypes.data, Xm.ctypes.data, nrhs, C.byref(so), _ptr(iters, C.c_int32),
                                      _ptr(relres, C.c_double)), hd.h)
-        X[...] = Xm.reshape(X.shape, order="F")
+        if not direct:
+            X[...] = Xm.reshape(X.shape, order="F")
     param.solveTime += time.perf_counter() - t0
     param.nPrec += int(iters.sum())
     param.iterations = iters
