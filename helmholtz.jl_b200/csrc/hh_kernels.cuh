@@ -506,6 +506,142 @@ __global__ void __launch_bounds__(256) k_fine3d_tma(FineOp<T> op, const __grid_c
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Coarse levels, 3-D, TMA production form: 27-point stencil with stored Galerkin coefficients.
+// A CTA (128 threads) owns a 32 x 4 tile of (i,j) columns and walks a chunk of z planes in the
+// scatter form of k_coarse3d_zmarch (three rolling accumulators per right-hand side).  Each
+// iteration consumes one stage staged by the TMA engine: the x tile of input plane zi with a
+// one-node halo for all KB right-hand sides, the three 9-coefficient sets that plane feeds (dk = -1
+// of plane zi+1, dk = 0 of plane zi, dk = +1 of plane zi-1), and b / dinv of the output plane zi-1
+// that completes in this iteration.  Out-of-range planes, halos and surplus RHS slots are zero-filled
+// by the hardware, so the loop has no boundary cases.  The 27 coefficients of a node are read once
+// per KB (up to 8) right-hand sides.
+// ---------------------------------------------------------------------------------------------
+template <typename T, int MODE, int KB>
+struct CoarseTmaCfg {
+    static constexpr int TX = 32, TY = 4;
+    static constexpr int PX = TX + 2;
+    static constexpr int XT = (TY + 2) * PX;
+    static constexpr int BT = TY * TX;
+    static constexpr int ES = (int)sizeof(cx<T>);
+    static constexpr int al(int b) { return (b + 127) / 128 * 128; }
+    static constexpr int OFF_X = 0;
+    static constexpr int OFF_C = al(KB * XT * ES);             // 3 sets of 9 coefficient tiles
+    static constexpr int CSET = al(9 * BT * ES);
+    static constexpr int OFF_B = OFF_C + 3 * CSET;
+    static constexpr int OFF_D = OFF_B + (MODE != MODE_APPLY ? al(KB * BT * ES) : 0);
+    static constexpr int STAGE_BYTES = OFF_D + (MODE == MODE_JACOBI ? al(BT * ES) : 0);
+    static constexpr uint32_t TX_BYTES = KB * XT * ES + 27 * BT * ES + (MODE != MODE_APPLY ? KB * BT * ES : 0) +
+                                         (MODE == MODE_JACOBI ? BT * ES : 0);
+    static constexpr int NS = 2;
+};
+
+template <typename T, int MODE, int KB>
+__global__ void __launch_bounds__(128) k_coarse3d_tma(const __grid_constant__ TmaDesc tm_x,
+                                                      const __grid_constant__ TmaDesc tm_c,
+                                                      const __grid_constant__ TmaDesc tm_b,
+                                                      const __grid_constant__ TmaDesc tm_d, cx<T>* __restrict__ out,
+                                                      int n0, int n1, int n2, int64_t ld, int nrhs, int zchunk,
+                                                      int groups) {
+    typedef CoarseTmaCfg<T, MODE, KB> Cfg;
+    constexpr int TX = Cfg::TX, TY = Cfg::TY, PX = Cfg::PX, NS = Cfg::NS;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + (size_t)NS * Cfg::STAGE_BYTES);
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int i0 = (blockIdx.x / groups) * TX, j0 = blockIdx.y * TY;
+    const int i = i0 + tx, j = j0 + ty;
+    const int r0 = (blockIdx.x % groups) * KB;
+    const int z0 = blockIdx.z * zchunk;
+    const int z1 = min(n2, z0 + zchunk);
+    const int niter = z1 - z0 + 2;  // input planes z0-1 .. z1
+    const bool active = (i < n0) && (j < n1);
+    auto issue = [&](int s, int zi) {
+        unsigned char* st = smem_raw + (size_t)s * Cfg::STAGE_BYTES;
+        mbar_expect_tx(&bars[s], Cfg::TX_BYTES);
+        tma_load_4d(st + Cfg::OFF_X, &tm_x, 2 * (i0 - 1), j0 - 1, zi, r0, &bars[s]);
+        tma_load_4d(st + Cfg::OFF_C, &tm_c, 2 * i0, j0, zi + 1, 0, &bars[s]);                  // dk = -1 of plane zi+1
+        tma_load_4d(st + Cfg::OFF_C + Cfg::CSET, &tm_c, 2 * i0, j0, zi, 9, &bars[s]);          // dk =  0 of plane zi
+        tma_load_4d(st + Cfg::OFF_C + 2 * Cfg::CSET, &tm_c, 2 * i0, j0, zi - 1, 18, &bars[s]); // dk = +1 of plane zi-1
+        if (MODE != MODE_APPLY) tma_load_4d(st + Cfg::OFF_B, &tm_b, 2 * i0, j0, zi - 1, r0, &bars[s]);
+        if (MODE == MODE_JACOBI) tma_load_3d(st + Cfg::OFF_D, &tm_d, 2 * i0, j0, zi - 1, &bars[s]);
+    };
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < NS; ++s) mbar_init(&bars[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        for (int s = 0; s < NS && s < niter; ++s) issue(s, z0 - 1 + s);
+    }
+    __syncthreads();
+    const cx<T> zero = mk<T>(T(0), T(0));
+    cx<T> acc[3][KB], xprev[KB];
+#pragma unroll
+    for (int q = 0; q < KB; ++q) {
+        acc[0][q] = acc[1][q] = acc[2][q] = zero;
+        xprev[q] = zero;
+    }
+    const int cidx = (ty + 1) * PX + (tx + 1);
+    const int bidx = ty * TX + tx;
+    const int64_t pxy = (active ? i : 0) + (int64_t)n0 * (active ? j : 0);
+    const int64_t sz = (int64_t)n0 * n1;
+#pragma unroll 1
+    for (int it = 0; it < niter; ++it) {
+        const int zi = z0 - 1 + it;
+        const int s = it % NS;
+        const unsigned char* st = smem_raw + (size_t)s * Cfg::STAGE_BYTES;
+        mbar_wait(&bars[s], (uint32_t)((it / NS) & 1));
+        const cx<T>* sx = reinterpret_cast<const cx<T>*>(st + Cfg::OFF_X);
+        const cx<T>* cm = reinterpret_cast<const cx<T>*>(st + Cfg::OFF_C);
+        const cx<T>* c0 = reinterpret_cast<const cx<T>*>(st + Cfg::OFF_C + Cfg::CSET);
+        const cx<T>* cp = reinterpret_cast<const cx<T>*>(st + Cfg::OFF_C + 2 * Cfg::CSET);
+#pragma unroll
+        for (int dj = -1; dj <= 1; ++dj) {
+#pragma unroll
+            for (int di = -1; di <= 1; ++di) {
+                const int sxy = (di + 1) + 3 * (dj + 1);
+                const cx<T> fm = cm[sxy * Cfg::BT + bidx];
+                const cx<T> f0 = c0[sxy * Cfg::BT + bidx];
+                const cx<T> fp = cp[sxy * Cfg::BT + bidx];
+#pragma unroll
+                for (int q = 0; q < KB; ++q) {
+                    const cx<T> xv = sx[q * Cfg::XT + cidx + di + dj * PX];
+                    cfma(acc[2][q], fm, xv);
+                    cfma(acc[1][q], f0, xv);
+                    cfma(acc[0][q], fp, xv);
+                }
+            }
+        }
+        // output plane zi-1 is complete
+        const int zo = zi - 1;
+        if (active && zo >= z0 && zo < z1) {
+            const int64_t p = pxy + (int64_t)zo * sz;
+            const cx<T>* sb = reinterpret_cast<const cx<T>*>(st + Cfg::OFF_B);
+            cx<T> dv = zero;
+            if (MODE == MODE_JACOBI) dv = reinterpret_cast<const cx<T>*>(st + Cfg::OFF_D)[bidx];
+#pragma unroll
+            for (int q = 0; q < KB; ++q) {
+                if (r0 + q < nrhs) {
+                    const int64_t o = (int64_t)(r0 + q) * ld + p;
+                    if (MODE == MODE_APPLY) {
+                        out[o] = acc[0][q];
+                    } else {
+                        const cx<T> bv = sb[q * Cfg::BT + bidx];
+                        if (MODE == MODE_RESID) out[o] = bv - acc[0][q];
+                        else out[o] = xprev[q] + dv * (bv - acc[0][q]);
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < KB; ++q) {
+            acc[0][q] = acc[1][q];
+            acc[1][q] = acc[2][q];
+            acc[2][q] = zero;
+            xprev[q] = sx[q * Cfg::XT + cidx];
+        }
+        __syncthreads();
+        if (threadIdx.x == 0 && it + NS < niter) issue(s, zi + NS);
+    }
+}
+
 // centre coefficient (incl. Laplacian diagonal) and damp/centre as arrays, for the TMA-staged kernels
 template <typename T, int DIM>
 __global__ void __launch_bounds__(256) k_fine_precompute(FineOp<T> op, cx<T>* __restrict__ cdiag, cx<T>* __restrict__ dinv,

@@ -445,12 +445,17 @@ class Solver : public SolverBase {
         k_fine3d_tma<T, MODE, KB, NS><<<g, 256, smem, stream>>>(op, tx_, tb_, tc_, td_, x, out, ld, nrhs, zchunk, groups);
     }
     TmaDesc make_tmap_n(const void* base, int64_t ld, int bx, int by, int kb, int nrhs) const {
+        return make_tmap_g(base, pb.n, ld, bx, by, kb, nrhs);
+    }
+    // tensor over a complex block on an n[0] x n[1] x n[2] grid viewed as reals: dims (2*n0, n1, n2[, nvec]),
+    // box (2*bx, by, 1[, kb]); nvec == 0 -> rank 3
+    static TmaDesc make_tmap_g(const void* base, const int* n, int64_t ld, int bx, int by, int kb, int nrhs) {
         static_assert(sizeof(TmaDesc) == sizeof(CUtensorMap), "CUtensorMap is 128 bytes");
         TmaDesc d;
         const cuuint64_t es = sizeof(T);
         const int rank = nrhs > 0 ? 4 : 3;
-        cuuint64_t dims[4] = {(cuuint64_t)2 * pb.n[0], (cuuint64_t)pb.n[1], (cuuint64_t)pb.n[2], (cuuint64_t)std::max(nrhs, 1)};
-        cuuint64_t strides[3] = {2 * es * pb.n[0], 2 * es * (cuuint64_t)pb.n[0] * pb.n[1], 2 * es * (cuuint64_t)ld};
+        cuuint64_t dims[4] = {(cuuint64_t)2 * n[0], (cuuint64_t)n[1], (cuuint64_t)n[2], (cuuint64_t)std::max(nrhs, 1)};
+        cuuint64_t strides[3] = {2 * es * n[0], 2 * es * (cuuint64_t)n[0] * n[1], 2 * es * (cuuint64_t)ld};
         cuuint32_t box[4] = {(cuuint32_t)(2 * bx), (cuuint32_t)by, 1, (cuuint32_t)kb};
         cuuint32_t estr[4] = {1, 1, 1, 1};
         CUresult r = encode_fn()((CUtensorMap*)&d, sizeof(T) == 8 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32,
@@ -469,6 +474,45 @@ class Solver : public SolverBase {
         if (mode == MODE_APPLY) tma3d_mode<MODE_APPLY>(op, x, b, out, ld, nrhs);
         else if (mode == MODE_RESID) tma3d_mode<MODE_RESID>(op, x, b, out, ld, nrhs);
         else tma3d_mode<MODE_JACOBI>(op, x, b, out, ld, nrhs);
+    }
+    bool tma_ok_level(const Level& L) const {
+        if (pb.dim != 3 || fine_kernel != FK_TMA) return false;
+        const int64_t es = 2 * sizeof(T);
+        return (es * L.n[0]) % 16 == 0 && (es * L.n[0] * L.n[1]) % 16 == 0 && (es * L.N) % 16 == 0;
+    }
+    template <int MODE, int KB>
+    void coarse_tma_launch(const Level& L, const C* x, const C* b, C* out, int nrhs) {
+        typedef CoarseTmaCfg<T, MODE, KB> Cfg;
+        constexpr size_t smem = (size_t)Cfg::NS * Cfg::STAGE_BYTES + Cfg::NS * sizeof(uint64_t);
+        static bool attr_set = false;
+        if (!attr_set) {
+            HH_CUDA(cudaFuncSetAttribute(k_coarse3d_tma<T, MODE, KB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            attr_set = true;
+        }
+        const int groups = (nrhs + KB - 1) / KB;
+        const int tx = (L.n[0] + Cfg::TX - 1) / Cfg::TX, ty = (L.n[1] + Cfg::TY - 1) / Cfg::TY;
+        int zchunk, nzc;
+        zchunks(L.n[2], tx * ty, groups, 32, zchunk, nzc);
+        // one CTA per SM is resident: aim for a few waves, not for many tiny chunks
+        while (nzc > 1 && (int64_t)tx * ty * groups * nzc > 148 * 6) {
+            zchunk = std::min(L.n[2], zchunk * 2);
+            nzc = (L.n[2] + zchunk - 1) / zchunk;
+        }
+        dim3 g(tx * groups, ty, nzc);
+        TmaDesc mx = make_tmap_g(x, L.n, L.N, Cfg::TX + 2, Cfg::TY + 2, KB, nrhs);
+        TmaDesc mc = make_tmap_g(L.coef.p, L.n, L.N, Cfg::TX, Cfg::TY, 9, 27);
+        TmaDesc mb = (MODE != MODE_APPLY) ? make_tmap_g(b, L.n, L.N, Cfg::TX, Cfg::TY, KB, nrhs) : mx;
+        TmaDesc md = (MODE == MODE_JACOBI) ? make_tmap_g(L.dinv.p, L.n, L.N, Cfg::TX, Cfg::TY, 1, 0) : mx;
+        k_coarse3d_tma<T, MODE, KB><<<g, 128, smem, stream>>>(mx, mc, mb, md, out, L.n[0], L.n[1], L.n[2], L.N, nrhs, zchunk, groups);
+    }
+    template <int MODE>
+    void coarse_tma_mode(const Level& L, const C* x, const C* b, C* out, int nrhs) {
+        int kb = 1;
+        while (kb * 2 <= nrhs && kb * 2 <= 8) kb *= 2;
+        if (kb == 8) coarse_tma_launch<MODE, 8>(L, x, b, out, nrhs);
+        else if (kb == 4) coarse_tma_launch<MODE, 4>(L, x, b, out, nrhs);
+        else if (kb == 2) coarse_tma_launch<MODE, 2>(L, x, b, out, nrhs);
+        else coarse_tma_launch<MODE, 1>(L, x, b, out, nrhs);
     }
     static int coarse_kb(int nrhs) {
         const int pref = sizeof(T) == 8 ? 4 : 8;
@@ -515,7 +559,12 @@ class Solver : public SolverBase {
         grid3(L.n, pb.dim, g, blk);
         const double N = (double)L.N;
         const int NS = pb.dim == 3 ? 27 : 9;
-        const int KB = (pb.dim == 3 && fine_kernel != FK_SIMPLE) ? coarse_kb(nrhs) : 4;
+        const bool use_tma = tma_ok_level(L) && ((uintptr_t)x % 16 == 0) && (mode == MODE_APPLY || (uintptr_t)b % 16 == 0);
+        int KB = (pb.dim == 3 && fine_kernel != FK_SIMPLE) ? coarse_kb(nrhs) : 4;
+        if (use_tma) {
+            KB = 1;
+            while (KB * 2 <= nrhs && KB * 2 <= 8) KB *= 2;
+        }
         const double coefb = NS * S * N * ((nrhs + KB - 1) / KB);
         double bytes;
         int tag;
@@ -524,6 +573,14 @@ class Solver : public SolverBase {
         else bytes = 3 * S * N * nrhs + coefb + S * N, tag = T_COARSE_JACOBI;
         CoarseOp<T> op = coarse_op(L);
         const int64_t ld = L.N;
+        if (use_tma) {
+            launch(tag, bytes, [&] {
+                if (mode == MODE_APPLY) coarse_tma_mode<MODE_APPLY>(L, x, b, out, nrhs);
+                else if (mode == MODE_RESID) coarse_tma_mode<MODE_RESID>(L, x, b, out, nrhs);
+                else coarse_tma_mode<MODE_JACOBI>(L, x, b, out, nrhs);
+            });
+            return;
+        }
         if (pb.dim == 3 && fine_kernel != FK_SIMPLE) {
             launch(tag, bytes, [&] {
                 if (mode == MODE_APPLY) coarse3d_mode<MODE_APPLY>(L, x, b, out, nrhs);

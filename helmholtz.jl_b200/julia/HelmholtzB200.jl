@@ -1,0 +1,292 @@
+# HelmholtzB200.jl -- Julia shim over libhelmholtz_b200.so (include/helmholtz_b200.h).
+#
+# Drop-in for the acoustic solve path of JuliaInv/Helmholtz.jl: same exported names, argument orders and
+# return shapes (HelmholtzParam, GetHelmholtzOperator, GetHelmholtzShiftOP, getABL, getMaximalFrequency,
+# getMGparam, getShiftedLaplacianMultigridSolver, solveLinearSystem, solveLinearSystem!, copySolver, clear!).
+# Every solve is one `ccall` into the shared library; no arithmetic happens in Julia.
+#
+# NOTE: no Julia runtime exists in the build image, so this file is written against the C header and kept
+# trivially thin; the identical logic is exercised through the Python ctypes mirror (../api.py) by tests/.
+#
+# Reference lines mirrored: src/Helmholtz.jl:13-34; src/GetHelmholtz.jl:14-50,75-83,97-220;
+# src/ShiftedLaplacianMultigridSolver.jl:4-30,33-109; src/getPointSource.jl:63-112.
+module HelmholtzB200
+
+using LinearAlgebra
+
+export HelmholtzParam, getShiftedHelmholtzParam, GetHelmholtzOperator, GetHelmholtzShiftOP, getABL,
+       getMaximalFrequency, getAcousticPointSource, loc2cs, getTopPointSrc, getMidPointSrc,
+       MGparam, getMGparam, hierarchyExists, ShiftedLaplacianMultigridSolver,
+       getShiftedLaplacianMultigridSolver, copySolver, solveLinearSystem, solveLinearSystem!, clear!,
+       RegularMesh, getRegularMesh
+
+const LIB = get(ENV, "HELMHOLTZ_B200_LIB", joinpath(@__DIR__, "..", "lib", "libhelmholtz_b200.so"))
+
+const HH_OK = 0
+const HH_NOT_CONVERGED = 1
+const HH_C64, HH_C32 = 0, 1
+const HH_MAX_LEVELS = 12
+
+struct HHError <: Exception
+    code::Int
+    msg::String
+end
+Base.showerror(io::IO, e::HHError) = print(io, "libhelmholtz_b200 error ", e.code, ": ", e.msg)
+
+function check(rc::Integer, h::Ptr{Cvoid} = C_NULL)
+    if rc < 0
+        msg = unsafe_string(ccall((:hh_last_error, LIB), Cstring, (Ptr{Cvoid},), h))
+        throw(HHError(rc, msg))
+    end
+    return rc
+end
+
+# ---- jInv.Mesh.RegularMesh: only domain / n / h / dim cross the ABI.  With jInv loaded, pass its mesh instead. ----
+struct RegularMesh
+    domain::Vector{Float64}
+    n::Vector{Int64}
+    h::Vector{Float64}
+    dim::Int
+end
+getRegularMesh(domain, n) = (d = vec(Float64.(domain)); nn = vec(Int64.(n));
+                             RegularMesh(d, nn, (d[2:2:end] .- d[1:2:end]) ./ nn, length(nn)))
+
+# ---- src/Helmholtz.jl:13-20 ----
+mutable struct HelmholtzParam
+    Mesh
+    gamma::Array{Float64}
+    m::Array{Float64}
+    omega::Union{Float64,ComplexF64}
+    NeumannOnTop::Bool
+    Sommerfeld::Bool
+end
+getShiftedHelmholtzParam(p::HelmholtzParam, s::Float64) =
+    HelmholtzParam(p.Mesh, p.gamma .+ s * real(p.omega), p.m, p.omega, p.NeumannOnTop, p.Sommerfeld)
+
+# ---- device handle (HelmholtzParam + device state); freed by a finalizer ----
+mutable struct Handle
+    ptr::Ptr{Cvoid}
+    N::Int
+    VAL::DataType
+end
+function Handle(Mesh, m, omega, gamma, NeumannOnTop::Bool, Sommerfeld::Bool, orderNeumannBC::Int = 2;
+                VAL::DataType = ComplexF64, devices::Vector{Int32} = Int32[0])
+    nodes = Int64.(Mesh.n .+ 1)
+    h = Float64.(Mesh.h)
+    mm = vec(Float64.(m)); gg = vec(Float64.(gamma))
+    length(mm) == prod(nodes) == length(gg) || error("m and gamma must have prod(n+1) entries")
+    out = Ref{Ptr{Cvoid}}(C_NULL)
+    w = ComplexF64(omega)
+    rc = ccall((:hh_create_multi, LIB), Cint,
+               (Cint, Ptr{Int64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Cdouble, Cdouble, Cint, Cint, Cint, Cint,
+                Ptr{Cint}, Cint, Ref{Ptr{Cvoid}}),
+               Mesh.dim, nodes, h, mm, gg, real(w), imag(w), NeumannOnTop, Sommerfeld, orderNeumannBC,
+               VAL == ComplexF64 ? HH_C64 : HH_C32, devices, length(devices), out)
+    check(rc)
+    hd = Handle(out[], prod(nodes), VAL)
+    finalizer(x -> (x.ptr != C_NULL && ccall((:hh_destroy, LIB), Cint, (Ptr{Cvoid},), x.ptr); x.ptr = C_NULL), hd)
+    return hd
+end
+
+# ---- operator objects: matrix-free counterpart of the sparse H (src/GetHelmholtz.jl:33-50) ----
+struct HelmholtzShiftOP
+    shift::Float64
+    omega::Float64
+end
+GetHelmholtzShiftOP(mNodal::Array{Float64}, omega::Float64, shift::Float64) = HelmholtzShiftOP(shift, omega)
+
+struct HelmholtzOperator
+    hd::Handle
+    shift::Float64
+    adjoint::Bool
+end
+Base.:+(H::HelmholtzOperator, S::HelmholtzShiftOP) = HelmholtzOperator(H.hd, H.shift + S.shift, H.adjoint)
+Base.adjoint(H::HelmholtzOperator) = HelmholtzOperator(H.hd, H.shift, !H.adjoint)
+Base.size(H::HelmholtzOperator) = (H.hd.N, H.hd.N)
+function Base.:*(H::HelmholtzOperator, x::AbstractVecOrMat)
+    X = Array{H.hd.VAL}(reshape(x, H.hd.N, :))
+    Y = similar(X)
+    check(ccall((:hh_apply, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Int64, Cint, Cdouble, Cint),
+                H.hd.ptr, X, Y, size(X, 2), H.shift != 0.0, H.shift, H.adjoint), H.hd.ptr)
+    return ndims(x) == 1 ? vec(Y) : Y
+end
+
+function getABL(n::Array{Int64}, NeumannAtFirstDim::Bool, ABLpad::Array{Int64}, ABLamp::Float64)
+    gamma = zeros(Float64, tuple(n...))
+    check(ccall((:hh_get_abl, LIB), Cint, (Cint, Ptr{Int64}, Cint, Ptr{Int64}, Cdouble, Ptr{Float64}),
+                length(n), n, NeumannAtFirstDim, ABLpad, ABLamp, gamma))
+    return gamma
+end
+
+function getMaximalFrequency(m::Union{Array{Float64},Array{Float32},Float64}, M)
+    mm = vec(Float64.(m)); out = Ref{Cdouble}(0.0)
+    check(ccall((:hh_get_maximal_frequency, LIB), Cint, (Ptr{Float64}, Int64, Cint, Ptr{Float64}, Ref{Cdouble}),
+                mm, length(mm), M.dim, Float64.(M.h), out))
+    return out[]
+end
+
+# the three methods of src/GetHelmholtz.jl:14-16, 22-31, 33-50
+GetHelmholtzOperator(Hparam::HelmholtzParam, orderNeumannBC::Int64 = 2) =
+    GetHelmholtzOperator(Hparam.Mesh, Hparam.m, Hparam.omega, Hparam.gamma, Hparam.NeumannOnTop, Hparam.Sommerfeld, orderNeumannBC)
+function GetHelmholtzOperator(Msh, mNodal::Array{Float64}, omega::Union{Float64,ComplexF64}, gamma::Array,
+                              NeumannAtFirstDim::Bool, ABLpad::Array{Int64}, ABLamp::Float64, Sommerfeld::Bool,
+                              orderNeumannBC::Int64 = 2)
+    abl = getABL(Msh.n .+ 1, NeumannAtFirstDim, ABLpad, ABLamp)
+    gamma = isempty(gamma) ? abl : reshape(gamma, size(abl)) .+ abl
+    H = GetHelmholtzOperator(Msh, mNodal, omega, gamma, NeumannAtFirstDim, Sommerfeld, orderNeumannBC)
+    return H, gamma
+end
+GetHelmholtzOperator(Msh, mNodal::Array{Float64}, omega::Union{Float64,ComplexF64}, gamma::Array{Float64},
+                     NeumannAtFirstDim::Bool, Sommerfeld::Bool, orderNeumannBC::Int64 = 2) =
+    HelmholtzOperator(Handle(Msh, mNodal, omega, gamma, NeumannAtFirstDim, Sommerfeld, orderNeumannBC), 0.0, false)
+
+# ---- src/getPointSource.jl:63-112 ----
+loc2cs(n::Array{Int64}, sub::Array{Int64}) =
+    Int(ccall((:hh_point_source_index, LIB), Int64, (Cint, Ptr{Int64}, Ptr{Int64}), length(sub), n, sub))
+getTopPointSrc(Minv) = Minv.dim == 3 ? [div(Minv.n[1] + 1, 2); div(Minv.n[2] + 1, 2); 1] : [div(Minv.n[1] + 1, 2); 1]
+getMidPointSrc(Minv) = [div(Minv.n[d] + 1, 2) for d in 1:Minv.dim]
+function getAcousticPointSource(Minv, TYPE, src = getTopPointSrc(Minv))
+    n_nodes = Minv.n .+ 1
+    q = zeros(TYPE, tuple(n_nodes...))
+    q[loc2cs(n_nodes, src)] = 1.0 ./ (norm(Minv.h)^2)
+    return q, src
+end
+
+# ---- Multigrid.MGparam: the fields the reference sets / mutates; the hierarchy lives behind `hd` ----
+mutable struct MGparam
+    VAL::DataType
+    levels::Int64
+    numCores::Int64
+    maxOuterIter::Int64
+    relativeTol::Float64
+    relaxType::String
+    relaxParam::Float64
+    relaxPre::Union{Int64,Function}
+    relaxPost::Union{Int64,Function}
+    cycleType::Char
+    coarseSolveType::String
+    coarseIters::Int64
+    doTranspose::Int64
+    hd::Union{Nothing,Handle}
+    builtFor::Any
+end
+getMGparam(VAL::DataType, IND::DataType, levels, numCores, maxIter, relativeTol, relaxType, relaxParam, relaxPre, relaxPost,
+           cycleType, coarseSolveType, strongConnParam = 0.5, FilteringParam = 0.0, transferOperatorType = "FullWeighting") =
+    MGparam(VAL, levels, numCores, maxIter, relativeTol, relaxType, relaxParam, relaxPre, relaxPost, cycleType,
+            coarseSolveType, 10, 0, nothing, nothing)
+getMGparam(levels::Int64, args...) = getMGparam(ComplexF64, Int64, levels, args...)
+hierarchyExists(MG::MGparam) = MG.hd !== nothing && ccall((:hh_hierarchy_exists, LIB), Cint, (Ptr{Cvoid},), MG.hd.ptr) == 1
+
+struct hh_mg_options
+    levels::Int32; relax_type::Int32; cycle_type::Int32; coarse_type::Int32; coarse_iters::Int32; do_transpose::Int32
+    relax_pre::NTuple{HH_MAX_LEVELS,Int32}; relax_post::NTuple{HH_MAX_LEVELS,Int32}
+    relax_param::Float64; shift::NTuple{HH_MAX_LEVELS,Float64}
+end
+struct hh_solve_options
+    krylov::Int32; inner::Int32; max_iter::Int32; do_transpose::Int32; rel_tol::Float64
+end
+sweeps(v, l) = v isa Function ? Int32(v(l)) : Int32(v)
+function mg_options(MG::MGparam, shift::Vector{Float64}, doTranspose::Int)
+    relax = Dict("Jac" => 0, "Jac-GMRES" => 1)[MG.relaxType]
+    cyc = Dict('V' => 0, 'W' => 1, 'K' => 2)[MG.cycleType]
+    coarse = Dict("NoMUMPS" => 0, "Julia" => 0, "GMRES" => 1)[MG.coarseSolveType]
+    hh_mg_options(MG.levels, relax, cyc, coarse, MG.coarseIters, doTranspose,
+                  ntuple(l -> sweeps(MG.relaxPre, l), HH_MAX_LEVELS), ntuple(l -> sweeps(MG.relaxPost, l), HH_MAX_LEVELS),
+                  MG.relaxParam, ntuple(l -> shift[min(l, length(shift))], HH_MAX_LEVELS))
+end
+
+# ---- src/ShiftedLaplacianMultigridSolver.jl:4-30 ----
+mutable struct ShiftedLaplacianMultigridSolver
+    helmParam::HelmholtzParam
+    MG::MGparam
+    shift::Array{Float64}
+    Krylov::String
+    inner::Int64
+    doClear::Int64
+    verbose::Bool
+    setupTime::Real
+    nPrec::Int
+    solveTime::Real
+end
+getShiftedLaplacianMultigridSolver(helmParam::HelmholtzParam, MG::MGparam, shift::Array{Float64}, Krylov::String = "BiCGSTAB",
+                                   inner::Int64 = 5, verbose::Bool = false) =
+    ShiftedLaplacianMultigridSolver(helmParam, MG, shift, Krylov, inner, 0, verbose, 0.0, 0, 0.0)
+getShiftedLaplacianMultigridSolver(helmParam::HelmholtzParam, MG::MGparam, shift::Float64, Krylov::String = "BiCGSTAB",
+                                   inner::Int64 = 5, verbose::Bool = false) =
+    getShiftedLaplacianMultigridSolver(helmParam, MG, ones(MG.levels) * shift, Krylov, inner, verbose)
+
+function copySolver(s::ShiftedLaplacianMultigridSolver)  # :18-22 -- settings only, no hierarchy
+    MG = s.MG
+    MG2 = MGparam(MG.VAL, MG.levels, MG.numCores, MG.maxOuterIter, MG.relativeTol, MG.relaxType, MG.relaxParam, MG.relaxPre,
+                  MG.relaxPost, MG.cycleType, MG.coarseSolveType, MG.coarseIters, 0, nothing, nothing)
+    return getShiftedLaplacianMultigridSolver(s.helmParam, MG2, s.shift, s.Krylov, s.inner, s.verbose)
+end
+
+function clear!(MG::MGparam)
+    if MG.hd !== nothing
+        ccall((:hh_clear, LIB), Cint, (Ptr{Cvoid},), MG.hd.ptr)
+        finalize(MG.hd)
+    end
+    MG.hd = nothing; MG.builtFor = nothing
+end
+function clear!(s::ShiftedLaplacianMultigridSolver)  # :105-109
+    clear!(s.MG)
+    s.doClear = 0
+end
+
+function ensureHierarchy(param::ShiftedLaplacianMultigridSolver, doTranspose::Int)
+    MG = param.MG; hp = param.helmParam
+    sig = (MG.levels, MG.relaxType, MG.relaxParam, [sweeps(MG.relaxPre, l) for l in 1:MG.levels],
+           [sweeps(MG.relaxPost, l) for l in 1:MG.levels], MG.cycleType, MG.coarseSolveType, MG.coarseIters, param.shift[1], doTranspose)
+    if MG.hd === nothing
+        MG.hd = Handle(hp.Mesh, hp.m, hp.omega, hp.gamma, hp.NeumannOnTop, hp.Sommerfeld, 2; VAL = MG.VAL)
+    end
+    if !hierarchyExists(MG) || MG.builtFor != sig   # MGsetup (:50-66) / transposeHierarchy (:68-70)
+        o = Ref(mg_options(MG, vec(param.shift), doTranspose))
+        check(ccall((:hh_setup, LIB), Cint, (Ptr{Cvoid}, Ref{hh_mg_options}), MG.hd.ptr, o), MG.hd.ptr)
+        MG.builtFor = sig; MG.doTranspose = doTranspose
+    end
+    return MG.hd
+end
+
+# in-place variant (jInv.LinearSolvers.solveLinearSystem!)
+function solveLinearSystem!(ShiftedHT, B, X, param::ShiftedLaplacianMultigridSolver, doTranspose::Int64 = 0)
+    param.helmParam.omega isa ComplexF64 && imag(param.helmParam.omega) != 0 &&
+        throw(MethodError(GetHelmholtzShiftOP, (param.helmParam.m, param.helmParam.omega, param.shift[1])))  # :77
+    if param.doClear == 1
+        clear!(param.MG)
+    end
+    if norm(B) == 0.0                                  # :40-43
+        X .= 0
+        return X, param
+    end
+    tt = time_ns()
+    hd = ensureHierarchy(param, doTranspose)
+    param.setupTime += (time_ns() - tt) / 1e9
+    MG = param.MG
+    Bm = Array{MG.VAL}(reshape(B, hd.N, :)); nrhs = size(Bm, 2)
+    Xm = (X isa Array{MG.VAL} && length(X) == length(Bm)) ? X : similar(Bm)
+    iters = zeros(Int32, nrhs); relres = zeros(Float64, nrhs)
+    so = Ref(hh_solve_options(param.Krylov == "GMRES" ? 0 : 1, max(param.inner, 1), MG.maxOuterIter, doTranspose, MG.relativeTol))
+    tt = time_ns()
+    rc = check(ccall((:hh_solve, LIB), Cint,
+                     (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Int64, Ref{hh_solve_options}, Ptr{Int32}, Ptr{Float64}),
+                     hd.ptr, Bm, Xm, nrhs, so, iters, relres), hd.ptr)
+    param.solveTime += (time_ns() - tt) / 1e9
+    param.nPrec += sum(iters)
+    Xm === X || (X .= reshape(Xm, size(X)))
+    if rc == HH_NOT_CONVERGED
+        println("WARNING: MG solver reached maximum iterations without convergence")   # :97-99
+    end
+    return X, param
+end
+
+function solveLinearSystem(ShiftedHT, B, param::ShiftedLaplacianMultigridSolver, doTranspose::Int64 = 0)
+    if size(B, 2) == 1
+        B = vec(B)                                     # :34-36
+    end
+    X = zeros(param.MG.VAL, size(B))
+    return solveLinearSystem!(ShiftedHT, B, X, param, doTranspose)
+end
+
+end # module
