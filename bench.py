@@ -3,7 +3,7 @@
 
 Workload (BASELINE.json configs[3], SURVEY.md section 8d "config 4"): 3-D 257^3-node random-smooth velocity
 model, 10 points per wavelength, absorbing layer + Sommerfeld, 256 point sources on a 16 x 16 top-plane
-grid, shift 0.2, 3-level V(2,2) damped-Jacobi Galerkin multigrid with an inexact Jacobi-GMRES(10) coarsest
+grid, shift 0.2, 3-level W(1,2) damped-Jacobi Galerkin multigrid with an inexact Jacobi-GMRES(10) coarsest
 solve, right-preconditioned FGMRES(5) to a 1e-6 relative residual, ComplexF64.
 
 A step = one batched solve of `--nrhs` right-hand sides (a slice of the 256 sources) on every GPU.  Right-hand
@@ -60,13 +60,13 @@ def workload(pkg, n):
     gamma = cfg["gamma0_frac"] * w * np.ones(m.shape) + pkg.getABL(mesh.n + 1, True, cfg["pad"], w)
     srcs = pkg.workloads.point_sources_top_grid(mesh.n + 1, 16, 16)
     return dict(cfg=cfg, mesh=mesh, m=m, w=w, gamma=gamma, srcs=srcs,
-                settings=dict(levels=3, shift=0.2, relax="Jac", relax_param=0.8, pre=2, post=2, cycle="V", coarse="GMRES",
+                settings=dict(levels=3, shift=0.2, relax="Jac", relax_param=0.8, pre=1, post=2, cycle="W", coarse="GMRES",
                               coarse_iters=10, krylov="GMRES", inner=5, tol=1e-6, max_cycles=30))
 
 
 def workload_name(n, nrhs, prec):
     return (f"config4: 3-D {n}^3 nodes, random-smooth velocity 1.5-4.5 km/s (seed 1234), 10 ppw, ABL+Sommerfeld, 256 point "
-            f"sources on a 16x16 top-plane grid ({nrhs} per step per GPU), shift 0.2, 3-level V(2,2) Jacobi(0.8) Galerkin MG, "
+            f"sources on a 16x16 top-plane grid ({nrhs} per step per GPU), shift 0.2, 3-level W(1,2) Jacobi(0.8) Galerkin MG, "
             f"coarsest Jacobi-GMRES(10), FGMRES(5), tol 1e-6, {'ComplexF64' if prec == 'c128' else 'ComplexF32'}")
 
 
@@ -221,7 +221,7 @@ def iterations_to_tol(n):
                 return float(d[str(n)])
         except Exception:
             pass
-    return {257: 42.3, 129: 35.5, 65: 26.0}.get(n, 42.3)
+    return {257: 29.0, 129: 24.0, 65: 18.0}.get(n, 29.0)
 
 
 # ----------------------------------------------------------------------------------------------------

@@ -1134,12 +1134,14 @@ __global__ void __launch_bounds__(256) k_multidot(VecList<T> V, const cx<T>* __r
     }
 }
 
-// w <- w + sum_i coef[r*cstride + i] * V_i   (i < NV), optionally accumulating |w_new|^2 partials
-// into partial[r*nblk + blk].  `negate` subtracts instead (Gram-Schmidt).
+// w <- (w + sum_i coef[r*cstride + i] * V_i) * post[r]   (i < NV; post == nullptr: no scaling), optionally
+// accumulating |w_new|^2 partials into partial[r*nblk + blk].  `negate` subtracts (Gram-Schmidt).  The
+// post-scale writes the next Arnoldi vector already (approximately) normalised, so no separate scaling
+// pass over the vector is needed (scaled-basis GMRES, see k_gmres_hcol).
 template <typename T, int NV, bool WITH_NORM>
 __global__ void __launch_bounds__(256) k_multiaxpy(VecList<T> V, cx<T>* __restrict__ w, int64_t N, int64_t ld,
                                                    const zc* __restrict__ coef, int cstride, int negate,
-                                                   zc* __restrict__ partial) {
+                                                   const zc* __restrict__ post, zc* __restrict__ partial) {
     __shared__ double sm[32];
     const int r = blockIdx.y, nblk = gridDim.x;
     const int64_t base = (int64_t)r * ld;
@@ -1149,11 +1151,13 @@ __global__ void __launch_bounds__(256) k_multiaxpy(VecList<T> V, cx<T>* __restri
         const zc cc = coef[(int64_t)r * cstride + i];
         c[i] = negate ? mk<T>((T)-cc.x, (T)-cc.y) : mk<T>((T)cc.x, (T)cc.y);
     }
+    const T ps = post ? (T)post[r].x : T(1);
     double nrm = 0.0;
     for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < N; p += (int64_t)nblk * blockDim.x) {
         cx<T> wv = w[base + p];
 #pragma unroll
         for (int i = 0; i < NV; ++i) cfma(wv, c[i], V.v[i][base + p]);
+        wv = ps * wv;
         w[base + p] = wv;
         if (WITH_NORM) nrm += (double)wv.x * wv.x + (double)wv.y * wv.y;
     }
@@ -1204,42 +1208,74 @@ __device__ __forceinline__ zc reduce_partials(const zc* partial, int64_t idx, in
     return mk<double>(warp_sum(sx), warp_sum(sy));
 }
 
+// Scaled-basis GMRES.  The stored Arnoldi vectors v~_i = d_i v_i are only approximately normalised
+// (d_0 = ||r||, d_{i+1} ~ 1): the next vector is written as (w - sum c_i v~_i) / beta_est in the same pass
+// that orthogonalises it, with beta_est^2 = ||w||^2 - sum |<v~_i,w>|^2/d_i^2 known from the dot pass, and its
+// true norm d_{i+1} is measured in that pass.  All relations are exact for any positive beta_est (a poor
+// estimate only makes d_{i+1} differ from 1), the Hessenberg matrix is that of the unit basis
+// (h_ij = g_i/(d_i d_j), h_{j+1,j} = beta_est d_{j+1}/d_j), and the update uses y_j/d_j on the stored
+// preconditioned vectors z~_j = M v~_j.  This removes the separate "v = w/||w||" pass over the vectors.
 struct GmresState {
     // per RHS r:  H[r][(m+1)*m] column-major (ldh = m+1), cs[r][m] (real in .x), sn[r][m], s[r][m+1],
-    // hcol[r][m+1] (raw Gram-Schmidt coefficients of the current column), y[r][m]
+    // hcol[r][m+1]: Gram-Schmidt update coefficients g_i/d_i^2 of the current column, y[r][m]: y_j/d_j
     zc *H, *cs, *sn, *s, *hcol, *y;
     double *bnorm, *err;  // per RHS
-    zc* scale;            // per RHS: 1/h_{j+1,j} (or 1/beta), 0 when frozen
+    zc* scale;            // per RHS: 1/beta_est of the current column (0 when frozen)
     int *done, *jdone, *nprec;
-    int m;  // restart length
+    int m;       // restart length
+    double* d;   // [r][m+1] norms of the stored basis vectors
+    double* acc; // [r][2]: ||w||^2 and sum |g_i|^2/d_i^2 of the current column
 };
 
-// after the multidot: hcol[r][i] = <v_i, w>, i <= j
+// after a multidot group: g_i = <v~_i, w>, i0 <= i < i0+nv (<= j); the first group also carries ||w||^2
 __global__ void k_gmres_hcol(GmresState st, const zc* __restrict__ partial, int nblk, int j, int i0, int nv) {
     const int r = blockIdx.x, nrhs = gridDim.x;
+    const int ldh = st.m + 1;
+    const bool lead = (threadIdx.x & 31) == 0;
+    double sumsq = 0.0;
     for (int i = 0; i < nv; ++i) {
-        const zc h = reduce_partials(partial, (int64_t)i * nrhs + r, nblk);
-        if ((threadIdx.x & 31) == 0) st.hcol[(int64_t)r * (st.m + 1) + i0 + i] = st.done[r] ? mk<double>(0.0, 0.0) : h;
+        const zc g = reduce_partials(partial, (int64_t)i * nrhs + r, nblk);
+        if (lead) {
+            const double di = st.d[(int64_t)r * ldh + i0 + i], dj = st.d[(int64_t)r * ldh + j];
+            const bool ok = !st.done[r] && di > 0.0 && dj > 0.0;
+            st.hcol[(int64_t)r * ldh + i0 + i] = ok ? (1.0 / (di * di)) * g : mk<double>(0.0, 0.0);
+            st.H[(int64_t)r * ldh * st.m + (int64_t)j * ldh + i0 + i] = ok ? (1.0 / (di * dj)) * g : mk<double>(0.0, 0.0);
+            if (ok) sumsq += (g.x * g.x + g.y * g.y) / (di * di);
+        }
+    }
+    zc nw = mk<double>(0.0, 0.0);
+    if (i0 == 0) nw = reduce_partials(partial, (int64_t)nv * nrhs + r, nblk);
+    if (!lead) return;
+    double* acc = st.acc + 2 * (int64_t)r;
+    if (i0 == 0) {
+        acc[0] = nw.x;
+        acc[1] = 0.0;
+    }
+    acc[1] += sumsq;
+    if (i0 + nv == j + 1) {  // last group: the estimate of ||w - sum ...||
+        double be2 = acc[0] - acc[1];
+        const double floor2 = 1e-6 * acc[0];  // any positive value is valid; keeps d_{j+1} within [~1e-3, 1]
+        if (!(be2 > floor2)) be2 = floor2;
+        st.scale[r] = mk<double>((st.done[r] || !(be2 > 0.0)) ? 0.0 : 1.0 / sqrt(be2), 0.0);
     }
 }
 
-// after the orthogonalisation: h_{j+1,j} = ||w||, apply/compute Givens rotations, residual estimate
+// after the orthogonalisation pass: d_{j+1} = ||v~_{j+1}||, h_{j+1,j}, Givens rotations, residual estimate
 __global__ void k_gmres_givens(GmresState st, const zc* __restrict__ partial, int nblk, int j, double tol) {
     const int r = blockIdx.x;
     const zc nn = reduce_partials(partial, r, nblk);
     if ((threadIdx.x & 31) != 0) return;
     const int m = st.m, ldh = m + 1;
-    if (st.done[r]) {
-        st.scale[r] = mk<double>(0.0, 0.0);
-        return;
-    }
+    if (st.done[r]) return;
     zc* Hc = st.H + (int64_t)r * ldh * m + (int64_t)j * ldh;
-    zc* hc = st.hcol + (int64_t)r * ldh;
     zc* cs = st.cs + (int64_t)r * m;
     zc* sn = st.sn + (int64_t)r * m;
     zc* s = st.s + (int64_t)r * ldh;
-    const double hn = sqrt(nn.x);
-    for (int i = 0; i <= j; ++i) Hc[i] = hc[i];
+    double* d = st.d + (int64_t)r * ldh;
+    const double dn = sqrt(nn.x);
+    d[j + 1] = dn;
+    const double sc = st.scale[r].x;
+    const double hn = (sc > 0.0 && d[j] > 0.0) ? dn / (sc * d[j]) : 0.0;
     Hc[j + 1] = mk<double>(hn, 0.0);
     for (int k = 0; k < j; ++k) {
         const zc t = cs[k].x * Hc[k] + sn[k] * Hc[k + 1];
@@ -1273,12 +1309,11 @@ __global__ void k_gmres_givens(GmresState st, const zc* __restrict__ partial, in
     st.err[r] = err;
     st.jdone[r] = j + 1;
     st.nprec[r] += 1;
-    st.scale[r] = mk<double>(hn > 0.0 ? 1.0 / hn : 0.0, 0.0);
     if (!(err > tol)) st.done[r] = 1;  // also catches NaN -> stops; host checks for NaN separately
     if (err != err) st.done[r] = 2;
 }
 
-// y = H(1:jd,1:jd) \ s(1:jd), zero beyond jd  (jd = jdone[r]; 0 if the RHS took no step this cycle)
+// y = H(1:jd,1:jd) \ s(1:jd); stored as y_i/d_i (coefficients of the stored z~_i), zero beyond jd
 __global__ void k_gmres_solve_y(GmresState st, int nrhs) {
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= nrhs) return;
@@ -1286,6 +1321,7 @@ __global__ void k_gmres_solve_y(GmresState st, int nrhs) {
     const int jd = st.jdone[r];
     const zc* H = st.H + (int64_t)r * ldh * m;
     const zc* s = st.s + (int64_t)r * ldh;
+    const double* d = st.d + (int64_t)r * ldh;
     zc* y = st.y + (int64_t)r * m;
     for (int i = 0; i < m; ++i) y[i] = mk<double>(0.0, 0.0);
     for (int i = jd - 1; i >= 0; --i) {
@@ -1293,11 +1329,12 @@ __global__ void k_gmres_solve_y(GmresState st, int nrhs) {
         for (int k = i + 1; k < jd; ++k) acc = acc - H[(int64_t)k * ldh + i] * y[k];
         y[i] = cdiv(acc, H[(int64_t)i * ldh + i]);
     }
+    for (int i = 0; i < jd; ++i) y[i] = (d[i] > 0.0 ? 1.0 / d[i] : 0.0) * y[i];
     st.jdone[r] = 0;
 }
 
-// start of a cycle: beta = ||r|| from norm partials; s = beta e1; scale = 1/beta; err = beta/bnorm.
-// first != 0: this is ||b||: record bnorm, mark zero right-hand sides done.
+// start of a cycle: beta = ||r|| from norm partials; v~_0 = r is used unscaled (d_0 = beta), s = beta e1,
+// err = beta/bnorm.  first != 0: this is ||b||: record bnorm, mark zero right-hand sides done.
 __global__ void k_gmres_begin(GmresState st, const zc* __restrict__ partial, int nblk, int first, double tol) {
     const int r = blockIdx.x;
     const zc nn = reduce_partials(partial, r, nblk);
@@ -1320,7 +1357,8 @@ __global__ void k_gmres_begin(GmresState st, const zc* __restrict__ partial, int
     zc* s = st.s + (int64_t)r * ldh;
     for (int i = 0; i < ldh; ++i) s[i] = mk<double>(0.0, 0.0);
     s[0] = mk<double>(beta, 0.0);
-    st.scale[r] = mk<double>((st.done[r] || beta == 0.0) ? 0.0 : 1.0 / beta, 0.0);
+    st.d[(int64_t)r * ldh] = beta;
+    st.scale[r] = mk<double>(0.0, 0.0);
 }
 
 // ---- BiCGSTAB: per-RHS scalars and the p-update -------------------------------------------------

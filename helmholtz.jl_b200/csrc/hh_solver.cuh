@@ -199,7 +199,7 @@ class Solver : public SolverBase {
 
     struct GmresMem {
         DevBuf<zc> H, cs, sn, s, hcol, y, scale;
-        DevBuf<double> bnorm, err;
+        DevBuf<double> bnorm, err, d, acc;
         DevBuf<int> done, jdone, nprec;
         GmresState st{};
     };
@@ -659,7 +659,7 @@ class Solver : public SolverBase {
         return nblk;
     }
     int multiaxpy(const C* const* V, int nv, C* w, int64_t N, int nrhs, const zc* coef, int cstride, bool negate,
-                  bool with_norm, zc* partial) {
+                  bool with_norm, zc* partial, const zc* post = nullptr) {
         HH_REQUIRE(nv >= 1 && nv <= HH_MAXV, HH_ERR_ARG, "multiaxpy: bad vector count");
         const int nblk = vec_blocks(N, nrhs);
         VecList<T> L;
@@ -668,8 +668,8 @@ class Solver : public SolverBase {
         launch(T_AXPY, S * (double)N * nrhs * (nv + 2), [&] {
 #define HH_MA(NV)                                                                                                 \
     case NV:                                                                                                      \
-        if (with_norm) k_multiaxpy<T, NV, true><<<g, 256, 0, stream>>>(L, w, N, N, coef, cstride, negate, partial); \
-        else k_multiaxpy<T, NV, false><<<g, 256, 0, stream>>>(L, w, N, N, coef, cstride, negate, partial);          \
+        if (with_norm) k_multiaxpy<T, NV, true><<<g, 256, 0, stream>>>(L, w, N, N, coef, cstride, negate, post, partial); \
+        else k_multiaxpy<T, NV, false><<<g, 256, 0, stream>>>(L, w, N, N, coef, cstride, negate, post, partial);          \
         break;
             switch (nv) { HH_MA(1) HH_MA(2) HH_MA(3) HH_MA(4) HH_MA(5) HH_MA(6) HH_MA(7) HH_MA(8) }
 #undef HH_MA
@@ -894,7 +894,9 @@ class Solver : public SolverBase {
         g.done.alloc(nrhs);
         g.jdone.alloc(nrhs);
         g.nprec.alloc(nrhs);
-        g.st = GmresState{g.H.p, g.cs.p, g.sn.p, g.s.p, g.hcol.p, g.y.p, g.bnorm.p, g.err.p, g.scale.p, g.done.p, g.jdone.p, g.nprec.p, m};
+        g.d.alloc((size_t)nrhs * (m + 1));
+        g.acc.alloc((size_t)nrhs * 2);
+        g.st = GmresState{g.H.p, g.cs.p, g.sn.p, g.s.p, g.hcol.p, g.y.p, g.bnorm.p, g.err.p, g.scale.p, g.done.p, g.jdone.p, g.nprec.p, m, g.d.p, g.acc.p};
     }
 
     // ------------------------------------------------------------------ generic operator access per level
@@ -909,12 +911,13 @@ class Solver : public SolverBase {
 
     // Orthogonalise w against V_0..V_j (classical Gram-Schmidt in one fused pass over the vectors),
     // then the Givens update.  Leaves 1/||w|| in st.scale.
-    void gmres_orthogonalise(GmresMem& g, C* const* V, int j, C* w, int64_t N, int nrhs, double tol) {
+    // V[0..j] are the stored (scaled) basis vectors, w = A z~_j on entry, the next basis vector on exit.
+    void gmres_orthogonalise(GmresMem& g, const C* const* V, int j, C* w, int64_t N, int nrhs, double tol) {
         const C* vv[HH_MAXV];
         for (int i0 = 0; i0 <= j; i0 += HH_MAXV) {
             const int nv = std::min(HH_MAXV, j + 1 - i0);
             for (int i = 0; i < nv; ++i) vv[i] = V[i0 + i];
-            const int nblk = multidot(vv, nv, w, N, nrhs, false, d_partial.p);
+            const int nblk = multidot(vv, nv, w, N, nrhs, i0 == 0, d_partial.p);
             launch(T_SCALAR, 0, [&] { k_gmres_hcol<<<nrhs, 32, 0, stream>>>(g.st, d_partial.p, nblk, j, i0, nv); });
         }
         int nblk = 0;
@@ -922,7 +925,8 @@ class Solver : public SolverBase {
             const int nv = std::min(HH_MAXV, j + 1 - i0);
             for (int i = 0; i < nv; ++i) vv[i] = V[i0 + i];
             const bool last = (i0 + HH_MAXV > j);
-            nblk = multiaxpy(vv, nv, w, N, nrhs, g.hcol.p + i0, g.st.m + 1, true, last, d_partial.p);
+            nblk = multiaxpy(vv, nv, w, N, nrhs, g.hcol.p + i0, g.st.m + 1, true, last, d_partial.p,
+                             last ? g.scale.p : nullptr);
         }
         launch(T_SCALAR, 0, [&] { k_gmres_givens<<<nrhs, 32, 0, stream>>>(g.st, d_partial.p, nblk, j, tol); });
     }
@@ -945,12 +949,12 @@ class Solver : public SolverBase {
         HH_REQUIRE(nsteps >= 1 && nsteps <= ws.steps, HH_ERR_STATE, "small_gmres workspace");
         const int64_t N = L.N;
         const int64_t vs = N * kcap;
-        std::vector<C*> V(nsteps + 1);
-        for (int i = 0; i <= nsteps; ++i) V[i] = ws.v.p + (int64_t)i * vs;
-        if (x_is_zero) copy_vec(b, V[0], N, nrhs);
-        else level_apply(l, MODE_RESID, x, b, V[0], nrhs);
+        std::vector<C*> W(nsteps + 1);            // writable slots
+        std::vector<const C*> V(nsteps + 1);      // the basis as read
+        for (int i = 0; i <= nsteps; ++i) V[i] = W[i] = ws.v.p + (int64_t)i * vs;
+        if (x_is_zero) V[0] = b;  // r0 = b: used in place, unscaled (d_0 = ||b||)
+        else level_apply(l, MODE_RESID, x, b, W[0], nrhs);
         gmres_begin(g, V[0], N, nrhs, true, 0.0);
-        scale_vec(V[0], V[0], N, nrhs, g.scale.p, 1);
         for (int j = 0; j < nsteps; ++j) {
             C* z;
             if (prec == 0) {
@@ -960,15 +964,14 @@ class Solver : public SolverBase {
                 z = ws.z.p + (int64_t)j * vs;
                 cycle(l, V[j], z, true, nrhs);
             }
-            level_apply(l, MODE_APPLY, z, nullptr, V[j + 1], nrhs);
-            gmres_orthogonalise(g, V.data(), j, V[j + 1], N, nrhs, 0.0);
-            if (j + 1 < nsteps) scale_vec(V[j + 1], V[j + 1], N, nrhs, g.scale.p, 1);
+            level_apply(l, MODE_APPLY, z, nullptr, W[j + 1], nrhs);
+            gmres_orthogonalise(g, V.data(), j, W[j + 1], N, nrhs, 0.0);
         }
         gmres_solve_y(g, nrhs);
         const C* vv[HH_MAXV];
         if (prec == 0) {
-            // t = sum_j y_j v_j  (accumulated into V[nsteps], free now), then x (+)= dinv .* t
-            C* t = V[nsteps];
+            // t = sum_j y_j v_j  (accumulated into the last slot, free now), then x (+)= dinv .* t
+            C* t = W[nsteps];
             zero_vec(t, N, nrhs);
             for (int i0 = 0; i0 < nsteps; i0 += HH_MAXV) {
                 const int nv = std::min(HH_MAXV, nsteps - i0);
@@ -1172,21 +1175,21 @@ class Solver : public SolverBase {
             alloc_gmres_state(outer, m, nrhs);
             outer_cap = nrhs;
         }
-        std::vector<C*> V(m + 1), Z(m);
-        for (int i = 0; i <= m; ++i) V[i] = kry.p + (int64_t)i * vs;
+        std::vector<C*> W(m + 1), Z(m);
+        std::vector<const C*> V(m + 1);
+        for (int i = 0; i <= m; ++i) V[i] = W[i] = kry.p + (int64_t)i * vs;
         for (int i = 0; i < m; ++i) Z[i] = kry.p + (int64_t)(m + 1 + i) * vs;
         const FineOp<T> Hop = krylov_op(o.do_transpose);  // Afun: the un-shifted operator (GetHelmholtz.jl:85-95)
         zero_vec(X, N, nrhs);
-        // r0 = b (x0 = 0); bnorm
+        // r0 = b (x0 = 0): the first basis vector is B itself, used in place and unscaled (d_0 = ||b||)
+        V[0] = B;
         gmres_begin(outer, B, N, nrhs, true, o.rel_tol);
-        scale_vec(B, V[0], N, nrhs, outer.scale.p, 1);
         bool all_done = fetch_done(outer.done.p, nrhs);
         for (int cyc = 0; cyc < o.max_iter && !all_done; ++cyc) {
             for (int j = 0; j < m; ++j) {
                 precondition(V[j], Z[j], nrhs);
-                fine_stencil(MODE_APPLY, Hop, Z[j], nullptr, V[j + 1], N, nrhs, T(0));
-                gmres_orthogonalise(outer, V.data(), j, V[j + 1], N, nrhs, o.rel_tol);
-                scale_vec(V[j + 1], V[j + 1], N, nrhs, outer.scale.p, 1);
+                fine_stencil(MODE_APPLY, Hop, Z[j], nullptr, W[j + 1], N, nrhs, T(0));
+                gmres_orthogonalise(outer, V.data(), j, W[j + 1], N, nrhs, o.rel_tol);
                 all_done = fetch_done(outer.done.p, nrhs);
                 if (all_done) break;
             }
@@ -1198,10 +1201,10 @@ class Solver : public SolverBase {
                 multiaxpy(zz, nv, X, N, nrhs, outer.y.p + i0, m, false, false, d_partial.p);
             }
             if (all_done || cyc + 1 == o.max_iter) break;
-            // restart: r = b - H x
-            fine_stencil(MODE_RESID, Hop, X, B, V[0], N, nrhs, T(0));
-            gmres_begin(outer, V[0], N, nrhs, false, o.rel_tol);
-            scale_vec(V[0], V[0], N, nrhs, outer.scale.p, 1);
+            // restart: r = b - H x  (again used unscaled as the first basis vector)
+            V[0] = W[0];
+            fine_stencil(MODE_RESID, Hop, X, B, W[0], N, nrhs, T(0));
+            gmres_begin(outer, W[0], N, nrhs, false, o.rel_tol);
             all_done = fetch_done(outer.done.p, nrhs);
         }
         return finish(outer.nprec.p, outer.err.p, nrhs, iters, relres, all_done);
