@@ -507,6 +507,135 @@ __global__ void __launch_bounds__(256) k_fine3d_tma(FineOp<T> op, const __grid_c
 }
 
 // ---------------------------------------------------------------------------------------------
+// Fused start of a cycle on the fine level (3-D, TMA form): the first Jacobi sweep from a zero guess,
+// x1 = dinv .* b, is never written and re-read -- the kernel stages b and dinv WITH halo, forms x1 on
+// the fly at the centre and the six neighbours, and directly produces
+//   SECOND = 0 :  x1 and the residual r = b - A x1          (pre-smoothing count 1: x1, r in one pass)
+//   SECOND = 1 :  x2 = x1 + dinv .* (b - A x1)               (the first two sweeps in one pass)
+// Algorithmic bytes per node per RHS: S read + 2S / S written, instead of 2S + 3S for two kernels.
+// ---------------------------------------------------------------------------------------------
+template <typename T, int KB>
+struct FineFirstCfg {
+    static constexpr int TX = 32, TY = 8, PX = TX + 2;
+    static constexpr int XT = (TY + 2) * PX;
+    static constexpr int BT = TY * TX;
+    static constexpr int ES = (int)sizeof(cx<T>);
+    static constexpr int al(int b) { return (b + 127) / 128 * 128; }
+    static constexpr int OFF_B = 0;                       // b tiles with halo, KB right-hand sides
+    static constexpr int OFF_D = al(KB * XT * ES);        // dinv tile with halo
+    static constexpr int OFF_C = OFF_D + al(XT * ES);     // centre coefficient tile
+    static constexpr int STAGE_BYTES = OFF_C + al(BT * ES);
+    static constexpr uint32_t TX_BYTES = KB * XT * ES + XT * ES + BT * ES;
+};
+
+template <typename T, int SECOND, int KB, int NS>
+__global__ void __launch_bounds__(256) k_fine3d_tma_first(FineOp<T> op, const __grid_constant__ TmaDesc tm_b,
+                                                          const __grid_constant__ TmaDesc tm_d,
+                                                          const __grid_constant__ TmaDesc tm_c,
+                                                          const cx<T>* __restrict__ b, cx<T>* __restrict__ out,
+                                                          cx<T>* __restrict__ out2, int64_t ld, int nrhs, int zchunk,
+                                                          int groups) {
+    typedef FineFirstCfg<T, KB> Cfg;
+    constexpr int TX = Cfg::TX, TY = Cfg::TY, PX = Cfg::PX;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + (size_t)NS * Cfg::STAGE_BYTES);
+    const int n0 = op.n[0], n1 = op.n[1], n2 = op.n[2];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int i0 = (blockIdx.x / groups) * TX, j0 = blockIdx.y * TY;
+    const int i = i0 + tx, j = j0 + ty;
+    const int r0 = (blockIdx.x % groups) * KB;
+    const int z0 = blockIdx.z * zchunk;
+    const int z1 = min(n2, z0 + zchunk);
+    const int zl = min(z1, n2 - 1);
+    const int64_t sy = n0, sz = (int64_t)n0 * n1;
+    const bool active = (i < n0) && (j < n1);
+    auto issue = [&](int s, int z) {
+        unsigned char* st = smem_raw + (size_t)s * Cfg::STAGE_BYTES;
+        mbar_expect_tx(&bars[s], Cfg::TX_BYTES);
+        tma_load_4d(st + Cfg::OFF_B, &tm_b, 2 * (i0 - 1), j0 - 1, z, r0, &bars[s]);
+        tma_load_3d(st + Cfg::OFF_D, &tm_d, 2 * (i0 - 1), j0 - 1, z, &bars[s]);
+        tma_load_3d(st + Cfg::OFF_C, &tm_c, 2 * i0, j0, z, &bars[s]);
+    };
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < NS; ++s) mbar_init(&bars[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        for (int s = 0; s < NS && z0 + s <= zl; ++s) issue(s, z0 + s);
+    }
+    __syncthreads();
+    const int ic = active ? i : 0, jc = active ? j : 0;
+    const T wxm = fine_w(op, 0, 0, ic, n0), wxp = fine_w(op, 0, 1, ic, n0);
+    const T wym = fine_w(op, 1, 0, jc, n1), wyp = fine_w(op, 1, 1, jc, n1);
+    const int64_t pxy = ic + sy * jc;
+    const int cidx = (ty + 1) * PX + (tx + 1);
+    const int bidx = ty * TX + tx;
+    cx<T> tm_[KB], tc[KB], tp[KB];  // x1 = dinv .* b at planes z-1, z, z+1 of this column
+    mbar_wait(&bars[0], 0);
+    {
+        const cx<T> d0 = reinterpret_cast<const cx<T>*>(smem_raw + Cfg::OFF_D)[cidx];
+        const cx<T> dm = (z0 > 0 && active) ? op.dinv[pxy + (int64_t)(z0 - 1) * sz] : mk<T>(T(0), T(0));
+#pragma unroll
+        for (int q = 0; q < KB; ++q) {
+            tc[q] = d0 * reinterpret_cast<const cx<T>*>(smem_raw + Cfg::OFF_B)[q * Cfg::XT + cidx];
+            const int r = min(r0 + q, nrhs - 1);
+            tm_[q] = (z0 > 0 && active) ? dm * b[(int64_t)r * ld + pxy + (int64_t)(z0 - 1) * sz] : mk<T>(T(0), T(0));
+        }
+    }
+#pragma unroll 1
+    for (int z = z0; z < z1; ++z) {
+        const int s = (z - z0) % NS;
+        const unsigned char* st = smem_raw + (size_t)s * Cfg::STAGE_BYTES;
+        const bool zlast = (z == n2 - 1);
+        if (!zlast) {
+            const int s1 = (z + 1 - z0) % NS;
+            mbar_wait(&bars[s1], (uint32_t)(((z + 1 - z0) / NS) & 1));
+            const unsigned char* st1 = smem_raw + (size_t)s1 * Cfg::STAGE_BYTES;
+            const cx<T> d1 = reinterpret_cast<const cx<T>*>(st1 + Cfg::OFF_D)[cidx];
+#pragma unroll
+            for (int q = 0; q < KB; ++q) tp[q] = d1 * reinterpret_cast<const cx<T>*>(st1 + Cfg::OFF_B)[q * Cfg::XT + cidx];
+        } else {
+#pragma unroll
+            for (int q = 0; q < KB; ++q) tp[q] = mk<T>(T(0), T(0));
+        }
+        if (active) {
+            const cx<T>* sb = reinterpret_cast<const cx<T>*>(st + Cfg::OFF_B);
+            const cx<T>* sd = reinterpret_cast<const cx<T>*>(st + Cfg::OFF_D) + cidx;
+            const cx<T> c = reinterpret_cast<const cx<T>*>(st + Cfg::OFF_C)[bidx];
+            const cx<T> dW = sd[-1], dE = sd[1], dS = sd[-PX], dN = sd[PX], dC = sd[0];
+            const T wzm = fine_w(op, 2, 0, z, n2), wzp = fine_w(op, 2, 1, z, n2);
+            const int64_t p = pxy + (int64_t)z * sz;
+#pragma unroll
+            for (int q = 0; q < KB; ++q) {
+                const cx<T>* bt = sb + q * Cfg::XT + cidx;
+                cx<T> a = c * tc[q];
+                rfma(a, -wxm, dW * bt[-1]);  // halo cells outside the grid are zero-filled (b and dinv)
+                rfma(a, -wxp, dE * bt[1]);
+                rfma(a, -wym, dS * bt[-PX]);
+                rfma(a, -wyp, dN * bt[PX]);
+                rfma(a, -wzm, tm_[q]);
+                rfma(a, -wzp, tp[q]);
+                if (r0 + q < nrhs) {
+                    const int64_t o = (int64_t)(r0 + q) * ld + p;
+                    const cx<T> res = bt[0] - a;
+                    if (SECOND == 0) {
+                        out[o] = tc[q];
+                        out2[o] = res;
+                    } else {
+                        out[o] = tc[q] + dC * res;
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < KB; ++q) {
+            tm_[q] = tc[q];
+            tc[q] = tp[q];
+        }
+        __syncthreads();
+        if (threadIdx.x == 0 && z + NS <= zl) issue(s, z + NS);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Coarse levels, 3-D, TMA production form: 27-point stencil with stored Galerkin coefficients.
 // A CTA (128 threads) owns a 32 x 4 tile of (i,j) columns and walks a chunk of z planes in the
 // scatter form of k_coarse3d_zmarch (three rolling accumulators per right-hand side).  Each

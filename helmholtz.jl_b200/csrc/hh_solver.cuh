@@ -44,6 +44,8 @@ enum Tag {
     T_FINE_RESID,
     T_FINE_JACOBI,
     T_FINE_JACOBI0,
+    T_FINE_FIRST_RESID,
+    T_FINE_FIRST_JACOBI,
     T_COARSE_APPLY,
     T_COARSE_RESID,
     T_COARSE_JACOBI,
@@ -60,7 +62,8 @@ enum Tag {
     T_NTAGS
 };
 static const char* const kTagNames[T_NTAGS] = {
-    "fine_apply",   "fine_resid",   "fine_jacobi",    "fine_jacobi0", "coarse_apply", "coarse_resid",
+    "fine_apply",   "fine_resid",   "fine_jacobi",    "fine_jacobi0", "fine_first_resid", "fine_first_jacobi",
+    "coarse_apply", "coarse_resid",
     "coarse_jacobi", "coarse_jacobi0", "restrict",    "prolong",      "coarsest_dense", "krylov_dot",
     "krylov_axpy",  "krylov_scale", "copy",           "scalar",       "setup"};
 
@@ -228,6 +231,8 @@ class Solver : public SolverBase {
         fine_kernel = FK_TMA;
         if (e && !strcmp(e, "zmarch")) fine_kernel = FK_ZMARCH;
         if (e && !strcmp(e, "simple")) fine_kernel = FK_SIMPLE;
+        const char* f = getenv("HH_FUSE_FIRST");  // A/B switch of the fused cycle start (default on)
+        fuse_first = !(f && f[0] == '0');
     }
     ~Solver() override {}
 
@@ -464,6 +469,44 @@ class Solver : public SolverBase {
                                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         HH_REQUIRE(r == CUDA_SUCCESS, HH_ERR_CUDA, "cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")");
         return d;
+    }
+    // fused first sweep from zero + (residual | second sweep); see k_fine3d_tma_first
+    template <int SECOND, int KB>
+    void tma3d_first_launch(const FineOp<T>& op, const C* b, C* out, C* out2, int64_t ld, int nrhs) {
+        typedef FineFirstCfg<T, KB> Cfg;
+        constexpr int NS = 4;
+        constexpr size_t smem = (size_t)NS * Cfg::STAGE_BYTES + NS * sizeof(uint64_t);
+        static bool attr_set = false;
+        if (!attr_set) {
+            HH_CUDA(cudaFuncSetAttribute(k_fine3d_tma_first<T, SECOND, KB, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            attr_set = true;
+        }
+        const int groups = (nrhs + KB - 1) / KB;
+        const int tx = (pb.n[0] + Cfg::TX - 1) / Cfg::TX, ty = (pb.n[1] + Cfg::TY - 1) / Cfg::TY;
+        int zchunk, nzc;
+        zchunks(pb.n[2], tx * ty, groups, 64, zchunk, nzc);
+        dim3 g(tx * groups, ty, nzc);
+        TmaDesc mb = make_tmap_n(b, ld, Cfg::TX + 2, Cfg::TY + 2, KB, nrhs);
+        TmaDesc md = make_tmap_n(op.dinv, ld, Cfg::TX + 2, Cfg::TY + 2, 1, 0);
+        TmaDesc mc = make_tmap_n(op.cdiag, ld, Cfg::TX, Cfg::TY, 1, 0);
+        k_fine3d_tma_first<T, SECOND, KB, NS><<<g, 256, smem, stream>>>(op, mb, md, mc, b, out, out2, ld, nrhs, zchunk, groups);
+    }
+    bool can_fuse_first(const FineOp<T>& op, const C* b, int64_t ld) const {
+        return op.cdiag != nullptr && op.dinv != nullptr && tma_ok(ld) && ((uintptr_t)b % 16 == 0) && fuse_first;
+    }
+    // second == 0: out = x1, out2 = b - A x1;  second == 1: out = x2
+    void fine_first(int second, const FineOp<T>& op, const C* b, C* out, C* out2, int64_t ld, int nrhs) {
+        const double N = (double)pb.N();
+        const double bytes = (second == 0 ? 3.0 : 2.0) * S * N * nrhs + 2.0 * S * N;
+        launch(second == 0 ? T_FINE_FIRST_RESID : T_FINE_FIRST_JACOBI, bytes, [&] {
+            if (second == 0) {
+                if (nrhs >= 2) tma3d_first_launch<0, 2>(op, b, out, out2, ld, nrhs);
+                else tma3d_first_launch<0, 1>(op, b, out, out2, ld, nrhs);
+            } else {
+                if (nrhs >= 2) tma3d_first_launch<1, 2>(op, b, out, out2, ld, nrhs);
+                else tma3d_first_launch<1, 1>(op, b, out, out2, ld, nrhs);
+            }
+        });
     }
     template <int MODE>
     void tma3d_mode(const FineOp<T>& op, const C* x, const C* b, C* out, int64_t ld, int nrhs) {
@@ -1048,8 +1091,25 @@ class Solver : public SolverBase {
         Level& Cc = levels[l + 1];
         C* xx = x;
         C* tt = F.pt;
-        smooth(l, opt.relax_pre[l], b, xx, tt, x_is_zero, false, nrhs);
-        level_apply(l, MODE_RESID, xx, b, tt, nrhs);
+        const int npre = opt.relax_pre[l];
+        if (l == 0 && x_is_zero && opt.relax_type == HH_RELAX_JAC && npre >= 1 && can_fuse_first(mg_fine, b, F.N)) {
+            if (npre == 1) {
+                fine_first(0, mg_fine, b, xx, tt, F.N, nrhs);  // x1 and r = b - A x1 in one pass
+            } else {
+                // first two sweeps in one pass, written so that the remaining npre-2 ping-pong sweeps end in xx
+                C* cur = ((npre - 2) % 2 == 0) ? xx : tt;
+                C* oth = (cur == xx) ? tt : xx;
+                fine_first(1, mg_fine, b, cur, nullptr, F.N, nrhs);
+                for (int sw = 2; sw < npre; ++sw) {
+                    level_apply(l, MODE_JACOBI, cur, b, oth, nrhs);
+                    std::swap(cur, oth);
+                }
+                level_apply(l, MODE_RESID, xx, b, tt, nrhs);
+            }
+        } else {
+            smooth(l, npre, b, xx, tt, x_is_zero, false, nrhs);
+            level_apply(l, MODE_RESID, xx, b, tt, nrhs);
+        }
         restrict_to(F, Cc, tt, Cc.pb, nrhs);
         if (l + 1 == Lmax) {
             coarsest_solve(l + 1, Cc.pb, Cc.px, nrhs);
@@ -1295,6 +1355,7 @@ class Solver : public SolverBase {
    private:
     enum { FK_TMA = 0, FK_ZMARCH = 1, FK_SIMPLE = 2 };
     int fine_kernel = FK_TMA;
+    bool fuse_first = true;
     DevBuf<C> mg_cdiag, mg_dinv, h_cdiag[2];
     FineOp<T> h_op[2];
     bool h_op_valid[2] = {false, false};
