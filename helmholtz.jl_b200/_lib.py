@@ -93,6 +93,8 @@ SIGNATURES = {
     "hh_profile_num_tags": (C.c_int, []),
     "hh_profile_tag_name": (C.c_char_p, [C.c_int]),
     "hh_profile_get": (C.c_int, [_p, C.c_int, _i64p, _dp, _dp]),
+    "hh_profile_num_entries": (C.c_int, [_p]),
+    "hh_profile_entry": (C.c_int, [_p, C.c_int, _ip, _i64p, _dp, _dp]),
 }
 
 _lib = None

@@ -125,6 +125,19 @@ def _current_device():
     return 0
 
 
+def _as_block(x, N, dtype):
+    """View x as an N x k column-major block of `dtype` without copying when it already is one
+    (numpy's default reshape of a Fortran-ordered array would silently copy)."""
+    a = np.asarray(x)
+    if a.ndim == 1:
+        a = a.reshape(N, 1) if a.flags.c_contiguous else np.ascontiguousarray(a).reshape(N, 1)
+    elif a.ndim != 2 or a.shape[0] != N:
+        a = a.reshape((N, -1), order="F")
+    if a.dtype != dtype or not a.flags.f_contiguous:
+        a = np.asfortranarray(a, dtype=dtype)
+    return a
+
+
 def _is_torch_cuda(x):
     try:
         import torch
@@ -187,9 +200,8 @@ class HelmholtzOperator:
             L.check(hd.lib.hh_apply_device(hd.h, xx.data_ptr(), y.data_ptr(), xx.shape[0], int(self.shift != 0.0),
                                            self.shift, int(self.adjoint)), hd.h)
             return y.reshape(x.shape)
-        x = np.asarray(x)
-        vec = x.ndim == 1
-        X = np.asfortranarray(x.reshape(hd.N, -1), dtype=hd.dtype)
+        vec = np.ndim(x) == 1
+        X = _as_block(x, hd.N, hd.dtype)
         Y = np.empty_like(X, order="F")
         L.check(hd.lib.hh_apply(hd.h, X.ctypes.data, Y.ctypes.data, X.shape[1], int(self.shift != 0.0), self.shift,
                                 int(self.adjoint)), hd.h)
@@ -463,7 +475,7 @@ def solveLinearSystem_(ShiftedHT, B, X, param, doTranspose=0):
             X.zero_()
             return X, param
     else:
-        if np.linalg.norm(B) == 0.0:
+        if not np.any(B):  # norm(B) == 0.0
             X[...] = 0
             return X, param
     t0 = time.perf_counter()
@@ -489,7 +501,7 @@ def solveLinearSystem_(ShiftedHT, B, X, param, doTranspose=0):
         rc = L.check(hd.lib.hh_solve_device(hd.h, Bt.data_ptr(), Xt.data_ptr(), nrhs, C.byref(so),
                                             _ptr(iters, C.c_int32), _ptr(relres, C.c_double)), hd.h)
     else:
-        Bm = np.asfortranarray(np.asarray(B).reshape(hd.N, -1), dtype=hd.dtype)
+        Bm = _as_block(B, hd.N, hd.dtype)
         nrhs = Bm.shape[1]
         # write straight into the caller's X when it already is an N x nrhs column-major block of the right type
         direct = isinstance(X, np.ndarray) and X.dtype == hd.dtype and X.size == Bm.size and X.flags.f_contiguous

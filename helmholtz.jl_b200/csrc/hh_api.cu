@@ -574,4 +574,32 @@ int hh_profile_get(hh_handle_t h, int tag, int64_t* launches, double* millisecon
     });
 }
 
+// entries = launches with identical work (same kernel class and algorithmic bytes per launch)
+int hh_profile_num_entries(hh_handle_t h) {
+    if (!h) return 0;
+    try {
+        SolverBase* s = h->subs[0].get();
+        cudaSetDevice(s->device);
+        s->prof.flush(s->stream);
+        return (int)s->prof.entries.size();
+    } catch (...) {
+        return 0;
+    }
+}
+
+int hh_profile_entry(hh_handle_t h, int index, int* tag, int64_t* launches, double* milliseconds,
+                     double* algorithmic_bytes_per_launch) {
+    if (!h) return HH_ERR_ARG;
+    return guarded(h, [&]() -> int {
+        SolverBase* s = h->subs[0].get();
+        HH_REQUIRE(index >= 0 && index < (int)s->prof.entries.size(), HH_ERR_ARG, "hh_profile_entry: bad index");
+        const auto& e = s->prof.entries[index];
+        if (tag) *tag = e.tag;
+        if (launches) *launches = e.count;
+        if (milliseconds) *milliseconds = e.ms;
+        if (algorithmic_bytes_per_launch) *algorithmic_bytes_per_launch = e.bytes / (double)e.count;
+        return HH_OK;
+    });
+}
+
 }  // extern "C"

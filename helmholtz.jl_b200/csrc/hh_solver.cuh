@@ -72,7 +72,16 @@ struct Profiler {
         int tag;
         cudaEvent_t a, b;
         double bytes;
+        int64_t sub;
     };
+    // launches with identical work: (kernel class, algorithmic bytes per launch)
+    struct Entry {
+        int tag;
+        int64_t sub;
+        int64_t count;
+        double ms, bytes;
+    };
+    std::vector<Entry> entries;
     bool on = false;
     std::vector<Rec> recs;
     std::vector<cudaEvent_t> pool;
@@ -98,6 +107,16 @@ struct Profiler {
             count[r.tag] += 1;
             ms[r.tag] += t;
             bytes[r.tag] += r.bytes;
+            bool found = false;
+            for (auto& e : entries)
+                if (e.tag == r.tag && e.sub == r.sub) {
+                    e.count += 1;
+                    e.ms += t;
+                    e.bytes += r.bytes;
+                    found = true;
+                    break;
+                }
+            if (!found) entries.push_back({r.tag, r.sub, 1, (double)t, r.bytes});
             pool.push_back(r.a);
             pool.push_back(r.b);
         }
@@ -105,6 +124,7 @@ struct Profiler {
     }
     void reset() {
         recs.clear();
+        entries.clear();
         for (int i = 0; i < T_NTAGS; ++i) count[i] = 0, ms[i] = 0, bytes[i] = 0;
     }
     ~Profiler() {
@@ -307,13 +327,14 @@ class Solver : public SolverBase {
     // ------------------------------------------------------------------ launch plumbing
     template <class F>
     void launch(int tag, double bytes, F&& f) {
+        const int64_t sub = (int64_t)bytes;
         ++launches;
         if (prof.on) {
             cudaEvent_t a = prof.get(), b = prof.get();
             HH_CUDA(cudaEventRecord(a, stream));
             f();
             HH_CUDA(cudaEventRecord(b, stream));
-            prof.recs.push_back({tag, a, b, bytes});
+            prof.recs.push_back({tag, a, b, bytes, sub});
             if (prof.recs.size() >= 8192) prof.flush(stream);
         } else {
             f();

@@ -180,6 +180,10 @@ int hh_profile_num_tags(void);
 const char* hh_profile_tag_name(int tag);
 /* launches, summed device milliseconds and summed algorithmic bytes of kernel class `tag` */
 int hh_profile_get(hh_handle_t h, int tag, int64_t* launches, double* milliseconds, double* algorithmic_bytes);
+/* finer view: one entry per (kernel class, algorithmic bytes per launch), i.e. launches doing identical work */
+int hh_profile_num_entries(hh_handle_t h);
+int hh_profile_entry(hh_handle_t h, int index, int* tag, int64_t* launches, double* milliseconds,
+                     double* algorithmic_bytes_per_launch);
 
 #ifdef __cplusplus
 }
