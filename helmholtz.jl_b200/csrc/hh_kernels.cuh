@@ -507,6 +507,203 @@ __global__ void __launch_bounds__(256) k_fine3d_tma(FineOp<T> op, const __grid_c
 }
 
 // ---------------------------------------------------------------------------------------------
+// Fused coarse-grid correction + first post-smoothing sweep on the fine level (3-D, TMA form):
+//   x' = x + P xc ;  out = x' + dinv .* (b - A x')
+// The tri-linear interpolation is applied to the staged x tile (with halo) in shared memory as each
+// plane arrives -- the coarse tiles of the two coarse planes that plane touches ride in the same stage
+// -- so x' is never written to and re-read from HBM.  Saves the 2S + S/8 pass of k_prolong_add.
+// ---------------------------------------------------------------------------------------------
+template <typename T, int KB>
+struct FineProCfg {
+    static constexpr int TX = 32, TY = 8, PX = TX + 2;
+    static constexpr int XT = (TY + 2) * PX;
+    static constexpr int BT = TY * TX;
+    static constexpr int CTX = TX / 2 + 2, CTY = TY / 2 + 2, CT = CTX * CTY;  // coarse tile (with halo)
+    static constexpr int ES = (int)sizeof(cx<T>);
+    static constexpr int al(int b) { return (b + 127) / 128 * 128; }
+    static constexpr int OFF_X = 0;
+    static constexpr int OFF_B = al(KB * XT * ES);
+    static constexpr int OFF_C = OFF_B + al(KB * BT * ES);
+    static constexpr int OFF_D = OFF_C + al(BT * ES);
+    static constexpr int OFF_XC = OFF_D + al(BT * ES);            // two coarse planes, KB right-hand sides each
+    static constexpr int XC_PLANE = al(KB * CT * ES);
+    static constexpr int STAGE_BYTES = OFF_XC + 2 * XC_PLANE;
+    static constexpr uint32_t TX_BYTES = KB * XT * ES + KB * BT * ES + 2 * BT * ES + 2 * KB * CT * ES;
+};
+
+// (P xc)(i,j,k) from the global coarse array (used once per column for the plane below the chunk)
+template <typename T>
+__device__ __forceinline__ cx<T> prolong_point(const cx<T>* __restrict__ xc, int i, int j, int k, int nc0, int nc1) {
+    const int oi = i & 1, oj = j & 1, ok = k & 1;
+    const cx<T>* c = xc + (i >> 1) + (int64_t)nc0 * ((j >> 1) + (int64_t)nc1 * (k >> 1));
+    cx<T> acc = mk<T>(T(0), T(0));
+    for (int a2 = 0; a2 <= ok; ++a2)
+        for (int a1 = 0; a1 <= oj; ++a1)
+            for (int a0 = 0; a0 <= oi; ++a0) acc = acc + c[a0 + (int64_t)nc0 * (a1 + (int64_t)nc1 * a2)];
+    return (T(1) / T(1 << (oi + oj + ok))) * acc;
+}
+
+template <typename T, int KB, int NS>
+__global__ void __launch_bounds__(256) k_fine3d_tma_pro(FineOp<T> op, const __grid_constant__ TmaDesc tm_x,
+                                                        const __grid_constant__ TmaDesc tm_b,
+                                                        const __grid_constant__ TmaDesc tm_c,
+                                                        const __grid_constant__ TmaDesc tm_d,
+                                                        const __grid_constant__ TmaDesc tm_xc,
+                                                        const cx<T>* __restrict__ x, const cx<T>* __restrict__ xcg,
+                                                        cx<T>* __restrict__ out, int64_t ld, int64_t ldc, int nc0,
+                                                        int nc1, int nrhs, int zchunk, int groups) {
+    typedef FineProCfg<T, KB> Cfg;
+    constexpr int TX = Cfg::TX, TY = Cfg::TY, PX = Cfg::PX;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + (size_t)NS * Cfg::STAGE_BYTES);
+    const int n0 = op.n[0], n1 = op.n[1], n2 = op.n[2];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int i0 = (blockIdx.x / groups) * TX, j0 = blockIdx.y * TY;
+    const int i = i0 + tx, j = j0 + ty;
+    const int r0 = (blockIdx.x % groups) * KB;
+    const int z0 = blockIdx.z * zchunk;
+    const int z1 = min(n2, z0 + zchunk);
+    const int zl = min(z1, n2 - 1);
+    const int64_t sy = n0, sz = (int64_t)n0 * n1;
+    const bool active = (i < n0) && (j < n1);
+    const int Is = (i0 >> 1) - 1, Js = (j0 >> 1) - 1;  // origin of the coarse tile
+    auto issue = [&](int s, int z) {
+        unsigned char* st = smem_raw + (size_t)s * Cfg::STAGE_BYTES;
+        mbar_expect_tx(&bars[s], Cfg::TX_BYTES);
+        tma_load_4d(st + Cfg::OFF_X, &tm_x, 2 * (i0 - 1), j0 - 1, z, r0, &bars[s]);
+        tma_load_4d(st + Cfg::OFF_B, &tm_b, 2 * i0, j0, z, r0, &bars[s]);
+        tma_load_3d(st + Cfg::OFF_C, &tm_c, 2 * i0, j0, z, &bars[s]);
+        tma_load_3d(st + Cfg::OFF_D, &tm_d, 2 * i0, j0, z, &bars[s]);
+        tma_load_4d(st + Cfg::OFF_XC, &tm_xc, 2 * Is, Js, z >> 1, r0, &bars[s]);
+        tma_load_4d(st + Cfg::OFF_XC + Cfg::XC_PLANE, &tm_xc, 2 * Is, Js, (z >> 1) + 1, r0, &bars[s]);
+    };
+    // x tile of plane z (stage st) += P xc for every cell of the halo tile that lies inside the grid.  The
+    // tile geometry does not depend on z, so each thread's cells (offset in the x tile, offset in the coarse
+    // tile, parities) are computed once.
+    constexpr int NSLOT = (KB * Cfg::XT + 255) / 256;
+    int eoff[NSLOT], coff[NSLOT], par[NSLOT];  // par: bit0 = odd i, bit1 = odd j, bit2 = valid
+#pragma unroll
+    for (int t = 0; t < NSLOT; ++t) {
+        const int e = threadIdx.x + 256 * t;
+        eoff[t] = e;
+        coff[t] = 0;
+        par[t] = 0;
+        if (e < KB * Cfg::XT) {
+            const int q = e / Cfg::XT, rem = e - q * Cfg::XT;
+            const int row = rem / PX, col = rem - row * PX;
+            const int fi = i0 - 1 + col, fj = j0 - 1 + row;
+            if ((unsigned)fi < (unsigned)n0 && (unsigned)fj < (unsigned)n1) {
+                coff[t] = q * Cfg::CT + ((fj >> 1) - Js) * Cfg::CTX + ((fi >> 1) - Is);
+                par[t] = 4 | (fi & 1) | ((fj & 1) << 1);
+            }
+        }
+    }
+    auto correct = [&](unsigned char* st, int z) {
+        cx<T>* xs = reinterpret_cast<cx<T>*>(st + Cfg::OFF_X);
+        const cx<T>* c0 = reinterpret_cast<const cx<T>*>(st + Cfg::OFF_XC);
+        const int ok = z & 1;
+#pragma unroll
+        for (int t = 0; t < NSLOT; ++t) {
+            if (!(par[t] & 4)) continue;
+            const int oi = par[t] & 1, oj = (par[t] >> 1) & 1;
+            const cx<T>* p0 = c0 + coff[t];
+            cx<T> acc = p0[0];
+            if (oi) acc = acc + p0[1];
+            if (oj) {
+                acc = acc + p0[Cfg::CTX];
+                if (oi) acc = acc + p0[Cfg::CTX + 1];
+            }
+            if (ok) {
+                const cx<T>* p1 = p0 + Cfg::XC_PLANE / Cfg::ES;
+                acc = acc + p1[0];
+                if (oi) acc = acc + p1[1];
+                if (oj) {
+                    acc = acc + p1[Cfg::CTX];
+                    if (oi) acc = acc + p1[Cfg::CTX + 1];
+                }
+            }
+            cx<T> v = xs[eoff[t]];
+            rfma(v, T(1) / T(1 << (oi + oj + ok)), acc);
+            xs[eoff[t]] = v;
+        }
+    };
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < NS; ++s) mbar_init(&bars[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        for (int s = 0; s < NS && z0 + s <= zl; ++s) issue(s, z0 + s);
+    }
+    __syncthreads();
+    const int ic = active ? i : 0, jc = active ? j : 0;
+    const T wxm = fine_w(op, 0, 0, ic, n0), wxp = fine_w(op, 0, 1, ic, n0);
+    const T wym = fine_w(op, 1, 0, jc, n1), wyp = fine_w(op, 1, 1, jc, n1);
+    const int64_t pxy = ic + sy * jc;
+    const int cidx = (ty + 1) * PX + (tx + 1);
+    const int bidx = ty * TX + tx;
+    cx<T> xm[KB], xc[KB], xp[KB];
+    mbar_wait(&bars[0], 0);
+    correct(smem_raw, z0);
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < KB; ++q) {
+        xc[q] = reinterpret_cast<const cx<T>*>(smem_raw + Cfg::OFF_X)[q * Cfg::XT + cidx];
+        xm[q] = mk<T>(T(0), T(0));
+        if (z0 > 0 && active) {
+            const int r = min(r0 + q, nrhs - 1);
+            xm[q] = x[(int64_t)r * ld + pxy + (int64_t)(z0 - 1) * sz] +
+                    prolong_point<T>(xcg + (int64_t)r * ldc, ic, jc, z0 - 1, nc0, nc1);
+        }
+    }
+#pragma unroll 1
+    for (int z = z0; z < z1; ++z) {
+        const int s = (z - z0) % NS;
+        const unsigned char* st = smem_raw + (size_t)s * Cfg::STAGE_BYTES;
+        const bool zlast = (z == n2 - 1);
+        if (!zlast) {
+            const int s1 = (z + 1 - z0) % NS;
+            mbar_wait(&bars[s1], (uint32_t)(((z + 1 - z0) / NS) & 1));
+            correct(smem_raw + (size_t)s1 * Cfg::STAGE_BYTES, z + 1);
+            __syncthreads();
+            const cx<T>* x1 = reinterpret_cast<const cx<T>*>(smem_raw + (size_t)s1 * Cfg::STAGE_BYTES + Cfg::OFF_X);
+#pragma unroll
+            for (int q = 0; q < KB; ++q) xp[q] = x1[q * Cfg::XT + cidx];
+        } else {
+#pragma unroll
+            for (int q = 0; q < KB; ++q) xp[q] = mk<T>(T(0), T(0));
+        }
+        if (active) {
+            const cx<T>* sx = reinterpret_cast<const cx<T>*>(st + Cfg::OFF_X);
+            const cx<T>* sb = reinterpret_cast<const cx<T>*>(st + Cfg::OFF_B);
+            const cx<T> c = reinterpret_cast<const cx<T>*>(st + Cfg::OFF_C)[bidx];
+            const cx<T> dinv = reinterpret_cast<const cx<T>*>(st + Cfg::OFF_D)[bidx];
+            const T wzm = fine_w(op, 2, 0, z, n2), wzp = fine_w(op, 2, 1, z, n2);
+            const int64_t p = pxy + (int64_t)z * sz;
+#pragma unroll
+            for (int q = 0; q < KB; ++q) {
+                const cx<T>* xt = sx + q * Cfg::XT + cidx;
+                cx<T> a = c * xc[q];
+                rfma(a, -wxm, xt[-1]);
+                rfma(a, -wxp, xt[1]);
+                rfma(a, -wym, xt[-PX]);
+                rfma(a, -wyp, xt[PX]);
+                rfma(a, -wzm, xm[q]);
+                rfma(a, -wzp, xp[q]);
+                if (r0 + q < nrhs) {
+                    const int64_t o = (int64_t)(r0 + q) * ld + p;
+                    out[o] = xc[q] + dinv * (sb[q * Cfg::BT + bidx] - a);
+                }
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < KB; ++q) {
+            xm[q] = xc[q];
+            xc[q] = xp[q];
+        }
+        __syncthreads();
+        if (threadIdx.x == 0 && z + NS <= zl) issue(s, z + NS);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Fused start of a cycle on the fine level (3-D, TMA form): the first Jacobi sweep from a zero guess,
 // x1 = dinv .* b, is never written and re-read -- the kernel stages b and dinv WITH halo, forms x1 on
 // the fly at the centre and the six neighbours, and directly produces

@@ -46,6 +46,7 @@ enum Tag {
     T_FINE_JACOBI0,
     T_FINE_FIRST_RESID,
     T_FINE_FIRST_JACOBI,
+    T_FINE_PROLONG_JACOBI,
     T_COARSE_APPLY,
     T_COARSE_RESID,
     T_COARSE_JACOBI,
@@ -62,7 +63,7 @@ enum Tag {
     T_NTAGS
 };
 static const char* const kTagNames[T_NTAGS] = {
-    "fine_apply",   "fine_resid",   "fine_jacobi",    "fine_jacobi0", "fine_first_resid", "fine_first_jacobi",
+    "fine_apply",   "fine_resid",   "fine_jacobi",    "fine_jacobi0", "fine_first_resid", "fine_first_jacobi", "fine_prolong_jacobi",
     "coarse_apply", "coarse_resid",
     "coarse_jacobi", "coarse_jacobi0", "restrict",    "prolong",      "coarsest_dense", "krylov_dot",
     "krylov_axpy",  "krylov_scale", "copy",           "scalar",       "setup"};
@@ -527,6 +528,40 @@ class Solver : public SolverBase {
                 if (nrhs >= 2) tma3d_first_launch<1, 2>(op, b, out, out2, ld, nrhs);
                 else tma3d_first_launch<1, 1>(op, b, out, out2, ld, nrhs);
             }
+        });
+    }
+    // fused coarse-grid correction + first post-smoothing sweep; see k_fine3d_tma_pro
+    template <int KB>
+    void tma3d_pro_launch(const FineOp<T>& op, const C* x, const C* b, const Level& Cc, const C* xc, C* out, int64_t ld, int nrhs) {
+        typedef FineProCfg<T, KB> Cfg;
+        constexpr int NS = 3;
+        constexpr size_t smem = (size_t)NS * Cfg::STAGE_BYTES + NS * sizeof(uint64_t);
+        static bool attr_set = false;
+        if (!attr_set) {
+            HH_CUDA(cudaFuncSetAttribute(k_fine3d_tma_pro<T, KB, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            attr_set = true;
+        }
+        const int groups = (nrhs + KB - 1) / KB;
+        const int tx = (pb.n[0] + Cfg::TX - 1) / Cfg::TX, ty = (pb.n[1] + Cfg::TY - 1) / Cfg::TY;
+        int zchunk, nzc;
+        zchunks(pb.n[2], tx * ty, groups, 64, zchunk, nzc);
+        dim3 g(tx * groups, ty, nzc);
+        TmaDesc mx = make_tmap_n(x, ld, Cfg::TX + 2, Cfg::TY + 2, KB, nrhs);
+        TmaDesc mb = make_tmap_n(b, ld, Cfg::TX, Cfg::TY, KB, nrhs);
+        TmaDesc mc = make_tmap_n(op.cdiag, ld, Cfg::TX, Cfg::TY, 1, 0);
+        TmaDesc md = make_tmap_n(op.dinv, ld, Cfg::TX, Cfg::TY, 1, 0);
+        TmaDesc mxc = make_tmap_g(xc, Cc.n, Cc.N, Cfg::CTX, Cfg::CTY, KB, nrhs);
+        k_fine3d_tma_pro<T, KB, NS><<<g, 256, smem, stream>>>(op, mx, mb, mc, md, mxc, x, xc, out, ld, Cc.N, Cc.n[0], Cc.n[1], nrhs, zchunk, groups);
+    }
+    bool can_fuse_prolong(const FineOp<T>& op, const C* x, const C* b, const Level& Cc, const C* xc, int64_t ld) const {
+        return fuse_first && op.cdiag != nullptr && op.dinv != nullptr && tma_ok(ld) && tma_ok_level(Cc) &&
+               ((uintptr_t)x % 16 == 0) && ((uintptr_t)b % 16 == 0) && ((uintptr_t)xc % 16 == 0);
+    }
+    void fine_prolong_jacobi(const FineOp<T>& op, const C* x, const C* b, const Level& Cc, const C* xc, C* out, int64_t ld, int nrhs) {
+        const double N = (double)pb.N();
+        launch(T_FINE_PROLONG_JACOBI, (3.0 * N + (double)Cc.N) * S * nrhs + 2.0 * S * N, [&] {
+            if (nrhs >= 2) tma3d_pro_launch<2>(op, x, b, Cc, xc, out, ld, nrhs);
+            else tma3d_pro_launch<1>(op, x, b, Cc, xc, out, ld, nrhs);
         });
     }
     template <int MODE>
@@ -1142,8 +1177,21 @@ class Solver : public SolverBase {
         } else {
             small_gmres(l + 1, 2, 1, Cc.pb, Cc.px, true, nrhs);
         }
-        prolong_add(F, Cc, xx, Cc.px, nrhs);
-        smooth(l, opt.relax_post[l], b, xx, tt, false, false, nrhs);
+        const int npost = opt.relax_post[l];
+        if (l == 0 && opt.relax_type == HH_RELAX_JAC && npost >= 1 && can_fuse_prolong(mg_fine, xx, b, Cc, Cc.px, F.N)) {
+            // x' = x + P xc and the first post-smoothing sweep in one pass (x' never touches HBM)
+            C* cur = tt;
+            C* oth = xx;
+            fine_prolong_jacobi(mg_fine, xx, b, Cc, Cc.px, tt, F.N, nrhs);
+            for (int sw = 1; sw < npost; ++sw) {
+                level_apply(l, MODE_JACOBI, cur, b, oth, nrhs);
+                std::swap(cur, oth);
+            }
+            if (cur != xx) copy_vec(cur, xx, F.N, nrhs);
+        } else {
+            prolong_add(F, Cc, xx, Cc.px, nrhs);
+            smooth(l, npost, b, xx, tt, false, false, nrhs);
+        }
     }
 
     void precondition(const C* b, C* z, int nrhs) {
