@@ -188,3 +188,81 @@ def test_transposed_solve(gpu_pkg, ho):
     # and back: the hierarchy is rebuilt for doTranspose = 0
     x, Ainv = pkg.solveLinearSystem(None, c["q"], Ainv, 0)
     assert np.linalg.norm(c["H"] @ x - c["q"]) / np.linalg.norm(c["q"]) < 1e-6
+
+
+def test_config3_layered_attenuation_129cubed(gpu_pkg, ho):
+    """BASELINE config 3: 3-D 129^3 layered model with depth-dependent attenuation, 16 sources on a 4x4 top-plane
+    grid, 3 levels, single GPU.  Size-independent property for all 16 (true residual of the un-shifted
+    operator <= 1e-6), and the first two solutions against the CPU port of the oracle (same algorithm:
+    identical iteration counts, solutions within 1e-6)."""
+    import os
+    import sys
+
+    from conftest import ROOT
+
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle_c
+
+    pkg = gpu_pkg
+    n = 129
+    cfg = pkg.workloads.config3(n=n)
+    mesh = pkg.getRegularMesh(cfg["domain"], cfg["n_cells"])
+    m = cfg["m"]
+    w = pkg.getMaximalFrequency(m, mesh)
+    gamma0 = cfg["gamma0_frac"] * w * cfg["att_profile"]
+    H, gamma = pkg.GetHelmholtzOperator(mesh, m, w, gamma0, True, cfg["pad"], w, True)
+    nodes = mesh.n + 1
+    srcs = pkg.workloads.point_sources_top_grid(nodes, 4, 4)
+    assert len(srcs) == 16
+    MG = pkg.getMGparam(pkg.ComplexF64, pkg.Int64, 3, 1, 30, 1e-6, "Jac", 0.8, 1, 2, "W", "GMRES", coarseIters=10)
+    hp = pkg.HelmholtzParam(mesh, gamma, m.ravel(order="F"), w, True, True)
+    A = pkg.getShiftedLaplacianMultigridSolver(hp, MG, 0.2, "GMRES", 5)
+    amp = 1.0 / mesh.h[0] ** 2
+    X, A = pkg.solvePointSources(A, srcs, np.full(16, amp))
+    N = n**3
+    B = np.zeros((N, 16), dtype=np.complex128, order="F")
+    for c, s in enumerate(srcs):
+        B[pkg.loc2cs(nodes, s) - 1, c] = amp
+    R = H @ X - B
+    res = np.linalg.norm(R, axis=0) / np.linalg.norm(B, axis=0)
+    assert res.max() < 1e-6
+    oc = oracle_c.OracleC(nodes, mesh.h, m, gamma, w, True, True, 0.2, 3, 0.8, 1, 2, "W", 10)
+    Xo, it, rr, _ = oc.solve(B[:, :2], inner=5, max_cycles=30, tol=1e-6)
+    assert list(it) == list(A.iterations[:2])
+    assert rel_err(X[:, :2], Xo) < 1e-6
+
+
+def test_update_model_frequency_sweep(gpu_pkg, ho):
+    """hh_update_model re-uses the handle for a new (model, omega): the hierarchy is invalidated and the next
+    solve is the solve of the new problem (frequency sweeps on one handle)."""
+    import ctypes as C
+
+    pkg = gpu_pkg
+    n = 33
+    cfg = pkg.workloads.config4(n=n, sigma=3.0, seed=5, pad=5)
+    mesh = pkg.getRegularMesh(cfg["domain"], cfg["n_cells"])
+    omesh = ho.getRegularMesh(cfg["domain"], cfg["n_cells"])
+    m = cfg["m"]
+    w1 = pkg.getMaximalFrequency(m, mesh)
+    q, _ = ho.getAcousticPointSource(omesh)
+    MG = pkg.getMGparam(pkg.ComplexF64, pkg.Int64, 2, 1, 40, 1e-8, "Jac", 0.8, 2, 2, "V", "NoMUMPS")
+    g1 = 0.01 * w1 * np.ones(m.shape) + pkg.getABL(mesh.n + 1, True, cfg["pad"], w1)
+    hp = pkg.HelmholtzParam(mesh, g1, m.ravel(order="F"), w1, True, True)
+    A = pkg.getShiftedLaplacianMultigridSolver(hp, MG, 0.2, "GMRES", 5)
+    x1, A = pkg.solveLinearSystem(None, q, A)
+    H1 = ho.GetHelmholtzOperator(omesh, m, w1, g1, True, True)
+    assert np.linalg.norm(H1 @ x1 - q) / np.linalg.norm(q) < 1e-7
+    # new frequency and attenuation on the same handle
+    w2 = 0.7 * w1
+    g2 = 0.02 * w2 * np.ones(m.shape) + pkg.getABL(mesh.n + 1, True, cfg["pad"], w2)
+    hd = MG._hd
+    mm = np.ascontiguousarray(m.ravel(order="F"))
+    gg = np.ascontiguousarray(g2.ravel(order="F"))
+    pkg._lib.check(hd.lib.hh_update_model(hd.h, mm.ctypes.data_as(C.POINTER(C.c_double)),
+                                          gg.ctypes.data_as(C.POINTER(C.c_double)), w2, 0.0), hd.h)
+    assert not pkg.hierarchyExists(MG)
+    A.helmParam = pkg.HelmholtzParam(mesh, g2, mm, w2, True, True)
+    x2, A = pkg.solveLinearSystem(None, q, A)
+    H2 = ho.GetHelmholtzOperator(omesh, m, w2, g2, True, True)
+    assert np.linalg.norm(H2 @ x2 - q) / np.linalg.norm(q) < 1e-7
+    assert np.linalg.norm(H1 @ x2 - q) / np.linalg.norm(q) > 1e-3  # really the new problem
