@@ -351,7 +351,7 @@ def run_b200(a):
             barrier()
             t0 = time.perf_counter()
             pkg.solveLinearSystem_(None, Bh_np, Xh, Ainv)
-            chk = float(abs(Xh[:, 0]).max())  # device -> host result is consumed
+            chk = float(abs(Xh[all_idx[step_sources(1000 + k)[0]], 0]))  # the result is in host memory: consume it
             torch.cuda.synchronize()
             dt = time.perf_counter() - t0
             if k > 0:

@@ -577,55 +577,81 @@ __global__ void __launch_bounds__(256) k_fine3d_tma_pro(FineOp<T> op, const __gr
         tma_load_4d(st + Cfg::OFF_XC, &tm_xc, 2 * Is, Js, z >> 1, r0, &bars[s]);
         tma_load_4d(st + Cfg::OFF_XC + Cfg::XC_PLANE, &tm_xc, 2 * Is, Js, (z >> 1) + 1, r0, &bars[s]);
     };
-    // x tile of plane z (stage st) += P xc for every cell of the halo tile that lies inside the grid.  The
-    // tile geometry does not depend on z, so each thread's cells (offset in the x tile, offset in the coarse
-    // tile, parities) are computed once.
-    constexpr int NSLOT = (KB * Cfg::XT + 255) / 256;
-    int eoff[NSLOT], coff[NSLOT], par[NSLOT];  // par: bit0 = odd i, bit1 = odd j, bit2 = valid
-#pragma unroll
-    for (int t = 0; t < NSLOT; ++t) {
-        const int e = threadIdx.x + 256 * t;
-        eoff[t] = e;
-        coff[t] = 0;
-        par[t] = 0;
-        if (e < KB * Cfg::XT) {
-            const int q = e / Cfg::XT, rem = e - q * Cfg::XT;
-            const int row = rem / PX, col = rem - row * PX;
-            const int fi = i0 - 1 + col, fj = j0 - 1 + row;
-            if ((unsigned)fi < (unsigned)n0 && (unsigned)fj < (unsigned)n1) {
-                coff[t] = q * Cfg::CT + ((fj >> 1) - Js) * Cfg::CTX + ((fi >> 1) - Is);
-                par[t] = 4 | (fi & 1) | ((fj & 1) << 1);
+    // Interpolation geometry does not depend on z: computed once per thread.
+    //  * its own column (centre cell of the tile): corrected when the plane's centre value enters the register
+    //    pipeline, and written back so that the neighbours see x' one iteration later;
+    //  * one cell of the halo ring (84 cells per RHS) for the first 84*KB threads.
+    // Both corrections of plane z+1 happen during iteration z and are ordered before their first use
+    // (iteration z+1) by the __syncthreads that ends every iteration: no extra barrier.
+    auto geom = [&](int fi, int fj, int q, int& coff, int& par) {
+        coff = 0;
+        par = 0;
+        if ((unsigned)fi < (unsigned)n0 && (unsigned)fj < (unsigned)n1) {
+            coff = q * Cfg::CT + ((fj >> 1) - Js) * Cfg::CTX + ((fi >> 1) - Is);
+            par = 4 | (fi & 1) | ((fj & 1) << 1);
+        }
+    };
+    auto interp = [&](const cx<T>* c0, int coff, int par, int ok) -> cx<T> {
+        const int oi = par & 1, oj = (par >> 1) & 1;
+        const cx<T>* p0 = c0 + coff;
+        cx<T> acc = p0[0];
+        if (oi) acc = acc + p0[1];
+        if (oj) {
+            acc = acc + p0[Cfg::CTX];
+            if (oi) acc = acc + p0[Cfg::CTX + 1];
+        }
+        if (ok) {
+            const cx<T>* p1 = p0 + Cfg::XC_PLANE / Cfg::ES;
+            acc = acc + p1[0];
+            if (oi) acc = acc + p1[1];
+            if (oj) {
+                acc = acc + p1[Cfg::CTX];
+                if (oi) acc = acc + p1[Cfg::CTX + 1];
             }
         }
+        return (T(1) / T(1 << (oi + oj + ok))) * acc;
+    };
+    const int cidx = (ty + 1) * PX + (tx + 1);
+    const int bidx = ty * TX + tx;
+    int ccoff[KB], cpar;  // centre
+    {
+        int par0 = 0;
+#pragma unroll
+        for (int q = 0; q < KB; ++q) geom(i, j, q, ccoff[q], par0);
+        cpar = par0;
     }
-    auto correct = [&](unsigned char* st, int z) {
+    int hoff = -1, hcoff = 0, hpar = 0;  // halo-ring cell of this thread (if any)
+    if (threadIdx.x < 84 * KB) {
+        const int q = threadIdx.x / 84, t = threadIdx.x - q * 84;
+        int row, col;
+        if (t < PX) {
+            row = 0;
+            col = t;
+        } else if (t < 2 * PX) {
+            row = TY + 1;
+            col = t - PX;
+        } else if (t < 2 * PX + TY) {
+            row = 1 + (t - 2 * PX);
+            col = 0;
+        } else {
+            row = 1 + (t - 2 * PX - TY);
+            col = TX + 1;
+        }
+        geom(i0 - 1 + col, j0 - 1 + row, q, hcoff, hpar);
+        if (hpar & 4) hoff = q * Cfg::XT + row * PX + col;
+    }
+    auto correct_plane = [&](unsigned char* st, int z, cx<T>* xv) {
         cx<T>* xs = reinterpret_cast<cx<T>*>(st + Cfg::OFF_X);
         const cx<T>* c0 = reinterpret_cast<const cx<T>*>(st + Cfg::OFF_XC);
         const int ok = z & 1;
 #pragma unroll
-        for (int t = 0; t < NSLOT; ++t) {
-            if (!(par[t] & 4)) continue;
-            const int oi = par[t] & 1, oj = (par[t] >> 1) & 1;
-            const cx<T>* p0 = c0 + coff[t];
-            cx<T> acc = p0[0];
-            if (oi) acc = acc + p0[1];
-            if (oj) {
-                acc = acc + p0[Cfg::CTX];
-                if (oi) acc = acc + p0[Cfg::CTX + 1];
-            }
-            if (ok) {
-                const cx<T>* p1 = p0 + Cfg::XC_PLANE / Cfg::ES;
-                acc = acc + p1[0];
-                if (oi) acc = acc + p1[1];
-                if (oj) {
-                    acc = acc + p1[Cfg::CTX];
-                    if (oi) acc = acc + p1[Cfg::CTX + 1];
-                }
-            }
-            cx<T> v = xs[eoff[t]];
-            rfma(v, T(1) / T(1 << (oi + oj + ok)), acc);
-            xs[eoff[t]] = v;
+        for (int q = 0; q < KB; ++q) {
+            cx<T> v = xs[q * Cfg::XT + cidx];
+            if (cpar & 4) v = v + interp(c0, ccoff[q], cpar, ok);
+            xs[q * Cfg::XT + cidx] = v;
+            xv[q] = v;
         }
+        if (hoff >= 0) xs[hoff] = xs[hoff] + interp(c0, hcoff, hpar, ok);
     };
     if (threadIdx.x == 0) {
         for (int s = 0; s < NS; ++s) mbar_init(&bars[s], 1);
@@ -637,15 +663,12 @@ __global__ void __launch_bounds__(256) k_fine3d_tma_pro(FineOp<T> op, const __gr
     const T wxm = fine_w(op, 0, 0, ic, n0), wxp = fine_w(op, 0, 1, ic, n0);
     const T wym = fine_w(op, 1, 0, jc, n1), wyp = fine_w(op, 1, 1, jc, n1);
     const int64_t pxy = ic + sy * jc;
-    const int cidx = (ty + 1) * PX + (tx + 1);
-    const int bidx = ty * TX + tx;
     cx<T> xm[KB], xc[KB], xp[KB];
     mbar_wait(&bars[0], 0);
-    correct(smem_raw, z0);
-    __syncthreads();
+    correct_plane(smem_raw, z0, xc);
+    __syncthreads();  // once per chunk: plane z0 is used in the first iteration already
 #pragma unroll
     for (int q = 0; q < KB; ++q) {
-        xc[q] = reinterpret_cast<const cx<T>*>(smem_raw + Cfg::OFF_X)[q * Cfg::XT + cidx];
         xm[q] = mk<T>(T(0), T(0));
         if (z0 > 0 && active) {
             const int r = min(r0 + q, nrhs - 1);
@@ -661,11 +684,7 @@ __global__ void __launch_bounds__(256) k_fine3d_tma_pro(FineOp<T> op, const __gr
         if (!zlast) {
             const int s1 = (z + 1 - z0) % NS;
             mbar_wait(&bars[s1], (uint32_t)(((z + 1 - z0) / NS) & 1));
-            correct(smem_raw + (size_t)s1 * Cfg::STAGE_BYTES, z + 1);
-            __syncthreads();
-            const cx<T>* x1 = reinterpret_cast<const cx<T>*>(smem_raw + (size_t)s1 * Cfg::STAGE_BYTES + Cfg::OFF_X);
-#pragma unroll
-            for (int q = 0; q < KB; ++q) xp[q] = x1[q * Cfg::XT + cidx];
+            correct_plane(smem_raw + (size_t)s1 * Cfg::STAGE_BYTES, z + 1, xp);
         } else {
 #pragma unroll
             for (int q = 0; q < KB; ++q) xp[q] = mk<T>(T(0), T(0));
