@@ -24,6 +24,8 @@ struct FineOp {
     T ih2[3];     // 1/h_d^2
     T BC;         // 2 (second-order Neumann ghost) or 1
     int n[3];     // node counts (n[2] == 1 in 2-D)
+    int sy;       // row pitch (elements) of every array this operator touches: n[0], or n[0]+1 when ComplexF32
+                  // rows are padded to a 16-byte multiple for TMA; the ghost column is never read or written
     int neumann_top;
     int adj;      // 1: conjugate transpose
     // optional precomputed diagonal arrays (k_fine_precompute): centre coefficient incl. the Laplacian
@@ -37,6 +39,8 @@ struct CoarseOp {
     const cx<T>* coef;  // [3^dim][N] stencil coefficients
     const cx<T>* dinv;  // [N] damping / diagonal
     int n[3];
+    int sy;             // row pitch (elements); N = padded node count sy*n[1]*n[2] = stride between coefficients
+    int64_t N;
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -96,7 +100,7 @@ __global__ void __launch_bounds__(256) k_fine_stencil(FineOp<T> op, const cx<T>*
     const int j = blockIdx.y * blockDim.y + threadIdx.y;
     const int k = (DIM == 3) ? blockIdx.z * blockDim.z + threadIdx.z : 0;
     if (i >= n0 || j >= n1 || k >= n2) return;
-    const int64_t sy = n0, sz = (int64_t)n0 * n1;
+    const int64_t sy = op.sy, sz = (int64_t)op.sy * n1;
     const int64_t p = i + sy * j + sz * k;
     const cx<T> c = fine_center<T, DIM>(op, p, i, j, k);
     const T wxm = fine_w(op, 0, 0, i, n0), wxp = fine_w(op, 0, 1, i, n0);
@@ -165,7 +169,7 @@ __global__ void __launch_bounds__(32 * TY, MINB) k_fine3d_zmarch(FineOp<T> op, c
     const int r0 = (blockIdx.x % groups) * KB;
     const int z0 = zc * zchunk;
     const int z1 = min(n2, z0 + zchunk);
-    const int64_t sy = n0, sz = (int64_t)n0 * n1;
+    const int64_t sy = op.sy, sz = (int64_t)op.sy * n1;
     const int64_t pxy = i + sy * j;
     const T wxm = fine_w(op, 0, 0, i, n0), wxp = fine_w(op, 0, 1, i, n0);
     const T wym = fine_w(op, 1, 0, j, n1), wyp = fine_w(op, 1, 1, j, n1);
@@ -248,8 +252,8 @@ __global__ void __launch_bounds__(32 * TY, MINB) k_coarse3d_zmarch(CoarseOp<T> o
     const int r0 = (blockIdx.x % groups) * KB;
     const int z0 = zc * zchunk;
     const int z1 = min(n2, z0 + zchunk);
-    const int64_t sy = n0, sz = (int64_t)n0 * n1;
-    const int64_t N = sz * n2;
+    const int64_t sy = op.sy, sz = (int64_t)op.sy * n1;
+    const int64_t N = op.N;
     const int64_t pxy = i + sy * j;
     const cx<T> zero = mk<T>(T(0), T(0));
     // acc[0]: output plane zi-1, acc[1]: zi, acc[2]: zi+1 while input plane zi is processed
@@ -381,7 +385,10 @@ struct alignas(64) TmaDesc {
 template <typename T, int MODE, int KB>
 struct FineTmaCfg {
     static constexpr int TX = 32, TY = 8;
-    static constexpr int PX = TX + 2;  // row pitch of the halo tile (elements)
+    // The TMA unit needs the innermost box coordinate to be a 16-byte multiple: a one-node x halo is fine for
+    // ComplexF64 (16 B per node); ComplexF32 (8 B) starts the halo tile two nodes to the left instead.
+    static constexpr int HX = sizeof(T) == 4 ? 2 : 1;
+    static constexpr int PX = TX + 2 * HX;  // row pitch of the halo tile (elements)
     static constexpr int XT = (TY + 2) * PX;
     static constexpr int BT = TY * TX;
     static constexpr int ES = (int)sizeof(cx<T>);
@@ -420,12 +427,12 @@ __global__ void __launch_bounds__(256) k_fine3d_tma(FineOp<T> op, const __grid_c
     const int z0 = blockIdx.z * zchunk;
     const int z1 = min(n2, z0 + zchunk);
     const int zl = min(z1, n2 - 1);  // last plane that must be staged (z+1 halo of the chunk)
-    const int64_t sy = n0, sz = (int64_t)n0 * n1;
+    const int64_t sy = op.sy, sz = (int64_t)op.sy * n1;
     const bool active = (i < n0) && (j < n1);
     auto issue = [&](int s, int z) {
         unsigned char* st = smem_raw + (size_t)s * Cfg::STAGE_BYTES;
         mbar_expect_tx(&bars[s], Cfg::TX_BYTES);
-        tma_load_4d(st + Cfg::OFF_X, &tm_x, 2 * (i0 - 1), j0 - 1, z, r0, &bars[s]);
+        tma_load_4d(st + Cfg::OFF_X, &tm_x, 2 * (i0 - Cfg::HX), j0 - 1, z, r0, &bars[s]);
         if (MODE != MODE_APPLY) tma_load_4d(st + Cfg::OFF_B, &tm_b, 2 * i0, j0, z, r0, &bars[s]);
         tma_load_3d(st + Cfg::OFF_C, &tm_c, 2 * i0, j0, z, &bars[s]);
         if (MODE == MODE_JACOBI) tma_load_3d(st + Cfg::OFF_D, &tm_d, 2 * i0, j0, z, &bars[s]);
@@ -441,8 +448,8 @@ __global__ void __launch_bounds__(256) k_fine3d_tma(FineOp<T> op, const __grid_c
     const T wxm = fine_w(op, 0, 0, ic, n0), wxp = fine_w(op, 0, 1, ic, n0);
     const T wym = fine_w(op, 1, 0, jc, n1), wyp = fine_w(op, 1, 1, jc, n1);
     const int64_t pxy = ic + sy * jc;
-    const int cidx = (ty + 1) * PX + (tx + 1);  // centre of this thread inside an x tile
-    const int bidx = ty * TX + tx;              // inside a b / diagonal tile
+    const int cidx = (ty + 1) * PX + (tx + Cfg::HX);  // centre of this thread inside an x tile
+    const int bidx = ty * TX + tx;                    // inside a b / diagonal tile
     cx<T> xm[KB], xc[KB], xp[KB];
     mbar_wait(&bars[0], 0);
 #pragma unroll
@@ -515,10 +522,14 @@ __global__ void __launch_bounds__(256) k_fine3d_tma(FineOp<T> op, const __grid_c
 // ---------------------------------------------------------------------------------------------
 template <typename T, int KB>
 struct FineProCfg {
-    static constexpr int TX = 32, TY = 8, PX = TX + 2;
+    static constexpr int TX = 32, TY = 8;
+    static constexpr int HX = sizeof(T) == 4 ? 2 : 1;  // see FineTmaCfg
+    static constexpr int PX = TX + 2 * HX;
     static constexpr int XT = (TY + 2) * PX;
     static constexpr int BT = TY * TX;
-    static constexpr int CTX = TX / 2 + 2, CTY = TY / 2 + 2, CT = CTX * CTY;  // coarse tile (with halo)
+    // coarse tile with halo: starts CH coarse nodes left of i0/2 (16-byte aligned start, even width for ComplexF32)
+    static constexpr int CH = sizeof(T) == 4 ? 2 : 1;
+    static constexpr int CTX = sizeof(T) == 4 ? TX / 2 + 4 : TX / 2 + 2, CTY = TY / 2 + 2, CT = CTX * CTY;
     static constexpr int ES = (int)sizeof(cx<T>);
     static constexpr int al(int b) { return (b + 127) / 128 * 128; }
     static constexpr int OFF_X = 0;
@@ -533,13 +544,13 @@ struct FineProCfg {
 
 // (P xc)(i,j,k) from the global coarse array (used once per column for the plane below the chunk)
 template <typename T>
-__device__ __forceinline__ cx<T> prolong_point(const cx<T>* __restrict__ xc, int i, int j, int k, int nc0, int nc1) {
+__device__ __forceinline__ cx<T> prolong_point(const cx<T>* __restrict__ xc, int i, int j, int k, int csy, int nc1) {
     const int oi = i & 1, oj = j & 1, ok = k & 1;
-    const cx<T>* c = xc + (i >> 1) + (int64_t)nc0 * ((j >> 1) + (int64_t)nc1 * (k >> 1));
+    const cx<T>* c = xc + (i >> 1) + (int64_t)csy * ((j >> 1) + (int64_t)nc1 * (k >> 1));
     cx<T> acc = mk<T>(T(0), T(0));
     for (int a2 = 0; a2 <= ok; ++a2)
         for (int a1 = 0; a1 <= oj; ++a1)
-            for (int a0 = 0; a0 <= oi; ++a0) acc = acc + c[a0 + (int64_t)nc0 * (a1 + (int64_t)nc1 * a2)];
+            for (int a0 = 0; a0 <= oi; ++a0) acc = acc + c[a0 + (int64_t)csy * (a1 + (int64_t)nc1 * a2)];
     return (T(1) / T(1 << (oi + oj + ok))) * acc;
 }
 
@@ -550,7 +561,7 @@ __global__ void __launch_bounds__(256) k_fine3d_tma_pro(FineOp<T> op, const __gr
                                                         const __grid_constant__ TmaDesc tm_d,
                                                         const __grid_constant__ TmaDesc tm_xc,
                                                         const cx<T>* __restrict__ x, const cx<T>* __restrict__ xcg,
-                                                        cx<T>* __restrict__ out, int64_t ld, int64_t ldc, int nc0,
+                                                        cx<T>* __restrict__ out, int64_t ld, int64_t ldc, int csy,
                                                         int nc1, int nrhs, int zchunk, int groups) {
     typedef FineProCfg<T, KB> Cfg;
     constexpr int TX = Cfg::TX, TY = Cfg::TY, PX = Cfg::PX;
@@ -564,13 +575,13 @@ __global__ void __launch_bounds__(256) k_fine3d_tma_pro(FineOp<T> op, const __gr
     const int z0 = blockIdx.z * zchunk;
     const int z1 = min(n2, z0 + zchunk);
     const int zl = min(z1, n2 - 1);
-    const int64_t sy = n0, sz = (int64_t)n0 * n1;
+    const int64_t sy = op.sy, sz = (int64_t)op.sy * n1;
     const bool active = (i < n0) && (j < n1);
-    const int Is = (i0 >> 1) - 1, Js = (j0 >> 1) - 1;  // origin of the coarse tile
+    const int Is = (i0 >> 1) - Cfg::CH, Js = (j0 >> 1) - 1;  // origin of the coarse tile
     auto issue = [&](int s, int z) {
         unsigned char* st = smem_raw + (size_t)s * Cfg::STAGE_BYTES;
         mbar_expect_tx(&bars[s], Cfg::TX_BYTES);
-        tma_load_4d(st + Cfg::OFF_X, &tm_x, 2 * (i0 - 1), j0 - 1, z, r0, &bars[s]);
+        tma_load_4d(st + Cfg::OFF_X, &tm_x, 2 * (i0 - Cfg::HX), j0 - 1, z, r0, &bars[s]);
         tma_load_4d(st + Cfg::OFF_B, &tm_b, 2 * i0, j0, z, r0, &bars[s]);
         tma_load_3d(st + Cfg::OFF_C, &tm_c, 2 * i0, j0, z, &bars[s]);
         tma_load_3d(st + Cfg::OFF_D, &tm_d, 2 * i0, j0, z, &bars[s]);
@@ -611,7 +622,7 @@ __global__ void __launch_bounds__(256) k_fine3d_tma_pro(FineOp<T> op, const __gr
         }
         return (T(1) / T(1 << (oi + oj + ok))) * acc;
     };
-    const int cidx = (ty + 1) * PX + (tx + 1);
+    const int cidx = (ty + 1) * PX + (tx + Cfg::HX);
     const int bidx = ty * TX + tx;
     int ccoff[KB], cpar;  // centre
     {
@@ -623,22 +634,23 @@ __global__ void __launch_bounds__(256) k_fine3d_tma_pro(FineOp<T> op, const __gr
     int hoff = -1, hcoff = 0, hpar = 0;  // halo-ring cell of this thread (if any)
     if (threadIdx.x < 84 * KB) {
         const int q = threadIdx.x / 84, t = threadIdx.x - q * 84;
-        int row, col;
-        if (t < PX) {
+        constexpr int RW = TX + 2;  // width of the one-node ring rows
+        int row, col;              // col counted from the node i0-1
+        if (t < RW) {
             row = 0;
             col = t;
-        } else if (t < 2 * PX) {
+        } else if (t < 2 * RW) {
             row = TY + 1;
-            col = t - PX;
-        } else if (t < 2 * PX + TY) {
-            row = 1 + (t - 2 * PX);
+            col = t - RW;
+        } else if (t < 2 * RW + TY) {
+            row = 1 + (t - 2 * RW);
             col = 0;
         } else {
-            row = 1 + (t - 2 * PX - TY);
+            row = 1 + (t - 2 * RW - TY);
             col = TX + 1;
         }
         geom(i0 - 1 + col, j0 - 1 + row, q, hcoff, hpar);
-        if (hpar & 4) hoff = q * Cfg::XT + row * PX + col;
+        if (hpar & 4) hoff = q * Cfg::XT + row * PX + (col + Cfg::HX - 1);
     }
     auto correct_plane = [&](unsigned char* st, int z, cx<T>* xv) {
         cx<T>* xs = reinterpret_cast<cx<T>*>(st + Cfg::OFF_X);
@@ -673,7 +685,7 @@ __global__ void __launch_bounds__(256) k_fine3d_tma_pro(FineOp<T> op, const __gr
         if (z0 > 0 && active) {
             const int r = min(r0 + q, nrhs - 1);
             xm[q] = x[(int64_t)r * ld + pxy + (int64_t)(z0 - 1) * sz] +
-                    prolong_point<T>(xcg + (int64_t)r * ldc, ic, jc, z0 - 1, nc0, nc1);
+                    prolong_point<T>(xcg + (int64_t)r * ldc, ic, jc, z0 - 1, csy, nc1);
         }
     }
 #pragma unroll 1
@@ -732,7 +744,9 @@ __global__ void __launch_bounds__(256) k_fine3d_tma_pro(FineOp<T> op, const __gr
 // ---------------------------------------------------------------------------------------------
 template <typename T, int KB>
 struct FineFirstCfg {
-    static constexpr int TX = 32, TY = 8, PX = TX + 2;
+    static constexpr int TX = 32, TY = 8;
+    static constexpr int HX = sizeof(T) == 4 ? 2 : 1;  // see FineTmaCfg
+    static constexpr int PX = TX + 2 * HX;
     static constexpr int XT = (TY + 2) * PX;
     static constexpr int BT = TY * TX;
     static constexpr int ES = (int)sizeof(cx<T>);
@@ -763,13 +777,13 @@ __global__ void __launch_bounds__(256) k_fine3d_tma_first(FineOp<T> op, const __
     const int z0 = blockIdx.z * zchunk;
     const int z1 = min(n2, z0 + zchunk);
     const int zl = min(z1, n2 - 1);
-    const int64_t sy = n0, sz = (int64_t)n0 * n1;
+    const int64_t sy = op.sy, sz = (int64_t)op.sy * n1;
     const bool active = (i < n0) && (j < n1);
     auto issue = [&](int s, int z) {
         unsigned char* st = smem_raw + (size_t)s * Cfg::STAGE_BYTES;
         mbar_expect_tx(&bars[s], Cfg::TX_BYTES);
-        tma_load_4d(st + Cfg::OFF_B, &tm_b, 2 * (i0 - 1), j0 - 1, z, r0, &bars[s]);
-        tma_load_3d(st + Cfg::OFF_D, &tm_d, 2 * (i0 - 1), j0 - 1, z, &bars[s]);
+        tma_load_4d(st + Cfg::OFF_B, &tm_b, 2 * (i0 - Cfg::HX), j0 - 1, z, r0, &bars[s]);
+        tma_load_3d(st + Cfg::OFF_D, &tm_d, 2 * (i0 - Cfg::HX), j0 - 1, z, &bars[s]);
         tma_load_3d(st + Cfg::OFF_C, &tm_c, 2 * i0, j0, z, &bars[s]);
     };
     if (threadIdx.x == 0) {
@@ -782,7 +796,7 @@ __global__ void __launch_bounds__(256) k_fine3d_tma_first(FineOp<T> op, const __
     const T wxm = fine_w(op, 0, 0, ic, n0), wxp = fine_w(op, 0, 1, ic, n0);
     const T wym = fine_w(op, 1, 0, jc, n1), wyp = fine_w(op, 1, 1, jc, n1);
     const int64_t pxy = ic + sy * jc;
-    const int cidx = (ty + 1) * PX + (tx + 1);
+    const int cidx = (ty + 1) * PX + (tx + Cfg::HX);
     const int bidx = ty * TX + tx;
     cx<T> tm_[KB], tc[KB], tp[KB];  // x1 = dinv .* b at planes z-1, z, z+1 of this column
     mbar_wait(&bars[0], 0);
@@ -865,7 +879,8 @@ __global__ void __launch_bounds__(256) k_fine3d_tma_first(FineOp<T> op, const __
 template <typename T, int MODE, int KB>
 struct CoarseTmaCfg {
     static constexpr int TX = 32, TY = 4;
-    static constexpr int PX = TX + 2;
+    static constexpr int HX = sizeof(T) == 4 ? 2 : 1;  // see FineTmaCfg
+    static constexpr int PX = TX + 2 * HX;
     static constexpr int XT = (TY + 2) * PX;
     static constexpr int BT = TY * TX;
     static constexpr int ES = (int)sizeof(cx<T>);
@@ -886,8 +901,8 @@ __global__ void __launch_bounds__(128) k_coarse3d_tma(const __grid_constant__ Tm
                                                       const __grid_constant__ TmaDesc tm_c,
                                                       const __grid_constant__ TmaDesc tm_b,
                                                       const __grid_constant__ TmaDesc tm_d, cx<T>* __restrict__ out,
-                                                      int n0, int n1, int n2, int64_t ld, int nrhs, int zchunk,
-                                                      int groups) {
+                                                      int n0, int n1, int n2, int sy, int64_t ld, int nrhs,
+                                                      int zchunk, int groups) {
     typedef CoarseTmaCfg<T, MODE, KB> Cfg;
     constexpr int TX = Cfg::TX, TY = Cfg::TY, PX = Cfg::PX, NS = Cfg::NS;
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -903,7 +918,7 @@ __global__ void __launch_bounds__(128) k_coarse3d_tma(const __grid_constant__ Tm
     auto issue = [&](int s, int zi) {
         unsigned char* st = smem_raw + (size_t)s * Cfg::STAGE_BYTES;
         mbar_expect_tx(&bars[s], Cfg::TX_BYTES);
-        tma_load_4d(st + Cfg::OFF_X, &tm_x, 2 * (i0 - 1), j0 - 1, zi, r0, &bars[s]);
+        tma_load_4d(st + Cfg::OFF_X, &tm_x, 2 * (i0 - Cfg::HX), j0 - 1, zi, r0, &bars[s]);
         tma_load_4d(st + Cfg::OFF_C, &tm_c, 2 * i0, j0, zi + 1, 0, &bars[s]);                  // dk = -1 of plane zi+1
         tma_load_4d(st + Cfg::OFF_C + Cfg::CSET, &tm_c, 2 * i0, j0, zi, 9, &bars[s]);          // dk =  0 of plane zi
         tma_load_4d(st + Cfg::OFF_C + 2 * Cfg::CSET, &tm_c, 2 * i0, j0, zi - 1, 18, &bars[s]); // dk = +1 of plane zi-1
@@ -923,10 +938,10 @@ __global__ void __launch_bounds__(128) k_coarse3d_tma(const __grid_constant__ Tm
         acc[0][q] = acc[1][q] = acc[2][q] = zero;
         xprev[q] = zero;
     }
-    const int cidx = (ty + 1) * PX + (tx + 1);
+    const int cidx = (ty + 1) * PX + (tx + Cfg::HX);
     const int bidx = ty * TX + tx;
-    const int64_t pxy = (active ? i : 0) + (int64_t)n0 * (active ? j : 0);
-    const int64_t sz = (int64_t)n0 * n1;
+    const int64_t pxy = (active ? i : 0) + (int64_t)sy * (active ? j : 0);
+    const int64_t sz = (int64_t)sy * n1;
 #pragma unroll 1
     for (int it = 0; it < niter; ++it) {
         const int zi = z0 - 1 + it;
@@ -996,7 +1011,7 @@ __global__ void __launch_bounds__(256) k_fine_precompute(FineOp<T> op, cx<T>* __
     const int j = blockIdx.y * blockDim.y + threadIdx.y;
     const int k = (DIM == 3) ? blockIdx.z * blockDim.z + threadIdx.z : 0;
     if (i >= n0 || j >= n1 || k >= n2) return;
-    const int64_t p = i + (int64_t)n0 * j + (int64_t)n0 * n1 * k;
+    const int64_t p = i + (int64_t)op.sy * j + (int64_t)op.sy * n1 * k;
     const cx<T> c = fine_center<T, DIM>(op, p, i, j, k);
     cdiag[p] = c;
     if (dinv) dinv[p] = rdiv(damp, c);
@@ -1011,7 +1026,7 @@ __global__ void __launch_bounds__(256) k_fine_jacobi0(FineOp<T> op, const cx<T>*
     const int j = blockIdx.y * blockDim.y + threadIdx.y;
     const int k = (DIM == 3) ? blockIdx.z * blockDim.z + threadIdx.z : 0;
     if (i >= n0 || j >= n1 || k >= n2) return;
-    const int64_t p = i + (int64_t)n0 * j + (int64_t)n0 * n1 * k;
+    const int64_t p = i + (int64_t)op.sy * j + (int64_t)op.sy * n1 * k;
     const cx<T> dinv = rdiv(damp, fine_center<T, DIM>(op, p, i, j, k));
     for (int r = 0; r < nrhs; ++r) out[(int64_t)r * ld + p] = dinv * b[(int64_t)r * ld + p];
 }
@@ -1024,7 +1039,7 @@ __global__ void k_fine_diag(FineOp<T> op, zc* __restrict__ out) {
     const int j = blockIdx.y * blockDim.y + threadIdx.y;
     const int k = (DIM == 3) ? blockIdx.z * blockDim.z + threadIdx.z : 0;
     if (i >= n0 || j >= n1 || k >= n2) return;
-    const int64_t p = i + (int64_t)n0 * j + (int64_t)n0 * n1 * k;
+    const int64_t p = i + (int64_t)op.sy * j + (int64_t)op.sy * n1 * k;
     cx<T> c = fine_center<T, DIM>(op, p, i, j, k);
     const bool bi = (i == 0) | (i == n0 - 1), bj = (j == 0) | (j == n1 - 1);
     T lap = (bi ? op.BC : T(2)) * op.ih2[0] + (bj ? op.BC : T(2)) * op.ih2[1];
@@ -1045,8 +1060,8 @@ __global__ void __launch_bounds__(256) k_coarse_stencil(CoarseOp<T> op, const cx
     const int j = blockIdx.y * blockDim.y + threadIdx.y;
     const int k = (DIM == 3) ? blockIdx.z * blockDim.z + threadIdx.z : 0;
     if (i >= n0 || j >= n1 || k >= n2) return;
-    const int64_t sy = n0, sz = (int64_t)n0 * n1;
-    const int64_t N = sz * n2;
+    const int64_t sy = op.sy, sz = (int64_t)op.sy * n1;
+    const int64_t N = op.N;
     const int64_t p = i + sy * j + sz * k;
     for (int r0 = 0; r0 < nrhs; r0 += KB) {
         cx<T> acc[KB];
@@ -1107,7 +1122,7 @@ __global__ void __launch_bounds__(256) k_fine_dinv(FineOp<T> op, cx<T>* __restri
     const int j = blockIdx.y * blockDim.y + threadIdx.y;
     const int k = (DIM == 3) ? blockIdx.z * blockDim.z + threadIdx.z : 0;
     if (i >= n0 || j >= n1 || k >= n2) return;
-    const int64_t p = i + (int64_t)n0 * j + (int64_t)n0 * n1 * k;
+    const int64_t p = i + (int64_t)op.sy * j + (int64_t)op.sy * n1 * k;
     dinv[p] = rdiv(damp, fine_center<T, DIM>(op, p, i, j, k));
 }
 
@@ -1117,14 +1132,14 @@ __global__ void __launch_bounds__(256) k_fine_dinv(FineOp<T> op, cx<T>* __restri
 // ---------------------------------------------------------------------------------------------
 template <typename T, int DIM>
 __global__ void __launch_bounds__(256) k_restrict(const cx<T>* __restrict__ r, cx<T>* __restrict__ bc, int nf0, int nf1,
-                                                  int nf2, int nc0, int nc1, int nc2, int64_t ldf, int64_t ldc,
-                                                  int nrhs) {
+                                                  int nf2, int nc0, int nc1, int nc2, int fsy, int csy, int64_t ldf,
+                                                  int64_t ldc, int nrhs) {
     const int I = blockIdx.x * blockDim.x + threadIdx.x;
     const int J = blockIdx.y * blockDim.y + threadIdx.y;
     const int K = (DIM == 3) ? blockIdx.z * blockDim.z + threadIdx.z : 0;
     if (I >= nc0 || J >= nc1 || K >= nc2) return;
-    const int64_t sy = nf0, sz = (int64_t)nf0 * nf1;
-    const int64_t pc = I + (int64_t)nc0 * J + (int64_t)nc0 * nc1 * K;
+    const int64_t sy = fsy, sz = (int64_t)fsy * nf1;
+    const int64_t pc = I + (int64_t)csy * J + (int64_t)csy * nc1 * K;
     const int fi = 2 * I, fj = 2 * J, fk = (DIM == 3) ? 2 * K : 0;
     for (int q = 0; q < nrhs; ++q) {
         const cx<T>* rr = r + (int64_t)q * ldf;
@@ -1154,14 +1169,14 @@ __global__ void __launch_bounds__(256) k_restrict(const cx<T>* __restrict__ r, c
 // ---------------------------------------------------------------------------------------------
 template <typename T, int DIM>
 __global__ void __launch_bounds__(256) k_prolong_add(cx<T>* __restrict__ x, const cx<T>* __restrict__ xc, int nf0,
-                                                     int nf1, int nf2, int nc0, int nc1, int64_t ldf, int64_t ldc,
-                                                     int nrhs) {
+                                                     int nf1, int nf2, int fsy, int csy, int nc1, int64_t ldf,
+                                                     int64_t ldc, int nrhs) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int j = blockIdx.y * blockDim.y + threadIdx.y;
     const int k = (DIM == 3) ? blockIdx.z * blockDim.z + threadIdx.z : 0;
     if (i >= nf0 || j >= nf1 || k >= nf2) return;
-    const int64_t p = i + (int64_t)nf0 * j + (int64_t)nf0 * nf1 * k;
-    const int64_t cy = nc0, cz = (int64_t)nc0 * nc1;
+    const int64_t p = i + (int64_t)fsy * j + (int64_t)fsy * nf1 * k;
+    const int64_t cy = csy, cz = (int64_t)csy * nc1;
     const int I0 = i >> 1, J0 = j >> 1, K0 = k >> 1;
     const int oi = i & 1, oj = j & 1, ok = (DIM == 3) ? (k & 1) : 0;
     const T w = T(1) / T((1 << oi) * (1 << oj) * (1 << ok));
@@ -1200,7 +1215,7 @@ struct FineCoef {
     __device__ __forceinline__ cx<double> get(int i, int j, int k, int di, int dj, int dk) const {
         const int nz = (di != 0) + (dj != 0) + (dk != 0);
         if (nz == 0) {
-            const int64_t p = i + (int64_t)op.n[0] * j + (int64_t)op.n[0] * op.n[1] * k;
+            const int64_t p = i + (int64_t)op.sy * j + (int64_t)op.sy * op.n[1] * k;
             cx<T> c = fine_center<T, DIM>(op, p, i, j, k);
             return mk<double>((double)c.x, (double)c.y);
         }
@@ -1218,17 +1233,16 @@ struct StoredCoef {
     CoarseOp<T> op;
     __device__ __forceinline__ bool sparse7() const { return false; }
     __device__ __forceinline__ cx<double> get(int i, int j, int k, int di, int dj, int dk) const {
-        const int64_t N = (int64_t)op.n[0] * op.n[1] * op.n[2];
-        const int64_t p = i + (int64_t)op.n[0] * j + (int64_t)op.n[0] * op.n[1] * k;
+        const int64_t p = i + (int64_t)op.sy * j + (int64_t)op.sy * op.n[1] * k;
         const int s = (di + 1) + 3 * (dj + 1) + (DIM == 3 ? 9 * (dk + 1) : 0);
-        cx<T> c = op.coef[(int64_t)s * N + p];
+        cx<T> c = op.coef[(int64_t)s * op.N + p];
         return mk<double>((double)c.x, (double)c.y);
     }
 };
 
 template <typename T, int DIM, typename Coef>
 __global__ void __launch_bounds__(128) k_galerkin(Coef A, int nf0, int nf1, int nf2, int nc0, int nc1, int nc2,
-                                                  cx<T>* __restrict__ coefc) {
+                                                  int csy, int64_t cN, cx<T>* __restrict__ coefc) {
     const int64_t Nc = (int64_t)nc0 * nc1 * nc2;
     const int NS = (DIM == 3) ? 27 : 9;
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1282,13 +1296,16 @@ __global__ void __launch_bounds__(128) k_galerkin(Coef A, int nf0, int nf1, int 
             }
         }
     }
-    coefc[t] = mk<T>((T)acc.x, (T)acc.y);
+    coefc[(int64_t)s * cN + I + (int64_t)csy * J + (int64_t)csy * nc1 * K] = mk<T>((T)acc.x, (T)acc.y);
 }
 
 template <typename T>
 __global__ void k_coarse_dinv(const cx<T>* __restrict__ center, cx<T>* __restrict__ dinv, int64_t N, T damp) {
     const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (p < N) dinv[p] = rdiv(damp, center[p]);
+    if (p < N) {
+        const cx<T> c = center[p];
+        dinv[p] = (c.x == T(0) && c.y == T(0)) ? mk<T>(T(0), T(0)) : rdiv(damp, c);  // ghost nodes of a padded level stay 0
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1300,7 +1317,7 @@ __global__ void k_coarse_dinv(const cx<T>* __restrict__ center, cx<T>* __restric
 // ---------------------------------------------------------------------------------------------
 template <typename T, int DIM>
 __global__ void k_band_fill(CoarseOp<T> op, zc* __restrict__ band, int bw) {
-    const int64_t N = (int64_t)op.n[0] * op.n[1] * op.n[2];
+    const int64_t N = (int64_t)op.n[0] * op.n[1] * op.n[2];  // logical unknowns of the dense band matrix
     const int NS = (DIM == 3) ? 27 : 9;
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= N * NS) return;
@@ -1312,7 +1329,7 @@ __global__ void k_band_fill(CoarseOp<T> op, zc* __restrict__ band, int bw) {
         (unsigned)(k + dk) >= (unsigned)op.n[2])
         return;
     const int64_t off = di + (int64_t)op.n[0] * dj + (int64_t)op.n[0] * op.n[1] * dk;
-    const cx<T> c = op.coef[t];
+    const cx<T> c = op.coef[(int64_t)s * op.N + i + (int64_t)op.sy * j + (int64_t)op.sy * op.n[1] * k];
     band[p * (2 * (int64_t)bw + 1) + (off + bw)] = mk<double>((double)c.x, (double)c.y);
 }
 
@@ -1529,6 +1546,19 @@ __global__ void __launch_bounds__(256) k_copy(const cx<T>* __restrict__ in, cx<T
     const int r = blockIdx.y;
     for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < N; p += (int64_t)gridDim.x * blockDim.x)
         out[(int64_t)r * ld_out + p] = in[(int64_t)r * ld_in + p];
+}
+
+// dst (row pitch dsy, leading dimension dld) <- src (row pitch ssy, leading dimension sld); rows of n0 nodes
+template <typename U>
+__global__ void __launch_bounds__(256) k_repitch(const U* __restrict__ src, U* __restrict__ dst, int n0, int64_t rows,
+                                                 int ssy, int dsy, int64_t sld, int64_t dld) {
+    const int r = blockIdx.y;
+    const int64_t tot = rows * n0;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < tot; t += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t row = t / n0;
+        const int i = (int)(t - row * n0);
+        dst[(int64_t)r * dld + row * dsy + i] = src[(int64_t)r * sld + row * ssy + i];
+    }
 }
 
 // scatter point sources: B[idx[r] + r*ld] = val[r]  (B zeroed beforehand)

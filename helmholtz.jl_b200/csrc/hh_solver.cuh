@@ -235,7 +235,9 @@ class Solver : public SolverBase {
     };
     struct Level {
         int n[3] = {1, 1, 1};
-        int64_t N = 0;
+        int p0 = 1;                 // row pitch of every array of this level (n[0], or n[0]+1: see pitch_of)
+        int64_t N = 0;              // padded node count p0*n[1]*n[2] = leading dimension of the level's vectors
+        int64_t Nlog = 0;           // logical node count
         DevBuf<C> coef, dinv;       // l >= 1 (dinv also on l = 0 when Jac-GMRES is used)
         DevBuf<C> x, b, t;          // work vectors N x kcap (l >= 1); l = 0 owns only t
         SmallWs gs;                 // Jac-GMRES smoother / inexact coarsest solve (Jacobi-preconditioned)
@@ -254,6 +256,7 @@ class Solver : public SolverBase {
         if (e && !strcmp(e, "simple")) fine_kernel = FK_SIMPLE;
         const char* f = getenv("HH_FUSE_FIRST");  // A/B switch of the fused cycle start (default on)
         fuse_first = !(f && f[0] == '0');
+        use_pitch = sizeof(T) == 4 && pb.dim == 3 && fine_kernel == FK_TMA;
     }
     ~Solver() override {}
 
@@ -276,14 +279,34 @@ class Solver : public SolverBase {
         }
         HH_CUDA(cudaMemcpy(d_m.p, hm.data(), N * sizeof(T), cudaMemcpyHostToDevice));
         HH_CUDA(cudaMemcpy(d_g.p, hg.data(), N * sizeof(T), cudaMemcpyHostToDevice));
+        if (fine_sy() != pb.n[0]) {  // pitched copies for the kernels that work on the internal (padded) vectors
+            const int64_t Np = fineN();
+            d_mp.alloc(Np);
+            d_gp.alloc(Np);
+            HH_CUDA(cudaMemsetAsync(d_mp.p, 0, Np * sizeof(T), stream));
+            HH_CUDA(cudaMemsetAsync(d_gp.p, 0, Np * sizeof(T), stream));
+            const int64_t rows = (int64_t)pb.n[1] * pb.n[2];
+            k_repitch<T><<<dim3(592, 1), 256, 0, stream>>>(d_m.p, d_mp.p, pb.n[0], rows, pb.n[0], fine_sy(), 0, 0);
+            k_repitch<T><<<dim3(592, 1), 256, 0, stream>>>(d_g.p, d_gp.p, pb.n[0], rows, pb.n[0], fine_sy(), 0, 0);
+            HH_CUDA(cudaStreamSynchronize(stream));
+        }
         h_op_valid[0] = h_op_valid[1] = false;
         clear();
     }
 
-    FineOp<T> fine_op(double shift, int adj) const {
+    // Row pitch of the internal fine-level arrays.  TMA needs 16-byte multiples for every global stride: always
+    // true for ComplexF64; ComplexF32 rows of an odd node count are padded by one (never touched) ghost node.
+    int pitch_of(int n0) const { return (use_pitch && (n0 & 1)) ? n0 + 1 : n0; }
+    int fine_sy() const { return pitch_of(pb.n[0]); }
+    int64_t fineN() const { return (int64_t)fine_sy() * pb.n[1] * pb.n[2]; }
+
+    // pitched = true: the operator on the solver's internal vectors; false: on dense caller arrays (hh_apply)
+    FineOp<T> fine_op(double shift, int adj, bool pitched = false) const {
         FineOp<T> op;
-        op.m = d_m.p;
-        op.g = d_g.p;
+        const bool pp = pitched && fine_sy() != pb.n[0];
+        op.m = pp ? d_mp.p : d_m.p;
+        op.g = pp ? d_gp.p : d_g.p;
+        op.sy = pp ? fine_sy() : pb.n[0];
         const double wr = pb.w_re, wi = pb.w_im;
         op.a = (T)(wr * wr - wi * wi);
         op.b = (T)(2.0 * wr * wi);
@@ -302,11 +325,16 @@ class Solver : public SolverBase {
         op.dinv = nullptr;
         return op;
     }
-    // diagonal arrays for the bulk-async kernels (3-D only)
+    // diagonal arrays for the TMA-staged kernels (3-D only), in the layout of `op`
     void precompute_diag(FineOp<T>& op, DevBuf<C>& cd, DevBuf<C>* dv, T damp) {
-        if (!tma_ok(pb.N())) return;
-        cd.alloc(pb.N());
-        if (dv) dv->alloc(pb.N());
+        const int64_t Np = (int64_t)op.sy * pb.n[1] * pb.n[2];
+        if (!tma_ok(op, Np)) return;
+        cd.alloc(Np);
+        HH_CUDA(cudaMemsetAsync(cd.p, 0, Np * sizeof(C), stream));
+        if (dv) {
+            dv->alloc(Np);
+            HH_CUDA(cudaMemsetAsync(dv->p, 0, Np * sizeof(C), stream));
+        }
         dim3 g, blk;
         grid3(pb.n, pb.dim, g, blk);
         FineOp<T> o = op;
@@ -318,7 +346,7 @@ class Solver : public SolverBase {
     const FineOp<T>& krylov_op(int transpose) {
         const int t = transpose ? 1 : 0;
         if (!h_op_valid[t]) {
-            h_op[t] = fine_op(0.0, t);
+            h_op[t] = fine_op(0.0, t, true);
             precompute_diag(h_op[t], h_cdiag[t], nullptr, T(0));
             h_op_valid[t] = true;
         }
@@ -375,7 +403,7 @@ class Solver : public SolverBase {
         if (mode == MODE_APPLY) bytes = 2 * S * N * nrhs + coefb, tag = T_FINE_APPLY;
         else if (mode == MODE_RESID) bytes = 3 * S * N * nrhs + coefb, tag = T_FINE_RESID;
         else bytes = 3 * S * N * nrhs + coefb, tag = T_FINE_JACOBI;
-        if (op.cdiag != nullptr && (mode != MODE_JACOBI || op.dinv != nullptr) && tma_ok(ld) &&
+        if (op.cdiag != nullptr && (mode != MODE_JACOBI || op.dinv != nullptr) && tma_ok(op, ld) &&
             ((uintptr_t)x % 16 == 0) && (mode == MODE_APPLY || (uintptr_t)b % 16 == 0)) {
             launch(tag, bytes + S * N * (mode == MODE_JACOBI ? 2.0 : 1.0) - coefb,
                    [&] { tma3d_dispatch(mode, op, x, b, out, ld, nrhs); });
@@ -444,10 +472,10 @@ class Solver : public SolverBase {
         return fn;
     }
     // TMA needs 16-byte aligned global strides: always true for ComplexF64, for ComplexF32 only on even grids
-    bool tma_ok(int64_t ld) const {
+    bool tma_ok(const FineOp<T>& op, int64_t ld) const {
         if (pb.dim != 3 || fine_kernel != FK_TMA) return false;
         const int64_t es = 2 * sizeof(T);
-        return (es * pb.n[0]) % 16 == 0 && (es * pb.n[0] * pb.n[1]) % 16 == 0 && (es * ld) % 16 == 0;
+        return (es * op.sy) % 16 == 0 && (es * op.sy * pb.n[1]) % 16 == 0 && (es * ld) % 16 == 0;
     }
     template <int MODE, int KB>
     void tma3d_launch(const FineOp<T>& op, const C* x, const C* b, C* out, int64_t ld, int nrhs) {
@@ -465,24 +493,24 @@ class Solver : public SolverBase {
         zchunks(pb.n[2], tx * ty, groups, 64, zchunk, nzc);
         dim3 g(tx * groups, ty, nzc);
         // the RHS extent of the x / b maps is the true nrhs so that surplus slots of the last group are zero-filled
-        TmaDesc tx_ = make_tmap_n(x, ld, Cfg::TX + 2, Cfg::TY + 2, KB, nrhs);
-        TmaDesc tb_ = (MODE != MODE_APPLY) ? make_tmap_n(b, ld, Cfg::TX, Cfg::TY, KB, nrhs) : tx_;
-        TmaDesc tc_ = make_tmap_n(op.cdiag, ld, Cfg::TX, Cfg::TY, 1, 0);
-        TmaDesc td_ = (MODE == MODE_JACOBI) ? make_tmap_n(op.dinv, ld, Cfg::TX, Cfg::TY, 1, 0) : tc_;
+        TmaDesc tx_ = make_tmap_n(x, op.sy, ld, Cfg::PX, Cfg::TY + 2, KB, nrhs);
+        TmaDesc tb_ = (MODE != MODE_APPLY) ? make_tmap_n(b, op.sy, ld, Cfg::TX, Cfg::TY, KB, nrhs) : tx_;
+        TmaDesc tc_ = make_tmap_n(op.cdiag, op.sy, ld, Cfg::TX, Cfg::TY, 1, 0);
+        TmaDesc td_ = (MODE == MODE_JACOBI) ? make_tmap_n(op.dinv, op.sy, ld, Cfg::TX, Cfg::TY, 1, 0) : tc_;
         k_fine3d_tma<T, MODE, KB, NS><<<g, 256, smem, stream>>>(op, tx_, tb_, tc_, td_, x, out, ld, nrhs, zchunk, groups);
     }
-    TmaDesc make_tmap_n(const void* base, int64_t ld, int bx, int by, int kb, int nrhs) const {
-        return make_tmap_g(base, pb.n, ld, bx, by, kb, nrhs);
+    TmaDesc make_tmap_n(const void* base, int sy, int64_t ld, int bx, int by, int kb, int nrhs) const {
+        return make_tmap_g(base, pb.n, sy, ld, bx, by, kb, nrhs);
     }
     // tensor over a complex block on an n[0] x n[1] x n[2] grid viewed as reals: dims (2*n0, n1, n2[, nvec]),
     // box (2*bx, by, 1[, kb]); nvec == 0 -> rank 3
-    static TmaDesc make_tmap_g(const void* base, const int* n, int64_t ld, int bx, int by, int kb, int nrhs) {
+    static TmaDesc make_tmap_g(const void* base, const int* n, int sy, int64_t ld, int bx, int by, int kb, int nrhs) {
         static_assert(sizeof(TmaDesc) == sizeof(CUtensorMap), "CUtensorMap is 128 bytes");
         TmaDesc d;
         const cuuint64_t es = sizeof(T);
         const int rank = nrhs > 0 ? 4 : 3;
         cuuint64_t dims[4] = {(cuuint64_t)2 * n[0], (cuuint64_t)n[1], (cuuint64_t)n[2], (cuuint64_t)std::max(nrhs, 1)};
-        cuuint64_t strides[3] = {2 * es * n[0], 2 * es * (cuuint64_t)n[0] * n[1], 2 * es * (cuuint64_t)ld};
+        cuuint64_t strides[3] = {2 * es * sy, 2 * es * (cuuint64_t)sy * n[1], 2 * es * (cuuint64_t)ld};
         cuuint32_t box[4] = {(cuuint32_t)(2 * bx), (cuuint32_t)by, 1, (cuuint32_t)kb};
         cuuint32_t estr[4] = {1, 1, 1, 1};
         CUresult r = encode_fn()((CUtensorMap*)&d, sizeof(T) == 8 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32,
@@ -508,13 +536,13 @@ class Solver : public SolverBase {
         int zchunk, nzc;
         zchunks(pb.n[2], tx * ty, groups, 64, zchunk, nzc);
         dim3 g(tx * groups, ty, nzc);
-        TmaDesc mb = make_tmap_n(b, ld, Cfg::TX + 2, Cfg::TY + 2, KB, nrhs);
-        TmaDesc md = make_tmap_n(op.dinv, ld, Cfg::TX + 2, Cfg::TY + 2, 1, 0);
-        TmaDesc mc = make_tmap_n(op.cdiag, ld, Cfg::TX, Cfg::TY, 1, 0);
+        TmaDesc mb = make_tmap_n(b, op.sy, ld, Cfg::PX, Cfg::TY + 2, KB, nrhs);
+        TmaDesc md = make_tmap_n(op.dinv, op.sy, ld, Cfg::PX, Cfg::TY + 2, 1, 0);
+        TmaDesc mc = make_tmap_n(op.cdiag, op.sy, ld, Cfg::TX, Cfg::TY, 1, 0);
         k_fine3d_tma_first<T, SECOND, KB, NS><<<g, 256, smem, stream>>>(op, mb, md, mc, b, out, out2, ld, nrhs, zchunk, groups);
     }
     bool can_fuse_first(const FineOp<T>& op, const C* b, int64_t ld) const {
-        return op.cdiag != nullptr && op.dinv != nullptr && tma_ok(ld) && ((uintptr_t)b % 16 == 0) && fuse_first;
+        return op.cdiag != nullptr && op.dinv != nullptr && tma_ok(op, ld) && ((uintptr_t)b % 16 == 0) && fuse_first;
     }
     // second == 0: out = x1, out2 = b - A x1;  second == 1: out = x2
     void fine_first(int second, const FineOp<T>& op, const C* b, C* out, C* out2, int64_t ld, int nrhs) {
@@ -546,20 +574,20 @@ class Solver : public SolverBase {
         int zchunk, nzc;
         zchunks(pb.n[2], tx * ty, groups, 64, zchunk, nzc);
         dim3 g(tx * groups, ty, nzc);
-        TmaDesc mx = make_tmap_n(x, ld, Cfg::TX + 2, Cfg::TY + 2, KB, nrhs);
-        TmaDesc mb = make_tmap_n(b, ld, Cfg::TX, Cfg::TY, KB, nrhs);
-        TmaDesc mc = make_tmap_n(op.cdiag, ld, Cfg::TX, Cfg::TY, 1, 0);
-        TmaDesc md = make_tmap_n(op.dinv, ld, Cfg::TX, Cfg::TY, 1, 0);
-        TmaDesc mxc = make_tmap_g(xc, Cc.n, Cc.N, Cfg::CTX, Cfg::CTY, KB, nrhs);
-        k_fine3d_tma_pro<T, KB, NS><<<g, 256, smem, stream>>>(op, mx, mb, mc, md, mxc, x, xc, out, ld, Cc.N, Cc.n[0], Cc.n[1], nrhs, zchunk, groups);
+        TmaDesc mx = make_tmap_n(x, op.sy, ld, Cfg::PX, Cfg::TY + 2, KB, nrhs);
+        TmaDesc mb = make_tmap_n(b, op.sy, ld, Cfg::TX, Cfg::TY, KB, nrhs);
+        TmaDesc mc = make_tmap_n(op.cdiag, op.sy, ld, Cfg::TX, Cfg::TY, 1, 0);
+        TmaDesc md = make_tmap_n(op.dinv, op.sy, ld, Cfg::TX, Cfg::TY, 1, 0);
+        TmaDesc mxc = make_tmap_g(xc, Cc.n, Cc.p0, Cc.N, Cfg::CTX, Cfg::CTY, KB, nrhs);
+        k_fine3d_tma_pro<T, KB, NS><<<g, 256, smem, stream>>>(op, mx, mb, mc, md, mxc, x, xc, out, ld, Cc.N, Cc.p0, Cc.n[1], nrhs, zchunk, groups);
     }
     bool can_fuse_prolong(const FineOp<T>& op, const C* x, const C* b, const Level& Cc, const C* xc, int64_t ld) const {
-        return fuse_first && op.cdiag != nullptr && op.dinv != nullptr && tma_ok(ld) && tma_ok_level(Cc) &&
+        return fuse_first && op.cdiag != nullptr && op.dinv != nullptr && tma_ok(op, ld) && tma_ok_level(Cc) &&
                ((uintptr_t)x % 16 == 0) && ((uintptr_t)b % 16 == 0) && ((uintptr_t)xc % 16 == 0);
     }
     void fine_prolong_jacobi(const FineOp<T>& op, const C* x, const C* b, const Level& Cc, const C* xc, C* out, int64_t ld, int nrhs) {
         const double N = (double)pb.N();
-        launch(T_FINE_PROLONG_JACOBI, (3.0 * N + (double)Cc.N) * S * nrhs + 2.0 * S * N, [&] {
+        launch(T_FINE_PROLONG_JACOBI, (3.0 * N + (double)Cc.Nlog) * S * nrhs + 2.0 * S * N, [&] {
             if (nrhs >= 2) tma3d_pro_launch<2>(op, x, b, Cc, xc, out, ld, nrhs);
             else tma3d_pro_launch<1>(op, x, b, Cc, xc, out, ld, nrhs);
         });
@@ -577,7 +605,7 @@ class Solver : public SolverBase {
     bool tma_ok_level(const Level& L) const {
         if (pb.dim != 3 || fine_kernel != FK_TMA) return false;
         const int64_t es = 2 * sizeof(T);
-        return (es * L.n[0]) % 16 == 0 && (es * L.n[0] * L.n[1]) % 16 == 0 && (es * L.N) % 16 == 0;
+        return (es * L.p0) % 16 == 0 && (es * L.p0 * L.n[1]) % 16 == 0 && (es * L.N) % 16 == 0;
     }
     template <int MODE, int KB>
     void coarse_tma_launch(const Level& L, const C* x, const C* b, C* out, int nrhs) {
@@ -598,11 +626,11 @@ class Solver : public SolverBase {
             nzc = (L.n[2] + zchunk - 1) / zchunk;
         }
         dim3 g(tx * groups, ty, nzc);
-        TmaDesc mx = make_tmap_g(x, L.n, L.N, Cfg::TX + 2, Cfg::TY + 2, KB, nrhs);
-        TmaDesc mc = make_tmap_g(L.coef.p, L.n, L.N, Cfg::TX, Cfg::TY, 9, 27);
-        TmaDesc mb = (MODE != MODE_APPLY) ? make_tmap_g(b, L.n, L.N, Cfg::TX, Cfg::TY, KB, nrhs) : mx;
-        TmaDesc md = (MODE == MODE_JACOBI) ? make_tmap_g(L.dinv.p, L.n, L.N, Cfg::TX, Cfg::TY, 1, 0) : mx;
-        k_coarse3d_tma<T, MODE, KB><<<g, 128, smem, stream>>>(mx, mc, mb, md, out, L.n[0], L.n[1], L.n[2], L.N, nrhs, zchunk, groups);
+        TmaDesc mx = make_tmap_g(x, L.n, L.p0, L.N, Cfg::PX, Cfg::TY + 2, KB, nrhs);
+        TmaDesc mc = make_tmap_g(L.coef.p, L.n, L.p0, L.N, Cfg::TX, Cfg::TY, 9, 27);
+        TmaDesc mb = (MODE != MODE_APPLY) ? make_tmap_g(b, L.n, L.p0, L.N, Cfg::TX, Cfg::TY, KB, nrhs) : mx;
+        TmaDesc md = (MODE == MODE_JACOBI) ? make_tmap_g(L.dinv.p, L.n, L.p0, L.N, Cfg::TX, Cfg::TY, 1, 0) : mx;
+        k_coarse3d_tma<T, MODE, KB><<<g, 128, smem, stream>>>(mx, mc, mb, md, out, L.n[0], L.n[1], L.n[2], L.p0, L.N, nrhs, zchunk, groups);
     }
     template <int MODE>
     void coarse_tma_mode(const Level& L, const C* x, const C* b, C* out, int nrhs) {
@@ -651,12 +679,14 @@ class Solver : public SolverBase {
         op.coef = L.coef.p;
         op.dinv = L.dinv.p;
         for (int d = 0; d < 3; ++d) op.n[d] = L.n[d];
+        op.sy = L.p0;
+        op.N = L.N;
         return op;
     }
     void coarse_stencil(int mode, const Level& L, const C* x, const C* b, C* out, int nrhs) {
         dim3 g, blk;
         grid3(L.n, pb.dim, g, blk);
-        const double N = (double)L.N;
+        const double N = (double)L.Nlog;
         const int NS = pb.dim == 3 ? 27 : 9;
         const bool use_tma = tma_ok_level(L) && ((uintptr_t)x % 16 == 0) && (mode == MODE_APPLY || (uintptr_t)b % 16 == 0);
         int KB = (pb.dim == 3 && fine_kernel != FK_SIMPLE) ? coarse_kb(nrhs) : 4;
@@ -708,21 +738,21 @@ class Solver : public SolverBase {
     void restrict_to(const Level& F, const Level& Cc, const C* r, C* bc, int nrhs) {
         dim3 g, blk;
         grid3(Cc.n, pb.dim, g, blk);
-        launch(T_RESTRICT, S * ((double)F.N + (double)Cc.N) * nrhs, [&] {
+        launch(T_RESTRICT, S * ((double)F.Nlog + (double)Cc.Nlog) * nrhs, [&] {
             if (pb.dim == 3)
-                k_restrict<T, 3><<<g, blk, 0, stream>>>(r, bc, F.n[0], F.n[1], F.n[2], Cc.n[0], Cc.n[1], Cc.n[2], F.N, Cc.N, nrhs);
+                k_restrict<T, 3><<<g, blk, 0, stream>>>(r, bc, F.n[0], F.n[1], F.n[2], Cc.n[0], Cc.n[1], Cc.n[2], F.p0, Cc.p0, F.N, Cc.N, nrhs);
             else
-                k_restrict<T, 2><<<g, blk, 0, stream>>>(r, bc, F.n[0], F.n[1], 1, Cc.n[0], Cc.n[1], 1, F.N, Cc.N, nrhs);
+                k_restrict<T, 2><<<g, blk, 0, stream>>>(r, bc, F.n[0], F.n[1], 1, Cc.n[0], Cc.n[1], 1, F.p0, Cc.p0, F.N, Cc.N, nrhs);
         });
     }
     void prolong_add(const Level& F, const Level& Cc, C* x, const C* xc, int nrhs) {
         dim3 g, blk;
         grid3(F.n, pb.dim, g, blk);
-        launch(T_PROLONG, S * (2.0 * (double)F.N + (double)Cc.N) * nrhs, [&] {
+        launch(T_PROLONG, S * (2.0 * (double)F.Nlog + (double)Cc.Nlog) * nrhs, [&] {
             if (pb.dim == 3)
-                k_prolong_add<T, 3><<<g, blk, 0, stream>>>(x, xc, F.n[0], F.n[1], F.n[2], Cc.n[0], Cc.n[1], F.N, Cc.N, nrhs);
+                k_prolong_add<T, 3><<<g, blk, 0, stream>>>(x, xc, F.n[0], F.n[1], F.n[2], F.p0, Cc.p0, Cc.n[1], F.N, Cc.N, nrhs);
             else
-                k_prolong_add<T, 2><<<g, blk, 0, stream>>>(x, xc, F.n[0], F.n[1], 1, Cc.n[0], Cc.n[1], F.N, Cc.N, nrhs);
+                k_prolong_add<T, 2><<<g, blk, 0, stream>>>(x, xc, F.n[0], F.n[1], 1, F.p0, Cc.p0, Cc.n[1], F.N, Cc.N, nrhs);
         });
     }
 
@@ -808,7 +838,9 @@ class Solver : public SolverBase {
         opt = o;
         levels.resize(o.levels);
         for (int d = 0; d < 3; ++d) levels[0].n[d] = pb.n[d];
-        levels[0].N = pb.N();
+        levels[0].p0 = fine_sy();
+        levels[0].N = fineN();
+        levels[0].Nlog = pb.N();
         for (int l = 1; l < o.levels; ++l) {
             for (int d = 0; d < 3; ++d) {
                 const int nf = levels[l - 1].n[d];
@@ -821,9 +853,13 @@ class Solver : public SolverBase {
                     levels[l].n[d] = 1;
                 }
             }
-            levels[l].N = (int64_t)levels[l].n[0] * levels[l].n[1] * levels[l].n[2];
+            levels[l].Nlog = (int64_t)levels[l].n[0] * levels[l].n[1] * levels[l].n[2];
+            // the exact coarsest solve works on a dense unknown numbering: no padding on that level
+            const bool dense_level = (l == o.levels - 1 && o.coarse_type == HH_COARSE_LU);
+            levels[l].p0 = dense_level ? levels[l].n[0] : pitch_of(levels[l].n[0]);
+            levels[l].N = (int64_t)levels[l].p0 * levels[l].n[1] * levels[l].n[2];
         }
-        mg_fine = fine_op(o.shift[0], o.do_transpose);
+        mg_fine = fine_op(o.shift[0], o.do_transpose, true);
         if (o.levels > 1) precompute_diag(mg_fine, mg_cdiag, &mg_dinv, (T)o.relax_param);
         const int NS = pb.dim == 3 ? 27 : 9;
         const int center = pb.dim == 3 ? 13 : 4;
@@ -832,24 +868,25 @@ class Solver : public SolverBase {
             Level& Lf = levels[l - 1];
             Lc.coef.alloc((size_t)NS * Lc.N);
             Lc.dinv.alloc(Lc.N);
-            const int64_t tot = Lc.N * NS;
+            HH_CUDA(cudaMemsetAsync(Lc.coef.p, 0, (size_t)NS * Lc.N * sizeof(C), stream));  // ghost columns stay zero
+            const int64_t tot = Lc.Nlog * NS;
             const unsigned nb = (unsigned)((tot + 127) / 128);
             launch(T_SETUP, 0, [&] {
                 if (l == 1) {
                     if (pb.dim == 3) {
                         FineCoef<T, 3> A{mg_fine};
-                        k_galerkin<T, 3, FineCoef<T, 3>><<<nb, 128, 0, stream>>>(A, Lf.n[0], Lf.n[1], Lf.n[2], Lc.n[0], Lc.n[1], Lc.n[2], Lc.coef.p);
+                        k_galerkin<T, 3, FineCoef<T, 3>><<<nb, 128, 0, stream>>>(A, Lf.n[0], Lf.n[1], Lf.n[2], Lc.n[0], Lc.n[1], Lc.n[2], Lc.p0, Lc.N, Lc.coef.p);
                     } else {
                         FineCoef<T, 2> A{mg_fine};
-                        k_galerkin<T, 2, FineCoef<T, 2>><<<nb, 128, 0, stream>>>(A, Lf.n[0], Lf.n[1], 1, Lc.n[0], Lc.n[1], 1, Lc.coef.p);
+                        k_galerkin<T, 2, FineCoef<T, 2>><<<nb, 128, 0, stream>>>(A, Lf.n[0], Lf.n[1], 1, Lc.n[0], Lc.n[1], 1, Lc.p0, Lc.N, Lc.coef.p);
                     }
                 } else {
                     if (pb.dim == 3) {
                         StoredCoef<T, 3> A{coarse_op(Lf)};
-                        k_galerkin<T, 3, StoredCoef<T, 3>><<<nb, 128, 0, stream>>>(A, Lf.n[0], Lf.n[1], Lf.n[2], Lc.n[0], Lc.n[1], Lc.n[2], Lc.coef.p);
+                        k_galerkin<T, 3, StoredCoef<T, 3>><<<nb, 128, 0, stream>>>(A, Lf.n[0], Lf.n[1], Lf.n[2], Lc.n[0], Lc.n[1], Lc.n[2], Lc.p0, Lc.N, Lc.coef.p);
                     } else {
                         StoredCoef<T, 2> A{coarse_op(Lf)};
-                        k_galerkin<T, 2, StoredCoef<T, 2>><<<nb, 128, 0, stream>>>(A, Lf.n[0], Lf.n[1], 1, Lc.n[0], Lc.n[1], 1, Lc.coef.p);
+                        k_galerkin<T, 2, StoredCoef<T, 2>><<<nb, 128, 0, stream>>>(A, Lf.n[0], Lf.n[1], 1, Lc.n[0], Lc.n[1], 1, Lc.p0, Lc.N, Lc.coef.p);
                     }
                 }
             });
@@ -860,6 +897,7 @@ class Solver : public SolverBase {
         if (o.relax_type == HH_RELAX_JAC_GMRES || (o.levels == 1 && o.coarse_type == HH_COARSE_GMRES)) {
             Level& L0 = levels[0];
             L0.dinv.alloc(L0.N);
+            HH_CUDA(cudaMemsetAsync(L0.dinv.p, 0, (size_t)L0.N * sizeof(C), stream));
             dim3 g, blk;
             grid3(pb.n, pb.dim, g, blk);
             launch(T_SETUP, 0, [&] {
@@ -879,7 +917,7 @@ class Solver : public SolverBase {
         HH_REQUIRE(Lc >= 1, HH_ERR_UNSUPPORTED,
                    "coarse_type LU needs levels >= 2 (the fine level is matrix-free; use GMRES for a 1-level solve)");
         Level& L = levels[Lc];
-        const int64_t N = L.N;
+        const int64_t N = L.Nlog;  // == L.N: this level is never padded
         const int bw = pb.dim == 3 ? (1 + L.n[0] + L.n[0] * L.n[1]) : (1 + L.n[0]);
         const double need = (double)N * N * (16.0 + sizeof(C)) + (double)N * (2.0 * bw + 1) * 16.0;
         size_t fr = 0, tot = 0;
@@ -913,7 +951,20 @@ class Solver : public SolverBase {
         HH_REQUIRE(have_hierarchy && level >= 1 && level < (int)levels.size(), HH_ERR_ARG, "bad level");
         HH_CUDA(cudaSetDevice(device));
         HH_CUDA(cudaStreamSynchronize(stream));
-        HH_CUDA(cudaMemcpy(out, levels[level].coef.p, levels[level].coef.n * sizeof(C), cudaMemcpyDeviceToHost));
+        const Level& L = levels[level];
+        if (L.N == L.Nlog) {
+            HH_CUDA(cudaMemcpy(out, L.coef.p, L.coef.n * sizeof(C), cudaMemcpyDeviceToHost));
+            return;
+        }
+        // padded level: strip the ghost column on the host
+        std::vector<C> tmp(L.coef.n);
+        HH_CUDA(cudaMemcpy(tmp.data(), L.coef.p, L.coef.n * sizeof(C), cudaMemcpyDeviceToHost));
+        C* o = (C*)out;
+        const int NS = pb.dim == 3 ? 27 : 9;
+        const int64_t rows = (int64_t)L.n[1] * L.n[2];
+        for (int s = 0; s < NS; ++s)
+            for (int64_t r = 0; r < rows; ++r)
+                std::memcpy(o + (int64_t)s * L.Nlog + r * L.n[0], tmp.data() + (int64_t)s * L.N + r * L.p0, L.n[0] * sizeof(C));
     }
     void get_diagonal(int shifted, double shift, double* out) override {
         HH_CUDA(cudaSetDevice(device));
@@ -954,10 +1005,10 @@ class Solver : public SolverBase {
         if (nrhs <= kcap) return;
         for (int l = 0; l < (int)levels.size(); ++l) {
             Level& L = levels[l];
-            L.t.alloc((size_t)L.N * nrhs);
+            alloc_zero(L.t, (size_t)L.N * nrhs);
             if (l >= 1) {
-                L.x.alloc((size_t)L.N * nrhs);
-                L.b.alloc((size_t)L.N * nrhs);
+                alloc_zero(L.x, (size_t)L.N * nrhs);
+                alloc_zero(L.b, (size_t)L.N * nrhs);
             }
             L.px = L.x.p;
             L.pb = L.b.p;
@@ -965,13 +1016,13 @@ class Solver : public SolverBase {
             const int gs = gmres_small_steps(l);
             L.gs.steps = gs;
             if (gs > 0) {
-                L.gs.v.alloc((size_t)(gs + 1) * L.N * nrhs);
+                alloc_zero(L.gs.v, (size_t)(gs + 1) * L.N * nrhs);
                 alloc_gmres_state(L.gs.g, gs, nrhs);
             }
             L.ks.steps = kcycle_level(l) ? 2 : 0;
             if (L.ks.steps) {
-                L.ks.v.alloc((size_t)3 * L.N * nrhs);
-                L.ks.z.alloc((size_t)2 * L.N * nrhs);
+                alloc_zero(L.ks.v, (size_t)3 * L.N * nrhs);
+                alloc_zero(L.ks.z, (size_t)2 * L.N * nrhs);
                 alloc_gmres_state(L.ks.g, 2, nrhs);
             }
         }
@@ -980,6 +1031,10 @@ class Solver : public SolverBase {
         d_partial.alloc((size_t)(HH_MAXV + 1) * std::max(nrhs, 1) * nblk_max);
     }
 
+    void alloc_zero(DevBuf<C>& b, size_t count) {
+        b.alloc(count);
+        HH_CUDA(cudaMemsetAsync(b.p, 0, count * sizeof(C), stream));
+    }
     void alloc_gmres_state(GmresMem& g, int m, int nrhs) {
         g.H.alloc((size_t)nrhs * (m + 1) * m);
         g.cs.alloc((size_t)nrhs * m);
@@ -1204,8 +1259,30 @@ class Solver : public SolverBase {
         HH_REQUIRE(have_hierarchy, HH_ERR_STATE, "hh_setup has not been called");
         ensure_level_memory((int)nrhs);
         ensure_const();
+        if (padded()) {
+            DevBuf<C> bp, zp;
+            alloc_zero(bp, (size_t)levels[0].N * nrhs);
+            alloc_zero(zp, (size_t)levels[0].N * nrhs);
+            repitch((const C*)dB, bp.p, (int)nrhs, true);
+            precondition(bp.p, zp.p, (int)nrhs);
+            repitch(zp.p, (C*)dZ, (int)nrhs, false);
+            HH_CUDA(cudaStreamSynchronize(stream));
+            return;
+        }
         precondition((const C*)dB, (C*)dZ, (int)nrhs);
         HH_CUDA(cudaStreamSynchronize(stream));
+    }
+    // internal fine-level vectors are padded (ComplexF32 on an odd grid with the TMA kernels)?
+    bool padded() const { return have_hierarchy && levels[0].N != pb.N(); }
+    // dense caller block (leading dimension pb.N()) <-> padded internal block (leading dimension levels[0].N)
+    void repitch(const C* src, C* dst, int nrhs, bool to_padded) {
+        const int64_t rows = (int64_t)pb.n[1] * pb.n[2];
+        const int n0 = pb.n[0], p0 = levels[0].p0;
+        dim3 g(std::max(1, 592 / std::max(nrhs, 1)), nrhs);
+        launch(T_COPY, 2 * S * (double)pb.N() * nrhs, [&] {
+            if (to_padded) k_repitch<C><<<g, 256, 0, stream>>>(src, dst, n0, rows, n0, p0, pb.N(), levels[0].N);
+            else k_repitch<C><<<g, 256, 0, stream>>>(src, dst, n0, rows, p0, n0, levels[0].N, pb.N());
+        });
     }
 
     void apply_device(const void* dX, void* dY, int64_t nrhs, int shifted, double shift, int transpose) override {
@@ -1246,15 +1323,16 @@ class Solver : public SolverBase {
         double avail = (double)fr;
         // memory we already hold for work vectors counts as available for re-use
         avail += (double)kcap * level_bytes_per_rhs() + (double)kry.n * sizeof(C);
-        const double per = level_bytes_per_rhs() + (double)krylov_vectors(o) * pb.N() * S;
+        const int64_t Nf = have_hierarchy ? levels[0].N : pb.N();
+        const double per = level_bytes_per_rhs() + (double)(krylov_vectors(o) + (padded() ? 2 : 0)) * Nf * S;
         int64_t k = (int64_t)std::floor(0.90 * avail / per);
         return std::max<int64_t>(k, 0);
     }
     void ensure_krylov_memory(const hh_solve_options& o, int nrhs) {
-        const size_t need = (size_t)krylov_vectors(o) * pb.N() * nrhs;
+        const size_t need = (size_t)(krylov_vectors(o) + (padded() ? 2 : 0)) * levels[0].N * nrhs;
         if (need > kry.n || nrhs > kry_cap) {
             kry.release();
-            kry.alloc(need);
+            alloc_zero(kry, need);
             kry_cap = nrhs;
         }
     }
@@ -1274,8 +1352,22 @@ class Solver : public SolverBase {
         ensure_krylov_memory(o, nrhs);
         ensure_const();
         int rc;
-        if (o.krylov == HH_KRYLOV_GMRES) rc = fgmres((const C*)dB, (C*)dX, nrhs, o, iters, relres);
-        else rc = bicgstab((const C*)dB, (C*)dX, nrhs, o, iters, relres);
+        const C* Bs = (const C*)dB;
+        C* Xs = (C*)dX;
+        if (padded()) {  // work on padded copies (the last two blocks of the Krylov arena); ghost nodes stay zero
+            const int64_t vs = levels[0].N * kry_cap;
+            C* bp = kry.p + (int64_t)krylov_vectors(o) * vs;
+            C* xp = bp + vs;
+            repitch(Bs, bp, nrhs, true);
+            Bs = bp;
+            Xs = xp;
+        }
+        if (o.krylov == HH_KRYLOV_GMRES) rc = fgmres(Bs, Xs, nrhs, o, iters, relres);
+        else rc = bicgstab(Bs, Xs, nrhs, o, iters, relres);
+        if (padded()) {
+            repitch(Xs, (C*)dX, nrhs, false);
+            HH_CUDA(cudaStreamSynchronize(stream));
+        }
         solve_seconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
         return rc;
     }
@@ -1298,7 +1390,7 @@ class Solver : public SolverBase {
     // (ShiftedLaplacianMultigridSolver.jl:89).
     int fgmres(const C* B, C* X, int nrhs, const hh_solve_options& o, int32_t* iters, double* relres) {
         const int m = o.inner;
-        const int64_t N = pb.N();
+        const int64_t N = levels[0].N;
         const int64_t vs = N * kry_cap;
         if (outer.st.m != m || outer_cap < nrhs) {
             alloc_gmres_state(outer, m, nrhs);
@@ -1363,7 +1455,7 @@ class Solver : public SolverBase {
         int cap = 0;
     };
     int bicgstab(const C* B, C* X, int nrhs, const hh_solve_options& o, int32_t* iters, double* relres) {
-        const int64_t N = pb.N();
+        const int64_t N = levels[0].N;
         const int64_t vs = N * kry_cap;
         if (bicg.cap < nrhs) {
             BicgMem& g = bicg;
@@ -1425,6 +1517,8 @@ class Solver : public SolverBase {
     enum { FK_TMA = 0, FK_ZMARCH = 1, FK_SIMPLE = 2 };
     int fine_kernel = FK_TMA;
     bool fuse_first = true;
+    bool use_pitch = false;
+    DevBuf<T> d_mp, d_gp;
     DevBuf<C> mg_cdiag, mg_dinv, h_cdiag[2];
     FineOp<T> h_op[2];
     bool h_op_valid[2] = {false, false};
