@@ -47,11 +47,12 @@ def parse():
     ap.add_argument("--cpu-iters", type=int, default=5, help="preconditioned iterations per CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--tol", type=float, default=1e-6, help="relative residual tolerance (1e-6 = the named metric)")
     return ap.parse_args()
 
 
 # ----------------------------------------------------------------------------------------------------
-def workload(pkg, n):
+def workload(pkg, n, tol=1e-6):
     """config 4 at n^3 nodes (sigma and pad scale with the grid so that small smoke sizes stay sensible)."""
     cfg = pkg.workloads.config4(n=n, sigma=8.0 * (n - 1) / 256, seed=1234, pad=max(4, 16 * (n - 1) // 256))
     mesh = pkg.getRegularMesh(cfg["domain"], cfg["n_cells"])
@@ -61,7 +62,7 @@ def workload(pkg, n):
     srcs = pkg.workloads.point_sources_top_grid(mesh.n + 1, 16, 16)
     return dict(cfg=cfg, mesh=mesh, m=m, w=w, gamma=gamma, srcs=srcs,
                 settings=dict(levels=3, shift=0.2, relax="Jac", relax_param=0.8, pre=1, post=2, cycle="W", coarse="GMRES",
-                              coarse_iters=10, krylov="GMRES", inner=5, tol=1e-6, max_cycles=30))
+                              coarse_iters=10, krylov="GMRES", inner=5, tol=tol, max_cycles=30))
 
 
 def workload_name(n, nrhs, prec):
@@ -176,7 +177,7 @@ def run_reference(a):
     if rank != 0:
         return
     pkg = graft.load_package()
-    wl = workload(pkg, a.n)
+    wl = workload(pkg, a.n, a.tol)
     iters_needed = iterations_to_tol(a.n)
     vals = []
     setup = None
@@ -240,7 +241,7 @@ def run_b200(a):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     pkg = graft.load_package()
     lib = pkg._lib.load()
-    wl = workload(pkg, a.n)
+    wl = workload(pkg, a.n, a.tol)
     s = wl["settings"]
     mesh = wl["mesh"]
     prec = np.complex128 if a.prec == "c128" else np.complex64
@@ -394,7 +395,7 @@ def run_b200(a):
             "config": {"workload": workload_name(a.n, a.nrhs, a.prec), "rhs_per_step_per_gpu": a.nrhs,
                        "parallelism": f"rhs-sharding x{world} (independent columns, no data-path collective)",
                        "l2": "inputs larger than L2: every vector block is %.0f MB, no flush needed" % (N * a.nrhs * (16 if a.prec == "c128" else 8) / 1e6),
-                       "iterations_mean": float(its.mean()), "iterations_max": int(its.max()),
+                       "rel_tol": a.tol, "iterations_mean": float(its.mean()), "iterations_max": int(its.max()),
                        "true_relres_max_last_step": true_res},
             "e2e": e2e,
             "gpu_launches": launches,

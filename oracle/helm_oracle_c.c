@@ -639,3 +639,7 @@ double horc_solve_fgmres(Oracle* o, const zc* B, zc* X, int nrhs, int inner, int
 }
 
 int horc_num_threads(void) { return omp_get_max_threads(); }
+/* torchrun exports OMP_NUM_THREADS=1 to every rank; the CPU arm (rank 0 only) asks for all host cores explicitly */
+void horc_set_threads(int n) {
+    if (n > 0) omp_set_num_threads(n);
+}

@@ -39,6 +39,7 @@ def load(build_if_missing=True):
     lib.horc_solve_fgmres.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int,
                                       C.POINTER(C.c_int32), dp]
     lib.horc_num_threads.restype = C.c_int
+    lib.horc_set_threads.argtypes = [C.c_int]
     _lib = lib
     return lib
 
@@ -50,6 +51,8 @@ class OracleC:
                  npost=2, cycle="V", coarse_iters=10, order_bc=2):
         lib = load()
         self.lib = lib
+        # all host cores unless HH_CPU_THREADS says otherwise (torchrun forces OMP_NUM_THREADS=1 on every rank)
+        lib.horc_set_threads(int(os.environ.get("HH_CPU_THREADS", os.cpu_count() or 1)))
         nn = np.ascontiguousarray(np.asarray(n_nodes, dtype=np.int64))
         hh = np.ascontiguousarray(np.asarray(h, dtype=np.float64))
         mm = np.ascontiguousarray(np.asarray(m, dtype=np.float64).ravel(order="F"))
