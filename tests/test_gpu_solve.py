@@ -266,3 +266,41 @@ def test_update_model_frequency_sweep(gpu_pkg, ho):
     H2 = ho.GetHelmholtzOperator(omesh, m, w2, g2, True, True)
     assert np.linalg.norm(H2 @ x2 - q) / np.linalg.norm(q) < 1e-7
     assert np.linalg.norm(H1 @ x2 - q) / np.linalg.norm(q) > 1e-3  # really the new problem
+
+
+def test_device_tensor_path_equals_host_path_and_error_paths(gpu_pkg, ho):
+    """hh_solve_device (zero-copy on torch CUDA tensors) returns the same iterates as hh_solve (host arrays);
+    impossible hierarchies fail loudly with the library's message."""
+    import torch
+
+    pkg = gpu_pkg
+    n = 17
+    cfg = pkg.workloads.config4(n=n, sigma=2.0, seed=9, pad=3)
+    mesh = pkg.getRegularMesh(cfg["domain"], cfg["n_cells"])
+    m = cfg["m"]
+    w = pkg.getMaximalFrequency(m, mesh)
+    gamma = 0.01 * w * np.ones(m.shape) + pkg.getABL(mesh.n + 1, True, cfg["pad"], w)
+    rng = np.random.default_rng(2)
+    B = rng.standard_normal((n**3, 3)) + 1j * rng.standard_normal((n**3, 3))
+    hp = pkg.HelmholtzParam(mesh, gamma, m.ravel(order="F"), w, True, True)
+    for prec, tdt, tol in ((np.complex128, torch.complex128, 1e-13), (np.complex64, torch.complex64, 1e-5)):
+        MG = pkg.getMGparam(prec, pkg.Int64, 2, 1, 30, 1e-6 if prec == np.complex128 else 1e-4, "Jac", 0.8, 2, 2, "V", "NoMUMPS")
+        A = pkg.getShiftedLaplacianMultigridSolver(hp, MG, 0.2, "GMRES", 5)
+        Xh, A = pkg.solveLinearSystem(None, B.astype(prec), A)
+        it_h = A.iterations.copy()
+        Bt = torch.as_tensor(np.ascontiguousarray(B.T.astype(prec)), device="cuda")  # rows = right-hand sides
+        Xt, A = pkg.solveLinearSystem(None, Bt, A)
+        assert Xt.dtype == tdt and Xt.shape == Bt.shape
+        assert np.array_equal(A.iterations, it_h)
+        assert rel_err(Xt.cpu().numpy().T, Xh) < tol
+    # too many levels for the grid: 17 -> 9 -> 5 -> 3 -> 2 (even) cannot coarsen again
+    MG = pkg.getMGparam(pkg.ComplexF64, pkg.Int64, 6, 1, 30, 1e-6, "Jac", 0.8, 2, 2, "V", "GMRES")
+    A = pkg.getShiftedLaplacianMultigridSolver(hp, MG, 0.2, "GMRES", 5)
+    with pytest.raises(pkg._lib.HelmholtzB200Error) as e:
+        pkg.solveLinearSystem(None, B, A)
+    assert "cannot coarsen" in str(e.value)
+    # exact coarsest solve on a 1-level "hierarchy" is not available (the fine level is matrix-free)
+    MG = pkg.getMGparam(pkg.ComplexF64, pkg.Int64, 1, 1, 30, 1e-6, "Jac", 0.8, 2, 2, "V", "NoMUMPS")
+    A = pkg.getShiftedLaplacianMultigridSolver(hp, MG, 0.2, "GMRES", 5)
+    with pytest.raises(pkg._lib.HelmholtzB200Error):
+        pkg.solveLinearSystem(None, B, A)
