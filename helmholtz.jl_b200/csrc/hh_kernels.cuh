@@ -1529,25 +1529,6 @@ __global__ void __launch_bounds__(256) k_multiaxpy(VecList<T> V, cx<T>* __restri
     }
 }
 
-// out = alpha[r] * in  (per-RHS complex scalar; used for v = w / ||w||)
-template <typename T>
-__global__ void __launch_bounds__(256) k_scale(const cx<T>* __restrict__ in, cx<T>* __restrict__ out, int64_t N,
-                                               int64_t ld_in, int64_t ld_out, const zc* __restrict__ alpha, int astride) {
-    const int r = blockIdx.y;
-    const zc a = alpha[(int64_t)r * astride];
-    const cx<T> s = mk<T>((T)a.x, (T)a.y);
-    for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < N; p += (int64_t)gridDim.x * blockDim.x)
-        out[(int64_t)r * ld_out + p] = s * in[(int64_t)r * ld_in + p];
-}
-
-template <typename T>
-__global__ void __launch_bounds__(256) k_copy(const cx<T>* __restrict__ in, cx<T>* __restrict__ out, int64_t N,
-                                              int64_t ld_in, int64_t ld_out) {
-    const int r = blockIdx.y;
-    for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < N; p += (int64_t)gridDim.x * blockDim.x)
-        out[(int64_t)r * ld_out + p] = in[(int64_t)r * ld_in + p];
-}
-
 // dst (row pitch dsy, leading dimension dld) <- src (row pitch ssy, leading dimension sld); rows of n0 nodes
 template <typename U>
 __global__ void __launch_bounds__(256) k_repitch(const U* __restrict__ src, U* __restrict__ dst, int n0, int64_t rows,

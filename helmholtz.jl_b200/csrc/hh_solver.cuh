@@ -56,7 +56,6 @@ enum Tag {
     T_COARSEST_DENSE,
     T_DOT,
     T_AXPY,
-    T_SCALE,
     T_COPY,
     T_SCALAR,
     T_SETUP,
@@ -66,7 +65,7 @@ static const char* const kTagNames[T_NTAGS] = {
     "fine_apply",   "fine_resid",   "fine_jacobi",    "fine_jacobi0", "fine_first_resid", "fine_first_jacobi", "fine_prolong_jacobi",
     "coarse_apply", "coarse_resid",
     "coarse_jacobi", "coarse_jacobi0", "restrict",    "prolong",      "coarsest_dense", "krylov_dot",
-    "krylov_axpy",  "krylov_scale", "copy",           "scalar",       "setup"};
+    "krylov_axpy",  "copy",           "scalar",       "setup"};
 
 struct Profiler {
     struct Rec {
@@ -804,11 +803,6 @@ class Solver : public SolverBase {
 #undef HH_MA
         });
         return nblk;
-    }
-    void scale_vec(const C* in, C* out, int64_t N, int nrhs, const zc* alpha, int astride) {
-        dim3 g(vec_blocks(N, nrhs), nrhs);
-        launch(T_SCALE, 2 * S * (double)N * nrhs,
-               [&] { k_scale<T><<<g, 256, 0, stream>>>(in, out, N, N, N, alpha, astride); });
     }
 
     // ------------------------------------------------------------------ hierarchy (MGsetup)
