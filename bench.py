@@ -238,6 +238,9 @@ def run_b200(a):
     torch.cuda.set_device(local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        # NCCL_DEBUG=VERSION makes NCCL print its banner on stdout, ahead of the one JSON line this script owes
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     pkg = graft.load_package()
     lib = pkg._lib.load()
