@@ -10,8 +10,47 @@
 
 using namespace hh;
 
+// Device-side staging of host right-hand sides / solutions for hh_solve: two slots so that the copies of one
+// sub-batch overlap the solve of the other (copy stream + events), kept across calls.
+struct HostStage {
+    cudaStream_t cs = nullptr;
+    cudaEvent_t h2d[2] = {nullptr, nullptr}, solved[2] = {nullptr, nullptr}, d2h[2] = {nullptr, nullptr};
+    DevBuf<char> db[2], dx[2];
+    void init() {
+        if (cs) return;
+        HH_CUDA(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));  // must not serialise with the legacy stream
+        for (int i = 0; i < 2; ++i) {
+            HH_CUDA(cudaEventCreateWithFlags(&h2d[i], cudaEventDisableTiming));
+            HH_CUDA(cudaEventCreateWithFlags(&solved[i], cudaEventDisableTiming));
+            HH_CUDA(cudaEventCreateWithFlags(&d2h[i], cudaEventDisableTiming));
+        }
+    }
+    void ensure(size_t bytes) {
+        for (int i = 0; i < 2; ++i)
+            if (db[i].n < bytes) {
+                db[i].alloc(bytes);
+                dx[i].alloc(bytes);
+            }
+    }
+    void release() {
+        for (int i = 0; i < 2; ++i) {
+            db[i].release();
+            dx[i].release();
+        }
+    }
+    ~HostStage() {
+        for (int i = 0; i < 2; ++i) {
+            if (h2d[i]) cudaEventDestroy(h2d[i]);
+            if (solved[i]) cudaEventDestroy(solved[i]);
+            if (d2h[i]) cudaEventDestroy(d2h[i]);
+        }
+        if (cs) cudaStreamDestroy(cs);
+    }
+};
+
 struct hh_handle_s {
     std::vector<std::unique_ptr<SolverBase>> subs;  // one per device
+    std::vector<std::unique_ptr<HostStage>> stages; // one per device
     int precision = HH_C64;
     Problem pb;
     std::string err;
@@ -225,6 +264,7 @@ static int create_impl(int dim, const int64_t* n_nodes, const double* hsp, const
             HH_REQUIRE(devices[i] >= 0 && devices[i] < ndevices, HH_ERR_ARG, "hh_create: bad device ordinal");
             if (precision == HH_C64) h->subs.emplace_back(new Solver<double>(pb, devices[i]));
             else h->subs.emplace_back(new Solver<float>(pb, devices[i]));
+            h->stages.emplace_back(new HostStage);
         }
         for_each_sub(h.get(), [&](int i) { h->subs[i]->set_model(m, gamma, wre, wim); });
         h->pb.w_re = wre;
@@ -251,9 +291,10 @@ int hh_create_multi(int dim, const int64_t* n_nodes, const double* h, const doub
 int hh_destroy(hh_handle_t h) {
     if (!h) return HH_OK;
     return guarded(nullptr, [&]() -> int {
-        for (auto& s : h->subs) {
-            cudaSetDevice(s->device);
-            s.reset();
+        for (size_t i = 0; i < h->subs.size(); ++i) {
+            cudaSetDevice(h->subs[i]->device);
+            h->stages[i].reset();
+            h->subs[i].reset();
         }
         delete h;
         return HH_OK;
@@ -298,6 +339,7 @@ int hh_clear(hh_handle_t h) {
         for_each_sub(h, [&](int i) {
             cudaSetDevice(h->subs[i]->device);
             h->subs[i]->clear();
+            h->stages[i]->release();
         });
         return HH_OK;
     });
@@ -452,38 +494,56 @@ static int solve_host(hh_handle_t h, const void* B, const int64_t* idx, const do
         if (c1 <= c0) return;
         HH_CUDA(cudaSetDevice(s->device));
         const size_t es = s->elem_size();
-        // B and X chunks live on the device next to the Krylov vectors: reserve them first
-        size_t fr = 0, tot = 0;
-        HH_CUDA(cudaMemGetInfo(&fr, &tot));
+        HostStage& hs = *h->stages[i];
+        hs.init();
+        // Sub-batch size: what fits next to the Krylov / multigrid work vectors with two staging slots of (B, X);
+        // a range that would fit in one batch is still split in two so that the PCIe copies of one half overlap
+        // the solve of the other (HH_HOST_PIPELINE=0 disables the split).
+        const int64_t ncols = c1 - c0;
         int64_t kmax = s->max_rhs_per_batch(*opts);
-        // two more vectors per RHS (B, X)
-        const double per_now = (double)N * es;
         {
-            // shrink so that B and X fit as well (max_rhs_per_batch assumed they were caller memory)
-            const int kv = opts->krylov == HH_KRYLOV_GMRES ? 2 * opts->inner + 1 : 7;
-            kmax = (int64_t)((double)kmax * (double)(kv + 2) / (double)(kv + 4));
+            const double kv = (opts->krylov == HH_KRYLOV_GMRES ? 2 * opts->inner + 1 : 7) + 3.5;
+            kmax = (int64_t)((double)kmax * kv / (kv + 4.0));
         }
-        (void)per_now;
-        kmax = std::min<int64_t>(std::max<int64_t>(kmax, 1), c1 - c0);
-        DevBuf<char> db, dx;
-        db.alloc((size_t)N * kmax * es);
-        dx.alloc((size_t)N * kmax * es);
+        kmax = std::min<int64_t>(std::max<int64_t>(kmax, 1), ncols);
+        const char* pe = getenv("HH_HOST_PIPELINE");
+        const bool pipeline = !(pe && pe[0] == '0');
+        int64_t kb = kmax;
+        if (pipeline && ncols >= 8 && kmax >= (ncols + 1) / 2) kb = (ncols + 1) / 2;
+        hs.ensure((size_t)N * kb * es);
+        const int64_t nb = (ncols + kb - 1) / kb;
         std::vector<int64_t> idx0;
-        for (int64_t c = c0; c < c1; c += kmax) {
-            const int64_t k = std::min(kmax, c1 - c);
+        auto stage_in = [&](int64_t bidx) {  // enqueue the right-hand sides of sub-batch bidx into its slot
+            const int slot = (int)(bidx & 1);
+            const int64_t c = c0 + bidx * kb, k = std::min(kb, c1 - c);
             if (idx) {
                 idx0.resize(k);
                 for (int64_t r = 0; r < k; ++r) idx0[r] = idx[c + r] - 1;
-                s->scatter_point_sources(db.p, idx0.data(), val + 2 * c, k);
+                s->scatter_point_sources(hs.db[slot].p, idx0.data(), val + 2 * c, k);  // on the compute stream
             } else {
-                HH_CUDA(cudaMemcpyAsync(db.p, (const char*)B + (size_t)c * N * es, (size_t)N * k * es, cudaMemcpyHostToDevice, s->stream));
+                HH_CUDA(cudaMemcpyAsync(hs.db[slot].p, (const char*)B + (size_t)c * N * es, (size_t)N * k * es,
+                                        cudaMemcpyHostToDevice, hs.cs));
+                HH_CUDA(cudaEventRecord(hs.h2d[slot], hs.cs));
             }
-            int r = s->solve_device(db.p, dx.p, k, *opts, iters_out ? iters_out + c : nullptr,
+        };
+        stage_in(0);
+        for (int64_t bidx = 0; bidx < nb; ++bidx) {
+            const int slot = (int)(bidx & 1);
+            const int64_t c = c0 + bidx * kb, k = std::min(kb, c1 - c);
+            // prefetch the next sub-batch: its B slot was last read by solve(bidx-1), which has returned
+            if (bidx + 1 < nb) stage_in(bidx + 1);
+            if (!idx) HH_CUDA(cudaStreamWaitEvent(s->stream, hs.h2d[slot], 0));
+            if (bidx >= 2) HH_CUDA(cudaStreamWaitEvent(s->stream, hs.d2h[slot], 0));  // X slot still being copied out?
+            int r = s->solve_device(hs.db[slot].p, hs.dx[slot].p, k, *opts, iters_out ? iters_out + c : nullptr,
                                     relres_out ? relres_out + c : nullptr);
             rcs[i] = std::max(rcs[i], r);
-            HH_CUDA(cudaMemcpyAsync((char*)X + (size_t)c * N * es, dx.p, (size_t)N * k * es, cudaMemcpyDeviceToHost, s->stream));
-            HH_CUDA(cudaStreamSynchronize(s->stream));
+            HH_CUDA(cudaEventRecord(hs.solved[slot], s->stream));
+            HH_CUDA(cudaStreamWaitEvent(hs.cs, hs.solved[slot], 0));
+            HH_CUDA(cudaMemcpyAsync((char*)X + (size_t)c * N * es, hs.dx[slot].p, (size_t)N * k * es, cudaMemcpyDeviceToHost, hs.cs));
+            HH_CUDA(cudaEventRecord(hs.d2h[slot], hs.cs));
         }
+        HH_CUDA(cudaStreamSynchronize(hs.cs));
+        HH_CUDA(cudaStreamSynchronize(s->stream));
     });
     int rc = HH_OK;
     for (int r : rcs) rc = std::max(rc, r);
