@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(HERE, "lib", "libhelmholtz_b200.so")
 HH_OK = 0
 HH_NOT_CONVERGED = 1
 HH_ERR_ARG, HH_ERR_CUDA, HH_ERR_STATE, HH_ERR_NAN, HH_ERR_UNSUPPORTED, HH_ERR_ALLOC = -1, -2, -3, -4, -5, -6
-HH_C64, HH_C32 = 0, 1
+HH_C64, HH_C32, HH_C64_MIXED = 0, 1, 2
 HH_RELAX_JAC, HH_RELAX_JAC_GMRES = 0, 1
 HH_CYCLE_V, HH_CYCLE_W, HH_CYCLE_K = 0, 1, 2
 HH_COARSE_LU, HH_COARSE_GMRES = 0, 1

@@ -73,7 +73,7 @@ class _Handle:
     """Owns an hh_handle_t (HelmholtzParam + device state)."""
 
     def __init__(self, Mesh, m, omega, gamma, NeumannOnTop, Sommerfeld, orderNeumannBC=2, precision=ComplexF64,
-                 devices=None):
+                 devices=None, cycle_precision=None):
         lib = L.load()
         nodes = (np.asarray(Mesh.n, dtype=np.int64) + 1).copy()
         N = int(np.prod(nodes))
@@ -89,6 +89,11 @@ class _Handle:
         prec = L.HH_C64 if self.dtype == np.complex128 else L.HH_C32
         if self.dtype not in (np.dtype(np.complex128), np.dtype(np.complex64)):
             raise ValueError("precision must be ComplexF64 or ComplexF32")
+        if cycle_precision is not None and np.dtype(cycle_precision) != self.dtype:
+            # opt-in extension: ComplexF64 Krylov with the multigrid cycle evaluated in ComplexF32
+            if not (self.dtype == np.complex128 and np.dtype(cycle_precision) == np.complex64):
+                raise ValueError("cyclePrecision must be ComplexF32 on a ComplexF64 solver")
+            prec = L.HH_C64_MIXED
         w = complex(omega)
         out = C.c_void_p()
         if devices is None:
@@ -325,6 +330,7 @@ class MGparam:
         self.FilteringParam = FilteringParam
         self.transferOperatorType = transferOperatorType
         self.coarseIters = int(coarseIters)
+        self.cyclePrecision = None  # extension: ComplexF32 evaluates the cycle in single precision inside a ComplexF64 Krylov
         self.doTranspose = 0
         self._hd = None
         self._built_for = None
@@ -358,7 +364,7 @@ class MGparam:
         pre = tuple(int(self.relaxPre(l + 1)) if callable(self.relaxPre) else int(self.relaxPre) for l in range(self.levels))
         post = tuple(int(self.relaxPost(l + 1)) if callable(self.relaxPost) else int(self.relaxPost) for l in range(self.levels))
         return (self.levels, self.relaxType, self.relaxParam, pre, post, str(self.cycleType), self.coarseSolveType,
-                self.coarseIters, float(shift[0]), int(doTranspose))
+                self.coarseIters, float(shift[0]), int(doTranspose), str(self.cyclePrecision))
 
 
 def getMGparam(*args, **kw):
@@ -432,6 +438,7 @@ def copySolver(s):
     MG2 = MGparam(MG.VAL, MG.levels, MG.numCores, MG.maxOuterIter, MG.relativeTol, MG.relaxType, MG.relaxParam,
                   MG.relaxPre, MG.relaxPost, MG.cycleType, MG.coarseSolveType, MG.strongConnParam, MG.FilteringParam,
                   MG.transferOperatorType, MG.coarseIters)
+    MG2.cyclePrecision = MG.cyclePrecision
     s2 = getShiftedLaplacianMultigridSolver(s.helmParam, MG2, s.shift, s.Krylov, s.inner, s.verbose)
     s2.devices = s.devices
     return s2
@@ -441,8 +448,12 @@ def _ensure_hierarchy(param, doTranspose):
     MG = param.MG
     hp = param.helmParam
     sig = MG._signature(param.shift, doTranspose)
+    if MG._hd is not None and getattr(MG._hd, "cycle_precision", None) != MG.cyclePrecision:
+        clear(MG)  # the precision of the cycle is a property of the handle
     if MG._hd is None:
-        MG._hd = _Handle(hp.Mesh, hp.m, hp.omega, hp.gamma, hp.NeumannOnTop, hp.Sommerfeld, 2, MG.VAL, param.devices)
+        MG._hd = _Handle(hp.Mesh, hp.m, hp.omega, hp.gamma, hp.NeumannOnTop, hp.Sommerfeld, 2, MG.VAL, param.devices,
+                         MG.cyclePrecision)
+        MG._hd.cycle_precision = MG.cyclePrecision
     hd = MG._hd
     if (not hd.lib.hh_hierarchy_exists(hd.h)) or MG._built_for != sig:
         # first call (hierarchyExists == false, :50-66), a flipped doTranspose (transposeHierarchy, :68-70) or

@@ -51,6 +51,9 @@ struct HostStage {
 struct hh_handle_s {
     std::vector<std::unique_ptr<SolverBase>> subs;  // one per device
     std::vector<std::unique_ptr<HostStage>> stages; // one per device
+    // HH_C64_MIXED: the ComplexF32 companion of every replica (owns the hierarchy) and its staging blocks
+    std::vector<std::unique_ptr<SolverBase>> lows;
+    std::vector<std::unique_ptr<DevBuf<cx<float>>>> lo_b, lo_z;
     int precision = HH_C64;
     Problem pb;
     std::string err;
@@ -236,7 +239,7 @@ static int create_impl(int dim, const int64_t* n_nodes, const double* hsp, const
         *out = nullptr;
         HH_REQUIRE(dim == 2 || dim == 3, HH_ERR_ARG, "hh_create: dim must be 2 or 3");
         HH_REQUIRE(n_nodes && hsp && m && gamma, HH_ERR_ARG, "hh_create: NULL array");
-        HH_REQUIRE(precision == HH_C64 || precision == HH_C32, HH_ERR_ARG, "hh_create: bad precision");
+        HH_REQUIRE(precision == HH_C64 || precision == HH_C32 || precision == HH_C64_MIXED, HH_ERR_ARG, "hh_create: bad precision");
         HH_REQUIRE(order_bc == 1 || order_bc == 2, HH_ERR_ARG, "getNodalLaplacianMatrix: BC not supported");
         HH_REQUIRE(wre != 0.0, HH_ERR_ARG, "hh_create: Re(omega) must be non-zero");
         HH_REQUIRE(ndev >= 1 && devices, HH_ERR_ARG, "hh_create: no devices");
@@ -262,11 +265,46 @@ static int create_impl(int dim, const int64_t* n_nodes, const double* hsp, const
         h->pb = pb;
         for (int i = 0; i < ndev; ++i) {
             HH_REQUIRE(devices[i] >= 0 && devices[i] < ndevices, HH_ERR_ARG, "hh_create: bad device ordinal");
-            if (precision == HH_C64) h->subs.emplace_back(new Solver<double>(pb, devices[i]));
-            else h->subs.emplace_back(new Solver<float>(pb, devices[i]));
+            if (precision == HH_C32) h->subs.emplace_back(new Solver<float>(pb, devices[i]));
+            else h->subs.emplace_back(new Solver<double>(pb, devices[i]));
             h->stages.emplace_back(new HostStage);
+            if (precision == HH_C64_MIXED) {
+                h->lows.emplace_back(new Solver<float>(pb, devices[i]));
+                h->lo_b.emplace_back(new DevBuf<cx<float>>);
+                h->lo_z.emplace_back(new DevBuf<cx<float>>);
+                SolverBase* hi = h->subs[i].get();
+                SolverBase* lo = h->lows[i].get();
+                DevBuf<cx<float>>* bb = h->lo_b[i].get();
+                DevBuf<cx<float>>* zz = h->lo_z[i].get();
+                hi->krylov_only = true;
+                // z = M(b): b, z ComplexF64 blocks of the outer solver; the cycle runs on ComplexF32 copies
+                hi->prec_hook = [hi, lo, bb, zz](const void* b, void* z, int nrhs) {
+                    lo->stream = hi->stream;
+                    lo->ensure_cycle_memory(nrhs);
+                    const int64_t ldl = lo->internal_ld(), ldh = hi->internal_ld();
+                    const size_t need = (size_t)ldl * nrhs;
+                    if (bb->n < need) {
+                        bb->alloc(need);
+                        zz->alloc(need);
+                        HH_CUDA(cudaMemsetAsync(bb->p, 0, need * sizeof(cx<float>), hi->stream));  // ghost nodes stay zero
+                        HH_CUDA(cudaMemsetAsync(zz->p, 0, need * sizeof(cx<float>), hi->stream));
+                    }
+                    const int n0 = hi->pb.n[0];
+                    const int64_t rows = (int64_t)hi->pb.n[1] * hi->pb.n[2];
+                    dim3 g(std::max(1, 592 / std::max(nrhs, 1)), nrhs);
+                    k_convert<double, float><<<g, 256, 0, hi->stream>>>((const cx<double>*)b, bb->p, n0, rows, hi->internal_pitch(),
+                                                                       lo->internal_pitch(), ldh, ldl);
+                    lo->precondition_internal(bb->p, zz->p, nrhs);
+                    k_convert<float, double><<<g, 256, 0, hi->stream>>>(zz->p, (cx<double>*)z, n0, rows, lo->internal_pitch(),
+                                                                       hi->internal_pitch(), ldl, ldh);
+                    hi->launches += 2;
+                };
+            }
         }
-        for_each_sub(h.get(), [&](int i) { h->subs[i]->set_model(m, gamma, wre, wim); });
+        for_each_sub(h.get(), [&](int i) {
+            h->subs[i]->set_model(m, gamma, wre, wim);
+            if (!h->lows.empty()) h->lows[i]->set_model(m, gamma, wre, wim);
+        });
         h->pb.w_re = wre;
         h->pb.w_im = wim;
         *out = h.release();
@@ -294,6 +332,11 @@ int hh_destroy(hh_handle_t h) {
         for (size_t i = 0; i < h->subs.size(); ++i) {
             cudaSetDevice(h->subs[i]->device);
             h->stages[i].reset();
+            if (!h->lows.empty()) {
+                h->lo_b[i].reset();
+                h->lo_z[i].reset();
+                h->lows[i].reset();
+            }
             h->subs[i].reset();
         }
         delete h;
@@ -315,7 +358,10 @@ int hh_update_model(hh_handle_t h, const double* m, const double* gamma, double 
     if (!h) return HH_ERR_ARG;
     return guarded(h, [&]() -> int {
         HH_REQUIRE(m && gamma && omega_re != 0.0, HH_ERR_ARG, "hh_update_model: bad arguments");
-        for_each_sub(h, [&](int i) { h->subs[i]->set_model(m, gamma, omega_re, omega_im); });
+        for_each_sub(h, [&](int i) {
+            h->subs[i]->set_model(m, gamma, omega_re, omega_im);
+            if (!h->lows.empty()) h->lows[i]->set_model(m, gamma, omega_re, omega_im);
+        });
         h->pb.w_re = omega_re;
         h->pb.w_im = omega_im;
         return HH_OK;
@@ -326,7 +372,13 @@ int hh_setup(hh_handle_t h, const hh_mg_options* opts) {
     if (!h) return HH_ERR_ARG;
     return guarded(h, [&]() -> int {
         HH_REQUIRE(opts != nullptr, HH_ERR_ARG, "hh_setup: opts is NULL");
-        for_each_sub(h, [&](int i) { h->subs[i]->setup(*opts); });
+        for_each_sub(h, [&](int i) {
+            h->subs[i]->setup(*opts);
+            if (!h->lows.empty()) {
+                h->lows[i]->stream = h->subs[i]->stream;
+                h->lows[i]->setup(*opts);
+            }
+        });
         h->opts = *opts;
         h->have_opts = true;
         return HH_OK;
@@ -340,17 +392,25 @@ int hh_clear(hh_handle_t h) {
             cudaSetDevice(h->subs[i]->device);
             h->subs[i]->clear();
             h->stages[i]->release();
+            if (!h->lows.empty()) {
+                h->lows[i]->clear();
+                h->lo_b[i]->release();
+                h->lo_z[i]->release();
+            }
         });
         return HH_OK;
     });
 }
 
-int hh_hierarchy_exists(hh_handle_t h) { return (h && h->subs[0]->hierarchy_exists()) ? 1 : 0; }
+int hh_hierarchy_exists(hh_handle_t h) {
+    if (!h) return 0;
+    return (h->lows.empty() ? h->subs[0]->hierarchy_exists() : h->lows[0]->hierarchy_exists()) ? 1 : 0;
+}
 
 int hh_level_nodes(hh_handle_t h, int level, int64_t* out) {
     if (!h || !out) return HH_ERR_ARG;
     return guarded(h, [&]() -> int {
-        h->subs[0]->level_nodes(level, out);
+        (h->lows.empty() ? h->subs[0] : h->lows[0])->level_nodes(level, out);
         return HH_OK;
     });
 }
@@ -358,6 +418,7 @@ int hh_level_nodes(hh_handle_t h, int level, int64_t* out) {
 int hh_get_level_stencil(hh_handle_t h, int level, void* coef_out) {
     if (!h || !coef_out) return HH_ERR_ARG;
     return guarded(h, [&]() -> int {
+        HH_REQUIRE(h->lows.empty(), HH_ERR_UNSUPPORTED, "hh_get_level_stencil: not available on a mixed-precision handle");
         h->subs[0]->get_level_stencil(level, coef_out);
         return HH_OK;
     });
@@ -380,6 +441,20 @@ int hh_apply_device(hh_handle_t h, const void* dX, void* dY, int64_t nrhs, int s
         h->subs[0]->apply_device(dX, dY, nrhs, shifted, shift, transpose);
         return HH_OK;
     });
+}
+
+// right-hand sides replica i can hold at once next to its work vectors (and its ComplexF32 companion's, if mixed)
+static int64_t batch_limit(hh_handle_t h, int i, const hh_solve_options& o) {
+    SolverBase* s = h->subs[i].get();
+    if (h->lows.empty()) return s->max_rhs_per_batch(o);
+    SolverBase* lo = h->lows[i].get();
+    HH_CUDA(cudaSetDevice(s->device));
+    size_t fr = 0, tot = 0;
+    HH_CUDA(cudaMemGetInfo(&fr, &tot));
+    const double staging = 2.0 * (double)lo->internal_ld() * sizeof(cx<float>);
+    const double per = s->per_rhs_bytes(o) + lo->cycle_bytes_per_rhs() + staging;
+    const double held = s->held_bytes() + lo->held_bytes() + (double)(h->lo_b[i]->n + h->lo_z[i]->n) * sizeof(cx<float>);
+    return std::max<int64_t>((int64_t)std::floor(0.90 * ((double)fr + held) / per), 0);
 }
 
 // split [0,nrhs) into contiguous column ranges, one per replica
@@ -462,7 +537,7 @@ int hh_solve_device(hh_handle_t h, const void* dB, void* dX, int64_t nrhs, const
         check_solve_opts(opts);
         HH_REQUIRE(h->subs.size() == 1, HH_ERR_UNSUPPORTED, "device-pointer entry points need a single-device handle");
         SolverBase* s = h->subs[0].get();
-        const int64_t kmax = s->max_rhs_per_batch(*opts);
+        const int64_t kmax = batch_limit(h, 0, *opts);
         HH_REQUIRE(kmax >= 1, HH_ERR_ALLOC, "not enough device memory for one right-hand side");
         const int64_t N = h->pb.N();
         const size_t es = s->elem_size();
@@ -500,7 +575,7 @@ static int solve_host(hh_handle_t h, const void* B, const int64_t* idx, const do
         // a range that would fit in one batch is still split in two so that the PCIe copies of one half overlap
         // the solve of the other (HH_HOST_PIPELINE=0 disables the split).
         const int64_t ncols = c1 - c0;
-        int64_t kmax = s->max_rhs_per_batch(*opts);
+        int64_t kmax = batch_limit(h, i, *opts);
         {
             const double kv = (opts->krylov == HH_KRYLOV_GMRES ? 2 * opts->inner + 1 : 7) + 3.5;
             kmax = (int64_t)((double)kmax * kv / (kv + 4.0));
@@ -580,6 +655,10 @@ int hh_get_counters(hh_handle_t h, double* setup_seconds, double* solve_seconds,
         c += s->n_prec;
         d += s->launches;
     }
+    for (auto& s : h->lows) {
+        a = std::max(a, s->setup_seconds);
+        d += s->launches;
+    }
     if (setup_seconds) *setup_seconds = a;
     if (solve_seconds) *solve_seconds = b;
     if (n_prec) *n_prec = c;
@@ -590,11 +669,12 @@ int hh_get_counters(hh_handle_t h, double* setup_seconds, double* solve_seconds,
 int hh_profile_enable(hh_handle_t h, int on) {
     if (!h) return HH_ERR_ARG;
     return guarded(h, [&]() -> int {
-        for (auto& s : h->subs) {
-            HH_CUDA(cudaSetDevice(s->device));
-            if (!on) s->prof.flush(s->stream);
-            s->prof.on = on != 0;
-        }
+        for (auto* v : {&h->subs, &h->lows})
+            for (auto& s : *v) {
+                HH_CUDA(cudaSetDevice(s->device));
+                if (!on) s->prof.flush(s->stream);
+                s->prof.on = on != 0;
+            }
         return HH_OK;
     });
 }
@@ -602,11 +682,12 @@ int hh_profile_enable(hh_handle_t h, int on) {
 int hh_profile_reset(hh_handle_t h) {
     if (!h) return HH_ERR_ARG;
     return guarded(h, [&]() -> int {
-        for (auto& s : h->subs) {
-            HH_CUDA(cudaSetDevice(s->device));
-            s->prof.flush(s->stream);
-            s->prof.reset();
-        }
+        for (auto* v : {&h->subs, &h->lows})
+            for (auto& s : *v) {
+                HH_CUDA(cudaSetDevice(s->device));
+                s->prof.flush(s->stream);
+                s->prof.reset();
+            }
         return HH_OK;
     });
 }
@@ -620,13 +701,14 @@ int hh_profile_get(hh_handle_t h, int tag, int64_t* launches, double* millisecon
     return guarded(h, [&]() -> int {
         int64_t n = 0;
         double ms = 0, by = 0;
-        for (auto& s : h->subs) {
-            HH_CUDA(cudaSetDevice(s->device));
-            s->prof.flush(s->stream);
-            n += s->prof.count[tag];
-            ms += s->prof.ms[tag];
-            by += s->prof.bytes[tag];
-        }
+        for (auto* v : {&h->subs, &h->lows})
+            for (auto& s : *v) {
+                HH_CUDA(cudaSetDevice(s->device));
+                s->prof.flush(s->stream);
+                n += s->prof.count[tag];
+                ms += s->prof.ms[tag];
+                by += s->prof.bytes[tag];
+            }
         if (launches) *launches = n;
         if (milliseconds) *milliseconds = ms;
         if (algorithmic_bytes) *algorithmic_bytes = by;
@@ -641,7 +723,12 @@ int hh_profile_num_entries(hh_handle_t h) {
         SolverBase* s = h->subs[0].get();
         cudaSetDevice(s->device);
         s->prof.flush(s->stream);
-        return (int)s->prof.entries.size();
+        int n = (int)s->prof.entries.size();
+        if (!h->lows.empty()) {
+            h->lows[0]->prof.flush(h->lows[0]->stream);
+            n += (int)h->lows[0]->prof.entries.size();
+        }
+        return n;
     } catch (...) {
         return 0;
     }
@@ -652,8 +739,10 @@ int hh_profile_entry(hh_handle_t h, int index, int* tag, int64_t* launches, doub
     if (!h) return HH_ERR_ARG;
     return guarded(h, [&]() -> int {
         SolverBase* s = h->subs[0].get();
-        HH_REQUIRE(index >= 0 && index < (int)s->prof.entries.size(), HH_ERR_ARG, "hh_profile_entry: bad index");
-        const auto& e = s->prof.entries[index];
+        const int n0 = (int)s->prof.entries.size();
+        const int n1 = h->lows.empty() ? 0 : (int)h->lows[0]->prof.entries.size();
+        HH_REQUIRE(index >= 0 && index < n0 + n1, HH_ERR_ARG, "hh_profile_entry: bad index");
+        const auto& e = index < n0 ? s->prof.entries[index] : h->lows[0]->prof.entries[index - n0];
         if (tag) *tag = e.tag;
         if (launches) *launches = e.count;
         if (milliseconds) *milliseconds = e.ms;

@@ -1542,6 +1542,21 @@ __global__ void __launch_bounds__(256) k_repitch(const U* __restrict__ src, U* _
     }
 }
 
+// precision conversion between blocks with different row pitches (mixed precision: ComplexF64 Krylov vectors <->
+// ComplexF32 multigrid vectors); rows of n0 nodes, ghost nodes of a padded destination are left untouched (zero)
+template <typename TS, typename TD>
+__global__ void __launch_bounds__(256) k_convert(const cx<TS>* __restrict__ src, cx<TD>* __restrict__ dst, int n0,
+                                                 int64_t rows, int ssy, int dsy, int64_t sld, int64_t dld) {
+    const int r = blockIdx.y;
+    const int64_t tot = rows * n0;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < tot; t += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t row = t / n0;
+        const int i = (int)(t - row * n0);
+        const cx<TS> v = src[(int64_t)r * sld + row * ssy + i];
+        dst[(int64_t)r * dld + row * dsy + i] = mk<TD>((TD)v.x, (TD)v.y);
+    }
+}
+
 // scatter point sources: B[idx[r] + r*ld] = val[r]  (B zeroed beforehand)
 template <typename T>
 __global__ void k_point_sources(cx<T>* __restrict__ B, int64_t ld, const int64_t* __restrict__ idx,

@@ -9,6 +9,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <functional>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -202,6 +203,18 @@ struct SolverBase {
     virtual int64_t max_rhs_per_batch(const hh_solve_options& o) = 0;
     virtual size_t elem_size() const = 0;
     virtual void scatter_point_sources(void* dB, const int64_t* idx0, const double* val, int64_t nrhs) = 0;
+    // ---- mixed precision (HH_C64_MIXED): a ComplexF64 Krylov solver whose preconditioner is the multigrid cycle of a
+    // ComplexF32 solver.  The outer solver is "krylov_only" (no hierarchy of its own) and calls prec_hook; the inner
+    // one exposes its cycle on blocks in its internal (possibly padded) layout.
+    virtual void precondition_internal(const void* b, void* z, int nrhs) = 0;
+    virtual void ensure_cycle_memory(int nrhs) = 0;
+    virtual int64_t internal_ld() const = 0;
+    virtual int internal_pitch() const = 0;
+    virtual double per_rhs_bytes(const hh_solve_options& o) = 0;
+    virtual double held_bytes() const = 0;
+    virtual double cycle_bytes_per_rhs() const = 0;
+    std::function<void(const void*, void*, int)> prec_hook;
+    bool krylov_only = false;
     Problem pb;
     int device = 0;
     cudaStream_t stream = 0;
@@ -830,11 +843,16 @@ class Solver : public SolverBase {
         HH_REQUIRE(o.coarse_type == HH_COARSE_LU || o.coarse_type == HH_COARSE_GMRES, HH_ERR_ARG, "bad coarse_type");
         clear();
         opt = o;
-        levels.resize(o.levels);
+        levels.resize(krylov_only ? 1 : o.levels);
         for (int d = 0; d < 3; ++d) levels[0].n[d] = pb.n[d];
         levels[0].p0 = fine_sy();
         levels[0].N = fineN();
         levels[0].Nlog = pb.N();
+        if (krylov_only) {  // the cycle lives in another solver (prec_hook): only the fine-level geometry is needed
+            have_hierarchy = true;
+            setup_seconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+            return;
+        }
         for (int l = 1; l < o.levels; ++l) {
             for (int d = 0; d < 3; ++d) {
                 const int nf = levels[l - 1].n[d];
@@ -986,6 +1004,7 @@ class Solver : public SolverBase {
     bool kcycle_level(int l) const { return opt.cycle_type == HH_CYCLE_K && l >= 1 && l < opt.levels - 1; }
     double level_bytes_per_rhs() const {
         double b = 0;
+        if (krylov_only) return 0.0;
         for (int l = 0; l < (int)levels.size(); ++l) {
             const double N = (double)levels[l].N;
             b += (l == 0 ? 1.0 : 3.0) * N * S;
@@ -997,6 +1016,11 @@ class Solver : public SolverBase {
     }
     void ensure_level_memory(int nrhs) {
         if (nrhs <= kcap) return;
+        if (krylov_only) {
+            kcap = nrhs;
+            d_partial.alloc((size_t)(HH_MAXV + 1) * std::max(nrhs, 1) * (148 * 8 + 8));
+            return;
+        }
         for (int l = 0; l < (int)levels.size(); ++l) {
             Level& L = levels[l];
             alloc_zero(L.t, (size_t)L.N * nrhs);
@@ -1244,9 +1268,26 @@ class Solver : public SolverBase {
     }
 
     void precondition(const C* b, C* z, int nrhs) {
-        cycle(0, b, z, true, nrhs);
+        if (prec_hook) prec_hook(b, z, nrhs);  // mixed precision: the cycle of the ComplexF32 companion solver
+        else cycle(0, b, z, true, nrhs);
         ++n_prec;
     }
+    void precondition_internal(const void* b, void* z, int nrhs) override {
+        HH_REQUIRE(have_hierarchy && !krylov_only, HH_ERR_STATE, "no hierarchy");
+        cycle(0, (const C*)b, (C*)z, true, nrhs);
+    }
+    void ensure_cycle_memory(int nrhs) override {
+        ensure_level_memory(nrhs);
+        ensure_const();
+    }
+    int64_t internal_ld() const override { return have_hierarchy ? levels[0].N : fineN(); }
+    int internal_pitch() const override { return fine_sy(); }
+    double per_rhs_bytes(const hh_solve_options& o) override {
+        const int64_t Nf = have_hierarchy ? levels[0].N : pb.N();
+        return level_bytes_per_rhs() + (double)(krylov_vectors(o) + (padded() ? 2 : 0)) * Nf * S;
+    }
+    double cycle_bytes_per_rhs() const override { return level_bytes_per_rhs(); }
+    double held_bytes() const override { return (double)kcap * level_bytes_per_rhs() + (double)kry.n * sizeof(C); }
 
     void cycle_device(const void* dB, void* dZ, int64_t nrhs) override {
         HH_CUDA(cudaSetDevice(device));

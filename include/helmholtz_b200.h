@@ -59,6 +59,10 @@ extern "C" {
  * paper runs, examples/PointSourceADR/runExperiments.jl:77) */
 #define HH_C64 0 /* ComplexF64: B, X are double[2] per entry */
 #define HH_C32 1 /* ComplexF32: B, X are float[2]  per entry */
+/* Opt-in extension (no counterpart in the reference): ComplexF64 API, Krylov vectors, operator applies and residuals,
+ * with the multigrid cycle (the flexible preconditioner) evaluated in ComplexF32.  FGMRES / BiCGSTAB converge to the
+ * same ComplexF64 tolerance; the cycle moves half the bytes. */
+#define HH_C64_MIXED 2
 
 /* MGparam.relaxType (test/ShiftedLaplacianTest.jl:55-56) */
 #define HH_RELAX_JAC 0

@@ -23,6 +23,7 @@ ap.add_argument("--pre", type=int, default=2)
 ap.add_argument("--post", type=int, default=2)
 ap.add_argument("--krylov", default="GMRES")
 ap.add_argument("--sigma", type=float, default=None)
+ap.add_argument("--entries", action="store_true")
 a = ap.parse_args()
 pkg = g.load_package()
 n = a.n
@@ -32,11 +33,13 @@ print("model %.1fs" % (time.time() - t0), flush=True)
 mesh = pkg.getRegularMesh(cfg["domain"], cfg["n_cells"])
 m = cfg["m"]
 w = pkg.getMaximalFrequency(m, mesh)
-prec = np.complex128 if a.prec == "c128" else np.complex64
+prec = np.complex64 if a.prec == "c64" else np.complex128
 gamma = 0.01 * w * np.ones(m.shape) + pkg.getABL(mesh.n + 1, True, cfg["pad"], w)
 MG = pkg.getMGparam(prec, pkg.Int64, a.levels, 1, a.maxit, a.tol, a.relax, a.omega_relax, a.pre, a.post, a.cycle, a.coarse,
                     coarseIters=a.coarse_iters)
 hp = pkg.HelmholtzParam(mesh, gamma, m.ravel(order="F"), w, True, True)
+if a.prec == "mixed":
+    MG.cyclePrecision = pkg.ComplexF32
 Ainv = pkg.getShiftedLaplacianMultigridSolver(hp, MG, a.shift, a.krylov, a.inner)
 t0 = time.time()
 hd = pkg.api._ensure_hierarchy(Ainv, 0)
@@ -44,7 +47,7 @@ print("setup %.2fs" % (time.time() - t0), flush=True)
 N = n**3
 g1 = int(np.ceil(np.sqrt(a.nrhs)))
 srcs = pkg.workloads.point_sources_top_grid(mesh.n + 1, g1, g1)[: a.nrhs]
-tdt = torch.complex128 if a.prec == "c128" else torch.complex64
+tdt = torch.complex64 if a.prec == "c64" else torch.complex128
 B = torch.zeros((a.nrhs, N), dtype=tdt, device="cuda")
 for c, s in enumerate(srcs):
     B[c, pkg.loc2cs(mesh.n + 1, s) - 1] = 1.0 / mesh.h[0] ** 2
@@ -73,3 +76,13 @@ for t in range(lib.hh_profile_num_tags()):
 for name, cnt, ms, by in sorted(rows, key=lambda r: -r[2]):
     print("%-16s n=%6d  %9.2f ms (%5.1f%%)  avg %8.3f ms  %8.1f GB/s" % (name, cnt, ms, 100 * ms / tot, ms / cnt, by / ms / 1e6 if ms else 0))
 print("sum kernels %.1f ms" % tot)
+if a.entries:
+    ents = []
+    for e in range(lib.hh_profile_num_entries(hd.h)):
+        tag, cnt, ms, by = C.c_int(), C.c_int64(), C.c_double(), C.c_double()
+        lib.hh_profile_entry(hd.h, e, C.byref(tag), C.byref(cnt), C.byref(ms), C.byref(by))
+        ents.append((lib.hh_profile_tag_name(tag.value).decode(), cnt.value, ms.value, by.value))
+    print("per (tag, bytes-per-launch) entries:")
+    for name, cnt, ms, by in sorted(ents, key=lambda r: -r[2])[:40]:
+        print("%-20s n=%6d  %9.2f ms (%5.1f%%)  avg %8.4f ms  %7.1f MB/launch  %8.1f GB/s" % (
+            name, cnt, ms, 100 * ms / tot, ms / cnt, by / 1e6, by * cnt / ms / 1e6 if ms else 0))

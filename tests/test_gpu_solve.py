@@ -339,3 +339,39 @@ def test_host_path_sub_batches_match_single_columns(gpu_pkg, ho):
     finally:
         del os.environ["HH_HOST_PIPELINE"]
     assert np.array_equal(A.iterations, its) and rel_err(X3, X) < 1e-12
+
+
+def test_mixed_precision_cycle_inside_f64_krylov(gpu_pkg, ho):
+    """Opt-in extension HH_C64_MIXED: ComplexF64 FGMRES / BiCGSTAB whose multigrid cycle runs in ComplexF32.  The
+    solution meets the ComplexF64 tolerance against the sparse direct solve, with (nearly) the iteration count of
+    the pure ComplexF64 solve."""
+    pkg = gpu_pkg
+    n = 33
+    cfg = pkg.workloads.config4(n=n, sigma=3.0, seed=7, pad=6)
+    mesh = ho.getRegularMesh(cfg["domain"], cfg["n_cells"])
+    pmesh = pkg.getRegularMesh(cfg["domain"], cfg["n_cells"])
+    m = cfg["m"]
+    w = ho.getMaximalFrequency(m, mesh)
+    H, gamma = ho.GetHelmholtzOperatorABL(mesh, m, w, 0.01 * w * np.ones(m.shape), True, cfg["pad"], w, True)
+    srcs = pkg.workloads.point_sources_top_grid(mesh.nodes, 2, 2)
+    B = np.zeros((n**3, len(srcs)), dtype=np.complex128)
+    for c, s_ in enumerate(srcs):
+        B[ho.loc2cs(mesh.nodes, s_) - 1, c] = 1.0 / mesh.h[0] ** 2
+    hp = pkg.HelmholtzParam(pmesh, gamma, m.ravel(order="F"), w, True, True)
+    lu = spla.splu(H.tocsc())
+    ref_iters = None
+    for cyc_prec in (None, pkg.ComplexF32):
+        for kry in ("GMRES", "BiCGSTAB"):
+            MG = pkg.getMGparam(pkg.ComplexF64, pkg.Int64, 3, 1, 60, 1e-9, "Jac", 0.8, 1, 2, "W", "GMRES", coarseIters=10)
+            MG.cyclePrecision = cyc_prec
+            A = pkg.getShiftedLaplacianMultigridSolver(hp, MG, 0.2, kry, 5)
+            X, A = pkg.solveLinearSystem(None, B, A)
+            assert X.dtype == np.complex128
+            for c in range(B.shape[1]):
+                assert rel_err(X[:, c], lu.solve(B[:, c])) < 1e-6
+            assert np.abs(H @ X - B).max() / np.abs(B).max() < 1e-6
+            if kry == "GMRES":
+                if cyc_prec is None:
+                    ref_iters = A.iterations.copy()
+                else:
+                    assert np.all(np.abs(A.iterations - ref_iters) <= 2)
