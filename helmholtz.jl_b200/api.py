@@ -73,7 +73,7 @@ class _Handle:
     """Owns an hh_handle_t (HelmholtzParam + device state)."""
 
     def __init__(self, Mesh, m, omega, gamma, NeumannOnTop, Sommerfeld, orderNeumannBC=2, precision=ComplexF64,
-                 devices=None, cycle_precision=None):
+                 devices=None, cycle_precision=None, slabs=None, levels=None):
         lib = L.load()
         nodes = (np.asarray(Mesh.n, dtype=np.int64) + 1).copy()
         N = int(np.prod(nodes))
@@ -99,10 +99,33 @@ class _Handle:
         if devices is None:
             devices = [_current_device()]
         devs = np.asarray(devices, dtype=np.int32)
-        rc = lib.hh_create_multi(self.dim, _ptr(nodes, C.c_int64), _ptr(h, C.c_double), _ptr(mm, C.c_double),
-                                 _ptr(gg, C.c_double), w.real, w.imag, int(bool(NeumannOnTop)), int(bool(Sommerfeld)),
-                                 int(orderNeumannBC), prec, _ptr(devs, C.c_int), len(devs), C.byref(out))
-        L.check(rc, None)
+        common = (self.dim, _ptr(nodes, C.c_int64), _ptr(h, C.c_double), _ptr(mm, C.c_double), _ptr(gg, C.c_double),
+                  w.real, w.imag, int(bool(NeumannOnTop)), int(bool(Sommerfeld)), int(orderNeumannBC), prec)
+        self.slabs = slabs
+        self.planes = (0, int(nodes[-1]))  # planes of the last dimension the caller's B / X hold
+        if slabs is None:
+            rc = lib.hh_create_multi(*common, _ptr(devs, C.c_int), len(devs), C.byref(out))
+            L.check(rc, None)
+        else:
+            # one grid split into slabs along the last dimension (include/helmholtz_b200.h, hh_create_slab_*)
+            if levels is None:
+                raise ValueError("a slab handle needs the number of multigrid levels")
+            if slabs["mode"] == "local":
+                sd = np.asarray(slabs.get("devices", devs), dtype=np.int32)
+                rc = lib.hh_create_slab_local(*common, _ptr(sd, C.c_int), len(sd), int(levels), C.byref(out))
+                L.check(rc, None)
+                devs = sd
+            elif slabs["mode"] == "nccl":
+                uid = (C.c_char * 128).from_buffer_copy(bytes(slabs["unique_id"]))
+                rc = lib.hh_create_slab_nccl(*common, int(devs[0]), int(levels), int(slabs["rank"]), int(slabs["nranks"]),
+                                             C.cast(uid, C.c_void_p), C.byref(out))
+                L.check(rc, None)
+                o0, o1 = C.c_int64(), C.c_int64()
+                lib.hh_slab_info(out, None, None, None, C.byref(o0), C.byref(o1))
+                self.planes = (int(o0.value), int(o1.value))
+                self.N = int(np.prod(nodes[:-1])) * (self.planes[1] - self.planes[0])  # owned nodes: size of B / X here
+            else:
+                raise ValueError("slabs['mode'] must be 'local' or 'nccl'")
         self.h = out
         self.devices = [int(d) for d in devs]
         self.lib = lib
@@ -423,6 +446,10 @@ class ShiftedLaplacianMultigridSolver:
         self.iterations = None
         self.relres = None
         self.devices = None
+        # extension: one grid split into slabs over several GPUs, {"mode": "local", "devices": [...]} (this process
+        # drives all slabs; B, X stay whole-grid arrays) or {"mode": "nccl", "rank", "nranks", "unique_id"} (one process
+        # per GPU; B, X hold this rank's planes, see slabPlanes)
+        self.slabs = None
 
 
 def getShiftedLaplacianMultigridSolver(helmParam, MG, shift, Krylov="BiCGSTAB", inner=5, verbose=False):
@@ -441,6 +468,7 @@ def copySolver(s):
     MG2.cyclePrecision = MG.cyclePrecision
     s2 = getShiftedLaplacianMultigridSolver(s.helmParam, MG2, s.shift, s.Krylov, s.inner, s.verbose)
     s2.devices = s.devices
+    s2.slabs = s.slabs
     return s2
 
 
@@ -450,10 +478,14 @@ def _ensure_hierarchy(param, doTranspose):
     sig = MG._signature(param.shift, doTranspose)
     if MG._hd is not None and getattr(MG._hd, "cycle_precision", None) != MG.cyclePrecision:
         clear(MG)  # the precision of the cycle is a property of the handle
+    if MG._hd is not None and (MG._hd.slabs is not None or getattr(param, "slabs", None) is not None) and \
+            (MG._hd.slabs is not getattr(param, "slabs", None) or MG._hd.levels != MG.levels):
+        clear(MG)  # the slab partition depends on the number of levels
     if MG._hd is None:
         MG._hd = _Handle(hp.Mesh, hp.m, hp.omega, hp.gamma, hp.NeumannOnTop, hp.Sommerfeld, 2, MG.VAL, param.devices,
-                         MG.cyclePrecision)
+                         MG.cyclePrecision, getattr(param, "slabs", None), MG.levels)
         MG._hd.cycle_precision = MG.cyclePrecision
+        MG._hd.levels = MG.levels
     hd = MG._hd
     if (not hd.lib.hh_hierarchy_exists(hd.h)) or MG._built_for != sig:
         # first call (hierarchyExists == false, :50-66), a flipped doTranspose (transposeHierarchy, :68-70) or
@@ -584,3 +616,28 @@ def solvePointSources(param, srcs, amplitudes=None, doTranspose=0):
     if rc == L.HH_NOT_CONVERGED:
         print("WARNING: MG solver reached maximum iterations without convergence")
     return X, param
+
+
+# ------------------------------------------------------------------ slab decomposition helpers
+def slabUniqueId():
+    """128-byte NCCL communicator id (call on one rank, broadcast to the others)."""
+    buf = (C.c_char * 128)()
+    L.check(L.load().hh_nccl_unique_id(C.cast(buf, C.c_void_p)), None)
+    return bytes(buf)
+
+
+def slabPartition(n3_nodes, levels, nranks, rank):
+    """Plane geometry of slab `rank`: one dict per level (0 = fine) with own0, own1, koff, nloc, zb, ze, n2g."""
+    out = np.zeros(7 * int(levels), dtype=np.int64)
+    rc = L.load().hh_slab_partition(int(n3_nodes), int(levels), int(nranks), int(rank), _ptr(out, C.c_int64))
+    if rc != 0:
+        raise ValueError("no slab partition: cells of the last dimension must be divisible by 2^(levels-1) and the "
+                         "coarsest level needs at least one cell per slab")
+    keys = ("own0", "own1", "koff", "nloc", "zb", "ze", "n2g")
+    return [dict(zip(keys, (int(v) for v in out[7 * l:7 * l + 7]))) for l in range(int(levels))]
+
+
+def slabPlanes(param):
+    """Planes [k0, k1) of the last dimension that B / X of this process hold (whole grid unless NCCL slabs)."""
+    hd = _ensure_hierarchy(param, param.MG.doTranspose)
+    return hd.planes

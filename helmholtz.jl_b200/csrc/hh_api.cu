@@ -55,7 +55,12 @@ struct hh_handle_s {
     std::vector<std::unique_ptr<SolverBase>> lows;
     std::vector<std::unique_ptr<DevBuf<cx<float>>>> lo_b, lo_z;
     int precision = HH_C64;
-    Problem pb;
+    Problem pb;  // the whole grid (also for slab handles, whose replicas each describe one slab)
+    // slab decomposition of one problem (hh_slab.cuh): 0 = none (subs are replicas that share the right-hand sides out),
+    // 1 = one host thread per slab inside this process (caller arrays are whole-grid arrays),
+    // 2 = this process holds one slab, NCCL between the processes (caller arrays hold the owned planes)
+    int slab_mode = 0;
+    std::shared_ptr<ThreadGroup> grp;
     std::string err;
     bool have_opts = false;
     hh_mg_options opts{};
@@ -108,9 +113,15 @@ static void for_each_sub(hh_handle_t h, F&& f) {
                 code[i] = HH_ERR_STATE;
                 msg[i] = e.what();
             }
+            if (code[i] != 0 && h->grp) h->grp->fail();  // slabs run in lockstep: release the ones waiting on this one
         });
     }
     for (auto& t : th) t.join();
+    if (h->grp) h->grp->reset();
+    // report the slab that failed first-hand rather than the ones it released
+    for (int i = 0; i < n; ++i)
+        if (code[i] != 0 && msg[i].find("another slab") == std::string::npos)
+            throw hh::Error(code[i], "device replica " + std::to_string(i) + ": " + msg[i]);
     for (int i = 0; i < n; ++i)
         if (code[i] != 0) throw hh::Error(code[i], "device replica " + std::to_string(i) + ": " + msg[i]);
 }
@@ -230,10 +241,53 @@ int64_t hh_point_source_index(int dim, const int64_t* n, const int64_t* sub) {
     return -1;
 }
 
+// one solver (plus its ComplexF32 companion when the precision is mixed) for the grid `pb` on `device`
+static void add_replica(hh_handle_s* h, const Problem& pb, int precision, int device) {
+    const size_t i = h->subs.size();
+    if (precision == HH_C32) h->subs.emplace_back(new Solver<float>(pb, device));
+    else h->subs.emplace_back(new Solver<double>(pb, device));
+    h->stages.emplace_back(new HostStage);
+    if (precision == HH_C64_MIXED) {
+        h->lows.emplace_back(new Solver<float>(pb, device));
+        h->lo_b.emplace_back(new DevBuf<cx<float>>);
+        h->lo_z.emplace_back(new DevBuf<cx<float>>);
+        SolverBase* hi = h->subs[i].get();
+        SolverBase* lo = h->lows[i].get();
+        DevBuf<cx<float>>* bb = h->lo_b[i].get();
+        DevBuf<cx<float>>* zz = h->lo_z[i].get();
+        hi->krylov_only = true;
+        // z = M(b): b, z ComplexF64 blocks of the outer solver; the cycle runs on ComplexF32 copies
+        hi->prec_hook = [hi, lo, bb, zz](const void* b, void* z, int nrhs) {
+            lo->stream = hi->stream;
+            lo->ensure_cycle_memory(nrhs);
+            const int64_t ldl = lo->internal_ld(), ldh = hi->internal_ld();
+            const size_t need = (size_t)ldl * nrhs;
+            if (bb->n < need) {
+                bb->alloc(need);
+                zz->alloc(need);
+                HH_CUDA(cudaMemsetAsync(bb->p, 0, need * sizeof(cx<float>), hi->stream));  // ghost nodes stay zero
+                HH_CUDA(cudaMemsetAsync(zz->p, 0, need * sizeof(cx<float>), hi->stream));
+            }
+            const int n0 = hi->pb.n[0];
+            const int64_t rows = (int64_t)hi->pb.n[1] * hi->pb.n[2];
+            dim3 g(std::max(1, 592 / std::max(nrhs, 1)), nrhs);
+            k_convert<double, float><<<g, 256, 0, hi->stream>>>((const cx<double>*)b, bb->p, n0, rows, hi->internal_pitch(),
+                                                               lo->internal_pitch(), ldh, ldl);
+            lo->precondition_internal(bb->p, zz->p, nrhs);
+            k_convert<float, double><<<g, 256, 0, hi->stream>>>(zz->p, (cx<double>*)z, n0, rows, lo->internal_pitch(),
+                                                               hi->internal_pitch(), ldl, ldh);
+            hi->launches += 2;
+        };
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
+// slab_mode 0: `ndev` replicas of the whole grid.  1: `ndev` slabs of one grid inside this process.  2: slab `rank` of
+// `nranks` on devices[0], NCCL communicator from `uid`.
 static int create_impl(int dim, const int64_t* n_nodes, const double* hsp, const double* m, const double* gamma,
                        double wre, double wim, int neumann_on_top, int sommerfeld, int order_bc, int precision,
-                       const int* devices, int ndev, hh_handle_t* out) {
+                       const int* devices, int ndev, hh_handle_t* out, int slab_mode = 0, int levels = 0, int rank = 0,
+                       int nranks = 1, const void* uid = nullptr) {
     return guarded(nullptr, [&]() -> int {
         HH_REQUIRE(out != nullptr, HH_ERR_ARG, "hh_create: out is NULL");
         *out = nullptr;
@@ -263,47 +317,47 @@ static int create_impl(int dim, const int64_t* n_nodes, const double* hsp, const
         std::unique_ptr<hh_handle_s> h(new hh_handle_s);
         h->precision = precision;
         h->pb = pb;
-        for (int i = 0; i < ndev; ++i) {
+        h->slab_mode = slab_mode;
+        for (int i = 0; i < ndev; ++i)
             HH_REQUIRE(devices[i] >= 0 && devices[i] < ndevices, HH_ERR_ARG, "hh_create: bad device ordinal");
-            if (precision == HH_C32) h->subs.emplace_back(new Solver<float>(pb, devices[i]));
-            else h->subs.emplace_back(new Solver<double>(pb, devices[i]));
-            h->stages.emplace_back(new HostStage);
-            if (precision == HH_C64_MIXED) {
-                h->lows.emplace_back(new Solver<float>(pb, devices[i]));
-                h->lo_b.emplace_back(new DevBuf<cx<float>>);
-                h->lo_z.emplace_back(new DevBuf<cx<float>>);
-                SolverBase* hi = h->subs[i].get();
-                SolverBase* lo = h->lows[i].get();
-                DevBuf<cx<float>>* bb = h->lo_b[i].get();
-                DevBuf<cx<float>>* zz = h->lo_z[i].get();
-                hi->krylov_only = true;
-                // z = M(b): b, z ComplexF64 blocks of the outer solver; the cycle runs on ComplexF32 copies
-                hi->prec_hook = [hi, lo, bb, zz](const void* b, void* z, int nrhs) {
-                    lo->stream = hi->stream;
-                    lo->ensure_cycle_memory(nrhs);
-                    const int64_t ldl = lo->internal_ld(), ldh = hi->internal_ld();
-                    const size_t need = (size_t)ldl * nrhs;
-                    if (bb->n < need) {
-                        bb->alloc(need);
-                        zz->alloc(need);
-                        HH_CUDA(cudaMemsetAsync(bb->p, 0, need * sizeof(cx<float>), hi->stream));  // ghost nodes stay zero
-                        HH_CUDA(cudaMemsetAsync(zz->p, 0, need * sizeof(cx<float>), hi->stream));
-                    }
-                    const int n0 = hi->pb.n[0];
-                    const int64_t rows = (int64_t)hi->pb.n[1] * hi->pb.n[2];
-                    dim3 g(std::max(1, 592 / std::max(nrhs, 1)), nrhs);
-                    k_convert<double, float><<<g, 256, 0, hi->stream>>>((const cx<double>*)b, bb->p, n0, rows, hi->internal_pitch(),
-                                                                       lo->internal_pitch(), ldh, ldl);
-                    lo->precondition_internal(bb->p, zz->p, nrhs);
-                    k_convert<float, double><<<g, 256, 0, hi->stream>>>(zz->p, (cx<double>*)z, n0, rows, lo->internal_pitch(),
-                                                                       hi->internal_pitch(), ldl, ldh);
-                    hi->launches += 2;
-                };
+        if (slab_mode == 0) {
+            for (int i = 0; i < ndev; ++i) add_replica(h.get(), pb, precision, devices[i]);
+        } else {
+            HH_REQUIRE(dim == 3, HH_ERR_UNSUPPORTED, "slab decomposition needs a 3-D grid");
+            HH_REQUIRE(levels >= 1 && levels <= HH_MAX_LEVELS, HH_ERR_ARG, "slab decomposition: levels out of range");
+            const int nr = slab_mode == 1 ? ndev : nranks;
+            HH_REQUIRE(slab_mode == 1 || (ndev == 1 && uid != nullptr && rank >= 0 && rank < nranks), HH_ERR_ARG,
+                       "hh_create_slab_nccl: bad rank / communicator id");
+            if (slab_mode == 1) h->grp = std::make_shared<ThreadGroup>(nr);
+            for (int q = 0; q < (slab_mode == 1 ? ndev : 1); ++q) {
+                const int r = slab_mode == 1 ? q : rank;
+                std::vector<SlabLevel> geo;
+                HH_REQUIRE(slab_partition(pb.n[2], levels, nr, r, geo), HH_ERR_ARG,
+                           "slab decomposition: the cells of the last dimension must be divisible by 2^(levels-1) and the "
+                           "coarsest level needs at least one cell per slab");
+                Problem pl = pb;
+                pl.n[2] = geo[0].nloc;
+                add_replica(h.get(), pl, precision, devices[q]);
+                std::shared_ptr<SlabTransport> tr;
+                if (slab_mode == 1) {
+                    tr = std::make_shared<ThreadTransport>(r, h->grp);
+                } else {
+                    HH_CUDA(cudaSetDevice(devices[q]));
+                    tr = std::make_shared<NcclTransport>(r, nr, uid);
+                }
+                h->subs[q]->slab = tr;
+                h->subs[q]->sgeo = geo;
+                if (!h->lows.empty()) {
+                    h->lows[q]->slab = tr;
+                    h->lows[q]->sgeo = geo;
+                }
             }
         }
         for_each_sub(h.get(), [&](int i) {
-            h->subs[i]->set_model(m, gamma, wre, wim);
-            if (!h->lows.empty()) h->lows[i]->set_model(m, gamma, wre, wim);
+            // a slab reads its planes (halo planes included) out of the whole-grid arrays
+            const int64_t off = slab_mode ? (int64_t)h->subs[i]->sgeo[0].koff * pb.n[0] * pb.n[1] : 0;
+            h->subs[i]->set_model(m + off, gamma + off, wre, wim);
+            if (!h->lows.empty()) h->lows[i]->set_model(m + off, gamma + off, wre, wim);
         });
         h->pb.w_re = wre;
         h->pb.w_im = wim;
@@ -324,6 +378,57 @@ int hh_create_multi(int dim, const int64_t* n_nodes, const double* h, const doub
                     int precision, const int* devices, int n_devices, hh_handle_t* out) {
     return create_impl(dim, n_nodes, h, m, gamma, omega_re, omega_im, neumann_on_top, sommerfeld, order_neumann_bc,
                        precision, devices, n_devices, out);
+}
+
+int hh_slab_partition(int64_t n3_nodes, int levels, int nranks, int rank, int64_t* out) {
+    if (!out || levels < 1 || levels > HH_MAX_LEVELS || n3_nodes >= (1 << 30)) return HH_ERR_ARG;
+    std::vector<SlabLevel> geo;
+    if (!slab_partition((int)n3_nodes, levels, nranks, rank, geo)) return HH_ERR_ARG;
+    for (int l = 0; l < levels; ++l) {
+        const SlabLevel& g = geo[l];
+        const int64_t v[7] = {g.own0, g.own1, g.koff, g.nloc, g.zb, g.ze, g.n2g};
+        for (int q = 0; q < 7; ++q) out[7 * l + q] = v[q];
+    }
+    return HH_OK;
+}
+
+int hh_nccl_unique_id(void* id128) {
+    return guarded(nullptr, [&]() -> int {
+        HH_REQUIRE(id128 != nullptr, HH_ERR_ARG, "hh_nccl_unique_id: NULL");
+        NcclApi& api = NcclApi::get();
+        HH_REQUIRE(api.ok, HH_ERR_UNSUPPORTED, api.error);
+        ncclUniqueId id;
+        HH_NCCL(api.GetUniqueId(&id));
+        memcpy(id128, &id, sizeof(id));
+        return HH_OK;
+    });
+}
+
+int hh_create_slab_local(int dim, const int64_t* n_nodes, const double* h, const double* m, const double* gamma,
+                         double omega_re, double omega_im, int neumann_on_top, int sommerfeld, int order_neumann_bc,
+                         int precision, const int* devices, int n_slabs, int levels, hh_handle_t* out) {
+    return create_impl(dim, n_nodes, h, m, gamma, omega_re, omega_im, neumann_on_top, sommerfeld, order_neumann_bc,
+                       precision, devices, n_slabs, out, 1, levels);
+}
+
+int hh_create_slab_nccl(int dim, const int64_t* n_nodes, const double* h, const double* m, const double* gamma,
+                        double omega_re, double omega_im, int neumann_on_top, int sommerfeld, int order_neumann_bc,
+                        int precision, int device, int levels, int rank, int nranks, const void* unique_id,
+                        hh_handle_t* out) {
+    return create_impl(dim, n_nodes, h, m, gamma, omega_re, omega_im, neumann_on_top, sommerfeld, order_neumann_bc,
+                       precision, &device, 1, out, 2, levels, rank, nranks, unique_id);
+}
+
+int hh_slab_info(hh_handle_t h, int* mode, int* n_slabs, int* rank, int64_t* own0, int64_t* own1) {
+    if (!h) return HH_ERR_ARG;
+    const SolverBase* s = h->subs[0].get();
+    if (mode) *mode = h->slab_mode;
+    if (n_slabs) *n_slabs = s->slab ? s->slab->nranks : 1;
+    if (rank) *rank = (h->slab_mode == 2) ? s->slab->rank : 0;
+    // planes of the last dimension the caller's arrays hold
+    if (own0) *own0 = (h->slab_mode == 2) ? s->sgeo[0].own0 : 0;
+    if (own1) *own1 = (h->slab_mode == 2) ? s->sgeo[0].own1 : h->pb.n[2];
+    return HH_OK;
 }
 
 int hh_destroy(hh_handle_t h) {
@@ -359,8 +464,9 @@ int hh_update_model(hh_handle_t h, const double* m, const double* gamma, double 
     return guarded(h, [&]() -> int {
         HH_REQUIRE(m && gamma && omega_re != 0.0, HH_ERR_ARG, "hh_update_model: bad arguments");
         for_each_sub(h, [&](int i) {
-            h->subs[i]->set_model(m, gamma, omega_re, omega_im);
-            if (!h->lows.empty()) h->lows[i]->set_model(m, gamma, omega_re, omega_im);
+            const int64_t off = h->slab_mode ? (int64_t)h->subs[i]->sgeo[0].koff * h->pb.n[0] * h->pb.n[1] : 0;
+            h->subs[i]->set_model(m + off, gamma + off, omega_re, omega_im);
+            if (!h->lows.empty()) h->lows[i]->set_model(m + off, gamma + off, omega_re, omega_im);
         });
         h->pb.w_re = omega_re;
         h->pb.w_im = omega_im;
@@ -424,6 +530,18 @@ int hh_get_level_stencil(hh_handle_t h, int level, void* coef_out) {
     });
 }
 
+// Galerkin stencil of one slab (local planes, halo planes included): parity hook for MGsetup under slab decomposition
+int hh_slab_level_stencil(hh_handle_t h, int slab, int level, int64_t* n_local_out, void* coef_out) {
+    if (!h) return HH_ERR_ARG;
+    return guarded(h, [&]() -> int {
+        HH_REQUIRE(h->lows.empty(), HH_ERR_UNSUPPORTED, "hh_slab_level_stencil: not available on a mixed-precision handle");
+        HH_REQUIRE(slab >= 0 && slab < (int)h->subs.size(), HH_ERR_ARG, "hh_slab_level_stencil: bad slab index");
+        if (n_local_out) h->subs[slab]->level_nodes(level, n_local_out);
+        if (coef_out) h->subs[slab]->get_level_stencil(level, coef_out);
+        return HH_OK;
+    });
+}
+
 int hh_get_diagonal(hh_handle_t h, int shifted, double shift, double* diag_out) {
     if (!h || !diag_out) return HH_ERR_ARG;
     return guarded(h, [&]() -> int {
@@ -457,6 +575,114 @@ static int64_t batch_limit(hh_handle_t h, int i, const hh_solve_options& o) {
     return std::max<int64_t>((int64_t)std::floor(0.90 * ((double)fr + held) / per), 0);
 }
 
+// ---- slab handles: how replica i sees the caller's host arrays ----
+// ld: elements between consecutive right-hand sides, off: offset of the slab's first owned plane, nown: owned nodes
+static void slab_host_view(hh_handle_t h, int i, int64_t& ld, int64_t& off, int64_t& nown) {
+    const SolverBase* s = h->subs[i].get();
+    nown = s->caller_N();
+    if (h->slab_mode == 1) {
+        ld = h->pb.N();
+        off = (int64_t)s->sgeo[0].own0 * h->pb.n[0] * h->pb.n[1];
+    } else {
+        ld = nown;
+        off = 0;
+    }
+}
+// nodes per right-hand side of the device blocks handed to the *_device entry points
+static int64_t device_block_N(hh_handle_t h) { return h->slab_mode == 2 ? h->subs[0]->caller_N() : h->pb.N(); }
+
+// right-hand sides per batch that every slab can hold (the slabs solve in lockstep, so they must agree)
+static int64_t slab_batch_limit(hh_handle_t h, const hh_solve_options& o) {
+    int64_t k = INT64_MAX;
+    for (size_t i = 0; i < h->subs.size(); ++i) k = std::min(k, batch_limit(h, (int)i, o));
+    if (h->slab_mode == 2) {
+        SolverBase* s = h->subs[0].get();
+        DevBuf<double> d;
+        d.alloc(1);
+        double v = (double)k;
+        HH_CUDA(cudaMemcpyAsync(d.p, &v, sizeof(double), cudaMemcpyHostToDevice, s->stream));
+        s->slab->allreduce(s->stream, d.p, 1, true);
+        HH_CUDA(cudaMemcpyAsync(&v, d.p, sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+        HH_CUDA(cudaStreamSynchronize(s->stream));
+        k = (int64_t)v;
+    }
+    return k;
+}
+
+// k columns of `rows` elements between a strided host block and a dense device block (one copy per column: pitches of
+// whole-grid blocks exceed what cudaMemcpy2D accepts)
+static void copy_columns(bool to_device, char* dev, const char* host, size_t rows_bytes, size_t host_ld_bytes, int64_t k,
+                         cudaStream_t st) {
+    for (int64_t r = 0; r < k; ++r) {
+        char* d = dev + (size_t)r * rows_bytes;
+        const char* hp = host + (size_t)r * host_ld_bytes;
+        if (to_device) HH_CUDA(cudaMemcpyAsync(d, hp, rows_bytes, cudaMemcpyHostToDevice, st));
+        else HH_CUDA(cudaMemcpyAsync(const_cast<char*>(hp), d, rows_bytes, cudaMemcpyDeviceToHost, st));
+    }
+}
+
+// host-pointer apply / solve on a slab handle: every replica works on all right-hand sides and its own planes
+static void slab_apply_host(hh_handle_t h, const void* X, void* Y, int64_t nrhs, int shifted, double shift, int transpose) {
+    for_each_sub(h, [&](int i) {
+        SolverBase* s = h->subs[i].get();
+        HH_CUDA(cudaSetDevice(s->device));
+        int64_t ld, off, nown;
+        slab_host_view(h, i, ld, off, nown);
+        const size_t es = s->elem_size();
+        DevBuf<char> dx, dy;
+        dx.alloc((size_t)nown * nrhs * es);
+        dy.alloc((size_t)nown * nrhs * es);
+        copy_columns(true, dx.p, (const char*)X + (size_t)off * es, (size_t)nown * es, (size_t)ld * es, nrhs, s->stream);
+        s->apply_device(dx.p, dy.p, nrhs, shifted, shift, transpose);
+        copy_columns(false, dy.p, (const char*)Y + (size_t)off * es, (size_t)nown * es, (size_t)ld * es, nrhs, s->stream);
+        HH_CUDA(cudaStreamSynchronize(s->stream));
+    });
+}
+
+static int slab_solve_host(hh_handle_t h, const void* B, const int64_t* idx, const double* val, void* X, int64_t nrhs,
+                           const hh_solve_options* opts, int32_t* iters_out, double* relres_out) {
+    int64_t kmax = slab_batch_limit(h, *opts);
+    {   // room for the staging blocks of B and X next to the work vectors
+        const double kv = (opts->krylov == HH_KRYLOV_GMRES ? 2 * opts->inner + 1 : 7) + 3.5;
+        kmax = (int64_t)((double)kmax * kv / (kv + 2.0));
+    }
+    HH_REQUIRE(kmax >= 1, HH_ERR_ALLOC, "not enough device memory for one right-hand side");
+    kmax = std::min(kmax, nrhs);
+    const int nsub = (int)h->subs.size();
+    std::vector<int> rcs(nsub, HH_OK);
+    for_each_sub(h, [&](int i) {
+        SolverBase* s = h->subs[i].get();
+        HH_CUDA(cudaSetDevice(s->device));
+        int64_t ld, off, nown;
+        slab_host_view(h, i, ld, off, nown);
+        const size_t es = s->elem_size();
+        DevBuf<char> db, dx;
+        db.alloc((size_t)nown * kmax * es);
+        dx.alloc((size_t)nown * kmax * es);
+        std::vector<int64_t> idx0;
+        for (int64_t c = 0; c < nrhs; c += kmax) {
+            const int64_t k = std::min(kmax, nrhs - c);
+            if (idx) {
+                idx0.resize(k);
+                for (int64_t r = 0; r < k; ++r) idx0[r] = idx[c + r] - 1;
+                s->scatter_point_sources(db.p, idx0.data(), val + 2 * c, k);
+            } else {
+                copy_columns(true, db.p, (const char*)B + ((size_t)c * ld + off) * es, (size_t)nown * es, (size_t)ld * es, k, s->stream);
+            }
+            // the slabs compute identical iteration counts / residuals: the first one reports them
+            const bool rep = (i == 0);
+            int r = s->solve_device(db.p, dx.p, k, *opts, (rep && iters_out) ? iters_out + c : nullptr,
+                                    (rep && relres_out) ? relres_out + c : nullptr);
+            rcs[i] = std::max(rcs[i], r);
+            copy_columns(false, dx.p, (const char*)X + ((size_t)c * ld + off) * es, (size_t)nown * es, (size_t)ld * es, k, s->stream);
+            HH_CUDA(cudaStreamSynchronize(s->stream));
+        }
+    });
+    int rc = HH_OK;
+    for (int r : rcs) rc = std::max(rc, r);
+    return rc;
+}
+
 // split [0,nrhs) into contiguous column ranges, one per replica
 static void column_range(int64_t nrhs, int nparts, int part, int64_t& c0, int64_t& c1) {
     const int64_t base = nrhs / nparts, rem = nrhs % nparts;
@@ -468,6 +694,10 @@ int hh_apply(hh_handle_t h, const void* X, void* Y, int64_t nrhs, int shifted, d
     if (!h) return HH_ERR_ARG;
     return guarded(h, [&]() -> int {
         HH_REQUIRE(X && Y && nrhs >= 1, HH_ERR_ARG, "hh_apply: bad arguments");
+        if (h->slab_mode) {
+            slab_apply_host(h, X, Y, nrhs, shifted, shift, transpose);
+            return HH_OK;
+        }
         const int64_t N = h->pb.N();
         for_each_sub(h, [&](int i) {
             SolverBase* s = h->subs[i].get();
@@ -499,6 +729,7 @@ int hh_cycle_device(hh_handle_t h, const void* dB, void* dZ, int64_t nrhs) {
     if (!h) return HH_ERR_ARG;
     return guarded(h, [&]() -> int {
         HH_REQUIRE(dB && dZ && nrhs >= 1 && dB != dZ, HH_ERR_ARG, "hh_cycle_device: bad arguments");
+        HH_REQUIRE(h->slab_mode == 0, HH_ERR_UNSUPPORTED, "hh_cycle_device is not available on a slab handle");
         HH_REQUIRE(h->subs.size() == 1, HH_ERR_UNSUPPORTED, "device-pointer entry points need a single-device handle");
         h->subs[0]->cycle_device(dB, dZ, nrhs);
         return HH_OK;
@@ -509,6 +740,7 @@ int hh_cycle(hh_handle_t h, const void* B, void* Z, int64_t nrhs) {
     if (!h) return HH_ERR_ARG;
     return guarded(h, [&]() -> int {
         HH_REQUIRE(B && Z && nrhs >= 1, HH_ERR_ARG, "hh_cycle: bad arguments");
+        HH_REQUIRE(h->slab_mode == 0, HH_ERR_UNSUPPORTED, "hh_cycle is not available on a slab handle");
         SolverBase* s = h->subs[0].get();
         HH_CUDA(cudaSetDevice(s->device));
         const int64_t N = h->pb.N();
@@ -537,9 +769,9 @@ int hh_solve_device(hh_handle_t h, const void* dB, void* dX, int64_t nrhs, const
         check_solve_opts(opts);
         HH_REQUIRE(h->subs.size() == 1, HH_ERR_UNSUPPORTED, "device-pointer entry points need a single-device handle");
         SolverBase* s = h->subs[0].get();
-        const int64_t kmax = batch_limit(h, 0, *opts);
+        const int64_t kmax = h->slab_mode ? slab_batch_limit(h, *opts) : batch_limit(h, 0, *opts);
         HH_REQUIRE(kmax >= 1, HH_ERR_ALLOC, "not enough device memory for one right-hand side");
-        const int64_t N = h->pb.N();
+        const int64_t N = device_block_N(h);
         const size_t es = s->elem_size();
         int rc = HH_OK;
         for (int64_t c = 0; c < nrhs; c += kmax) {
@@ -562,6 +794,7 @@ static int solve_host(hh_handle_t h, const void* B, const int64_t* idx, const do
     if (idx)
         for (int64_t r = 0; r < nrhs; ++r)
             HH_REQUIRE(idx[r] >= 1 && idx[r] <= N, HH_ERR_ARG, "point source index out of range (1-based)");
+    if (h->slab_mode) return slab_solve_host(h, B, idx, val, X, nrhs, opts, iters_out, relres_out);
     for_each_sub(h, [&](int i) {
         SolverBase* s = h->subs[i].get();
         int64_t c0, c1;

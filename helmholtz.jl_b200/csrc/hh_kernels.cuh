@@ -28,6 +28,11 @@ struct FineOp {
                   // rows are padded to a 16-byte multiple for TMA; the ghost column is never read or written
     int neumann_top;
     int adj;      // 1: conjugate transpose
+    // Slab decomposition along the last dimension (one slab per GPU): the arrays hold local planes 0..n[2]-1, local
+    // plane z is global plane z + koff of n2g, and the kernels compute planes zb <= z < ze only (the planes outside
+    // that range are halo / alignment planes filled by the halo exchange).  Whole grid: koff = 0, n2g = n[2], zb = 0,
+    // ze = n[2].
+    int koff, n2g, zb, ze;
     // optional precomputed diagonal arrays (k_fine_precompute): centre coefficient incl. the Laplacian
     // diagonal, and damp/centre.  Used by the TMA-staged production kernels.
     const cx<T>* cdiag;
@@ -41,13 +46,15 @@ struct CoarseOp {
     int n[3];
     int sy;             // row pitch (elements); N = padded node count sy*n[1]*n[2] = stride between coefficients
     int64_t N;
+    int zb, ze;         // planes computed (slab decomposition: the owned planes; whole grid: 0, n[2]), see FineOp
 };
 
 // ---------------------------------------------------------------------------------------------
 // fine-level coefficient evaluation
 // ---------------------------------------------------------------------------------------------
 template <typename T, int DIM>
-__device__ __forceinline__ cx<T> fine_center(const FineOp<T>& op, int64_t p, int i, int j, int k) {
+__device__ __forceinline__ cx<T> fine_center(const FineOp<T>& op, int64_t p, int i, int j, int kl) {
+    const int k = kl + op.koff;  // global plane (boundary faces are global)
     const T mv = op.m[p];
     const T gv = op.g[p] * op.inv_wr;
     T re = -mv * (op.a + op.b * gv);
@@ -61,12 +68,12 @@ __device__ __forceinline__ cx<T> fine_center(const FineOp<T>& op, int64_t p, int
     } else {
         if (bi) sf += op.somm[0];
         if (bj) sf += op.somm[1];
-        if ((k == 0 && !op.neumann_top) || k == op.n[2] - 1) sf += op.somm[2];
+        if ((k == 0 && !op.neumann_top) || k == op.n2g - 1) sf += op.somm[2];
     }
     if (sf != T(0)) im += sf * sqrt(mv);
     re += (bi ? op.BC : T(2)) * op.ih2[0];
     re += (bj ? op.BC : T(2)) * op.ih2[1];
-    if (DIM == 3) re += ((k == 0 || k == op.n[2] - 1) ? op.BC : T(2)) * op.ih2[2];
+    if (DIM == 3) re += ((k == 0 || k == op.n2g - 1) ? op.BC : T(2)) * op.ih2[2];
     if (op.adj) im = -im;
     return mk<T>(re, im);
 }
@@ -86,6 +93,12 @@ __device__ __forceinline__ T fine_w(const FineOp<T>& op, int d, int side, int id
     }
 }
 
+// same along the last dimension of a 3-D grid, for LOCAL plane z of a slab (weights follow the global plane)
+template <typename T>
+__device__ __forceinline__ T fine_wz(const FineOp<T>& op, int side, int z) {
+    return fine_w(op, 2, side, z + op.koff, op.n2g);
+}
+
 // ---------------------------------------------------------------------------------------------
 // K1/K2 (baseline form): fine-level stencil, one thread per node, KB right-hand sides per pass so
 // that m/gamma and the index arithmetic are amortised.  MODE selects the fused epilogue:
@@ -98,15 +111,16 @@ __global__ void __launch_bounds__(256) k_fine_stencil(FineOp<T> op, const cx<T>*
     const int n0 = op.n[0], n1 = op.n[1], n2 = op.n[2];
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int j = blockIdx.y * blockDim.y + threadIdx.y;
-    const int k = (DIM == 3) ? blockIdx.z * blockDim.z + threadIdx.z : 0;
-    if (i >= n0 || j >= n1 || k >= n2) return;
+    const int k = (DIM == 3) ? op.zb + blockIdx.z * blockDim.z + threadIdx.z : 0;
+    if (i >= n0 || j >= n1 || (DIM == 3 && k >= op.ze)) return;
+    (void)n2;
     const int64_t sy = op.sy, sz = (int64_t)op.sy * n1;
     const int64_t p = i + sy * j + sz * k;
     const cx<T> c = fine_center<T, DIM>(op, p, i, j, k);
     const T wxm = fine_w(op, 0, 0, i, n0), wxp = fine_w(op, 0, 1, i, n0);
     const T wym = fine_w(op, 1, 0, j, n1), wyp = fine_w(op, 1, 1, j, n1);
-    const T wzm = (DIM == 3) ? fine_w(op, 2, 0, k, n2) : T(0);
-    const T wzp = (DIM == 3) ? fine_w(op, 2, 1, k, n2) : T(0);
+    const T wzm = (DIM == 3) ? fine_wz(op, 0, k) : T(0);
+    const T wzp = (DIM == 3) ? fine_wz(op, 1, k) : T(0);
     // clamp neighbour offsets so that absent neighbours (weight 0) read the centre
     const int64_t oxm = wxm != T(0) ? -1 : 0, oxp = wxp != T(0) ? 1 : 0;
     const int64_t oym = wym != T(0) ? -sy : 0, oyp = wyp != T(0) ? sy : 0;
@@ -167,8 +181,8 @@ __global__ void __launch_bounds__(32 * TY, MINB) k_fine3d_zmarch(FineOp<T> op, c
     if (i >= n0 || j >= n1) return;
     const int zc = blockIdx.z;
     const int r0 = (blockIdx.x % groups) * KB;
-    const int z0 = zc * zchunk;
-    const int z1 = min(n2, z0 + zchunk);
+    const int z0 = op.zb + zc * zchunk;
+    const int z1 = min(op.ze, z0 + zchunk);
     const int64_t sy = op.sy, sz = (int64_t)op.sy * n1;
     const int64_t pxy = i + sy * j;
     const T wxm = fine_w(op, 0, 0, i, n0), wxp = fine_w(op, 0, 1, i, n0);
@@ -200,12 +214,14 @@ __global__ void __launch_bounds__(32 * TY, MINB) k_fine3d_zmarch(FineOp<T> op, c
         T re = -mv * (op.a + op.b * gv);
         T im = -mv * (op.b - op.a * gv) + op.shift_w2 * mv;
         T sf = sfxy;
-        if ((z == 0 && !op.neumann_top) || zlast) sf += op.somm[2];
+        const int zg = z + op.koff;
+        const bool gtop = (zg == 0), gbot = (zg == op.n2g - 1);
+        if ((gtop && !op.neumann_top) || gbot) sf += op.somm[2];
         if (sf != T(0)) im += sf * sqrt(mv);
-        re += lapxy + ((z == 0 || zlast) ? op.BC : T(2)) * op.ih2[2];
+        re += lapxy + ((gtop || gbot) ? op.BC : T(2)) * op.ih2[2];
         if (op.adj) im = -im;
         const cx<T> c = mk<T>(re, im);
-        const T wzm = fine_w(op, 2, 0, z, n2), wzp = fine_w(op, 2, 1, z, n2);
+        const T wzm = fine_wz(op, 0, z), wzp = fine_wz(op, 1, z);
         cx<T> dinv = mk<T>(T(0), T(0));
         if (MODE == MODE_JACOBI) dinv = rdiv(damp, c);
 #pragma unroll
@@ -250,8 +266,8 @@ __global__ void __launch_bounds__(32 * TY, MINB) k_coarse3d_zmarch(CoarseOp<T> o
     if (i >= n0 || j >= n1) return;
     const int zc = blockIdx.z;
     const int r0 = (blockIdx.x % groups) * KB;
-    const int z0 = zc * zchunk;
-    const int z1 = min(n2, z0 + zchunk);
+    const int z0 = op.zb + zc * zchunk;
+    const int z1 = min(op.ze, z0 + zchunk);
     const int64_t sy = op.sy, sz = (int64_t)op.sy * n1;
     const int64_t N = op.N;
     const int64_t pxy = i + sy * j;
@@ -424,8 +440,8 @@ __global__ void __launch_bounds__(256) k_fine3d_tma(FineOp<T> op, const __grid_c
     const int i0 = (blockIdx.x / groups) * TX, j0 = blockIdx.y * TY;
     const int i = i0 + tx, j = j0 + ty;
     const int r0 = (blockIdx.x % groups) * KB;
-    const int z0 = blockIdx.z * zchunk;
-    const int z1 = min(n2, z0 + zchunk);
+    const int z0 = op.zb + blockIdx.z * zchunk;
+    const int z1 = min(op.ze, z0 + zchunk);
     const int zl = min(z1, n2 - 1);  // last plane that must be staged (z+1 halo of the chunk)
     const int64_t sy = op.sy, sz = (int64_t)op.sy * n1;
     const bool active = (i < n0) && (j < n1);
@@ -479,7 +495,7 @@ __global__ void __launch_bounds__(256) k_fine3d_tma(FineOp<T> op, const __grid_c
             const cx<T> c = reinterpret_cast<const cx<T>*>(st + Cfg::OFF_C)[bidx];
             cx<T> dinv = mk<T>(T(0), T(0));
             if (MODE == MODE_JACOBI) dinv = reinterpret_cast<const cx<T>*>(st + Cfg::OFF_D)[bidx];
-            const T wzm = fine_w(op, 2, 0, z, n2), wzp = fine_w(op, 2, 1, z, n2);
+            const T wzm = fine_wz(op, 0, z), wzp = fine_wz(op, 1, z);
             const int64_t p = pxy + (int64_t)z * sz;
 #pragma unroll
             for (int q = 0; q < KB; ++q) {
@@ -572,8 +588,8 @@ __global__ void __launch_bounds__(256) k_fine3d_tma_pro(FineOp<T> op, const __gr
     const int i0 = (blockIdx.x / groups) * TX, j0 = blockIdx.y * TY;
     const int i = i0 + tx, j = j0 + ty;
     const int r0 = (blockIdx.x % groups) * KB;
-    const int z0 = blockIdx.z * zchunk;
-    const int z1 = min(n2, z0 + zchunk);
+    const int z0 = op.zb + blockIdx.z * zchunk;
+    const int z1 = min(op.ze, z0 + zchunk);
     const int zl = min(z1, n2 - 1);
     const int64_t sy = op.sy, sz = (int64_t)op.sy * n1;
     const bool active = (i < n0) && (j < n1);
@@ -706,7 +722,7 @@ __global__ void __launch_bounds__(256) k_fine3d_tma_pro(FineOp<T> op, const __gr
             const cx<T>* sb = reinterpret_cast<const cx<T>*>(st + Cfg::OFF_B);
             const cx<T> c = reinterpret_cast<const cx<T>*>(st + Cfg::OFF_C)[bidx];
             const cx<T> dinv = reinterpret_cast<const cx<T>*>(st + Cfg::OFF_D)[bidx];
-            const T wzm = fine_w(op, 2, 0, z, n2), wzp = fine_w(op, 2, 1, z, n2);
+            const T wzm = fine_wz(op, 0, z), wzp = fine_wz(op, 1, z);
             const int64_t p = pxy + (int64_t)z * sz;
 #pragma unroll
             for (int q = 0; q < KB; ++q) {
@@ -774,8 +790,8 @@ __global__ void __launch_bounds__(256) k_fine3d_tma_first(FineOp<T> op, const __
     const int i0 = (blockIdx.x / groups) * TX, j0 = blockIdx.y * TY;
     const int i = i0 + tx, j = j0 + ty;
     const int r0 = (blockIdx.x % groups) * KB;
-    const int z0 = blockIdx.z * zchunk;
-    const int z1 = min(n2, z0 + zchunk);
+    const int z0 = op.zb + blockIdx.z * zchunk;
+    const int z1 = min(op.ze, z0 + zchunk);
     const int zl = min(z1, n2 - 1);
     const int64_t sy = op.sy, sz = (int64_t)op.sy * n1;
     const bool active = (i < n0) && (j < n1);
@@ -831,7 +847,7 @@ __global__ void __launch_bounds__(256) k_fine3d_tma_first(FineOp<T> op, const __
             const cx<T>* sd = reinterpret_cast<const cx<T>*>(st + Cfg::OFF_D) + cidx;
             const cx<T> c = reinterpret_cast<const cx<T>*>(st + Cfg::OFF_C)[bidx];
             const cx<T> dW = sd[-1], dE = sd[1], dS = sd[-PX], dN = sd[PX], dC = sd[0];
-            const T wzm = fine_w(op, 2, 0, z, n2), wzp = fine_w(op, 2, 1, z, n2);
+            const T wzm = fine_wz(op, 0, z), wzp = fine_wz(op, 1, z);
             const int64_t p = pxy + (int64_t)z * sz;
 #pragma unroll
             for (int q = 0; q < KB; ++q) {
@@ -902,7 +918,7 @@ __global__ void __launch_bounds__(128) k_coarse3d_tma(const __grid_constant__ Tm
                                                       const __grid_constant__ TmaDesc tm_b,
                                                       const __grid_constant__ TmaDesc tm_d, cx<T>* __restrict__ out,
                                                       int n0, int n1, int n2, int sy, int64_t ld, int nrhs,
-                                                      int zchunk, int groups) {
+                                                      int zchunk, int groups, int zb, int ze) {
     typedef CoarseTmaCfg<T, MODE, KB> Cfg;
     constexpr int TX = Cfg::TX, TY = Cfg::TY, PX = Cfg::PX, NS = Cfg::NS;
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -911,8 +927,9 @@ __global__ void __launch_bounds__(128) k_coarse3d_tma(const __grid_constant__ Tm
     const int i0 = (blockIdx.x / groups) * TX, j0 = blockIdx.y * TY;
     const int i = i0 + tx, j = j0 + ty;
     const int r0 = (blockIdx.x % groups) * KB;
-    const int z0 = blockIdx.z * zchunk;
-    const int z1 = min(n2, z0 + zchunk);
+    const int z0 = zb + blockIdx.z * zchunk;
+    const int z1 = min(ze, z0 + zchunk);
+    (void)n2;
     const int niter = z1 - z0 + 2;  // input planes z0-1 .. z1
     const bool active = (i < n0) && (j < n1);
     auto issue = [&](int s, int zi) {
@@ -1058,8 +1075,8 @@ __global__ void __launch_bounds__(256) k_coarse_stencil(CoarseOp<T> op, const cx
     const int n0 = op.n[0], n1 = op.n[1], n2 = op.n[2];
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int j = blockIdx.y * blockDim.y + threadIdx.y;
-    const int k = (DIM == 3) ? blockIdx.z * blockDim.z + threadIdx.z : 0;
-    if (i >= n0 || j >= n1 || k >= n2) return;
+    const int k = (DIM == 3) ? op.zb + blockIdx.z * blockDim.z + threadIdx.z : 0;
+    if (i >= n0 || j >= n1 || (DIM == 3 && k >= op.ze)) return;
     const int64_t sy = op.sy, sz = (int64_t)op.sy * n1;
     const int64_t N = op.N;
     const int64_t p = i + sy * j + sz * k;
@@ -1133,11 +1150,15 @@ __global__ void __launch_bounds__(256) k_fine_dinv(FineOp<T> op, cx<T>* __restri
 template <typename T, int DIM>
 __global__ void __launch_bounds__(256) k_restrict(const cx<T>* __restrict__ r, cx<T>* __restrict__ bc, int nf0, int nf1,
                                                   int nf2, int nc0, int nc1, int nc2, int fsy, int csy, int64_t ldf,
-                                                  int64_t ldc, int nrhs) {
+                                                  int64_t ldc, int nrhs, int Kb, int Ke, int fkoff, int fn2g) {
+    // slab decomposition: coarse planes Kb <= K < Ke are computed; fine plane fk (local) exists iff its global index
+    // fk + fkoff lies in [0, fn2g).  Whole grid: Kb = 0, Ke = nc2, fkoff = 0, fn2g = nf2.
     const int I = blockIdx.x * blockDim.x + threadIdx.x;
     const int J = blockIdx.y * blockDim.y + threadIdx.y;
-    const int K = (DIM == 3) ? blockIdx.z * blockDim.z + threadIdx.z : 0;
-    if (I >= nc0 || J >= nc1 || K >= nc2) return;
+    const int K = (DIM == 3) ? Kb + blockIdx.z * blockDim.z + threadIdx.z : 0;
+    if (I >= nc0 || J >= nc1 || (DIM == 3 && K >= Ke)) return;
+    (void)nc2;
+    (void)nf2;
     const int64_t sy = fsy, sz = (int64_t)fsy * nf1;
     const int64_t pc = I + (int64_t)csy * J + (int64_t)csy * nc1 * K;
     const int fi = 2 * I, fj = 2 * J, fk = (DIM == 3) ? 2 * K : 0;
@@ -1146,7 +1167,7 @@ __global__ void __launch_bounds__(256) k_restrict(const cx<T>* __restrict__ r, c
         cx<T> acc = mk<T>(T(0), T(0));
 #pragma unroll
         for (int dk = (DIM == 3 ? -1 : 0); dk <= (DIM == 3 ? 1 : 0); ++dk) {
-            if ((unsigned)(fk + dk) >= (unsigned)nf2) continue;
+            if (DIM == 3 && (unsigned)(fk + dk + fkoff) >= (unsigned)fn2g) continue;
             const T wk = (DIM == 3) ? (dk == 0 ? T(0.5) : T(0.25)) : T(1);
 #pragma unroll
             for (int dj = -1; dj <= 1; ++dj) {
@@ -1170,11 +1191,12 @@ __global__ void __launch_bounds__(256) k_restrict(const cx<T>* __restrict__ r, c
 template <typename T, int DIM>
 __global__ void __launch_bounds__(256) k_prolong_add(cx<T>* __restrict__ x, const cx<T>* __restrict__ xc, int nf0,
                                                      int nf1, int nf2, int fsy, int csy, int nc1, int64_t ldf,
-                                                     int64_t ldc, int nrhs) {
+                                                     int64_t ldc, int nrhs, int zb, int ze) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int j = blockIdx.y * blockDim.y + threadIdx.y;
-    const int k = (DIM == 3) ? blockIdx.z * blockDim.z + threadIdx.z : 0;
-    if (i >= nf0 || j >= nf1 || k >= nf2) return;
+    const int k = (DIM == 3) ? zb + blockIdx.z * blockDim.z + threadIdx.z : 0;  // fine planes zb <= k < ze
+    if (i >= nf0 || j >= nf1 || (DIM == 3 && k >= ze)) return;
+    (void)nf2;
     const int64_t p = i + (int64_t)fsy * j + (int64_t)fsy * nf1 * k;
     const int64_t cy = csy, cz = (int64_t)csy * nc1;
     const int I0 = i >> 1, J0 = j >> 1, K0 = k >> 1;
@@ -1223,7 +1245,7 @@ struct FineCoef {
         T w;
         if (di != 0) w = fine_w(op, 0, di > 0, i, op.n[0]);
         else if (dj != 0) w = fine_w(op, 1, dj > 0, j, op.n[1]);
-        else w = fine_w(op, 2, dk > 0, k, op.n[2]);
+        else w = fine_wz(op, dk > 0, k);
         return mk<double>(-(double)w, 0.0);
     }
 };
@@ -1242,24 +1264,30 @@ struct StoredCoef {
 
 template <typename T, int DIM, typename Coef>
 __global__ void __launch_bounds__(128) k_galerkin(Coef A, int nf0, int nf1, int nf2, int nc0, int nc1, int nc2,
-                                                  int csy, int64_t cN, cx<T>* __restrict__ coefc) {
-    const int64_t Nc = (int64_t)nc0 * nc1 * nc2;
+                                                  int csy, int64_t cN, cx<T>* __restrict__ coefc, int Kb, int Ke,
+                                                  int fkoff, int fn2g, int ckoff, int cn2g) {
+    // slab decomposition (3-D): rows of the coarse planes Kb <= K < Ke are computed; a fine / coarse plane exists iff
+    // its global index (local + fkoff / ckoff) lies inside the global grid (fn2g / cn2g planes); the local arrays
+    // hold the halo planes those rows touch.  Whole grid: Kb = 0, Ke = nc2, offsets 0, fn2g = nf2, cn2g = nc2.
+    const int64_t Nc = (int64_t)nc0 * nc1 * (Ke - Kb);
     const int NS = (DIM == 3) ? 27 : 9;
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= Nc * NS) return;
+    (void)nf2;
+    (void)nc2;
     const int s = (int)(t / Nc);
     int64_t pc = t - (int64_t)s * Nc;
     const int I = (int)(pc % nc0);
     const int J = (int)((pc / nc0) % nc1);
-    const int K = (int)(pc / ((int64_t)nc0 * nc1));
+    const int K = Kb + (int)(pc / ((int64_t)nc0 * nc1));
     const int dI = s % 3 - 1, dJ = (s / 3) % 3 - 1, dK = (DIM == 3) ? (s / 9 - 1) : 0;
     const int JI = I + dI, JJ = J + dJ, JK = K + dK;  // coarse column node
     cx<double> acc = mk<double>(0.0, 0.0);
-    if ((unsigned)JI < (unsigned)nc0 && (unsigned)JJ < (unsigned)nc1 && (unsigned)JK < (unsigned)nc2) {
+    if ((unsigned)JI < (unsigned)nc0 && (unsigned)JJ < (unsigned)nc1 && (unsigned)(JK + ckoff) < (unsigned)cn2g) {
         const double rscale = (DIM == 3) ? 0.125 : 0.25;
         for (int ek = (DIM == 3 ? -1 : 0); ek <= (DIM == 3 ? 1 : 0); ++ek) {
             const int fk = 2 * K + ek;
-            if ((unsigned)fk >= (unsigned)nf2) continue;
+            if ((unsigned)(fk + fkoff) >= (unsigned)fn2g) continue;
             for (int ej = -1; ej <= 1; ++ej) {
                 const int fj = 2 * J + ej;
                 if ((unsigned)fj >= (unsigned)nf1) continue;
@@ -1270,7 +1298,7 @@ __global__ void __launch_bounds__(128) k_galerkin(Coef A, int nf0, int nf1, int 
                     // columns j = i + t of A that interpolate from coarse node (JI,JJ,JK)
                     for (int tk = (DIM == 3 ? -1 : 0); tk <= (DIM == 3 ? 1 : 0); ++tk) {
                         const int gk = fk + tk;
-                        if ((unsigned)gk >= (unsigned)nf2) continue;
+                        if ((unsigned)(gk + fkoff) >= (unsigned)fn2g) continue;
                         const int qk = (DIM == 3) ? gk - 2 * JK : 0;
                         if (qk < -1 || qk > 1) continue;
                         for (int tj = -1; tj <= 1; ++tj) {
@@ -1562,7 +1590,24 @@ template <typename T>
 __global__ void k_point_sources(cx<T>* __restrict__ B, int64_t ld, const int64_t* __restrict__ idx,
                                 const zc* __restrict__ val, int nrhs) {
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r < nrhs) B[(int64_t)r * ld + idx[r]] = mk<T>((T)val[r].x, (T)val[r].y);
+    if (r < nrhs && idx[r] >= 0) B[(int64_t)r * ld + idx[r]] = mk<T>((T)val[r].x, (T)val[r].y);  // < 0: another slab's node
+}
+
+// out[q] = sum over the nblk partials of quantity q (slab decomposition: the local sums that are all-reduced over the
+// slabs; the scalar kernels then run with nblk = 1).  One warp per quantity.
+__global__ void k_sum_partials(const zc* __restrict__ partial, int nq, int nblk, zc* __restrict__ out) {
+    const int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (q >= nq) return;
+    const int lane = threadIdx.x & 31;
+    double sx = 0.0, sy = 0.0;
+    for (int t = lane; t < nblk; t += 32) {
+        const zc v = partial[(int64_t)q * nblk + t];
+        sx += v.x;
+        sy += v.y;
+    }
+    sx = warp_sum(sx);
+    sy = warp_sum(sy);
+    if (lane == 0) out[q] = mk<double>(sx, sy);
 }
 
 // ---- small per-RHS scalar kernels (one warp per right-hand side; all state in double) ----------

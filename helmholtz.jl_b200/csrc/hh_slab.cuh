@@ -1,0 +1,280 @@
+// hh_slab.cuh -- slab domain decomposition of ONE problem over several GPUs (the grid that
+// exceeds one GPU, config 5): partition of the planes of the last dimension, and the two collectives the solve
+// needs -- neighbour halo exchange of planes and an all-reduce of the per-RHS dot/norm partials.
+//
+// Two transports implement them:
+//   * NcclTransport   one process per GPU (torchrun / Julia Distributed workers); ncclSend/ncclRecv groups over NVLink
+//                     for the halos, ncclAllReduce for the scalars.  libnccl is bound at run time (dlopen) so that the
+//                     library has no link-time dependency: inside a process that already loaded torch's NCCL that
+//                     copy is used.
+//   * ThreadTransport one process, one host thread per slab (the slabs may live on different devices -- peer copies
+//                     over NVLink -- or share a device, which is how the single-GPU tests cover this path).
+#pragma once
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include <condition_variable>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "hh_common.cuh"
+
+namespace hh {
+
+// (included by hh_solver.cuh after hh::Error / HH_CUDA / HH_REQUIRE are defined)
+
+// geometry of one multigrid level inside one slab (planes of the last dimension)
+struct SlabLevel {
+    int own0 = 0, own1 = 0;  // global planes owned: own0 <= k < own1
+    int koff = 0;            // global index of local plane 0
+    int nloc = 0;            // local planes held: alignment/halo planes below + owned + one halo plane above
+    int zb = 0, ze = 0;      // owned planes in local numbering
+    int n2g = 0;             // global plane count of the level
+};
+
+// Partition of an n3-plane grid with `levels` multigrid levels over `nranks` slabs.  The coarsest level's cells are
+// split as evenly as possible; finer levels follow by doubling, so that every slab owns the fine planes 2K-? its
+// coarse planes restrict from / interpolate to with a one-plane halo.  Below the owned range a slab keeps
+// 2^(levels-1-l) planes on level l (only the top one is exchanged): that keeps local plane 0 of every level at an even
+// global index, i.e. local coarsening "z >> 1" agrees with the global one.  Returns false when a slab would be empty.
+inline bool slab_partition(int n3, int levels, int nranks, int rank, std::vector<SlabLevel>& out) {
+    out.assign(levels, SlabLevel());
+    const int f0 = 1 << (levels - 1);
+    if (nranks < 1 || rank < 0 || rank >= nranks || n3 < 2 || ((n3 - 1) % f0) != 0) return false;
+    const int cells = (n3 - 1) / f0;  // cells of the coarsest level
+    if (cells < nranks) return false;
+    const int base = cells / nranks, rem = cells % nranks;
+    const int c0 = rank * base + std::min(rank, rem);
+    const int c1 = c0 + base + (rank < rem ? 1 : 0);
+    const bool first = rank == 0, last = rank == nranks - 1;
+    for (int l = 0; l < levels; ++l) {
+        const int f = 1 << (levels - 1 - l);
+        SlabLevel& s = out[l];
+        s.n2g = cells * f + 1;
+        s.own0 = c0 * f;
+        s.own1 = last ? s.n2g : c1 * f;
+        const int pad_lo = first ? 0 : f, pad_hi = last ? 0 : 1;
+        s.koff = s.own0 - pad_lo;
+        s.zb = pad_lo;
+        s.ze = pad_lo + (s.own1 - s.own0);
+        s.nloc = s.ze + pad_hi;
+    }
+    return true;
+}
+
+struct SlabTransport {
+    int rank = 0, nranks = 1;
+    virtual ~SlabTransport() {}
+    // For each of `nseg` segments (segment r starts at base + r*stride bytes): send `bytes` bytes at offset send_dn to
+    // the slab below and at send_up to the slab above; receive the neighbours' counterparts at recv_dn / recv_up.
+    // Enqueued on `st` of `device`; the first / last slab skips the missing side.
+    virtual void exchange(cudaStream_t st, int device, char* base, size_t stride, int nseg, size_t bytes, size_t send_dn,
+                          size_t recv_dn, size_t send_up, size_t recv_up) = 0;
+    // in-place reduction of n doubles on the device over all slabs; every slab receives bit-identical results
+    virtual void allreduce(cudaStream_t st, double* dbuf, int n, bool minimum) = 0;
+};
+
+// ------------------------------------------------------------------------------------------- NCCL
+struct NcclApi {
+    decltype(&ncclGetUniqueId) GetUniqueId = nullptr;
+    decltype(&ncclCommInitRank) CommInitRank = nullptr;
+    decltype(&ncclCommDestroy) CommDestroy = nullptr;
+    decltype(&ncclSend) Send = nullptr;
+    decltype(&ncclRecv) Recv = nullptr;
+    decltype(&ncclAllReduce) AllReduce = nullptr;
+    decltype(&ncclGroupStart) GroupStart = nullptr;
+    decltype(&ncclGroupEnd) GroupEnd = nullptr;
+    decltype(&ncclGetErrorString) GetErrorString = nullptr;
+    std::string error;
+    bool ok = false;
+    static NcclApi& get() {
+        static NcclApi api;
+        static std::once_flag once;
+        std::call_once(once, [] { api.load(); });
+        return api;
+    }
+    void load() {
+        const char* env = getenv("HH_NCCL_LIB");
+        void* h = nullptr;
+        const char* names[] = {env, "libnccl.so.2", "libnccl.so"};
+        for (const char* nm : names) {
+            if (!nm) continue;
+            h = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+            if (h) break;
+        }
+        if (!h) {
+            error = "libnccl.so.2 could not be loaded (set HH_NCCL_LIB)";
+            return;
+        }
+#define HH_NCCL_SYM(name)                                                          \
+    name = (decltype(name))dlsym(h, "nccl" #name);                                 \
+    if (!name) {                                                                   \
+        error = "symbol nccl" #name " is missing from the NCCL library";           \
+        return;                                                                    \
+    }
+        HH_NCCL_SYM(GetUniqueId)
+        HH_NCCL_SYM(CommInitRank)
+        HH_NCCL_SYM(CommDestroy)
+        HH_NCCL_SYM(Send)
+        HH_NCCL_SYM(Recv)
+        HH_NCCL_SYM(AllReduce)
+        HH_NCCL_SYM(GroupStart)
+        HH_NCCL_SYM(GroupEnd)
+        HH_NCCL_SYM(GetErrorString)
+#undef HH_NCCL_SYM
+        ok = true;
+    }
+};
+
+// ------------------------------------------------------------------------------------------- threads
+// shared state of the slabs of one in-process handle
+struct ThreadGroup {
+    int n = 0;
+    std::mutex mu;
+    std::condition_variable cv;
+    int waiting = 0;
+    uint64_t generation = 0;
+    bool failed = false;
+    struct Slot {
+        char* base = nullptr;
+        size_t stride = 0, send_dn = 0, send_up = 0;
+        int device = 0;
+        std::vector<double> red;
+    };
+    std::vector<Slot> slots;
+    explicit ThreadGroup(int n_) : n(n_), slots(n_) {}
+    // all slabs arrive, or any slab reported a failure (then every waiter throws instead of hanging)
+    bool barrier() {
+        std::unique_lock<std::mutex> lk(mu);
+        if (failed) return false;
+        const uint64_t gen = generation;
+        if (++waiting == n) {
+            waiting = 0;
+            ++generation;
+            cv.notify_all();
+            return true;
+        }
+        cv.wait(lk, [&] { return generation != gen || failed; });
+        return !failed;
+    }
+    void fail() {
+        std::lock_guard<std::mutex> lk(mu);
+        failed = true;
+        cv.notify_all();
+    }
+    void reset() {
+        std::lock_guard<std::mutex> lk(mu);
+        failed = false;
+        waiting = 0;
+    }
+};
+
+
+#define HH_NCCL(call)                                                                                          \
+    do {                                                                                                       \
+        ncclResult_t r__ = (call);                                                                             \
+        if (r__ != ncclSuccess)                                                                                \
+            throw hh::Error(HH_ERR_CUDA, std::string("NCCL: ") + #call + ": " + NcclApi::get().GetErrorString(r__)); \
+    } while (0)
+
+struct NcclTransport : SlabTransport {
+    ncclComm_t comm = nullptr;
+    NcclTransport(int rank_, int nranks_, const void* unique_id) {
+        rank = rank_;
+        nranks = nranks_;
+        NcclApi& api = NcclApi::get();
+        HH_REQUIRE(api.ok, HH_ERR_UNSUPPORTED, api.error);
+        ncclUniqueId id;
+        static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+        memcpy(&id, unique_id, sizeof(id));
+        HH_NCCL(api.CommInitRank(&comm, nranks, id, rank));
+    }
+    ~NcclTransport() override {
+        if (comm) NcclApi::get().CommDestroy(comm);
+    }
+    void exchange(cudaStream_t st, int, char* base, size_t stride, int nseg, size_t bytes, size_t send_dn, size_t recv_dn,
+                  size_t send_up, size_t recv_up) override {
+        NcclApi& api = NcclApi::get();
+        if (nranks == 1) return;
+        HH_NCCL(api.GroupStart());
+        for (int r = 0; r < nseg; ++r) {
+            char* seg = base + (size_t)r * stride;
+            if (rank > 0) {
+                HH_NCCL(api.Send(seg + send_dn, bytes, ncclChar, rank - 1, comm, st));
+                HH_NCCL(api.Recv(seg + recv_dn, bytes, ncclChar, rank - 1, comm, st));
+            }
+            if (rank < nranks - 1) {
+                HH_NCCL(api.Send(seg + send_up, bytes, ncclChar, rank + 1, comm, st));
+                HH_NCCL(api.Recv(seg + recv_up, bytes, ncclChar, rank + 1, comm, st));
+            }
+        }
+        HH_NCCL(api.GroupEnd());
+    }
+    void allreduce(cudaStream_t st, double* dbuf, int n, bool minimum) override {
+        if (nranks == 1) return;
+        HH_NCCL(NcclApi::get().AllReduce(dbuf, dbuf, (size_t)n, ncclDouble, minimum ? ncclMin : ncclSum, comm, st));
+    }
+};
+
+struct ThreadTransport : SlabTransport {
+    std::shared_ptr<ThreadGroup> grp;
+    std::vector<double> host;
+    ThreadTransport(int rank_, std::shared_ptr<ThreadGroup> g) : grp(std::move(g)) {
+        rank = rank_;
+        nranks = grp->n;
+    }
+    void sync() {
+        if (!grp->barrier()) throw hh::Error(HH_ERR_STATE, "another slab of this handle failed");
+    }
+    // pull model: every slab publishes where its outgoing planes are, then copies its neighbours' planes into its halos
+    void exchange(cudaStream_t st, int device, char* base, size_t stride, int nseg, size_t bytes, size_t send_dn,
+                  size_t recv_dn, size_t send_up, size_t recv_up) override {
+        if (nranks == 1) return;
+        ThreadGroup::Slot& me = grp->slots[rank];
+        me.base = base;
+        me.stride = stride;
+        me.send_dn = send_dn;
+        me.send_up = send_up;
+        me.device = device;
+        HH_CUDA(cudaStreamSynchronize(st));  // my outgoing planes are final
+        sync();
+        for (int r = 0; r < nseg; ++r) {
+            if (rank > 0) {
+                const ThreadGroup::Slot& nb = grp->slots[rank - 1];
+                HH_CUDA(cudaMemcpyPeerAsync(base + (size_t)r * stride + recv_dn, device, nb.base + (size_t)r * nb.stride + nb.send_up,
+                                            nb.device, bytes, st));
+            }
+            if (rank < nranks - 1) {
+                const ThreadGroup::Slot& nb = grp->slots[rank + 1];
+                HH_CUDA(cudaMemcpyPeerAsync(base + (size_t)r * stride + recv_up, device, nb.base + (size_t)r * nb.stride + nb.send_dn,
+                                            nb.device, bytes, st));
+            }
+        }
+        HH_CUDA(cudaStreamSynchronize(st));
+        sync();  // nobody overwrites planes a neighbour is still reading
+    }
+    void allreduce(cudaStream_t st, double* dbuf, int n, bool minimum) override {
+        if (nranks == 1) return;
+        std::vector<double>& mine = grp->slots[rank].red;
+        mine.resize(n);
+        HH_CUDA(cudaMemcpyAsync(mine.data(), dbuf, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, st));
+        HH_CUDA(cudaStreamSynchronize(st));
+        sync();
+        host.assign(n, 0.0);
+        for (int i = 0; i < n; ++i) {  // same order on every slab: identical results
+            double a = grp->slots[0].red[i];
+            for (int q = 1; q < nranks; ++q) {
+                const double v = grp->slots[q].red[i];
+                a = minimum ? std::min(a, v) : a + v;
+            }
+            host[i] = a;
+        }
+        sync();  // everybody has read the slots
+        HH_CUDA(cudaMemcpyAsync(dbuf, host.data(), (size_t)n * sizeof(double), cudaMemcpyHostToDevice, st));
+        HH_CUDA(cudaStreamSynchronize(st));
+    }
+};
+
+}  // namespace hh

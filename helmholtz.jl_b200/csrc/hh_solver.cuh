@@ -39,6 +39,10 @@ struct Error : std::runtime_error {
         if (!(cond)) throw hh::Error((code), (msg));     \
     } while (0)
 
+}  // namespace hh
+#include "hh_slab.cuh"
+namespace hh {
+
 // kernel classes for the per-kernel device timing (hh_profile_*)
 enum Tag {
     T_FINE_APPLY = 0,
@@ -60,13 +64,15 @@ enum Tag {
     T_COPY,
     T_SCALAR,
     T_SETUP,
+    T_HALO,
+    T_ALLREDUCE,
     T_NTAGS
 };
 static const char* const kTagNames[T_NTAGS] = {
     "fine_apply",   "fine_resid",   "fine_jacobi",    "fine_jacobi0", "fine_first_resid", "fine_first_jacobi", "fine_prolong_jacobi",
     "coarse_apply", "coarse_resid",
     "coarse_jacobi", "coarse_jacobi0", "restrict",    "prolong",      "coarsest_dense", "krylov_dot",
-    "krylov_axpy",  "copy",           "scalar",       "setup"};
+    "krylov_axpy",  "copy",           "scalar",       "setup",        "halo_exchange", "allreduce"};
 
 struct Profiler {
     struct Rec {
@@ -215,6 +221,14 @@ struct SolverBase {
     virtual double cycle_bytes_per_rhs() const = 0;
     std::function<void(const void*, void*, int)> prec_hook;
     bool krylov_only = false;
+    // Slab decomposition (hh_slab.cuh): `pb` then describes the LOCAL grid of this slab (pb.n[2] = sgeo[0].nloc planes,
+    // halo planes included), sgeo[l] the plane geometry of level l, and `slab` the collectives.  Caller-facing blocks
+    // (B, X of hh_solve_device) hold the owned planes only.
+    std::shared_ptr<SlabTransport> slab;
+    std::vector<SlabLevel> sgeo;
+    int64_t caller_N() const {
+        return slab ? (int64_t)pb.n[0] * pb.n[1] * (sgeo[0].own1 - sgeo[0].own0) : pb.N();
+    }
     Problem pb;
     int device = 0;
     cudaStream_t stream = 0;
@@ -250,6 +264,8 @@ class Solver : public SolverBase {
         int p0 = 1;                 // row pitch of every array of this level (n[0], or n[0]+1: see pitch_of)
         int64_t N = 0;              // padded node count p0*n[1]*n[2] = leading dimension of the level's vectors
         int64_t Nlog = 0;           // logical node count
+        int zb = 0, ze = 1;         // planes computed by the kernels (slab: the owned planes; else 0, n[2])
+        int koff = 0, n2g = 1;      // slab: global index of local plane 0, global plane count (else 0, n[2])
         DevBuf<C> coef, dinv;       // l >= 1 (dinv also on l = 0 when Jac-GMRES is used)
         DevBuf<C> x, b, t;          // work vectors N x kcap (l >= 1); l = 0 owns only t
         SmallWs gs;                 // Jac-GMRES smoother / inexact coarsest solve (Jacobi-preconditioned)
@@ -335,7 +351,48 @@ class Solver : public SolverBase {
         op.adj = adj;
         op.cdiag = nullptr;
         op.dinv = nullptr;
+        op.koff = slab ? sgeo[0].koff : 0;
+        op.n2g = slab ? sgeo[0].n2g : pb.n[2];
+        op.zb = slab ? sgeo[0].zb : 0;
+        op.ze = slab ? sgeo[0].ze : pb.n[2];
         return op;
+    }
+    // grid of the one-thread-per-node kernels that compute planes zb <= k < ze only
+    static void grid3z(const int n[3], int dim, int zb, int ze, dim3& g, dim3& b) {
+        int nn[3] = {n[0], n[1], dim == 3 ? ze - zb : 1};
+        grid3(nn, dim, g, b);
+    }
+
+    // ------------------------------------------------------------------ slab collectives
+    // fill the halo planes (zb-1 and ze) of every vector of the block `v` on level l from the neighbouring slabs
+    void halo_exchange(int l, const C* v, int nvec, int64_t ld = 0) {
+        if (!slab || slab->nranks == 1) return;
+        const Level& L = levels[l];
+        const size_t plane = (size_t)L.p0 * L.n[1] * sizeof(C);
+        launch(T_HALO, 2.0 * (double)plane * nvec * ((slab->rank > 0) + (slab->rank < slab->nranks - 1)), [&] {
+            slab->exchange(stream, device, (char*)const_cast<C*>(v), (size_t)(ld ? ld : L.N) * sizeof(C), nvec, plane,
+                           (size_t)L.zb * plane, (size_t)(L.zb - 1) * plane, (size_t)(L.ze - 1) * plane, (size_t)L.ze * plane);
+        });
+    }
+    // Sum the nblk partials of each of the nq quantities, all-reduce over the slabs and leave the result in `partial`
+    // in the layout of nblk = 1 (which is returned).  No-op without slabs.
+    int slab_reduce(zc* partial, int nq, int nblk) {
+        if (!slab || slab->nranks == 1) return nblk;
+        if (d_red.n < (size_t)nq) d_red.alloc((size_t)std::max(nq, 4096));
+        launch(T_SCALAR, 0, [&] { k_sum_partials<<<(nq + 7) / 8, 256, 0, stream>>>(partial, nq, nblk, d_red.p); });
+        launch(T_ALLREDUCE, 16.0 * nq, [&] { slab->allreduce(stream, (double*)d_red.p, 2 * nq, false); });
+        HH_CUDA(cudaMemcpyAsync(partial, d_red.p, (size_t)nq * sizeof(zc), cudaMemcpyDeviceToDevice, stream));
+        return 1;
+    }
+    // range of a level's vectors that the Krylov / reduction kernels work on (slab: the owned planes)
+    struct Span {
+        int64_t off, len, ld;
+    };
+    Span span(int l) const {
+        const Level& L = levels[l];
+        if (!slab) return Span{0, L.N, L.N};
+        const int64_t plane = (int64_t)L.p0 * L.n[1];
+        return Span{(int64_t)L.zb * plane, (int64_t)(L.ze - L.zb) * plane, L.N};
     }
     // diagonal arrays for the TMA-staged kernels (3-D only), in the layout of `op`
     void precompute_diag(FineOp<T>& op, DevBuf<C>& cd, DevBuf<C>* dv, T damp) {
@@ -407,7 +464,8 @@ class Solver : public SolverBase {
     // out = op(x) with MODE epilogue on the fine level
     void fine_stencil(int mode, const FineOp<T>& op, const C* x, const C* b, C* out, int64_t ld, int nrhs, T damp) {
         dim3 g, blk;
-        grid3(pb.n, pb.dim, g, blk);
+        grid3z(pb.n, pb.dim, op.zb, op.ze, g, blk);
+        halo_exchange(0, x, nrhs, ld);
         const double N = (double)pb.N();
         const double coefb = 2.0 * CR * N;
         double bytes;
@@ -451,7 +509,7 @@ class Solver : public SolverBase {
         const int groups = (nrhs + KB - 1) / KB;
         const int tx = (pb.n[0] + 31) / 32, ty = (pb.n[1] + TY - 1) / TY;
         int zchunk, nzc;
-        zchunks(pb.n[2], tx * ty, groups, 32, zchunk, nzc);
+        zchunks(op.ze - op.zb, tx * ty, groups, 32, zchunk, nzc);
         dim3 g(tx * groups, ty, nzc), blk(32, TY, 1);
         k_fine3d_zmarch<T, MODE, KB, TY, FINE_MINB><<<g, blk, 0, stream>>>(op, x, b, out, ld, nrhs, damp, zchunk, groups);
     }
@@ -502,7 +560,7 @@ class Solver : public SolverBase {
         const int groups = (nrhs + KB - 1) / KB;
         const int tx = (pb.n[0] + Cfg::TX - 1) / Cfg::TX, ty = (pb.n[1] + Cfg::TY - 1) / Cfg::TY;
         int zchunk, nzc;
-        zchunks(pb.n[2], tx * ty, groups, 64, zchunk, nzc);
+        zchunks(op.ze - op.zb, tx * ty, groups, 64, zchunk, nzc);
         dim3 g(tx * groups, ty, nzc);
         // the RHS extent of the x / b maps is the true nrhs so that surplus slots of the last group are zero-filled
         TmaDesc tx_ = make_tmap_n(x, op.sy, ld, Cfg::PX, Cfg::TY + 2, KB, nrhs);
@@ -546,7 +604,7 @@ class Solver : public SolverBase {
         const int groups = (nrhs + KB - 1) / KB;
         const int tx = (pb.n[0] + Cfg::TX - 1) / Cfg::TX, ty = (pb.n[1] + Cfg::TY - 1) / Cfg::TY;
         int zchunk, nzc;
-        zchunks(pb.n[2], tx * ty, groups, 64, zchunk, nzc);
+        zchunks(op.ze - op.zb, tx * ty, groups, 64, zchunk, nzc);
         dim3 g(tx * groups, ty, nzc);
         TmaDesc mb = make_tmap_n(b, op.sy, ld, Cfg::PX, Cfg::TY + 2, KB, nrhs);
         TmaDesc md = make_tmap_n(op.dinv, op.sy, ld, Cfg::PX, Cfg::TY + 2, 1, 0);
@@ -559,6 +617,7 @@ class Solver : public SolverBase {
     // second == 0: out = x1, out2 = b - A x1;  second == 1: out = x2
     void fine_first(int second, const FineOp<T>& op, const C* b, C* out, C* out2, int64_t ld, int nrhs) {
         const double N = (double)pb.N();
+        halo_exchange(0, b, nrhs, ld);
         const double bytes = (second == 0 ? 3.0 : 2.0) * S * N * nrhs + 2.0 * S * N;
         launch(second == 0 ? T_FINE_FIRST_RESID : T_FINE_FIRST_JACOBI, bytes, [&] {
             if (second == 0) {
@@ -584,7 +643,7 @@ class Solver : public SolverBase {
         const int groups = (nrhs + KB - 1) / KB;
         const int tx = (pb.n[0] + Cfg::TX - 1) / Cfg::TX, ty = (pb.n[1] + Cfg::TY - 1) / Cfg::TY;
         int zchunk, nzc;
-        zchunks(pb.n[2], tx * ty, groups, 64, zchunk, nzc);
+        zchunks(op.ze - op.zb, tx * ty, groups, 64, zchunk, nzc);
         dim3 g(tx * groups, ty, nzc);
         TmaDesc mx = make_tmap_n(x, op.sy, ld, Cfg::PX, Cfg::TY + 2, KB, nrhs);
         TmaDesc mb = make_tmap_n(b, op.sy, ld, Cfg::TX, Cfg::TY, KB, nrhs);
@@ -599,6 +658,8 @@ class Solver : public SolverBase {
     }
     void fine_prolong_jacobi(const FineOp<T>& op, const C* x, const C* b, const Level& Cc, const C* xc, C* out, int64_t ld, int nrhs) {
         const double N = (double)pb.N();
+        halo_exchange(0, x, nrhs, ld);
+        halo_exchange(1, xc, nrhs);
         launch(T_FINE_PROLONG_JACOBI, (3.0 * N + (double)Cc.Nlog) * S * nrhs + 2.0 * S * N, [&] {
             if (nrhs >= 2) tma3d_pro_launch<2>(op, x, b, Cc, xc, out, ld, nrhs);
             else tma3d_pro_launch<1>(op, x, b, Cc, xc, out, ld, nrhs);
@@ -631,18 +692,19 @@ class Solver : public SolverBase {
         const int groups = (nrhs + KB - 1) / KB;
         const int tx = (L.n[0] + Cfg::TX - 1) / Cfg::TX, ty = (L.n[1] + Cfg::TY - 1) / Cfg::TY;
         int zchunk, nzc;
-        zchunks(L.n[2], tx * ty, groups, 32, zchunk, nzc);
+        const int nz = L.ze - L.zb;
+        zchunks(nz, tx * ty, groups, 32, zchunk, nzc);
         // one CTA per SM is resident: aim for a few waves, not for many tiny chunks
         while (nzc > 1 && (int64_t)tx * ty * groups * nzc > 148 * 6) {
-            zchunk = std::min(L.n[2], zchunk * 2);
-            nzc = (L.n[2] + zchunk - 1) / zchunk;
+            zchunk = std::min(nz, zchunk * 2);
+            nzc = (nz + zchunk - 1) / zchunk;
         }
         dim3 g(tx * groups, ty, nzc);
         TmaDesc mx = make_tmap_g(x, L.n, L.p0, L.N, Cfg::PX, Cfg::TY + 2, KB, nrhs);
         TmaDesc mc = make_tmap_g(L.coef.p, L.n, L.p0, L.N, Cfg::TX, Cfg::TY, 9, 27);
         TmaDesc mb = (MODE != MODE_APPLY) ? make_tmap_g(b, L.n, L.p0, L.N, Cfg::TX, Cfg::TY, KB, nrhs) : mx;
         TmaDesc md = (MODE == MODE_JACOBI) ? make_tmap_g(L.dinv.p, L.n, L.p0, L.N, Cfg::TX, Cfg::TY, 1, 0) : mx;
-        k_coarse3d_tma<T, MODE, KB><<<g, 128, smem, stream>>>(mx, mc, mb, md, out, L.n[0], L.n[1], L.n[2], L.p0, L.N, nrhs, zchunk, groups);
+        k_coarse3d_tma<T, MODE, KB><<<g, 128, smem, stream>>>(mx, mc, mb, md, out, L.n[0], L.n[1], L.n[2], L.p0, L.N, nrhs, zchunk, groups, L.zb, L.ze);
     }
     template <int MODE>
     void coarse_tma_mode(const Level& L, const C* x, const C* b, C* out, int nrhs) {
@@ -665,7 +727,7 @@ class Solver : public SolverBase {
         const int groups = (nrhs + KB - 1) / KB;
         const int tx = (L.n[0] + 31) / 32, ty = (L.n[1] + TY - 1) / TY;
         int zchunk, nzc;
-        zchunks(L.n[2], tx * ty, groups, 16, zchunk, nzc);
+        zchunks(L.ze - L.zb, tx * ty, groups, 16, zchunk, nzc);
         dim3 g(tx * groups, ty, nzc), blk(32, TY, 1);
         k_coarse3d_zmarch<T, MODE, KB, TY, COARSE_MINB><<<g, blk, 0, stream>>>(coarse_op(L), x, b, out, L.N, nrhs, zchunk, groups);
     }
@@ -693,11 +755,14 @@ class Solver : public SolverBase {
         for (int d = 0; d < 3; ++d) op.n[d] = L.n[d];
         op.sy = L.p0;
         op.N = L.N;
+        op.zb = L.zb;
+        op.ze = L.ze;
         return op;
     }
     void coarse_stencil(int mode, const Level& L, const C* x, const C* b, C* out, int nrhs) {
         dim3 g, blk;
-        grid3(L.n, pb.dim, g, blk);
+        grid3z(L.n, pb.dim, L.zb, L.ze, g, blk);
+        halo_exchange((int)(&L - levels.data()), x, nrhs);
         const double N = (double)L.Nlog;
         const int NS = pb.dim == 3 ? 27 : 9;
         const bool use_tma = tma_ok_level(L) && ((uintptr_t)x % 16 == 0) && (mode == MODE_APPLY || (uintptr_t)b % 16 == 0);
@@ -749,22 +814,25 @@ class Solver : public SolverBase {
     }
     void restrict_to(const Level& F, const Level& Cc, const C* r, C* bc, int nrhs) {
         dim3 g, blk;
-        grid3(Cc.n, pb.dim, g, blk);
+        grid3z(Cc.n, pb.dim, Cc.zb, Cc.ze, g, blk);
+        halo_exchange((int)(&F - levels.data()), r, nrhs);
         launch(T_RESTRICT, S * ((double)F.Nlog + (double)Cc.Nlog) * nrhs, [&] {
             if (pb.dim == 3)
-                k_restrict<T, 3><<<g, blk, 0, stream>>>(r, bc, F.n[0], F.n[1], F.n[2], Cc.n[0], Cc.n[1], Cc.n[2], F.p0, Cc.p0, F.N, Cc.N, nrhs);
+                k_restrict<T, 3><<<g, blk, 0, stream>>>(r, bc, F.n[0], F.n[1], F.n[2], Cc.n[0], Cc.n[1], Cc.n[2], F.p0, Cc.p0, F.N, Cc.N, nrhs,
+                                                        Cc.zb, Cc.ze, F.koff, F.n2g);
             else
-                k_restrict<T, 2><<<g, blk, 0, stream>>>(r, bc, F.n[0], F.n[1], 1, Cc.n[0], Cc.n[1], 1, F.p0, Cc.p0, F.N, Cc.N, nrhs);
+                k_restrict<T, 2><<<g, blk, 0, stream>>>(r, bc, F.n[0], F.n[1], 1, Cc.n[0], Cc.n[1], 1, F.p0, Cc.p0, F.N, Cc.N, nrhs, 0, 1, 0, 1);
         });
     }
     void prolong_add(const Level& F, const Level& Cc, C* x, const C* xc, int nrhs) {
         dim3 g, blk;
-        grid3(F.n, pb.dim, g, blk);
+        grid3z(F.n, pb.dim, F.zb, F.ze, g, blk);
+        halo_exchange((int)(&Cc - levels.data()), xc, nrhs);
         launch(T_PROLONG, S * (2.0 * (double)F.Nlog + (double)Cc.Nlog) * nrhs, [&] {
             if (pb.dim == 3)
-                k_prolong_add<T, 3><<<g, blk, 0, stream>>>(x, xc, F.n[0], F.n[1], F.n[2], F.p0, Cc.p0, Cc.n[1], F.N, Cc.N, nrhs);
+                k_prolong_add<T, 3><<<g, blk, 0, stream>>>(x, xc, F.n[0], F.n[1], F.n[2], F.p0, Cc.p0, Cc.n[1], F.N, Cc.N, nrhs, F.zb, F.ze);
             else
-                k_prolong_add<T, 2><<<g, blk, 0, stream>>>(x, xc, F.n[0], F.n[1], 1, F.p0, Cc.p0, Cc.n[1], F.N, Cc.N, nrhs);
+                k_prolong_add<T, 2><<<g, blk, 0, stream>>>(x, xc, F.n[0], F.n[1], 1, F.p0, Cc.p0, Cc.n[1], F.N, Cc.N, nrhs, 0, 1);
         });
     }
 
@@ -779,43 +847,47 @@ class Solver : public SolverBase {
         launch(T_COPY, S * (double)N * nrhs, [&] { HH_CUDA(cudaMemsetAsync(v, 0, (size_t)N * nrhs * sizeof(C), stream)); });
     }
     // partial sums of conj(V_i).w (i<nv) [+ |w|^2 if with_norm]; returns nblk
-    int multidot(const C* const* V, int nv, const C* w, int64_t N, int nrhs, bool with_norm, zc* partial) {
+    int multidot(const C* const* V, int nv, const C* w, const Span& sp, int nrhs, bool with_norm, zc* partial) {
         HH_REQUIRE(nv >= 0 && nv <= HH_MAXV, HH_ERR_ARG, "multidot: too many vectors");
+        const int64_t N = sp.len, ld = sp.ld;
         const int nblk = vec_blocks(N, nrhs);
         HH_REQUIRE((size_t)(nv + 1) * nrhs * nblk <= d_partial.n, HH_ERR_STATE, "multidot: partial buffer too small");
         VecList<T> L;
-        for (int i = 0; i < HH_MAXV; ++i) L.v[i] = i < nv ? V[i] : nullptr;
+        for (int i = 0; i < HH_MAXV; ++i) L.v[i] = i < nv ? V[i] + sp.off : nullptr;
+        w += sp.off;
         dim3 g(nblk, nrhs);
         launch(T_DOT, S * (double)N * nrhs * (nv + 1), [&] {
 #define HH_MD(NV)                                                                              \
     case NV:                                                                                   \
-        if (with_norm) k_multidot<T, NV, true><<<g, 256, 0, stream>>>(L, w, N, N, partial);    \
-        else k_multidot<T, NV, false><<<g, 256, 0, stream>>>(L, w, N, N, partial);             \
+        if (with_norm) k_multidot<T, NV, true><<<g, 256, 0, stream>>>(L, w, N, ld, partial);   \
+        else k_multidot<T, NV, false><<<g, 256, 0, stream>>>(L, w, N, ld, partial);            \
         break;
             switch (nv) {
                 HH_MD(0) HH_MD(1) HH_MD(2) HH_MD(3) HH_MD(4) HH_MD(5) HH_MD(6) HH_MD(7) HH_MD(8)
             }
 #undef HH_MD
         });
-        return nblk;
+        return slab_reduce(partial, (nv + (with_norm ? 1 : 0)) * nrhs, nblk);
     }
-    int multiaxpy(const C* const* V, int nv, C* w, int64_t N, int nrhs, const zc* coef, int cstride, bool negate,
+    int multiaxpy(const C* const* V, int nv, C* w, const Span& sp, int nrhs, const zc* coef, int cstride, bool negate,
                   bool with_norm, zc* partial, const zc* post = nullptr) {
         HH_REQUIRE(nv >= 1 && nv <= HH_MAXV, HH_ERR_ARG, "multiaxpy: bad vector count");
+        const int64_t N = sp.len, ld = sp.ld;
         const int nblk = vec_blocks(N, nrhs);
         VecList<T> L;
-        for (int i = 0; i < HH_MAXV; ++i) L.v[i] = i < nv ? V[i] : nullptr;
+        for (int i = 0; i < HH_MAXV; ++i) L.v[i] = i < nv ? V[i] + sp.off : nullptr;
+        w += sp.off;
         dim3 g(nblk, nrhs);
         launch(T_AXPY, S * (double)N * nrhs * (nv + 2), [&] {
 #define HH_MA(NV)                                                                                                 \
     case NV:                                                                                                      \
-        if (with_norm) k_multiaxpy<T, NV, true><<<g, 256, 0, stream>>>(L, w, N, N, coef, cstride, negate, post, partial); \
-        else k_multiaxpy<T, NV, false><<<g, 256, 0, stream>>>(L, w, N, N, coef, cstride, negate, post, partial);          \
+        if (with_norm) k_multiaxpy<T, NV, true><<<g, 256, 0, stream>>>(L, w, N, ld, coef, cstride, negate, post, partial); \
+        else k_multiaxpy<T, NV, false><<<g, 256, 0, stream>>>(L, w, N, ld, coef, cstride, negate, post, partial);          \
         break;
             switch (nv) { HH_MA(1) HH_MA(2) HH_MA(3) HH_MA(4) HH_MA(5) HH_MA(6) HH_MA(7) HH_MA(8) }
 #undef HH_MA
         });
-        return nblk;
+        return with_norm ? slab_reduce(partial, nrhs, nblk) : nblk;
     }
 
     // ------------------------------------------------------------------ hierarchy (MGsetup)
@@ -833,6 +905,21 @@ class Solver : public SolverBase {
         for (int d = 0; d < pb.dim; ++d) out[d] = levels[level].n[d];
     }
 
+    void set_level_planes(int l) {
+        Level& L = levels[l];
+        if (slab) {
+            L.zb = sgeo[l].zb;
+            L.ze = sgeo[l].ze;
+            L.koff = sgeo[l].koff;
+            L.n2g = sgeo[l].n2g;
+        } else {
+            L.zb = 0;
+            L.ze = L.n[2];
+            L.koff = 0;
+            L.n2g = L.n[2];
+        }
+    }
+
     void setup(const hh_mg_options& o) override {
         HH_CUDA(cudaSetDevice(device));
         auto t0 = std::chrono::steady_clock::now();
@@ -841,6 +928,13 @@ class Solver : public SolverBase {
         HH_REQUIRE(o.relax_type == HH_RELAX_JAC || o.relax_type == HH_RELAX_JAC_GMRES, HH_ERR_ARG, "bad relax_type");
         HH_REQUIRE(o.cycle_type >= HH_CYCLE_V && o.cycle_type <= HH_CYCLE_K, HH_ERR_ARG, "bad cycle_type");
         HH_REQUIRE(o.coarse_type == HH_COARSE_LU || o.coarse_type == HH_COARSE_GMRES, HH_ERR_ARG, "bad coarse_type");
+        if (slab) {
+            HH_REQUIRE(pb.dim == 3 && fine_kernel != FK_SIMPLE, HH_ERR_UNSUPPORTED, "slab decomposition needs a 3-D grid");
+            HH_REQUIRE((int)sgeo.size() == o.levels, HH_ERR_ARG,
+                       "slab decomposition: hh_setup must use the number of levels given to hh_create_slab*");
+            HH_REQUIRE(o.coarse_type == HH_COARSE_GMRES, HH_ERR_UNSUPPORTED,
+                       "slab decomposition: the coarsest solve must be the inexact one (coarse_type GMRES)");
+        }
         clear();
         opt = o;
         levels.resize(krylov_only ? 1 : o.levels);
@@ -848,6 +942,7 @@ class Solver : public SolverBase {
         levels[0].p0 = fine_sy();
         levels[0].N = fineN();
         levels[0].Nlog = pb.N();
+        set_level_planes(0);
         if (krylov_only) {  // the cycle lives in another solver (prec_hook): only the fine-level geometry is needed
             have_hierarchy = true;
             setup_seconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
@@ -856,15 +951,17 @@ class Solver : public SolverBase {
         for (int l = 1; l < o.levels; ++l) {
             for (int d = 0; d < 3; ++d) {
                 const int nf = levels[l - 1].n[d];
-                if (d < pb.dim) {
+                if (d < pb.dim && !(slab && d == 2)) {
                     HH_REQUIRE(nf >= 3 && (nf % 2) == 1, HH_ERR_ARG,
                                "cannot coarsen: every level needs an odd node count >= 3 in each dimension (cells "
                                "divisible by 2^(levels-1))");
                     levels[l].n[d] = (nf + 1) / 2;
-                } else {
+                } else if (d >= pb.dim) {
                     levels[l].n[d] = 1;
                 }
             }
+            if (slab) levels[l].n[2] = sgeo[l].nloc;  // local planes of the slab (hh_slab.cuh)
+            set_level_planes(l);
             levels[l].Nlog = (int64_t)levels[l].n[0] * levels[l].n[1] * levels[l].n[2];
             // the exact coarsest solve works on a dense unknown numbering: no padding on that level
             const bool dense_level = (l == o.levels - 1 && o.coarse_type == HH_COARSE_LU);
@@ -881,24 +978,27 @@ class Solver : public SolverBase {
             Lc.coef.alloc((size_t)NS * Lc.N);
             Lc.dinv.alloc(Lc.N);
             HH_CUDA(cudaMemsetAsync(Lc.coef.p, 0, (size_t)NS * Lc.N * sizeof(C), stream));  // ghost columns stay zero
-            const int64_t tot = Lc.Nlog * NS;
+            const int64_t tot = (int64_t)Lc.n[0] * Lc.n[1] * (Lc.ze - Lc.zb) * NS;
             const unsigned nb = (unsigned)((tot + 127) / 128);
+            if (slab && l >= 2) halo_exchange(l - 1, Lf.coef.p, NS);  // rows of the fine planes just outside the slab
             launch(T_SETUP, 0, [&] {
                 if (l == 1) {
                     if (pb.dim == 3) {
                         FineCoef<T, 3> A{mg_fine};
-                        k_galerkin<T, 3, FineCoef<T, 3>><<<nb, 128, 0, stream>>>(A, Lf.n[0], Lf.n[1], Lf.n[2], Lc.n[0], Lc.n[1], Lc.n[2], Lc.p0, Lc.N, Lc.coef.p);
+                        k_galerkin<T, 3, FineCoef<T, 3>><<<nb, 128, 0, stream>>>(A, Lf.n[0], Lf.n[1], Lf.n[2], Lc.n[0], Lc.n[1], Lc.n[2], Lc.p0, Lc.N, Lc.coef.p,
+                                                                                 Lc.zb, Lc.ze, Lf.koff, Lf.n2g, Lc.koff, Lc.n2g);
                     } else {
                         FineCoef<T, 2> A{mg_fine};
-                        k_galerkin<T, 2, FineCoef<T, 2>><<<nb, 128, 0, stream>>>(A, Lf.n[0], Lf.n[1], 1, Lc.n[0], Lc.n[1], 1, Lc.p0, Lc.N, Lc.coef.p);
+                        k_galerkin<T, 2, FineCoef<T, 2>><<<nb, 128, 0, stream>>>(A, Lf.n[0], Lf.n[1], 1, Lc.n[0], Lc.n[1], 1, Lc.p0, Lc.N, Lc.coef.p, 0, 1, 0, 1, 0, 1);
                     }
                 } else {
                     if (pb.dim == 3) {
                         StoredCoef<T, 3> A{coarse_op(Lf)};
-                        k_galerkin<T, 3, StoredCoef<T, 3>><<<nb, 128, 0, stream>>>(A, Lf.n[0], Lf.n[1], Lf.n[2], Lc.n[0], Lc.n[1], Lc.n[2], Lc.p0, Lc.N, Lc.coef.p);
+                        k_galerkin<T, 3, StoredCoef<T, 3>><<<nb, 128, 0, stream>>>(A, Lf.n[0], Lf.n[1], Lf.n[2], Lc.n[0], Lc.n[1], Lc.n[2], Lc.p0, Lc.N, Lc.coef.p,
+                                                                                   Lc.zb, Lc.ze, Lf.koff, Lf.n2g, Lc.koff, Lc.n2g);
                     } else {
                         StoredCoef<T, 2> A{coarse_op(Lf)};
-                        k_galerkin<T, 2, StoredCoef<T, 2>><<<nb, 128, 0, stream>>>(A, Lf.n[0], Lf.n[1], 1, Lc.n[0], Lc.n[1], 1, Lc.p0, Lc.N, Lc.coef.p);
+                        k_galerkin<T, 2, StoredCoef<T, 2>><<<nb, 128, 0, stream>>>(A, Lf.n[0], Lf.n[1], 1, Lc.n[0], Lc.n[1], 1, Lc.p0, Lc.N, Lc.coef.p, 0, 1, 0, 1, 0, 1);
                     }
                 }
             });
@@ -1084,7 +1184,7 @@ class Solver : public SolverBase {
     // Orthogonalise w against V_0..V_j (classical Gram-Schmidt in one fused pass over the vectors),
     // then the Givens update.  Leaves 1/||w|| in st.scale.
     // V[0..j] are the stored (scaled) basis vectors, w = A z~_j on entry, the next basis vector on exit.
-    void gmres_orthogonalise(GmresMem& g, const C* const* V, int j, C* w, int64_t N, int nrhs, double tol) {
+    void gmres_orthogonalise(GmresMem& g, const C* const* V, int j, C* w, const Span& N, int nrhs, double tol) {
         const C* vv[HH_MAXV];
         for (int i0 = 0; i0 <= j; i0 += HH_MAXV) {
             const int nv = std::min(HH_MAXV, j + 1 - i0);
@@ -1102,7 +1202,7 @@ class Solver : public SolverBase {
         }
         launch(T_SCALAR, 0, [&] { k_gmres_givens<<<nrhs, 32, 0, stream>>>(g.st, d_partial.p, nblk, j, tol); });
     }
-    void gmres_begin(GmresMem& g, const C* r, int64_t N, int nrhs, bool first, double tol) {
+    void gmres_begin(GmresMem& g, const C* r, const Span& N, int nrhs, bool first, double tol) {
         const int nblk = multidot(nullptr, 0, r, N, nrhs, true, d_partial.p);
         launch(T_SCALAR, 0, [&] { k_gmres_begin<<<nrhs, 32, 0, stream>>>(g.st, d_partial.p, nblk, first ? 1 : 0, tol); });
     }
@@ -1120,13 +1220,14 @@ class Solver : public SolverBase {
         GmresMem& g = ws.g;
         HH_REQUIRE(nsteps >= 1 && nsteps <= ws.steps, HH_ERR_STATE, "small_gmres workspace");
         const int64_t N = L.N;
+        const Span sp = span(l);
         const int64_t vs = N * kcap;
         std::vector<C*> W(nsteps + 1);            // writable slots
         std::vector<const C*> V(nsteps + 1);      // the basis as read
         for (int i = 0; i <= nsteps; ++i) V[i] = W[i] = ws.v.p + (int64_t)i * vs;
         if (x_is_zero) V[0] = b;  // r0 = b: used in place, unscaled (d_0 = ||b||)
         else level_apply(l, MODE_RESID, x, b, W[0], nrhs);
-        gmres_begin(g, V[0], N, nrhs, true, 0.0);
+        gmres_begin(g, V[0], sp, nrhs, true, 0.0);
         for (int j = 0; j < nsteps; ++j) {
             C* z;
             if (prec == 0) {
@@ -1137,7 +1238,7 @@ class Solver : public SolverBase {
                 cycle(l, V[j], z, true, nrhs);
             }
             level_apply(l, MODE_APPLY, z, nullptr, W[j + 1], nrhs);
-            gmres_orthogonalise(g, V.data(), j, W[j + 1], N, nrhs, 0.0);
+            gmres_orthogonalise(g, V.data(), j, W[j + 1], sp, nrhs, 0.0);
         }
         gmres_solve_y(g, nrhs);
         const C* vv[HH_MAXV];
@@ -1148,19 +1249,19 @@ class Solver : public SolverBase {
             for (int i0 = 0; i0 < nsteps; i0 += HH_MAXV) {
                 const int nv = std::min(HH_MAXV, nsteps - i0);
                 for (int i = 0; i < nv; ++i) vv[i] = V[i0 + i];
-                multiaxpy(vv, nv, t, N, nrhs, g.y.p + i0, g.st.m, false, false, d_partial.p);
+                multiaxpy(vv, nv, t, sp, nrhs, g.y.p + i0, g.st.m, false, false, d_partial.p);
             }
             if (x_is_zero) {
                 diag_scale(l == 0 ? T_FINE_JACOBI0 : T_COARSE_JACOBI0, L.dinv.p, t, x, N, nrhs);
             } else {
                 diag_scale(l == 0 ? T_FINE_JACOBI0 : T_COARSE_JACOBI0, L.dinv.p, t, t, N, nrhs);
                 const C* one[1] = {t};
-                multiaxpy(one, 1, x, N, nrhs, d_one.p, 0, false, false, d_partial.p);
+                multiaxpy(one, 1, x, sp, nrhs, d_one.p, 0, false, false, d_partial.p);
             }
         } else {
             if (x_is_zero) zero_vec(x, N, nrhs);
             for (int i = 0; i < nsteps; ++i) vv[i] = ws.z.p + (int64_t)i * vs;
-            multiaxpy(vv, nsteps, x, N, nrhs, g.y.p, g.st.m, false, false, d_partial.p);
+            multiaxpy(vv, nsteps, x, sp, nrhs, g.y.p, g.st.m, false, false, d_partial.p);
         }
     }
 
@@ -1308,21 +1409,38 @@ class Solver : public SolverBase {
         HH_CUDA(cudaStreamSynchronize(stream));
     }
     // internal fine-level vectors are padded (ComplexF32 on an odd grid with the TMA kernels)?
-    bool padded() const { return have_hierarchy && levels[0].N != pb.N(); }
-    // dense caller block (leading dimension pb.N()) <-> padded internal block (leading dimension levels[0].N)
+    // (slab decomposition: caller blocks hold the owned planes only, internal ones the halo planes as well)
+    bool padded() const { return have_hierarchy && (levels[0].N != pb.N() || slab); }
+    // dense caller block (leading dimension caller_N()) <-> internal block (leading dimension levels[0].N, row pitch
+    // p0, owned planes starting at plane zb)
     void repitch(const C* src, C* dst, int nrhs, bool to_padded) {
-        const int64_t rows = (int64_t)pb.n[1] * pb.n[2];
-        const int n0 = pb.n[0], p0 = levels[0].p0;
+        const Level& L0 = levels[0];
+        const int64_t rows = (int64_t)pb.n[1] * (L0.ze - L0.zb);
+        const int n0 = pb.n[0], p0 = L0.p0;
+        const int64_t ioff = (int64_t)L0.zb * p0 * pb.n[1];
+        const int64_t cN = caller_N();
         dim3 g(std::max(1, 592 / std::max(nrhs, 1)), nrhs);
-        launch(T_COPY, 2 * S * (double)pb.N() * nrhs, [&] {
-            if (to_padded) k_repitch<C><<<g, 256, 0, stream>>>(src, dst, n0, rows, n0, p0, pb.N(), levels[0].N);
-            else k_repitch<C><<<g, 256, 0, stream>>>(src, dst, n0, rows, p0, n0, levels[0].N, pb.N());
+        launch(T_COPY, 2 * S * (double)cN * nrhs, [&] {
+            if (to_padded) k_repitch<C><<<g, 256, 0, stream>>>(src, dst + ioff, n0, rows, n0, p0, cN, L0.N);
+            else k_repitch<C><<<g, 256, 0, stream>>>(src + ioff, dst, n0, rows, p0, n0, L0.N, cN);
         });
     }
 
     void apply_device(const void* dX, void* dY, int64_t nrhs, int shifted, double shift, int transpose) override {
         HH_CUDA(cudaSetDevice(device));
         HH_REQUIRE(d_m.p != nullptr, HH_ERR_STATE, "no model set");
+        if (slab) {  // caller blocks hold the owned planes: go through blocks with halo planes
+            HH_REQUIRE(have_hierarchy, HH_ERR_STATE, "slab decomposition: hh_apply needs hh_setup first");
+            FineOp<T> op = fine_op(shifted ? shift : 0.0, transpose, true);
+            DevBuf<C> xi, yi;
+            alloc_zero(xi, (size_t)levels[0].N * nrhs);
+            alloc_zero(yi, (size_t)levels[0].N * nrhs);
+            repitch((const C*)dX, xi.p, (int)nrhs, true);
+            fine_stencil(MODE_APPLY, op, xi.p, nullptr, yi.p, levels[0].N, (int)nrhs, T(0));
+            repitch(yi.p, (C*)dY, (int)nrhs, false);
+            HH_CUDA(cudaStreamSynchronize(stream));
+            return;
+        }
         FineOp<T> op = fine_op(shifted ? shift : 0.0, transpose);
         fine_stencil(MODE_APPLY, op, (const C*)dX, nullptr, (C*)dY, pb.N(), (int)nrhs, T(0));
     }
@@ -1333,10 +1451,16 @@ class Solver : public SolverBase {
         DevBuf<zc> dv;
         di.alloc(nrhs);
         dv.alloc(nrhs);
-        HH_CUDA(cudaMemcpyAsync(di.p, idx0, nrhs * sizeof(int64_t), cudaMemcpyHostToDevice, stream));
+        std::vector<int64_t> loc(idx0, idx0 + nrhs);
+        if (slab) {  // global node index -> index inside the owned planes (or -1: the source lies in another slab)
+            const int64_t plane = (int64_t)pb.n[0] * pb.n[1];
+            for (auto& v : loc) v = (v >= sgeo[0].own0 * plane && v < sgeo[0].own1 * plane) ? v - sgeo[0].own0 * plane : -1;
+        }
+        const int64_t cN = caller_N();
+        HH_CUDA(cudaMemcpyAsync(di.p, loc.data(), nrhs * sizeof(int64_t), cudaMemcpyHostToDevice, stream));
         HH_CUDA(cudaMemcpyAsync(dv.p, val, nrhs * sizeof(zc), cudaMemcpyHostToDevice, stream));
-        HH_CUDA(cudaMemsetAsync(dB, 0, (size_t)pb.N() * nrhs * sizeof(C), stream));
-        launch(T_COPY, 0, [&] { k_point_sources<T><<<(unsigned)((nrhs + 127) / 128), 128, 0, stream>>>((C*)dB, pb.N(), di.p, dv.p, (int)nrhs); });
+        HH_CUDA(cudaMemsetAsync(dB, 0, (size_t)cN * nrhs * sizeof(C), stream));
+        launch(T_COPY, 0, [&] { k_point_sources<T><<<(unsigned)((nrhs + 127) / 128), 128, 0, stream>>>((C*)dB, cN, di.p, dv.p, (int)nrhs); });
         HH_CUDA(cudaStreamSynchronize(stream));
     }
 
@@ -1426,6 +1550,7 @@ class Solver : public SolverBase {
     int fgmres(const C* B, C* X, int nrhs, const hh_solve_options& o, int32_t* iters, double* relres) {
         const int m = o.inner;
         const int64_t N = levels[0].N;
+        const Span sp = span(0);
         const int64_t vs = N * kry_cap;
         if (outer.st.m != m || outer_cap < nrhs) {
             alloc_gmres_state(outer, m, nrhs);
@@ -1439,13 +1564,13 @@ class Solver : public SolverBase {
         zero_vec(X, N, nrhs);
         // r0 = b (x0 = 0): the first basis vector is B itself, used in place and unscaled (d_0 = ||b||)
         V[0] = B;
-        gmres_begin(outer, B, N, nrhs, true, o.rel_tol);
+        gmres_begin(outer, B, sp, nrhs, true, o.rel_tol);
         bool all_done = fetch_done(outer.done.p, nrhs);
         for (int cyc = 0; cyc < o.max_iter && !all_done; ++cyc) {
             for (int j = 0; j < m; ++j) {
                 precondition(V[j], Z[j], nrhs);
                 fine_stencil(MODE_APPLY, Hop, Z[j], nullptr, W[j + 1], N, nrhs, T(0));
-                gmres_orthogonalise(outer, V.data(), j, W[j + 1], N, nrhs, o.rel_tol);
+                gmres_orthogonalise(outer, V.data(), j, W[j + 1], sp, nrhs, o.rel_tol);
                 all_done = fetch_done(outer.done.p, nrhs);
                 if (all_done) break;
             }
@@ -1454,13 +1579,13 @@ class Solver : public SolverBase {
             for (int i0 = 0; i0 < m; i0 += HH_MAXV) {
                 const int nv = std::min(HH_MAXV, m - i0);
                 for (int i = 0; i < nv; ++i) zz[i] = Z[i0 + i];
-                multiaxpy(zz, nv, X, N, nrhs, outer.y.p + i0, m, false, false, d_partial.p);
+                multiaxpy(zz, nv, X, sp, nrhs, outer.y.p + i0, m, false, false, d_partial.p);
             }
             if (all_done || cyc + 1 == o.max_iter) break;
             // restart: r = b - H x  (again used unscaled as the first basis vector)
             V[0] = W[0];
             fine_stencil(MODE_RESID, Hop, X, B, W[0], N, nrhs, T(0));
-            gmres_begin(outer, W[0], N, nrhs, false, o.rel_tol);
+            gmres_begin(outer, W[0], sp, nrhs, false, o.rel_tol);
             all_done = fetch_done(outer.done.p, nrhs);
         }
         return finish(outer.nprec.p, outer.err.p, nrhs, iters, relres, all_done);
@@ -1491,6 +1616,7 @@ class Solver : public SolverBase {
     };
     int bicgstab(const C* B, C* X, int nrhs, const hh_solve_options& o, int32_t* iters, double* relres) {
         const int64_t N = levels[0].N;
+        const Span sp = span(0);
         const int64_t vs = N * kry_cap;
         if (bicg.cap < nrhs) {
             BicgMem& g = bicg;
@@ -1517,32 +1643,33 @@ class Solver : public SolverBase {
         copy_vec(B, rt, N, nrhs);
         zero_vec(p, N, nrhs);
         zero_vec(v, N, nrhs);
-        scalars(multidot(nullptr, 0, B, N, nrhs, true, d_partial.p), BICG_INIT);
+        scalars(multidot(nullptr, 0, B, sp, nrhs, true, d_partial.p), BICG_INIT);
         bool all_done = fetch_done(bicg.done.p, nrhs);
         const C* one[2];
         for (int it = 0; it < o.max_iter && !all_done; ++it) {
             one[0] = rt;
-            scalars(multidot(one, 1, r, N, nrhs, false, d_partial.p), BICG_RHO);
+            scalars(multidot(one, 1, r, sp, nrhs, false, d_partial.p), BICG_RHO);
             {
-                dim3 g(vec_blocks(N, nrhs), nrhs);
-                launch(T_AXPY, 4 * S * (double)N * nrhs,
-                       [&] { k_bicg_p<T><<<g, 256, 0, stream>>>(p, r, v, N, N, bicg.beta.p, bicg.omega.p); });
+                dim3 g(vec_blocks(sp.len, nrhs), nrhs);
+                launch(T_AXPY, 4 * S * (double)sp.len * nrhs, [&] {
+                    k_bicg_p<T><<<g, 256, 0, stream>>>(p + sp.off, r + sp.off, v + sp.off, sp.len, sp.ld, bicg.beta.p, bicg.omega.p);
+                });
             }
             precondition(p, ph, nrhs);
             fine_stencil(MODE_APPLY, Hop, ph, nullptr, v, N, nrhs, T(0));
             one[0] = rt;
-            scalars(multidot(one, 1, v, N, nrhs, false, d_partial.p), BICG_ALPHA);
+            scalars(multidot(one, 1, v, sp, nrhs, false, d_partial.p), BICG_ALPHA);
             one[0] = v;  // s = r - alpha v  (in place in r)
-            scalars(multiaxpy(one, 1, r, N, nrhs, bicg.neg_alpha.p, 1, false, true, d_partial.p), BICG_HALF);
+            scalars(multiaxpy(one, 1, r, sp, nrhs, bicg.neg_alpha.p, 1, false, true, d_partial.p), BICG_HALF);
             precondition(r, sh, nrhs);
             fine_stencil(MODE_APPLY, Hop, sh, nullptr, t, N, nrhs, T(0));
             one[0] = r;  // <s,t> and |t|^2
-            scalars(multidot(one, 1, t, N, nrhs, true, d_partial.p), BICG_OMEGA);
+            scalars(multidot(one, 1, t, sp, nrhs, true, d_partial.p), BICG_OMEGA);
             one[0] = ph;
             one[1] = sh;
-            multiaxpy(one, 2, X, N, nrhs, bicg.ao.p, 2, false, false, d_partial.p);
+            multiaxpy(one, 2, X, sp, nrhs, bicg.ao.p, 2, false, false, d_partial.p);
             one[0] = t;  // r = s - omega t
-            scalars(multiaxpy(one, 1, r, N, nrhs, bicg.neg_omega.p, 1, false, true, d_partial.p), BICG_END);
+            scalars(multiaxpy(one, 1, r, sp, nrhs, bicg.neg_omega.p, 1, false, true, d_partial.p), BICG_END);
             all_done = fetch_done(bicg.done.p, nrhs);
         }
         return finish(bicg.nprec.p, bicg.err.p, nrhs, iters, relres, all_done);
@@ -1566,7 +1693,7 @@ class Solver : public SolverBase {
     int kcap = 0;
     DevBuf<C> kry;
     int kry_cap = 0;
-    DevBuf<zc> d_partial, d_one;
+    DevBuf<zc> d_partial, d_one, d_red;
     GmresMem outer;
     int outer_cap = 0;
     BicgMem bicg;

@@ -15,3 +15,47 @@ def column_range(nrhs: int, nparts: int, part: int):
 
 def all_ranges(nrhs: int, nparts: int):
     return [column_range(nrhs, nparts, p) for p in range(nparts)]
+
+
+# ---- slab decomposition of ONE grid over the ranks (one process per GPU; include/helmholtz_b200.h hh_create_slab_nccl)
+def broadcast_unique_id(make_id, src=0):
+    """Rank `src` creates the 128-byte NCCL communicator id (make_id = api.slabUniqueId), every rank receives it.
+    Uses the process group the launcher set up (torch.distributed, gloo or nccl)."""
+    import torch.distributed as dist
+
+    box = [make_id() if dist.get_rank() == src else None]
+    dist.broadcast_object_list(box, src=src)
+    return box[0]
+
+
+def nccl_slabs():
+    """`slabs` entry of a solver for the calling rank of the default process group."""
+    import torch.distributed as dist
+
+    from . import api
+
+    return {"mode": "nccl", "rank": dist.get_rank(), "nranks": dist.get_world_size(),
+            "unique_id": broadcast_unique_id(api.slabUniqueId)}
+
+
+def gather_planes(X_local, planes, nodes, dst=0):
+    """Assemble the whole-grid block from the per-rank blocks of owned planes (verification / output only, not part of
+    the solve).  X_local: (n1*n2*(k1-k0)) x nrhs column-major numpy block of this rank, planes = (k0, k1).
+    Returns the N x nrhs block on rank `dst`, None elsewhere."""
+    import numpy as np
+    import torch.distributed as dist
+
+    parts = [None] * dist.get_world_size() if dist.get_rank() == dst else None
+    dist.gather_object((tuple(planes), np.asarray(X_local)), parts, dst=dst)
+    if parts is None:
+        return None
+    plane = int(nodes[0]) * int(nodes[1])
+    nrhs = parts[0][1].shape[1] if parts[0][1].ndim == 2 else 1
+    X = np.zeros((plane * int(nodes[2]), nrhs), dtype=parts[0][1].dtype, order="F")
+    seen = np.zeros(int(nodes[2]), dtype=np.int64)
+    for (k0, k1), blk in parts:
+        X[plane * k0:plane * k1, :] = np.asarray(blk).reshape((plane * (k1 - k0), nrhs), order="F")
+        seen[k0:k1] += 1
+    if not np.all(seen == 1):
+        raise ValueError("the ranks' plane ranges do not tile the grid")
+    return X

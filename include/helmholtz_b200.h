@@ -135,6 +135,40 @@ int hh_create_multi(int dim, const int64_t* n_nodes, const double* h, const doub
                     double omega_re, double omega_im, int neumann_on_top, int sommerfeld, int order_neumann_bc,
                     int precision, const int* devices, int n_devices, hh_handle_t* out);
 int hh_destroy(hh_handle_t h);
+
+/* -------- slab decomposition of ONE grid over several GPUs (the grid that exceeds one GPU; no counterpart in the
+ * reference, whose solve is single-node shared-memory: src/ShiftedLaplacianMultigridSolver.jl:33-102) --------
+ * The planes of the last dimension are split into contiguous slabs, one per GPU; every stencil-type kernel is preceded
+ * by a neighbour exchange of one halo plane per side and every dot / norm is all-reduced over the slabs, so each slab
+ * runs the same batched Krylov iteration in lockstep.  `levels` fixes the partition (slab cuts fall on planes of the
+ * coarsest level) and must equal hh_mg_options.levels at hh_setup; the coarsest solve must be HH_COARSE_GMRES.
+ *
+ * hh_create_slab_local: all slabs inside this process, one host thread per slab, halos by peer copies
+ *   (devices may repeat: several slabs on one GPU).  The handle is used like any other: m, gamma, B, X and the
+ *   arrays of hh_apply are whole-grid host arrays.
+ * hh_create_slab_nccl: this process holds slab `rank` of `nranks` (one process per GPU, e.g. under torchrun or Julia
+ *   Distributed); halos by ncclSend/ncclRecv, reductions by ncclAllReduce (libnccl.so.2 is bound at run time;
+ *   HH_NCCL_LIB overrides the path).  `unique_id`: 128 bytes from hh_nccl_unique_id on rank 0, broadcast by the caller.
+ *   m and gamma are whole-grid arrays; B, X (host or device) hold the planes own0 <= k < own1 of hh_slab_info only,
+ *   i.e. n1*n2*(own1-own0) entries per right-hand side; point-source indices stay whole-grid indices.
+ *   Every rank must make the same sequence of calls. */
+int hh_create_slab_local(int dim, const int64_t* n_nodes, const double* h, const double* m, const double* gamma,
+                         double omega_re, double omega_im, int neumann_on_top, int sommerfeld, int order_neumann_bc,
+                         int precision, const int* devices, int n_slabs, int levels, hh_handle_t* out);
+int hh_nccl_unique_id(void* id128);
+int hh_create_slab_nccl(int dim, const int64_t* n_nodes, const double* h, const double* m, const double* gamma,
+                        double omega_re, double omega_im, int neumann_on_top, int sommerfeld, int order_neumann_bc,
+                        int precision, int device, int levels, int rank, int nranks, const void* unique_id,
+                        hh_handle_t* out);
+/* mode: 0 no slabs, 1 local, 2 NCCL; planes own0 <= k < own1 of the last dimension are the ones the caller's B / X hold */
+int hh_slab_info(hh_handle_t h, int* mode, int* n_slabs, int* rank, int64_t* own0, int64_t* own1);
+/* host-only: the partition itself.  out[7*l + 0..6] = own0, own1, koff (global index of local plane 0), nloc (planes
+ * held, halo planes included), zb, ze (owned planes in local numbering), n2g (planes of level l), for l < levels. */
+int hh_slab_partition(int64_t n3_nodes, int levels, int nranks, int rank, int64_t* out);
+/* Galerkin stencil of level >= 1 held by slab `slab` of this process (0 for an NCCL handle), in the layout of
+ * hh_get_level_stencil on the slab's LOCAL grid n_local_out[3] (halo planes included; hh_slab_partition gives the
+ * plane geometry).  coef_out may be NULL to query the node counts only.  Parity hook for MGsetup under slabs. */
+int hh_slab_level_stencil(hh_handle_t h, int slab, int level, int64_t* n_local_out, void* coef_out);
 /* run all work of this handle on `cuda_stream` (a cudaStream_t; NULL = legacy default stream) */
 int hh_set_stream(hh_handle_t h, void* cuda_stream);
 /* new model / frequency on the same grid: invalidates the hierarchy (clear! + new HelmholtzParam) */

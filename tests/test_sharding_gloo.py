@@ -74,3 +74,49 @@ def test_column_range_matches_library_rule(pkg):
             assert max(sizes) - min(sizes) <= 1
     with pytest.raises(ValueError):
         pkg.sharding.column_range(4, 2, 2)
+
+
+# ---- slab decomposition of one grid over the ranks: host-side plumbing (partition, communicator id, gathering) ----
+def _slab_worker(rank, world, port, out):
+    import sys
+
+    sys.path.insert(0, ROOT)
+    import __graft_entry__ as graft
+
+    pkg = graft.load_package()
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    slabs = pkg.sharding.nccl_slabs()  # rank 0's id reaches every rank
+    nodes = (5, 3, 33)
+    geo = pkg.slabPartition(nodes[2], 3, world, rank)[0]
+    plane = nodes[0] * nodes[1]
+    # stand-in for this rank's solution block: the whole-grid node index, two right-hand sides
+    k0, k1 = geo["own0"], geo["own1"]
+    idx = np.arange(plane * k0, plane * k1, dtype=np.float64)
+    Xl = np.asfortranarray(np.stack([idx, -idx], axis=1))
+    X = pkg.sharding.gather_planes(Xl, (k0, k1), nodes)
+    ids = [None] * world
+    dist.all_gather_object(ids, (slabs["rank"], slabs["nranks"], slabs["unique_id"]))
+    if rank == 0:
+        out.put((ids, X))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_slab_plumbing_world2_gloo():
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_slab_worker, args=(r, 2, port, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    ids, X = out.get(timeout=180)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert [i[0] for i in ids] == [0, 1] and all(i[1] == 2 for i in ids)
+    assert len(ids[0][2]) == 128 and ids[0][2] == ids[1][2]
+    N = 5 * 3 * 33
+    assert X.shape == (N, 2)
+    assert np.array_equal(X[:, 0], np.arange(N)) and np.array_equal(X[:, 1], -np.arange(N))
