@@ -75,7 +75,7 @@ SIGNATURES = {
                                        C.c_int, _ip, C.c_int, C.c_int, C.POINTER(_p)]),
     "hh_nccl_unique_id": (C.c_int, [_p]),
     "hh_create_slab_nccl": (C.c_int, [C.c_int, _i64p, _dp, _dp, _dp, C.c_double, C.c_double, C.c_int, C.c_int, C.c_int,
-                                      C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _p, C.POINTER(_p)]),
+                                      C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _p, C.c_int64, C.c_int64, C.POINTER(_p)]),
     "hh_slab_info": (C.c_int, [_p, _ip, _ip, _ip, _i64p, _i64p]),
     "hh_slab_partition": (C.c_int, [C.c_int64, C.c_int, C.c_int, C.c_int, _i64p]),
     "hh_slab_level_stencil": (C.c_int, [_p, C.c_int, C.c_int, _i64p, _p]),

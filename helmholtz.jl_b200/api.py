@@ -79,8 +79,11 @@ class _Handle:
         N = int(np.prod(nodes))
         mm = np.ascontiguousarray(np.asarray(m, dtype=np.float64).ravel(order="F"))
         gg = np.ascontiguousarray(np.asarray(gamma, dtype=np.float64).ravel(order="F"))
-        if mm.size != N or gg.size != N:
-            raise ValueError(f"m and gamma must have prod(n+1) = {N} entries (got {mm.size}, {gg.size})")
+        # NCCL slabs: m / gamma may hold only the planes slabs["model_planes"] = (k0, k1) of the last dimension
+        mp0, mp1 = (slabs or {}).get("model_planes", (0, int(nodes[-1])))
+        Nm = int(np.prod(nodes[:-1])) * (mp1 - mp0)
+        if mm.size != Nm or gg.size != Nm:
+            raise ValueError(f"m and gamma must have {Nm} entries (got {mm.size}, {gg.size})")
         h = np.ascontiguousarray(np.asarray(Mesh.h, dtype=np.float64))
         self.dim = int(Mesh.dim)
         self.nodes = nodes
@@ -118,7 +121,7 @@ class _Handle:
             elif slabs["mode"] == "nccl":
                 uid = (C.c_char * 128).from_buffer_copy(bytes(slabs["unique_id"]))
                 rc = lib.hh_create_slab_nccl(*common, int(devs[0]), int(levels), int(slabs["rank"]), int(slabs["nranks"]),
-                                             C.cast(uid, C.c_void_p), C.byref(out))
+                                             C.cast(uid, C.c_void_p), int(mp0), int(mp1 - mp0), C.byref(out))
                 L.check(rc, None)
                 o0, o1 = C.c_int64(), C.c_int64()
                 lib.hh_slab_info(out, None, None, None, C.byref(o0), C.byref(o1))
@@ -511,7 +514,11 @@ def solveLinearSystem_(ShiftedHT, B, X, param, doTranspose=0):
     if param.doClear == 1:
         clear(MG)
     torch_in = _is_torch_cuda(B)
-    if torch_in:
+    # one process per slab: this process sees its planes of B only, the library detects zero columns after the all-reduce
+    local_view = (getattr(param, "slabs", None) or {}).get("mode") == "nccl"
+    if local_view:
+        pass
+    elif torch_in:
         import torch
 
         if float(torch.linalg.vector_norm(B)) == 0.0:  # :40-43

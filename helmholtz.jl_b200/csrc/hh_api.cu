@@ -61,6 +61,7 @@ struct hh_handle_s {
     // 2 = this process holds one slab, NCCL between the processes (caller arrays hold the owned planes)
     int slab_mode = 0;
     std::shared_ptr<ThreadGroup> grp;
+    int64_t model_plane0 = 0, model_planes = 0;  // planes of the last dimension the caller's m / gamma arrays hold
     std::string err;
     bool have_opts = false;
     hh_mg_options opts{};
@@ -287,7 +288,7 @@ static void add_replica(hh_handle_s* h, const Problem& pb, int precision, int de
 static int create_impl(int dim, const int64_t* n_nodes, const double* hsp, const double* m, const double* gamma,
                        double wre, double wim, int neumann_on_top, int sommerfeld, int order_bc, int precision,
                        const int* devices, int ndev, hh_handle_t* out, int slab_mode = 0, int levels = 0, int rank = 0,
-                       int nranks = 1, const void* uid = nullptr) {
+                       int nranks = 1, const void* uid = nullptr, int64_t model_plane0 = 0, int64_t model_planes = 0) {
     return guarded(nullptr, [&]() -> int {
         HH_REQUIRE(out != nullptr, HH_ERR_ARG, "hh_create: out is NULL");
         *out = nullptr;
@@ -353,9 +354,16 @@ static int create_impl(int dim, const int64_t* n_nodes, const double* hsp, const
                 }
             }
         }
+        h->model_plane0 = model_plane0;
+        h->model_planes = model_planes > 0 ? model_planes : pb.n[2];
+        if (slab_mode)
+            for (auto& sb : h->subs)
+                HH_REQUIRE(sb->sgeo[0].koff >= h->model_plane0 && sb->sgeo[0].koff + sb->sgeo[0].nloc <= h->model_plane0 + h->model_planes,
+                           HH_ERR_ARG, "slab decomposition: m / gamma do not hold all planes of the slab (halo planes "
+                                       "included; see hh_slab_partition: koff <= k < koff + nloc)");
         for_each_sub(h.get(), [&](int i) {
-            // a slab reads its planes (halo planes included) out of the whole-grid arrays
-            const int64_t off = slab_mode ? (int64_t)h->subs[i]->sgeo[0].koff * pb.n[0] * pb.n[1] : 0;
+            // a slab reads its planes (halo planes included) out of the caller's arrays
+            const int64_t off = slab_mode ? ((int64_t)h->subs[i]->sgeo[0].koff - h->model_plane0) * pb.n[0] * pb.n[1] : 0;
             h->subs[i]->set_model(m + off, gamma + off, wre, wim);
             if (!h->lows.empty()) h->lows[i]->set_model(m + off, gamma + off, wre, wim);
         });
@@ -414,9 +422,9 @@ int hh_create_slab_local(int dim, const int64_t* n_nodes, const double* h, const
 int hh_create_slab_nccl(int dim, const int64_t* n_nodes, const double* h, const double* m, const double* gamma,
                         double omega_re, double omega_im, int neumann_on_top, int sommerfeld, int order_neumann_bc,
                         int precision, int device, int levels, int rank, int nranks, const void* unique_id,
-                        hh_handle_t* out) {
+                        int64_t model_plane0, int64_t model_planes, hh_handle_t* out) {
     return create_impl(dim, n_nodes, h, m, gamma, omega_re, omega_im, neumann_on_top, sommerfeld, order_neumann_bc,
-                       precision, &device, 1, out, 2, levels, rank, nranks, unique_id);
+                       precision, &device, 1, out, 2, levels, rank, nranks, unique_id, model_plane0, model_planes);
 }
 
 int hh_slab_info(hh_handle_t h, int* mode, int* n_slabs, int* rank, int64_t* own0, int64_t* own1) {
@@ -464,7 +472,7 @@ int hh_update_model(hh_handle_t h, const double* m, const double* gamma, double 
     return guarded(h, [&]() -> int {
         HH_REQUIRE(m && gamma && omega_re != 0.0, HH_ERR_ARG, "hh_update_model: bad arguments");
         for_each_sub(h, [&](int i) {
-            const int64_t off = h->slab_mode ? (int64_t)h->subs[i]->sgeo[0].koff * h->pb.n[0] * h->pb.n[1] : 0;
+            const int64_t off = h->slab_mode ? ((int64_t)h->subs[i]->sgeo[0].koff - h->model_plane0) * h->pb.n[0] * h->pb.n[1] : 0;
             h->subs[i]->set_model(m + off, gamma + off, omega_re, omega_im);
             if (!h->lows.empty()) h->lows[i]->set_model(m + off, gamma + off, omega_re, omega_im);
         });

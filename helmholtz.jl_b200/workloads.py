@@ -76,3 +76,52 @@ def config4(n=257, sigma=8.0, seed=1234, pad=16):
     v = 1.5 + 3.0 * U
     return dict(domain=[0.0, L, 0.0, L, 0.0, L], n_cells=[n - 1] * 3, m=1.0 / v**2, pad=[pad] * 3, gamma0_frac=0.01,
                 shift=0.2, levels=3, cycle="V", relax_param=0.8)
+
+
+# ---- config 5: the grid that is split into slabs over several GPUs -------------------------------------------
+def smooth_random_field_fast(shape, sigma, seed):
+    """Same field as smooth_random_field (same random stream, same truncated Gaussian, edge replication), evaluated
+    with scipy.ndimage so that 513^3 takes seconds instead of hours."""
+    from scipy.ndimage import correlate1d
+
+    rng = np.random.default_rng(seed)
+    u = rng.random(shape, dtype=np.float64)
+    k = _gauss_kernel(sigma)
+    for ax in range(len(shape)):
+        u = correlate1d(u, k, axis=ax, mode="nearest")
+    u -= u.min()
+    u /= u.max()
+    return u
+
+
+def abl3d_planes(nodes, neumann_on_top, pad, amp, k0, k1):
+    """getABL (src/GetHelmholtz.jl:164-218) restricted to the planes k0 <= k < k1 of the last dimension: the profile
+    is separable, so a process that holds one slab never forms the whole-grid array.  Matches hh_get_abl."""
+    nodes = [int(v) for v in nodes]
+    g = []
+    for d in range(3):
+        nd, p = nodes[d], int(pad[d])
+        x0, x1 = (-1.0, 1.0) if d < 2 else (0.0, 1.0)
+        t = np.arange(nd, dtype=np.float64) / (nd - 1)
+        x = (1.0 - t) * x0 + t * x1
+        gd = np.zeros(nd)
+        if not (d == 2 and neumann_on_top):
+            gd[:p] += (x[:p] - x[p - 1]) ** 2
+        gd[nd - p:] += (x[nd - p:] - x[nd - p]) ** 2
+        gd /= (gd.max() + 1e-5)
+        g.append(gd)
+    v = (g[0][:, None, None] + g[1][None, :, None] + g[2][None, None, k0:k1]) * amp
+    return np.minimum(v, amp)
+
+
+def config5(n=513, sigma=16.0, seed=1234, pad=24, planes=None):
+    """Config 4's recipe on the 513^3 grid (sigma and pad doubled).  `planes` = (k0, k1): return m for those planes
+    of the last dimension only (what one slab's process needs); max_m is the whole-grid maximum (for omega_max)."""
+    L = 0.05 * (n - 1)  # 25.6 km at 513 nodes: h = 0.05 km, so 10 points per wavelength doubles config 4's frequency
+    U = smooth_random_field_fast((n, n, n), sigma, seed)
+    v_min = 1.5 + 3.0 * float(U.min())
+    k0, k1 = planes if planes is not None else (0, n)
+    v = 1.5 + 3.0 * U[:, :, k0:k1]
+    del U
+    return dict(domain=[0.0, L, 0.0, L, 0.0, L], n_cells=[n - 1] * 3, m=np.asfortranarray(1.0 / v**2), max_m=1.0 / v_min**2,
+                pad=[pad] * 3, gamma0_frac=0.01, shift=0.2, levels=3, cycle="W", relax_param=0.8, planes=(k0, k1))

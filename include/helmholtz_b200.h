@@ -149,7 +149,10 @@ int hh_destroy(hh_handle_t h);
  * hh_create_slab_nccl: this process holds slab `rank` of `nranks` (one process per GPU, e.g. under torchrun or Julia
  *   Distributed); halos by ncclSend/ncclRecv, reductions by ncclAllReduce (libnccl.so.2 is bound at run time;
  *   HH_NCCL_LIB overrides the path).  `unique_id`: 128 bytes from hh_nccl_unique_id on rank 0, broadcast by the caller.
- *   m and gamma are whole-grid arrays; B, X (host or device) hold the planes own0 <= k < own1 of hh_slab_info only,
+ *   m and gamma hold the planes model_plane0 <= k < model_plane0 + model_planes of the last dimension (0, 0 = the
+ *   whole grid; a process that cannot hold the whole model passes the slab's planes koff .. koff + nloc - 1 of
+ *   hh_slab_partition, halo planes included; hh_update_model uses the same convention);
+ *   B, X (host or device) hold the planes own0 <= k < own1 of hh_slab_info only,
  *   i.e. n1*n2*(own1-own0) entries per right-hand side; point-source indices stay whole-grid indices.
  *   Every rank must make the same sequence of calls. */
 int hh_create_slab_local(int dim, const int64_t* n_nodes, const double* h, const double* m, const double* gamma,
@@ -159,7 +162,7 @@ int hh_nccl_unique_id(void* id128);
 int hh_create_slab_nccl(int dim, const int64_t* n_nodes, const double* h, const double* m, const double* gamma,
                         double omega_re, double omega_im, int neumann_on_top, int sommerfeld, int order_neumann_bc,
                         int precision, int device, int levels, int rank, int nranks, const void* unique_id,
-                        hh_handle_t* out);
+                        int64_t model_plane0, int64_t model_planes, hh_handle_t* out);
 /* mode: 0 no slabs, 1 local, 2 NCCL; planes own0 <= k < own1 of the last dimension are the ones the caller's B / X hold */
 int hh_slab_info(hh_handle_t h, int* mode, int* n_slabs, int* rank, int64_t* own0, int64_t* own1);
 /* host-only: the partition itself.  out[7*l + 0..6] = own0, own1, koff (global index of local plane 0), nloc (planes
