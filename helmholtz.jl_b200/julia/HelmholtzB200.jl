@@ -88,6 +88,62 @@ function Handle(Mesh, m, omega, gamma, NeumannOnTop::Bool, Sommerfeld::Bool, ord
     return hd
 end
 
+# ---- one grid split into slabs along the last dimension over several GPUs (include/helmholtz_b200.h) ----
+# All slabs in this process (one host thread per slab; B, X stay whole-grid arrays): a drop-in for Handle.
+function SlabHandle(Mesh, m, omega, gamma, NeumannOnTop::Bool, Sommerfeld::Bool, levels::Int, orderNeumannBC::Int = 2;
+                    VAL::DataType = ComplexF64, devices::Vector{Int32} = Int32[0, 1])
+    nodes = Int64.(Mesh.n .+ 1)
+    h = Float64.(Mesh.h)
+    mm = vec(Float64.(m)); gg = vec(Float64.(gamma))
+    length(mm) == prod(nodes) == length(gg) || error("m and gamma must have prod(n+1) entries")
+    out = Ref{Ptr{Cvoid}}(C_NULL)
+    w = ComplexF64(omega)
+    rc = ccall((:hh_create_slab_local, LIB), Cint,
+               (Cint, Ptr{Int64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Cdouble, Cdouble, Cint, Cint, Cint, Cint,
+                Ptr{Cint}, Cint, Cint, Ref{Ptr{Cvoid}}),
+               Mesh.dim, nodes, h, mm, gg, real(w), imag(w), NeumannOnTop, Sommerfeld, orderNeumannBC,
+               VAL == ComplexF64 ? HH_C64 : HH_C32, devices, length(devices), levels, out)
+    check(rc)
+    hd = Handle(out[], prod(nodes), VAL)
+    finalizer(x -> (x.ptr != C_NULL && ccall((:hh_destroy, LIB), Cint, (Ptr{Cvoid},), x.ptr); x.ptr = C_NULL), hd)
+    return hd
+end
+# One process (Distributed worker) per GPU.  `id` = slabUniqueId() of one worker, sent to the others; m, gamma hold the
+# planes plane0+1 : plane0+nplanes of the last dimension (at least koff+1 : koff+nloc of slabPartition).  B and X of
+# this worker hold its owned planes (slabPlanes).
+function slabUniqueId()
+    id = zeros(UInt8, 128)
+    check(ccall((:hh_nccl_unique_id, LIB), Cint, (Ptr{UInt8},), id))
+    return id
+end
+function slabPartition(n3::Integer, levels::Integer, nranks::Integer, rank::Integer)
+    out = zeros(Int64, 7, levels)  # own0, own1, koff, nloc, zb, ze, n2g per level (0-based planes)
+    rc = ccall((:hh_slab_partition, LIB), Cint, (Int64, Cint, Cint, Cint, Ptr{Int64}), n3, levels, nranks, rank, out)
+    rc == 0 || error("no slab partition for these sizes")
+    return out
+end
+function SlabHandleNCCL(Mesh, m, omega, gamma, NeumannOnTop::Bool, Sommerfeld::Bool, levels::Int, rank::Int, nranks::Int,
+                        id::Vector{UInt8}, plane0::Int, nplanes::Int, orderNeumannBC::Int = 2;
+                        VAL::DataType = ComplexF64, device::Int = 0)
+    nodes = Int64.(Mesh.n .+ 1)
+    h = Float64.(Mesh.h)
+    mm = vec(Float64.(m)); gg = vec(Float64.(gamma))
+    out = Ref{Ptr{Cvoid}}(C_NULL)
+    w = ComplexF64(omega)
+    rc = ccall((:hh_create_slab_nccl, LIB), Cint,
+               (Cint, Ptr{Int64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Cdouble, Cdouble, Cint, Cint, Cint, Cint,
+                Cint, Cint, Cint, Cint, Ptr{UInt8}, Int64, Int64, Ref{Ptr{Cvoid}}),
+               Mesh.dim, nodes, h, mm, gg, real(w), imag(w), NeumannOnTop, Sommerfeld, orderNeumannBC,
+               VAL == ComplexF64 ? HH_C64 : HH_C32, device, levels, rank, nranks, id, plane0, nplanes, out)
+    check(rc)
+    o0 = Ref{Int64}(0); o1 = Ref{Int64}(0)
+    ccall((:hh_slab_info, LIB), Cint, (Ptr{Cvoid}, Ptr{Cint}, Ptr{Cint}, Ptr{Cint}, Ref{Int64}, Ref{Int64}),
+          out[], C_NULL, C_NULL, C_NULL, o0, o1)
+    hd = Handle(out[], Int(nodes[1] * nodes[2] * (o1[] - o0[])), VAL)  # N = nodes of the owned planes
+    finalizer(x -> (x.ptr != C_NULL && ccall((:hh_destroy, LIB), Cint, (Ptr{Cvoid},), x.ptr); x.ptr = C_NULL), hd)
+    return hd
+end
+
 # ---- operator objects: matrix-free counterpart of the sparse H (src/GetHelmholtz.jl:33-50) ----
 struct HelmholtzShiftOP
     shift::Float64
