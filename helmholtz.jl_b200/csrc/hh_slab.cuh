@@ -69,9 +69,10 @@ struct SlabTransport {
     virtual ~SlabTransport() {}
     // For each of `nseg` segments (segment r starts at base + r*stride bytes): send `bytes` bytes at offset send_dn to
     // the slab below and at send_up to the slab above; receive the neighbours' counterparts at recv_dn / recv_up.
-    // Enqueued on `st` of `device`; the first / last slab skips the missing side.
+    // Enqueued on `st` of `device`; the first / last slab skips the missing side.  fill_lower / fill_upper select which
+    // halo is wanted: the lower one (data moves up: send_up -> the upper neighbour's recv_dn), the upper one, or both.
     virtual void exchange(cudaStream_t st, int device, char* base, size_t stride, int nseg, size_t bytes, size_t send_dn,
-                          size_t recv_dn, size_t send_up, size_t recv_up) = 0;
+                          size_t recv_dn, size_t send_up, size_t recv_up, bool fill_lower, bool fill_upper) = 0;
     // in-place reduction of n doubles on the device over all slabs; every slab receives bit-identical results
     virtual void allreduce(cudaStream_t st, double* dbuf, int n, bool minimum) = 0;
 };
@@ -190,25 +191,56 @@ struct NcclTransport : SlabTransport {
         static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
         memcpy(&id, unique_id, sizeof(id));
         HH_NCCL(api.CommInitRank(&comm, nranks, id, rank));
+        const char* e = getenv("HH_HALO_PACK");
+        pack = !(e && e[0] == '0');
     }
     ~NcclTransport() override {
         if (comm) NcclApi::get().CommDestroy(comm);
+        if (stage) cudaFree(stage);
     }
+    // packed = one message per neighbour and direction: the nseg planes are gathered into / scattered from contiguous
+    // staging buffers by strided device copies (HH_HALO_PACK=0 sends every plane as its own message instead)
+    char* stage = nullptr;
+    size_t stage_bytes = 0;
+    bool pack = true;
     void exchange(cudaStream_t st, int, char* base, size_t stride, int nseg, size_t bytes, size_t send_dn, size_t recv_dn,
-                  size_t send_up, size_t recv_up) override {
+                  size_t send_up, size_t recv_up, bool fill_lower, bool fill_upper) override {
         NcclApi& api = NcclApi::get();
         if (nranks == 1) return;
+        const bool lo = rank > 0, hi = rank < nranks - 1;
+        // what this slab does: lower halo wanted -> send my top plane up, receive my lower halo from below; etc.
+        const bool s_up = fill_lower && hi, r_dn = fill_lower && lo, s_dn = fill_upper && lo, r_up = fill_upper && hi;
+        if (pack && nseg > 1) {
+            const size_t blk = (size_t)nseg * bytes;
+            if (stage_bytes < 4 * blk) {
+                HH_CUDA(cudaStreamSynchronize(st));
+                if (stage) cudaFree(stage);
+                stage = nullptr;
+                stage_bytes = 0;
+                cudaError_t e = cudaMalloc((void**)&stage, 4 * blk);
+                if (e != cudaSuccess) throw hh::Error(HH_ERR_ALLOC, "halo staging buffer: cudaMalloc failed");
+                stage_bytes = 4 * blk;
+            }
+            char *o_up = stage, *o_dn = stage + blk, *i_dn = stage + 2 * blk, *i_up = stage + 3 * blk;
+            if (s_up) HH_CUDA(cudaMemcpy2DAsync(o_up, bytes, base + send_up, stride, bytes, nseg, cudaMemcpyDeviceToDevice, st));
+            if (s_dn) HH_CUDA(cudaMemcpy2DAsync(o_dn, bytes, base + send_dn, stride, bytes, nseg, cudaMemcpyDeviceToDevice, st));
+            HH_NCCL(api.GroupStart());
+            if (s_up) HH_NCCL(api.Send(o_up, blk, ncclChar, rank + 1, comm, st));
+            if (r_dn) HH_NCCL(api.Recv(i_dn, blk, ncclChar, rank - 1, comm, st));
+            if (s_dn) HH_NCCL(api.Send(o_dn, blk, ncclChar, rank - 1, comm, st));
+            if (r_up) HH_NCCL(api.Recv(i_up, blk, ncclChar, rank + 1, comm, st));
+            HH_NCCL(api.GroupEnd());
+            if (r_dn) HH_CUDA(cudaMemcpy2DAsync(base + recv_dn, stride, i_dn, bytes, bytes, nseg, cudaMemcpyDeviceToDevice, st));
+            if (r_up) HH_CUDA(cudaMemcpy2DAsync(base + recv_up, stride, i_up, bytes, bytes, nseg, cudaMemcpyDeviceToDevice, st));
+            return;
+        }
         HH_NCCL(api.GroupStart());
         for (int r = 0; r < nseg; ++r) {
             char* seg = base + (size_t)r * stride;
-            if (rank > 0) {
-                HH_NCCL(api.Send(seg + send_dn, bytes, ncclChar, rank - 1, comm, st));
-                HH_NCCL(api.Recv(seg + recv_dn, bytes, ncclChar, rank - 1, comm, st));
-            }
-            if (rank < nranks - 1) {
-                HH_NCCL(api.Send(seg + send_up, bytes, ncclChar, rank + 1, comm, st));
-                HH_NCCL(api.Recv(seg + recv_up, bytes, ncclChar, rank + 1, comm, st));
-            }
+            if (s_up) HH_NCCL(api.Send(seg + send_up, bytes, ncclChar, rank + 1, comm, st));
+            if (r_dn) HH_NCCL(api.Recv(seg + recv_dn, bytes, ncclChar, rank - 1, comm, st));
+            if (s_dn) HH_NCCL(api.Send(seg + send_dn, bytes, ncclChar, rank - 1, comm, st));
+            if (r_up) HH_NCCL(api.Recv(seg + recv_up, bytes, ncclChar, rank + 1, comm, st));
         }
         HH_NCCL(api.GroupEnd());
     }
@@ -230,7 +262,7 @@ struct ThreadTransport : SlabTransport {
     }
     // pull model: every slab publishes where its outgoing planes are, then copies its neighbours' planes into its halos
     void exchange(cudaStream_t st, int device, char* base, size_t stride, int nseg, size_t bytes, size_t send_dn,
-                  size_t recv_dn, size_t send_up, size_t recv_up) override {
+                  size_t recv_dn, size_t send_up, size_t recv_up, bool fill_lower, bool fill_upper) override {
         if (nranks == 1) return;
         ThreadGroup::Slot& me = grp->slots[rank];
         me.base = base;
@@ -241,12 +273,12 @@ struct ThreadTransport : SlabTransport {
         HH_CUDA(cudaStreamSynchronize(st));  // my outgoing planes are final
         sync();
         for (int r = 0; r < nseg; ++r) {
-            if (rank > 0) {
+            if (rank > 0 && fill_lower) {
                 const ThreadGroup::Slot& nb = grp->slots[rank - 1];
                 HH_CUDA(cudaMemcpyPeerAsync(base + (size_t)r * stride + recv_dn, device, nb.base + (size_t)r * nb.stride + nb.send_up,
                                             nb.device, bytes, st));
             }
-            if (rank < nranks - 1) {
+            if (rank < nranks - 1 && fill_upper) {
                 const ThreadGroup::Slot& nb = grp->slots[rank + 1];
                 HH_CUDA(cudaMemcpyPeerAsync(base + (size_t)r * stride + recv_up, device, nb.base + (size_t)r * nb.stride + nb.send_dn,
                                             nb.device, bytes, st));

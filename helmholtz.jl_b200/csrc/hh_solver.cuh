@@ -365,13 +365,18 @@ class Solver : public SolverBase {
 
     // ------------------------------------------------------------------ slab collectives
     // fill the halo planes (zb-1 and ze) of every vector of the block `v` on level l from the neighbouring slabs
-    void halo_exchange(int l, const C* v, int nvec, int64_t ld = 0) {
+    // (sides: HALO_LOWER = plane zb-1 only, as restriction reads it; HALO_UPPER = plane ze only, as interpolation does)
+    enum { HALO_LOWER = 1, HALO_UPPER = 2, HALO_BOTH = 3 };
+    void halo_exchange(int l, const C* v, int nvec, int64_t ld = 0, int sides = HALO_BOTH) {
         if (!slab || slab->nranks == 1) return;
         const Level& L = levels[l];
         const size_t plane = (size_t)L.p0 * L.n[1] * sizeof(C);
-        launch(T_HALO, 2.0 * (double)plane * nvec * ((slab->rank > 0) + (slab->rank < slab->nranks - 1)), [&] {
+        const int nmsg = ((sides & HALO_LOWER) ? (slab->rank > 0) + (slab->rank < slab->nranks - 1) : 0) +
+                         ((sides & HALO_UPPER) ? (slab->rank > 0) + (slab->rank < slab->nranks - 1) : 0);
+        launch(T_HALO, (double)plane * nvec * nmsg, [&] {
             slab->exchange(stream, device, (char*)const_cast<C*>(v), (size_t)(ld ? ld : L.N) * sizeof(C), nvec, plane,
-                           (size_t)L.zb * plane, (size_t)(L.zb - 1) * plane, (size_t)(L.ze - 1) * plane, (size_t)L.ze * plane);
+                           (size_t)L.zb * plane, (size_t)(L.zb - 1) * plane, (size_t)(L.ze - 1) * plane, (size_t)L.ze * plane,
+                           (sides & HALO_LOWER) != 0, (sides & HALO_UPPER) != 0);
         });
     }
     // Sum the nblk partials of each of the nq quantities, all-reduce over the slabs and leave the result in `partial`
@@ -815,7 +820,7 @@ class Solver : public SolverBase {
     void restrict_to(const Level& F, const Level& Cc, const C* r, C* bc, int nrhs) {
         dim3 g, blk;
         grid3z(Cc.n, pb.dim, Cc.zb, Cc.ze, g, blk);
-        halo_exchange((int)(&F - levels.data()), r, nrhs);
+        halo_exchange((int)(&F - levels.data()), r, nrhs, 0, HALO_LOWER);
         launch(T_RESTRICT, S * ((double)F.Nlog + (double)Cc.Nlog) * nrhs, [&] {
             if (pb.dim == 3)
                 k_restrict<T, 3><<<g, blk, 0, stream>>>(r, bc, F.n[0], F.n[1], F.n[2], Cc.n[0], Cc.n[1], Cc.n[2], F.p0, Cc.p0, F.N, Cc.N, nrhs,
@@ -827,7 +832,7 @@ class Solver : public SolverBase {
     void prolong_add(const Level& F, const Level& Cc, C* x, const C* xc, int nrhs) {
         dim3 g, blk;
         grid3z(F.n, pb.dim, F.zb, F.ze, g, blk);
-        halo_exchange((int)(&Cc - levels.data()), xc, nrhs);
+        halo_exchange((int)(&Cc - levels.data()), xc, nrhs, 0, HALO_UPPER);
         launch(T_PROLONG, S * (2.0 * (double)F.Nlog + (double)Cc.Nlog) * nrhs, [&] {
             if (pb.dim == 3)
                 k_prolong_add<T, 3><<<g, blk, 0, stream>>>(x, xc, F.n[0], F.n[1], F.n[2], F.p0, Cc.p0, Cc.n[1], F.N, Cc.N, nrhs, F.zb, F.ze);
@@ -980,7 +985,7 @@ class Solver : public SolverBase {
             HH_CUDA(cudaMemsetAsync(Lc.coef.p, 0, (size_t)NS * Lc.N * sizeof(C), stream));  // ghost columns stay zero
             const int64_t tot = (int64_t)Lc.n[0] * Lc.n[1] * (Lc.ze - Lc.zb) * NS;
             const unsigned nb = (unsigned)((tot + 127) / 128);
-            if (slab && l >= 2) halo_exchange(l - 1, Lf.coef.p, NS);  // rows of the fine planes just outside the slab
+            if (slab && l >= 2) halo_exchange(l - 1, Lf.coef.p, NS, 0, HALO_LOWER);  // rows of the fine plane just below the slab
             launch(T_SETUP, 0, [&] {
                 if (l == 1) {
                     if (pb.dim == 3) {
