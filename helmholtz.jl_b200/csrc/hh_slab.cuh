@@ -75,6 +75,8 @@ struct SlabTransport {
                           size_t recv_dn, size_t send_up, size_t recv_up, bool fill_lower, bool fill_upper) = 0;
     // in-place reduction of n doubles on the device over all slabs; every slab receives bit-identical results
     virtual void allreduce(cudaStream_t st, double* dbuf, int n, bool minimum) = 0;
+    // true when exchange() only enqueues work on `st` (no host synchronisation): it may then overlap other streams
+    virtual bool stream_ordered() const { return false; }
 };
 
 // ------------------------------------------------------------------------------------------- NCCL
@@ -244,6 +246,7 @@ struct NcclTransport : SlabTransport {
         }
         HH_NCCL(api.GroupEnd());
     }
+    bool stream_ordered() const override { return true; }
     void allreduce(cudaStream_t st, double* dbuf, int n, bool minimum) override {
         if (nranks == 1) return;
         HH_NCCL(NcclApi::get().AllReduce(dbuf, dbuf, (size_t)n, ncclDouble, minimum ? ncclMin : ncclSum, comm, st));

@@ -105,9 +105,11 @@ struct Profiler {
         HH_CUDA(cudaEventCreate(&e));
         return e;
     }
+    cudaStream_t aux = nullptr;  // second stream events may have been recorded on (overlapped halo exchanges)
     void flush(cudaStream_t st) {
         if (recs.empty()) return;
         HH_CUDA(cudaStreamSynchronize(st));
+        if (aux) HH_CUDA(cudaStreamSynchronize(aux));
         for (auto& r : recs) {
             float t = 0.f;
             HH_CUDA(cudaEventElapsedTime(&t, r.a, r.b));
@@ -284,9 +286,21 @@ class Solver : public SolverBase {
         if (e && !strcmp(e, "simple")) fine_kernel = FK_SIMPLE;
         const char* f = getenv("HH_FUSE_FIRST");  // A/B switch of the fused cycle start (default on)
         fuse_first = !(f && f[0] == '0');
+        // opt-in: measured slower than exchange-then-compute on 8 B200 (profiles/bench_r01_config5_slab_n8_513_ab.jsonl)
+        const char* ho = getenv("HH_HALO_OVERLAP");
+        halo_overlap = ho && ho[0] == '1';
+        const char* hs = getenv("HH_HALO_SPLIT");
+        split_always = hs && hs[0] == '1';
         use_pitch = sizeof(T) == 4 && pb.dim == 3 && fine_kernel == FK_TMA;
     }
-    ~Solver() override {}
+    ~Solver() override {
+        if (comm_stream) {
+            cudaSetDevice(device);
+            cudaStreamDestroy(comm_stream);
+            cudaEventDestroy(ev_ready);
+            cudaEventDestroy(ev_landed);
+        }
+    }
 
     size_t elem_size() const override { return sizeof(C); }
 
@@ -367,18 +381,66 @@ class Solver : public SolverBase {
     // fill the halo planes (zb-1 and ze) of every vector of the block `v` on level l from the neighbouring slabs
     // (sides: HALO_LOWER = plane zb-1 only, as restriction reads it; HALO_UPPER = plane ze only, as interpolation does)
     enum { HALO_LOWER = 1, HALO_UPPER = 2, HALO_BOTH = 3 };
-    void halo_exchange(int l, const C* v, int nvec, int64_t ld = 0, int sides = HALO_BOTH) {
+    void halo_exchange(int l, const C* v, int nvec, int64_t ld = 0, int sides = HALO_BOTH, cudaStream_t on = nullptr) {
         if (!slab || slab->nranks == 1) return;
         const Level& L = levels[l];
         const size_t plane = (size_t)L.p0 * L.n[1] * sizeof(C);
         const int nmsg = ((sides & HALO_LOWER) ? (slab->rank > 0) + (slab->rank < slab->nranks - 1) : 0) +
                          ((sides & HALO_UPPER) ? (slab->rank > 0) + (slab->rank < slab->nranks - 1) : 0);
         launch(T_HALO, (double)plane * nvec * nmsg, [&] {
-            slab->exchange(stream, device, (char*)const_cast<C*>(v), (size_t)(ld ? ld : L.N) * sizeof(C), nvec, plane,
+            slab->exchange(on ? on : stream, device, (char*)const_cast<C*>(v), (size_t)(ld ? ld : L.N) * sizeof(C), nvec, plane,
                            (size_t)L.zb * plane, (size_t)(L.zb - 1) * plane, (size_t)(L.ze - 1) * plane, (size_t)L.ze * plane,
                            (sides & HALO_LOWER) != 0, (sides & HALO_UPPER) != 0);
-        });
+        }, on);
     }
+    // ---- halo exchange overlapped with the planes that do not need it ------------------------------------------
+    // A stencil-type kernel on planes [zb,ze) reads halo planes only for its first and last plane.  With a transport
+    // that is pure stream work (NCCL) the exchange can run on a second stream while the interior planes are computed;
+    // the one or two boundary planes follow once it has landed (HH_HALO_OVERLAP=1; off by default: on 8 B200 the NCCL
+    // copy kernels competing with the stencil kernels plus the two extra launches cost more than the hidden latency).  NCCL operations still never run concurrently with each
+    // other: the next one is issued after an event that follows everything enqueued so far.
+    struct HaloReq {
+        int level;
+        const C* v;
+        int64_t ld;
+    };
+    bool overlap_ok(int zb, int ze) const {
+        return slab && slab->nranks > 1 && slab->stream_ordered() && halo_overlap && (ze - zb) >= 4;
+    }
+    // calls run(z0, z1) for sub-ranges that together cover [zb,ze) exactly once
+    template <class F>
+    void with_halos(std::initializer_list<HaloReq> reqs, int nvec, int zb, int ze, F&& run) {
+        if (!overlap_ok(zb, ze)) {
+            for (const HaloReq& r : reqs) halo_exchange(r.level, r.v, nvec, r.ld);
+            if (split_always && slab && slab->nranks > 1 && (ze - zb) >= 4) {
+                // HH_HALO_SPLIT=1: the launch pattern of the overlapped path with any transport (single-GPU tests)
+                const int lo = slab->rank > 0 ? 1 : 0, hi = slab->rank < slab->nranks - 1 ? 1 : 0;
+                run(zb + lo, ze - hi);
+                if (lo) run(zb, zb + 1);
+                if (hi) run(ze - 1, ze);
+                return;
+            }
+            run(zb, ze);
+            return;
+        }
+        if (!comm_stream) {
+            HH_CUDA(cudaStreamCreateWithFlags(&comm_stream, cudaStreamNonBlocking));
+            HH_CUDA(cudaEventCreateWithFlags(&ev_ready, cudaEventDisableTiming));
+            HH_CUDA(cudaEventCreateWithFlags(&ev_landed, cudaEventDisableTiming));
+            prof.aux = comm_stream;
+        }
+        const int lo = slab->rank > 0 ? 1 : 0, hi = slab->rank < slab->nranks - 1 ? 1 : 0;
+        HH_CUDA(cudaEventRecord(ev_ready, stream));  // the producers of the vectors (and every earlier NCCL call)
+        HH_CUDA(cudaStreamWaitEvent(comm_stream, ev_ready, 0));
+        for (const HaloReq& r : reqs) halo_exchange(r.level, r.v, nvec, r.ld, HALO_BOTH, comm_stream);
+        HH_CUDA(cudaEventRecord(ev_landed, comm_stream));
+        run(zb + lo, ze - hi);
+        HH_CUDA(cudaStreamWaitEvent(stream, ev_landed, 0));
+        if (lo) run(zb, zb + 1);
+        if (hi) run(ze - 1, ze);
+    }
+    int zbeg(const Level& L) const { return rz_b >= 0 ? rz_b : L.zb; }
+    int zend(const Level& L) const { return rz_e >= 0 ? rz_e : L.ze; }
     // Sum the nblk partials of each of the nq quantities, all-reduce over the slabs and leave the result in `partial`
     // in the layout of nblk = 1 (which is returned).  No-op without slabs.
     int slab_reduce(zc* partial, int nq, int nblk) {
@@ -429,14 +491,14 @@ class Solver : public SolverBase {
 
     // ------------------------------------------------------------------ launch plumbing
     template <class F>
-    void launch(int tag, double bytes, F&& f) {
+    void launch(int tag, double bytes, F&& f, cudaStream_t on = nullptr) {
         const int64_t sub = (int64_t)bytes;
         ++launches;
         if (prof.on) {
             cudaEvent_t a = prof.get(), b = prof.get();
-            HH_CUDA(cudaEventRecord(a, stream));
+            HH_CUDA(cudaEventRecord(a, on ? on : stream));
             f();
-            HH_CUDA(cudaEventRecord(b, stream));
+            HH_CUDA(cudaEventRecord(b, on ? on : stream));
             prof.recs.push_back({tag, a, b, bytes, sub});
             if (prof.recs.size() >= 8192) prof.flush(stream);
         } else {
@@ -467,11 +529,18 @@ class Solver : public SolverBase {
 
     // ------------------------------------------------------------------ operator kernels
     // out = op(x) with MODE epilogue on the fine level
-    void fine_stencil(int mode, const FineOp<T>& op, const C* x, const C* b, C* out, int64_t ld, int nrhs, T damp) {
+    void fine_stencil(int mode, const FineOp<T>& op0, const C* x, const C* b, C* out, int64_t ld, int nrhs, T damp) {
+        with_halos({{0, x, ld}}, nrhs, op0.zb, op0.ze, [&](int z0, int z1) {
+            FineOp<T> o = op0;
+            o.zb = z0;
+            o.ze = z1;
+            fine_stencil_range(mode, o, x, b, out, ld, nrhs, damp);
+        });
+    }
+    void fine_stencil_range(int mode, const FineOp<T>& op, const C* x, const C* b, C* out, int64_t ld, int nrhs, T damp) {
         dim3 g, blk;
         grid3z(pb.n, pb.dim, op.zb, op.ze, g, blk);
-        halo_exchange(0, x, nrhs, ld);
-        const double N = (double)pb.N();
+        const double N = pb.dim == 3 ? (double)pb.n[0] * pb.n[1] * (op.ze - op.zb) : (double)pb.N();
         const double coefb = 2.0 * CR * N;
         double bytes;
         int tag;
@@ -620,9 +689,16 @@ class Solver : public SolverBase {
         return op.cdiag != nullptr && op.dinv != nullptr && tma_ok(op, ld) && ((uintptr_t)b % 16 == 0) && fuse_first;
     }
     // second == 0: out = x1, out2 = b - A x1;  second == 1: out = x2
-    void fine_first(int second, const FineOp<T>& op, const C* b, C* out, C* out2, int64_t ld, int nrhs) {
-        const double N = (double)pb.N();
-        halo_exchange(0, b, nrhs, ld);
+    void fine_first(int second, const FineOp<T>& op0, const C* b, C* out, C* out2, int64_t ld, int nrhs) {
+        with_halos({{0, b, ld}}, nrhs, op0.zb, op0.ze, [&](int z0, int z1) {
+            FineOp<T> o = op0;
+            o.zb = z0;
+            o.ze = z1;
+            fine_first_range(second, o, b, out, out2, ld, nrhs);
+        });
+    }
+    void fine_first_range(int second, const FineOp<T>& op, const C* b, C* out, C* out2, int64_t ld, int nrhs) {
+        const double N = (double)pb.n[0] * pb.n[1] * (op.ze - op.zb);
         const double bytes = (second == 0 ? 3.0 : 2.0) * S * N * nrhs + 2.0 * S * N;
         launch(second == 0 ? T_FINE_FIRST_RESID : T_FINE_FIRST_JACOBI, bytes, [&] {
             if (second == 0) {
@@ -661,11 +737,17 @@ class Solver : public SolverBase {
         return fuse_first && op.cdiag != nullptr && op.dinv != nullptr && tma_ok(op, ld) && tma_ok_level(Cc) &&
                ((uintptr_t)x % 16 == 0) && ((uintptr_t)b % 16 == 0) && ((uintptr_t)xc % 16 == 0);
     }
-    void fine_prolong_jacobi(const FineOp<T>& op, const C* x, const C* b, const Level& Cc, const C* xc, C* out, int64_t ld, int nrhs) {
-        const double N = (double)pb.N();
-        halo_exchange(0, x, nrhs, ld);
-        halo_exchange(1, xc, nrhs);
-        launch(T_FINE_PROLONG_JACOBI, (3.0 * N + (double)Cc.Nlog) * S * nrhs + 2.0 * S * N, [&] {
+    void fine_prolong_jacobi(const FineOp<T>& op0, const C* x, const C* b, const Level& Cc, const C* xc, C* out, int64_t ld, int nrhs) {
+        with_halos({{0, x, ld}, {1, xc, 0}}, nrhs, op0.zb, op0.ze, [&](int z0, int z1) {
+            FineOp<T> o = op0;
+            o.zb = z0;
+            o.ze = z1;
+            fine_prolong_jacobi_range(o, x, b, Cc, xc, out, ld, nrhs);
+        });
+    }
+    void fine_prolong_jacobi_range(const FineOp<T>& op, const C* x, const C* b, const Level& Cc, const C* xc, C* out, int64_t ld, int nrhs) {
+        const double N = (double)pb.n[0] * pb.n[1] * (op.ze - op.zb);
+        launch(T_FINE_PROLONG_JACOBI, (3.0 * N + 0.125 * N) * S * nrhs + 2.0 * S * N, [&] {
             if (nrhs >= 2) tma3d_pro_launch<2>(op, x, b, Cc, xc, out, ld, nrhs);
             else tma3d_pro_launch<1>(op, x, b, Cc, xc, out, ld, nrhs);
         });
@@ -697,7 +779,7 @@ class Solver : public SolverBase {
         const int groups = (nrhs + KB - 1) / KB;
         const int tx = (L.n[0] + Cfg::TX - 1) / Cfg::TX, ty = (L.n[1] + Cfg::TY - 1) / Cfg::TY;
         int zchunk, nzc;
-        const int nz = L.ze - L.zb;
+        const int nz = zend(L) - zbeg(L);
         zchunks(nz, tx * ty, groups, 32, zchunk, nzc);
         // one CTA per SM is resident: aim for a few waves, not for many tiny chunks
         while (nzc > 1 && (int64_t)tx * ty * groups * nzc > 148 * 6) {
@@ -709,7 +791,7 @@ class Solver : public SolverBase {
         TmaDesc mc = make_tmap_g(L.coef.p, L.n, L.p0, L.N, Cfg::TX, Cfg::TY, 9, 27);
         TmaDesc mb = (MODE != MODE_APPLY) ? make_tmap_g(b, L.n, L.p0, L.N, Cfg::TX, Cfg::TY, KB, nrhs) : mx;
         TmaDesc md = (MODE == MODE_JACOBI) ? make_tmap_g(L.dinv.p, L.n, L.p0, L.N, Cfg::TX, Cfg::TY, 1, 0) : mx;
-        k_coarse3d_tma<T, MODE, KB><<<g, 128, smem, stream>>>(mx, mc, mb, md, out, L.n[0], L.n[1], L.n[2], L.p0, L.N, nrhs, zchunk, groups, L.zb, L.ze);
+        k_coarse3d_tma<T, MODE, KB><<<g, 128, smem, stream>>>(mx, mc, mb, md, out, L.n[0], L.n[1], L.n[2], L.p0, L.N, nrhs, zchunk, groups, zbeg(L), zend(L));
     }
     template <int MODE>
     void coarse_tma_mode(const Level& L, const C* x, const C* b, C* out, int nrhs) {
@@ -732,7 +814,7 @@ class Solver : public SolverBase {
         const int groups = (nrhs + KB - 1) / KB;
         const int tx = (L.n[0] + 31) / 32, ty = (L.n[1] + TY - 1) / TY;
         int zchunk, nzc;
-        zchunks(L.ze - L.zb, tx * ty, groups, 16, zchunk, nzc);
+        zchunks(zend(L) - zbeg(L), tx * ty, groups, 16, zchunk, nzc);
         dim3 g(tx * groups, ty, nzc), blk(32, TY, 1);
         k_coarse3d_zmarch<T, MODE, KB, TY, COARSE_MINB><<<g, blk, 0, stream>>>(coarse_op(L), x, b, out, L.N, nrhs, zchunk, groups);
     }
@@ -760,15 +842,22 @@ class Solver : public SolverBase {
         for (int d = 0; d < 3; ++d) op.n[d] = L.n[d];
         op.sy = L.p0;
         op.N = L.N;
-        op.zb = L.zb;
-        op.ze = L.ze;
+        op.zb = zbeg(L);
+        op.ze = zend(L);
         return op;
     }
     void coarse_stencil(int mode, const Level& L, const C* x, const C* b, C* out, int nrhs) {
+        with_halos({{(int)(&L - levels.data()), x, 0}}, nrhs, L.zb, L.ze, [&](int z0, int z1) {
+            rz_b = z0;  // the launchers below read the plane range through zbeg / zend
+            rz_e = z1;
+            coarse_stencil_range(mode, L, x, b, out, nrhs);
+            rz_b = rz_e = -1;
+        });
+    }
+    void coarse_stencil_range(int mode, const Level& L, const C* x, const C* b, C* out, int nrhs) {
         dim3 g, blk;
-        grid3z(L.n, pb.dim, L.zb, L.ze, g, blk);
-        halo_exchange((int)(&L - levels.data()), x, nrhs);
-        const double N = (double)L.Nlog;
+        grid3z(L.n, pb.dim, zbeg(L), zend(L), g, blk);
+        const double N = pb.dim == 3 ? (double)L.n[0] * L.n[1] * (zend(L) - zbeg(L)) : (double)L.Nlog;
         const int NS = pb.dim == 3 ? 27 : 9;
         const bool use_tma = tma_ok_level(L) && ((uintptr_t)x % 16 == 0) && (mode == MODE_APPLY || (uintptr_t)b % 16 == 0);
         int KB = (pb.dim == 3 && fine_kernel != FK_SIMPLE) ? coarse_kb(nrhs) : 4;
@@ -1699,6 +1788,11 @@ class Solver : public SolverBase {
     DevBuf<C> kry;
     int kry_cap = 0;
     DevBuf<zc> d_partial, d_one, d_red;
+    cudaStream_t comm_stream = nullptr;  // halo exchanges that overlap the interior planes (with_halos)
+    cudaEvent_t ev_ready = nullptr, ev_landed = nullptr;
+    bool halo_overlap = false;           // HH_HALO_OVERLAP=1: exchange on a second stream while the interior planes run
+    bool split_always = false;
+    int rz_b = -1, rz_e = -1;            // plane range override of the coarse launchers (with_halos)
     GmresMem outer;
     int outer_cap = 0;
     BicgMem bicg;

@@ -35,6 +35,8 @@ def main():
     ap.add_argument("--tol", type=float, default=1e-6)
     ap.add_argument("--max-cycles", type=int, default=40)
     ap.add_argument("--ppw", type=float, default=10.0, help="points per wavelength at the slowest velocity")
+    ap.add_argument("--variants", default="default", help="comma-separated runs in one process; a variant may set A/B "
+                    "switches of the library as ENV=value joined by '+', e.g. HH_HALO_OVERLAP=1,HH_HALO_OVERLAP=0")
     a = ap.parse_args()
     import torch
     import torch.distributed as dist
@@ -67,9 +69,30 @@ def main():
     if a.prec == "mixed":
         MG.cyclePrecision = pkg.ComplexF32
     hp = pkg.HelmholtzParam(mesh, np.asfortranarray(gamma).ravel(order="F"), cfg["m"].ravel(order="F"), w, True, True)
+    variants = [v for v in a.variants.split(",") if v]
+    for variant in variants:
+        # A/B switches of the library are read when a handle is created: one handle per variant, same model
+        for kv in variant.split("+"):
+            if "=" in kv:
+                k, v = kv.split("=")
+                if k == "nrhs":
+                    a.nrhs = int(v)
+                elif k == "prec":  # c128 | mixed
+                    a.prec = v
+                    MG.cyclePrecision = pkg.ComplexF32 if v == "mixed" else None
+                else:
+                    os.environ[k] = v
+        run_variant(a, pkg, lib, torch, dist, rank, world, local, mesh, nodes, w, hp, MG, (mk0, mk1), t_model, variant, n)
+        pkg.clear(MG)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def run_variant(a, pkg, lib, torch, dist, rank, world, local, mesh, nodes, w, hp, MG, model_planes, t_model, variant, n):
+    tdt = torch.complex64 if a.prec == "c64" else torch.complex128
     A = pkg.getShiftedLaplacianMultigridSolver(hp, MG, 0.2, "GMRES", 5)
     A.devices = [local]
-    A.slabs = dict(pkg.sharding.nccl_slabs(), model_planes=(mk0, mk1))
+    A.slabs = dict(pkg.sharding.nccl_slabs(), model_planes=model_planes)
     torch.cuda.synchronize()
     dist.barrier()
     t0 = time.perf_counter()
@@ -162,9 +185,8 @@ def main():
                                                "avg_ms": round(d["ms"] / d["launches"], 4),
                                                "gbs": round(d["bytes"] / d["ms"] / 1e6, 1) if d["bytes"] else None} for d in tags},
         }
+        line["config"]["variant"] = variant
         print(json.dumps(line), flush=True)
-    dist.barrier()
-    dist.destroy_process_group()
 
 
 if __name__ == "__main__":

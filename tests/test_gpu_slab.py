@@ -187,3 +187,22 @@ def test_slab_error_paths(gpu_pkg):
     with pytest.raises(pkg._lib.HelmholtzB200Error) as e:
         pkg.solveLinearSystem(None, B, A)
     assert e.value.code == pkg._lib.HH_ERR_ARG
+
+
+def test_slab_split_launches_match(gpu_pkg, monkeypatch):
+    """HH_HALO_SPLIT=1: interior planes and the one or two boundary planes of every stencil-type kernel are separate
+    launches, as in the path that overlaps the NCCL halo exchange with the interior (same results)"""
+    pkg = gpu_pkg
+    mesh, m, w, gamma = _problem(pkg, nodes=(33, 25, 33))
+    B, _ = _rhs(pkg, mesh, np.complex128)
+    ref = _solver(pkg, mesh, m, w, gamma, np.complex128, 0)
+    Xr, ref = pkg.solveLinearSystem(None, B, ref)
+    monkeypatch.setenv("HH_HALO_SPLIT", "1")
+    for nslab, prec, tol in ((2, np.complex128, 1e-9), (3, np.complex128, 1e-9), (2, np.complex64, 2e-4)):
+        A = _solver(pkg, mesh, m, w, gamma, prec, nslab, tol=1e-8 if prec == np.complex128 else 1e-5)
+        X, A = pkg.solveLinearSystem(None, B.astype(prec), A)
+        if prec == np.complex128:
+            assert np.array_equal(A.iterations, ref.iterations)
+        assert rel_err(X, Xr) < tol
+        pkg.clear(A.MG)
+    pkg.clear(ref.MG)
