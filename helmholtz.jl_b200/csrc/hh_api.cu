@@ -533,6 +533,7 @@ int hh_get_level_stencil(hh_handle_t h, int level, void* coef_out) {
     if (!h || !coef_out) return HH_ERR_ARG;
     return guarded(h, [&]() -> int {
         HH_REQUIRE(h->lows.empty(), HH_ERR_UNSUPPORTED, "hh_get_level_stencil: not available on a mixed-precision handle");
+        HH_REQUIRE(h->slab_mode == 0, HH_ERR_UNSUPPORTED, "hh_get_level_stencil: use hh_slab_level_stencil on a slab handle");
         h->subs[0]->get_level_stencil(level, coef_out);
         return HH_OK;
     });
@@ -553,7 +554,19 @@ int hh_slab_level_stencil(hh_handle_t h, int slab, int level, int64_t* n_local_o
 int hh_get_diagonal(hh_handle_t h, int shifted, double shift, double* diag_out) {
     if (!h || !diag_out) return HH_ERR_ARG;
     return guarded(h, [&]() -> int {
-        h->subs[0]->get_diagonal(shifted, shift, diag_out);
+        if (h->slab_mode == 0) {
+            h->subs[0]->get_diagonal(shifted, shift, diag_out);
+            return HH_OK;
+        }
+        // slab handle: every slab evaluates its planes; the caller's array holds the planes its B / X hold
+        const int64_t plane = (int64_t)h->pb.n[0] * h->pb.n[1];
+        for (auto& sb : h->subs) {
+            const SlabLevel& g = sb->sgeo[0];
+            std::vector<double> loc((size_t)2 * plane * g.nloc);
+            sb->get_diagonal(shifted, shift, loc.data());
+            const int64_t dst0 = h->slab_mode == 1 ? g.own0 : 0;
+            std::memcpy(diag_out + 2 * plane * dst0, loc.data() + 2 * plane * g.zb, sizeof(double) * 2 * plane * (g.own1 - g.own0));
+        }
         return HH_OK;
     });
 }

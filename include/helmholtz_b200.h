@@ -154,7 +154,8 @@ int hh_destroy(hh_handle_t h);
  *   hh_slab_partition, halo planes included; hh_update_model uses the same convention);
  *   B, X (host or device) hold the planes own0 <= k < own1 of hh_slab_info only,
  *   i.e. n1*n2*(own1-own0) entries per right-hand side; point-source indices stay whole-grid indices.
- *   Every rank must make the same sequence of calls. */
+ *   Every rank must make the same sequence of calls; a rank that fails (e.g. out of memory) leaves the others waiting
+ *   in the next collective, as with any NCCL program: size the batch with the memory of the fullest GPU in mind. */
 int hh_create_slab_local(int dim, const int64_t* n_nodes, const double* h, const double* m, const double* gamma,
                          double omega_re, double omega_im, int neumann_on_top, int sommerfeld, int order_neumann_bc,
                          int precision, const int* devices, int n_slabs, int levels, hh_handle_t* out);

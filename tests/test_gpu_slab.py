@@ -206,3 +206,20 @@ def test_slab_split_launches_match(gpu_pkg, monkeypatch):
         assert rel_err(X, Xr) < tol
         pkg.clear(A.MG)
     pkg.clear(ref.MG)
+
+
+def test_slab_diagonal_matches_whole_grid(gpu_pkg):
+    """hh_get_diagonal on a slab handle: mass + Sommerfeld faces follow the global plane index"""
+    pkg = gpu_pkg
+    for neumann in (True, False):
+        mesh, m, w, gamma = _problem(pkg, neumann=neumann)
+        ref = _solver(pkg, mesh, m, w, gamma, np.complex128, 0, neumann=neumann)
+        A = _solver(pkg, mesh, m, w, gamma, np.complex128, 3, neumann=neumann)
+        out = []
+        for S in (ref, A):
+            hd = pkg.api._ensure_hierarchy(S, 0)
+            d = np.empty(hd.N, dtype=np.complex128)
+            pkg._lib.check(hd.lib.hh_get_diagonal(hd.h, 1, 0.2, d.view(np.float64).ctypes.data_as(C.POINTER(C.c_double))), hd.h)
+            out.append(d)
+            pkg.clear(S.MG)
+        assert rel_err(out[1], out[0]) < 1e-14
