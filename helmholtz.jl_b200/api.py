@@ -648,3 +648,27 @@ def slabPlanes(param):
     """Planes [k0, k1) of the last dimension that B / X of this process hold (whole grid unless NCCL slabs)."""
     hd = _ensure_hierarchy(param, param.MG.doTranspose)
     return hd.planes
+
+
+def GetHelmholtzOperatorHOStencil(Msh, mNodal, omega, gamma, NeumannAtFirstDim, Sommerfeld, beta=1.0):
+    """GetHelmholtzOperatorHO (src/GetHelmholtz.jl:54-72) as a stored stencil: coef[s, node], s the offset index
+    (d1+1) + 3(d2+1) (+ 9(d3+1)), ComplexF64, column-major nodes (hh_ho_stencil; host-side set-up)."""
+    nodes = (np.asarray(Msh.n, dtype=np.int64) + 1).copy()
+    dim = int(Msh.dim)
+    N = int(np.prod(nodes))
+    mm = np.ascontiguousarray(np.asarray(mNodal, dtype=np.float64).ravel(order="F"))
+    gg = np.ascontiguousarray(np.asarray(gamma, dtype=np.float64).ravel(order="F"))
+    if mm.size != N or gg.size != N:
+        raise ValueError(f"m and gamma must have prod(n+1) = {N} entries")
+    if np.isscalar(beta):
+        if dim == 3 and beta != 1:
+            raise ValueError("getSpreadNodalLaplacianAndMass: in 3-D beta is a pair (Laplacian, mass)")
+        beta = [float(beta), float(beta)]
+    bb = np.ascontiguousarray(np.asarray(beta, dtype=np.float64))
+    h = np.ascontiguousarray(np.asarray(Msh.h, dtype=np.float64))
+    w = complex(omega)
+    coef = np.empty((3 ** dim, N), dtype=np.complex128)
+    L.check(L.load().hh_ho_stencil(dim, _ptr(nodes, C.c_int64), _ptr(h, C.c_double), _ptr(mm, C.c_double), _ptr(gg, C.c_double),
+                                   w.real, w.imag, int(bool(NeumannAtFirstDim)), int(bool(Sommerfeld)), _ptr(bb, C.c_double),
+                                   _ptr(coef.view(np.float64), C.c_double)), None)
+    return coef

@@ -2,6 +2,7 @@
 // Catches every C++ exception, maps it to a status code + message, shards right-hand sides over
 // devices for multi-GPU handles, and implements the host-side set-up helpers of the reference
 // (getABL, getMaximalFrequency, loc2cs) that stay Float64 host work.
+#include <array>
 #include <memory>
 #include <mutex>
 #include <thread>
@@ -280,6 +281,101 @@ static void add_replica(hh_handle_s* h, const Problem& pb, int precision, int de
             hi->launches += 2;
         };
     }
+}
+
+// ---------------------------------------------------------------------------------------------
+// GetHelmholtzOperatorHO (src/GetHelmholtz.jl:54-72) on the spread nodal Laplacian and mass of
+// src/PlainNodalLaplacian.jl:49-141, as a stored 3^dim-point stencil.  The Kronecker construction
+//   Lap = G' Gs,  Gs = (1-b) [spread gradients] + b G,   H = Lap + M Diagonal(mass)
+// collapses to sums of tensor products of 1-D tridiagonal matrices: T_d = ddx' ddx (the first-order Neumann
+// Laplacian), A_d = av3term(n_d+1, 1/2) (spreading), B_d = av3term(n_d+1, beta_mass):
+//   2-D  Lap = T1 (x) [(1-b) A2 + b I] + [(1-b) A1 + b I] (x) T2,            M = 1/2 (B2 (x) I + I (x) B1)
+//   3-D  Lap = sum_d T_d (x) [b I(x)I + (1-b)/2 (A_e (x) I + I (x) A_f)],     M = 1/3 sum_d B_d (x) I (x) I
+// Host-side Float64 set-up like getABL; no device is needed.
+// ---------------------------------------------------------------------------------------------
+extern "C" int hh_ho_stencil(int dim, const int64_t* n_nodes, const double* hsp, const double* m, const double* gamma,
+                             double wre, double wim, int neumann_on_top, int sommerfeld, const double* beta, double* coef_out) {
+    return guarded(nullptr, [&]() -> int {
+        HH_REQUIRE((dim == 2 || dim == 3) && n_nodes && hsp && m && gamma && beta && coef_out, HH_ERR_ARG, "hh_ho_stencil: bad arguments");
+        HH_REQUIRE(wre != 0.0, HH_ERR_ARG, "hh_ho_stencil: Re(omega) must be non-zero");
+        int64_t n[3] = {1, 1, 1};
+        for (int d = 0; d < dim; ++d) {
+            HH_REQUIRE(n_nodes[d] >= 2 && hsp[d] > 0.0, HH_ERR_ARG, "hh_ho_stencil: node counts must be >= 2, spacings positive");
+            n[d] = n_nodes[d];
+        }
+        const int64_t N = n[0] * n[1] * n[2];
+        const double bl = beta[0], bm = dim == 3 ? beta[1] : beta[0];
+        // 1-D tridiagonal tables, entry [i][o+1] couples node i with node i+o
+        auto tri = [&](int d, double diag_in, double diag_end, double off) {
+            std::vector<std::array<double, 3>> t((size_t)n[d]);
+            for (int64_t i = 0; i < n[d]; ++i) {
+                const bool end = (i == 0 || i == n[d] - 1);
+                t[i][1] = end ? diag_end : diag_in;
+                t[i][0] = i > 0 ? off : 0.0;
+                t[i][2] = i < n[d] - 1 ? off : 0.0;
+            }
+            return t;
+        };
+        std::vector<std::array<double, 3>> T[3], A[3], B[3];
+        for (int d = 0; d < dim; ++d) {
+            const double ih2 = 1.0 / (hsp[d] * hsp[d]);
+            T[d] = tri(d, 2.0 * ih2, ih2, -ih2);                      // ddxCN' * ddxCN
+            A[d] = tri(d, 0.5, 0.75, 0.25);                           // av3term(n, 1/2)
+            B[d] = tri(d, bm, 0.5 + 0.5 * bm, 0.5 * (1.0 - bm));      // av3term(n, beta_mass)
+        }
+        // mass = -w^2 m (1 - i gamma / Re w) - Sommerfeld   (GetHelmholtz.jl:62-68; getSommerfeldBC :222-247, BC = 2)
+        const double w2r = wre * wre - wim * wim, w2i = 2.0 * wre * wim;
+        std::vector<double> mr((size_t)N), mi((size_t)N);
+        for (int64_t k = 0; k < n[2]; ++k)
+            for (int64_t j = 0; j < n[1]; ++j)
+                for (int64_t i = 0; i < n[0]; ++i) {
+                    const int64_t p = i + n[0] * (j + n[1] * k);
+                    const double g = gamma[p] / wre;
+                    double re = -m[p] * (w2r + w2i * g), im = -m[p] * (w2i - w2r * g);
+                    if (sommerfeld) {
+                        double sf = 0.0;
+                        const int64_t idx[3] = {i, j, k};
+                        for (int d = 0; d < dim; ++d) {
+                            const bool first = idx[d] == 0, last = idx[d] == n[d] - 1;
+                            const bool top = (d == dim - 1) && neumann_on_top;
+                            if ((first && !top) || last) sf += 2.0 / hsp[d];
+                        }
+                        im += wre * sf * std::sqrt(m[p]);
+                    }
+                    mr[p] = re;
+                    mi[p] = im;
+                }
+        const int NS = dim == 3 ? 27 : 9;
+        std::fill(coef_out, coef_out + (size_t)2 * NS * N, 0.0);
+        for (int64_t k = 0; k < n[2]; ++k)
+            for (int64_t j = 0; j < n[1]; ++j)
+                for (int64_t i = 0; i < n[0]; ++i) {
+                    const int64_t p = i + n[0] * (j + n[1] * k);
+                    for (int dk = (dim == 3 ? -1 : 0); dk <= (dim == 3 ? 1 : 0); ++dk)
+                        for (int dj = -1; dj <= 1; ++dj)
+                            for (int di = -1; di <= 1; ++di) {
+                                if (i + di < 0 || i + di >= n[0] || j + dj < 0 || j + dj >= n[1] || k + dk < 0 || k + dk >= n[2]) continue;
+                                const double I0 = di == 0, J0 = dj == 0, K0 = dk == 0;  // Kronecker deltas
+                                double lap, mm;
+                                if (dim == 2) {
+                                    lap = T[0][i][di + 1] * ((1.0 - bl) * A[1][j][dj + 1] + bl * J0) +
+                                          T[1][j][dj + 1] * ((1.0 - bl) * A[0][i][di + 1] + bl * I0);
+                                    mm = 0.5 * (B[1][j][dj + 1] * I0 + B[0][i][di + 1] * J0);
+                                } else {
+                                    const double a0 = A[0][i][di + 1], a1 = A[1][j][dj + 1], a2 = A[2][k][dk + 1];
+                                    lap = T[0][i][di + 1] * (bl * J0 * K0 + 0.5 * (1.0 - bl) * (a1 * K0 + J0 * a2)) +
+                                          T[1][j][dj + 1] * (bl * I0 * K0 + 0.5 * (1.0 - bl) * (a0 * K0 + I0 * a2)) +
+                                          T[2][k][dk + 1] * (bl * I0 * J0 + 0.5 * (1.0 - bl) * (a0 * J0 + I0 * a1));
+                                    mm = (1.0 / 3.0) * (B[1][j][dj + 1] * I0 * K0 + B[0][i][di + 1] * J0 * K0 + B[2][k][dk + 1] * I0 * J0);
+                                }
+                                const int64_t q = p + di + n[0] * (dj + n[1] * (int64_t)dk);  // column node: M * Diagonal(mass)
+                                const int s = (di + 1) + 3 * (dj + 1) + (dim == 3 ? 9 * (dk + 1) : 0);
+                                coef_out[2 * ((int64_t)s * N + p)] = lap + mm * mr[q];
+                                coef_out[2 * ((int64_t)s * N + p) + 1] = mm * mi[q];
+                            }
+                }
+        return HH_OK;
+    });
 }
 
 // ---------------------------------------------------------------------------------------------

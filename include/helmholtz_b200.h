@@ -119,6 +119,13 @@ int hh_device_count(int* count);
 int hh_get_abl(int dim, const int64_t* n_nodes, int neumann_on_top, const int64_t* pad, double amp, double* gamma_out);
 /* getMaximalFrequency(m,Mesh) */
 int hh_get_maximal_frequency(const double* m, int64_t n, int dim, const double* h, double* omega_max);
+/* GetHelmholtzOperatorHO(Mesh, m, omega, gamma, NeumannAtFirstDim, Sommerfeld, beta) (src/GetHelmholtz.jl:54-72 with
+ * getSpreadNodalLaplacianAndMass, src/PlainNodalLaplacian.jl:106-141) as a stored stencil: coef_out[s*N + node] complex
+ * (re,im) Float64, s = (d1+1)+3(d2+1)(+9(d3+1)) as in hh_get_level_stencil, 9 (2-D) or 27 (3-D) entries per node.
+ * beta: 2-D beta[0] (Laplacian and mass); 3-D beta[0] Laplacian, beta[1] mass (the reference's beta == 1 is {1,1}).
+ * Host-side set-up; the solver wiring of this operator is not built yet. */
+int hh_ho_stencil(int dim, const int64_t* n_nodes, const double* h, const double* m, const double* gamma, double omega_re,
+                  double omega_im, int neumann_on_top, int sommerfeld, const double* beta, double* coef_out);
 /* loc2cs: 1-based subscripts -> 1-based linear index */
 int64_t hh_point_source_index(int dim, const int64_t* n_nodes, const int64_t* sub);
 

@@ -233,6 +233,87 @@ def GetHelmholtzOperatorABL(mesh, mNodal, omega, gamma, NeumannAtFirstDim, ABLpa
     return H, gamma
 
 
+# --------------------------------------------------------------------------
+# High-order ("spread") operator: GetHelmholtzOperatorHO (src/GetHelmholtz.jl:54-72) on the spread nodal
+# Laplacian and mass of src/PlainNodalLaplacian.jl:49-141.  No test of the reference exercises it; the
+# restatement follows the Kronecker construction line by line.
+# --------------------------------------------------------------------------
+
+
+def ddxCN(n, h):
+    """PlainNodalLaplacian.jl:56-60 -- 1-D cell-centred derivative of nodal values, n x (n+1)."""
+    return sp.diags([-np.ones(n) / h, np.ones(n) / h], [0, 1], shape=(n, n + 1), format="csc")
+
+
+def av3term(n, alpha=5.0 / 6.0):
+    """PlainNodalLaplacian.jl:62-68 -- three-term average, first and last diagonal entry 1/2 + alpha/2."""
+    t = (1.0 - alpha) / 2.0
+    T = sp.diags([t * np.ones(n - 1), alpha * np.ones(n), t * np.ones(n - 1)], [-1, 0, 1], format="lil")
+    T[0, 0] = 0.5 + alpha / 2.0
+    T[n - 1, n - 1] = 0.5 + alpha / 2.0
+    return T.tocsc()
+
+
+def getNodalSpreadGradients(mesh: RegularMesh, avFunc):
+    """PlainNodalLaplacian.jl:71-104 -> (G, Gs)."""
+    n = mesh.n
+    h = mesh.h
+    eye = lambda k: sp.identity(int(k), format="csc")
+    if mesh.dim == 2:
+        t = ddxCN(int(n[0]), h[0])
+        D1 = sp.kron(eye(n[1] + 1), t)
+        D1s = sp.kron(avFunc(int(n[1] + 1)), t)
+        t = ddxCN(int(n[1]), h[1])
+        D2 = sp.kron(t, eye(n[0] + 1))
+        D2s = sp.kron(t, avFunc(int(n[0] + 1)))
+        return sp.vstack([D1, D2]).tocsc(), sp.vstack([D1s, D2s]).tocsc()
+    a1, a2, a3 = avFunc(int(n[0] + 1)), avFunc(int(n[1] + 1)), avFunc(int(n[2] + 1))
+    I1, I2, I3 = eye(n[0] + 1), eye(n[1] + 1), eye(n[2] + 1)
+    t = ddxCN(int(n[0]), h[0])
+    D1 = sp.kron(I3, sp.kron(I2, t))
+    D1s = 0.5 * (sp.kron(I3, sp.kron(a2, t)) + sp.kron(a3, sp.kron(I2, t)))
+    t = ddxCN(int(n[1]), h[1])
+    D2 = sp.kron(I3, sp.kron(t, I1))
+    D2s = 0.5 * (sp.kron(I3, sp.kron(t, a1)) + sp.kron(a3, sp.kron(t, I1)))
+    t = ddxCN(int(n[2]), h[2])
+    D3 = sp.kron(t, sp.kron(I2, I1))
+    D3s = 0.5 * (sp.kron(t, sp.kron(I2, a1)) + sp.kron(t, sp.kron(a2, I1)))
+    return sp.vstack([D1, D2, D3]).tocsc(), sp.vstack([D1s, D2s, D3s]).tocsc()
+
+
+def getSpreadNodalLaplacianAndMass(mesh: RegularMesh, beta):
+    """PlainNodalLaplacian.jl:106-141 -> (Lap, M).  2-D: beta scalar; 3-D: beta[0] Laplacian, beta[1] mass
+    (a scalar 1 means [1, 1])."""
+    n = mesh.n
+    eye = lambda k: sp.identity(int(k), format="csc")
+    avFunc = lambda k: av3term(k, 0.5)
+    G, Gs = getNodalSpreadGradients(mesh, avFunc)
+    if mesh.dim == 2:
+        b = float(beta)
+        Gs = (1.0 - b) * Gs + b * G
+        Lap = G.T @ Gs
+        M = 0.5 * sp.kron(av3term(int(n[1] + 1), b), eye(n[0] + 1)) + 0.5 * sp.kron(eye(n[1] + 1), av3term(int(n[0] + 1), b))
+        return Lap.tocsc(), M.tocsc()
+    if np.isscalar(beta):
+        if beta != 1:
+            raise ValueError("getSpreadNodalLaplacianAndMass: in 3-D beta is a pair (Laplacian, mass)")
+        beta = [1.0, 1.0]
+    Gs = (1.0 - beta[0]) * Gs + beta[0] * G
+    Lap = G.T @ Gs
+    I1, I2, I3 = eye(n[0] + 1), eye(n[1] + 1), eye(n[2] + 1)
+    M = (1.0 / 3.0) * (sp.kron(I3, sp.kron(av3term(int(n[1] + 1), beta[1]), I1)) +
+                       sp.kron(I3, sp.kron(I2, av3term(int(n[0] + 1), beta[1]))) +
+                       sp.kron(av3term(int(n[2] + 1), beta[1]), sp.kron(I2, I1)))
+    return Lap.tocsc(), M.tocsc()
+
+
+def GetHelmholtzOperatorHO(mesh, mNodal, omega, gamma, NeumannAtFirstDim, Sommerfeld, beta=1.0):
+    """GetHelmholtz.jl:54-72: H = Lap + M * Diagonal(mass), mass as in GetHelmholtzOperator."""
+    Lap, M = getSpreadNodalLaplacianAndMass(mesh, beta)
+    mass = helmholtz_diagonal(mesh, mNodal, omega, gamma, NeumannAtFirstDim, Sommerfeld)
+    return (Lap + M @ sp.diags(mass, 0, format="csc")).tocsc()
+
+
 def getMaximalFrequency(m, mesh):
     """GetHelmholtz.jl:75-79 (m is slowness squared)."""
     return (0.1 * 2 * math.pi) / (np.max(mesh.h) * math.sqrt(np.max(m)))
