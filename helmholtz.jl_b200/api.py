@@ -453,6 +453,8 @@ class ShiftedLaplacianMultigridSolver:
         # drives all slabs; B, X stay whole-grid arrays) or {"mode": "nccl", "rank", "nranks", "unique_id"} (one process
         # per GPU; B, X hold this rank's planes, see slabPlanes)
         self.slabs = None
+        # set when solveLinearSystem is handed a GetHelmholtzOperatorHO operator: [beta_Laplacian, beta_mass]
+        self.operatorHO = None
 
 
 def getShiftedLaplacianMultigridSolver(helmParam, MG, shift, Krylov="BiCGSTAB", inner=5, verbose=False):
@@ -472,6 +474,7 @@ def copySolver(s):
     s2 = getShiftedLaplacianMultigridSolver(s.helmParam, MG2, s.shift, s.Krylov, s.inner, s.verbose)
     s2.devices = s.devices
     s2.slabs = s.slabs
+    s2.operatorHO = s.operatorHO
     return s2
 
 
@@ -490,6 +493,16 @@ def _ensure_hierarchy(param, doTranspose):
         MG._hd.cycle_precision = MG.cyclePrecision
         MG._hd.levels = MG.levels
     hd = MG._hd
+    want_ho = getattr(param, "operatorHO", None)
+    if getattr(hd, "ho_beta", None) != want_ho:
+        # the fine-level operator of the handle: plain 5/7-point operator or GetHelmholtzOperatorHO (hh_set_operator_ho)
+        mm = np.ascontiguousarray(np.asarray(hp.m, dtype=np.float64).ravel(order="F"))
+        gg = np.ascontiguousarray(np.asarray(hp.gamma, dtype=np.float64).ravel(order="F"))
+        bb = np.ascontiguousarray(np.asarray(want_ho if want_ho is not None else [1.0, 1.0], dtype=np.float64))
+        L.check(hd.lib.hh_set_operator_ho(hd.h, int(want_ho is not None), _ptr(mm, C.c_double), _ptr(gg, C.c_double),
+                                          _ptr(bb, C.c_double)), hd.h)
+        hd.ho_beta = want_ho
+        MG._built_for = None
     if (not hd.lib.hh_hierarchy_exists(hd.h)) or MG._built_for != sig:
         # first call (hierarchyExists == false, :50-66), a flipped doTranspose (transposeHierarchy, :68-70) or
         # settings mutated since the last solve (the tests mutate MG.relaxType / MG.cycleType, test :86-87,138-139)
@@ -508,8 +521,13 @@ def solveLinearSystem_(ShiftedHT, B, X, param, doTranspose=0):
         raise TypeError("solveLinearSystem: complex omega is not supported by the shifted-Laplacian solver")
     if param.Krylov not in ("GMRES", "BiCGSTAB"):
         raise ValueError(f"Krylov {param.Krylov!r} is not supported (GMRES, BiCGSTAB)")
-    if isinstance(ShiftedHT, HelmholtzOperator) and abs(ShiftedHT.shift - float(param.shift[0])) > 0:
+    if isinstance(ShiftedHT, (HelmholtzOperator, HelmholtzOperatorHO)) and abs(ShiftedHT.shift - float(param.shift[0])) > 0:
         raise ValueError("the shifted operator passed in does not carry solver.shift[1]")
+    if isinstance(ShiftedHT, HelmholtzOperatorHO):
+        # the reference builds its hierarchy from the matrix it is handed (:65): an HO matrix gives an HO hierarchy
+        if doTranspose:
+            raise NotImplementedError("transposed solves with the high-order operator")
+        param.operatorHO = list(ShiftedHT.beta)
     MG = param.MG
     if param.doClear == 1:
         clear(MG)
@@ -672,3 +690,92 @@ def GetHelmholtzOperatorHOStencil(Msh, mNodal, omega, gamma, NeumannAtFirstDim, 
                                    w.real, w.imag, int(bool(NeumannAtFirstDim)), int(bool(Sommerfeld)), _ptr(bb, C.c_double),
                                    _ptr(coef.view(np.float64), C.c_double)), None)
     return coef
+
+
+class HelmholtzOperatorHO:
+    """What GetHelmholtzOperatorHO returns (src/GetHelmholtz.jl:54-72), kept as the stored stencil: `H @ x` on the
+    host (numpy, for checks), `H + GetHelmholtzShiftOP(...)`, `H.H`.  Passing it (or its adjoint view, as the reference's
+    callers do) to solveLinearSystem makes the solver run on this operator: hierarchy = Galerkin hierarchy of the
+    shifted operator, Krylov operator = H (hh_set_operator_ho)."""
+
+    def __init__(self, Msh, mNodal, omega, gamma, NeumannAtFirstDim, Sommerfeld, beta, shift=0.0, adjoint=False, coef=None):
+        self.Mesh, self.m, self.omega, self.gamma = Msh, np.asarray(mNodal, dtype=np.float64), omega, np.asarray(gamma, dtype=np.float64)
+        self.NeumannOnTop, self.Sommerfeld = bool(NeumannAtFirstDim), bool(Sommerfeld)
+        dim = int(Msh.dim)
+        if np.isscalar(beta):
+            if dim == 3 and beta != 1:
+                raise ValueError("getSpreadNodalLaplacianAndMass: in 3-D beta is a pair (Laplacian, mass)")
+            beta = [float(beta), float(beta)]
+        self.beta = [float(beta[0]), float(beta[1] if dim == 3 else beta[0])]
+        self.shift = float(shift)
+        self.adjoint = bool(adjoint)
+        self.nodes = np.asarray(Msh.n, dtype=np.int64) + 1
+        N = int(np.prod(self.nodes))
+        self.shape = (N, N)
+        self.dtype = np.dtype(np.complex128)
+        self._coef = coef
+
+    def __add__(self, other):
+        if isinstance(other, HelmholtzShiftOP):
+            return HelmholtzOperatorHO(self.Mesh, self.m, self.omega, self.gamma, self.NeumannOnTop, self.Sommerfeld, self.beta,
+                                       self.shift + other.shift, self.adjoint, self._coef)
+        return NotImplemented
+
+    __radd__ = __add__
+
+    @property
+    def H(self):
+        return HelmholtzOperatorHO(self.Mesh, self.m, self.omega, self.gamma, self.NeumannOnTop, self.Sommerfeld, self.beta,
+                                   self.shift, not self.adjoint, self._coef)
+
+    def stencil(self):
+        """coef[s, node] of the (shifted) operator, ComplexF64."""
+        if self._coef is None:
+            self._coef = GetHelmholtzOperatorHOStencil(self.Mesh, self.m, self.omega, self.gamma, self.NeumannOnTop,
+                                                       self.Sommerfeld, self.beta if int(self.Mesh.dim) == 3 else self.beta[0])
+        coef = self._coef
+        if self.shift != 0.0:
+            coef = coef.copy()
+            coef[coef.shape[0] // 2] += 1j * self.shift * float(np.real(self.omega)) ** 2 * self.m.ravel(order="F")
+        return coef
+
+    def matvec(self, x):
+        """y = H x (or H^H x for the adjoint view) on the host from the stored stencil."""
+        coef = self.stencil()
+        nd = [int(v) for v in self.nodes]
+        dim = len(nd)
+        X = np.asarray(x, dtype=np.complex128)
+        vec = X.ndim == 1
+        X = X.reshape((int(np.prod(nd)), -1), order="F")
+        k = X.shape[1]
+        Xg = X.reshape(nd + [k], order="F")
+        Y = np.zeros_like(Xg)
+        for s_ in range(coef.shape[0]):
+            off = [s_ % 3 - 1, (s_ // 3) % 3 - 1] + ([s_ // 9 - 1] if dim == 3 else [])
+            cg = coef[s_].reshape(nd, order="F")[..., None]
+            src = tuple(slice(max(0, o), nd[d] + min(0, o)) for d, o in enumerate(off))    # nodes p + off
+            dst = tuple(slice(max(0, -o), nd[d] + min(0, -o)) for d, o in enumerate(off))  # nodes p
+            if self.adjoint:   # (H^H x)_q = sum_p conj(H[p, q]) x_p with q = p + off
+                Y[src] += np.conj(cg[dst]) * Xg[dst]
+            else:              # (H x)_p = sum_off coef[off][p] x_{p+off}
+                Y[dst] += cg[dst] * Xg[src]
+        Y = Y.reshape(X.shape, order="F")
+        return Y[:, 0] if vec else Y
+
+    __matmul__ = matvec
+    __mul__ = matvec
+
+
+def GetHelmholtzOperatorHO(*args):
+    """src/GetHelmholtz.jl:18-20 and 54-72:
+      GetHelmholtzOperatorHO(Hparam[, beta])                                                   -> H
+      GetHelmholtzOperatorHO(Msh, m, omega, gamma, NeumannAtFirstDim, Sommerfeld[, beta])      -> H"""
+    if isinstance(args[0], HelmholtzParam):
+        hp = args[0]
+        beta = args[1] if len(args) > 1 else 1.0
+        return HelmholtzOperatorHO(hp.Mesh, np.asarray(hp.m).reshape(tuple(np.asarray(hp.Mesh.n) + 1), order="F"), hp.omega,
+                                   np.asarray(hp.gamma).reshape(tuple(np.asarray(hp.Mesh.n) + 1), order="F"), hp.NeumannOnTop,
+                                   hp.Sommerfeld, beta)
+    Msh, m, omega, gamma, neumann, somm = args[:6]
+    beta = args[6] if len(args) > 6 else 1.0
+    return HelmholtzOperatorHO(Msh, m, omega, gamma, neumann, somm, beta)

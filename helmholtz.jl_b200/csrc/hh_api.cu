@@ -296,84 +296,8 @@ static void add_replica(hh_handle_s* h, const Problem& pb, int precision, int de
 extern "C" int hh_ho_stencil(int dim, const int64_t* n_nodes, const double* hsp, const double* m, const double* gamma,
                              double wre, double wim, int neumann_on_top, int sommerfeld, const double* beta, double* coef_out) {
     return guarded(nullptr, [&]() -> int {
-        HH_REQUIRE((dim == 2 || dim == 3) && n_nodes && hsp && m && gamma && beta && coef_out, HH_ERR_ARG, "hh_ho_stencil: bad arguments");
-        HH_REQUIRE(wre != 0.0, HH_ERR_ARG, "hh_ho_stencil: Re(omega) must be non-zero");
-        int64_t n[3] = {1, 1, 1};
-        for (int d = 0; d < dim; ++d) {
-            HH_REQUIRE(n_nodes[d] >= 2 && hsp[d] > 0.0, HH_ERR_ARG, "hh_ho_stencil: node counts must be >= 2, spacings positive");
-            n[d] = n_nodes[d];
-        }
-        const int64_t N = n[0] * n[1] * n[2];
-        const double bl = beta[0], bm = dim == 3 ? beta[1] : beta[0];
-        // 1-D tridiagonal tables, entry [i][o+1] couples node i with node i+o
-        auto tri = [&](int d, double diag_in, double diag_end, double off) {
-            std::vector<std::array<double, 3>> t((size_t)n[d]);
-            for (int64_t i = 0; i < n[d]; ++i) {
-                const bool end = (i == 0 || i == n[d] - 1);
-                t[i][1] = end ? diag_end : diag_in;
-                t[i][0] = i > 0 ? off : 0.0;
-                t[i][2] = i < n[d] - 1 ? off : 0.0;
-            }
-            return t;
-        };
-        std::vector<std::array<double, 3>> T[3], A[3], B[3];
-        for (int d = 0; d < dim; ++d) {
-            const double ih2 = 1.0 / (hsp[d] * hsp[d]);
-            T[d] = tri(d, 2.0 * ih2, ih2, -ih2);                      // ddxCN' * ddxCN
-            A[d] = tri(d, 0.5, 0.75, 0.25);                           // av3term(n, 1/2)
-            B[d] = tri(d, bm, 0.5 + 0.5 * bm, 0.5 * (1.0 - bm));      // av3term(n, beta_mass)
-        }
-        // mass = -w^2 m (1 - i gamma / Re w) - Sommerfeld   (GetHelmholtz.jl:62-68; getSommerfeldBC :222-247, BC = 2)
-        const double w2r = wre * wre - wim * wim, w2i = 2.0 * wre * wim;
-        std::vector<double> mr((size_t)N), mi((size_t)N);
-        for (int64_t k = 0; k < n[2]; ++k)
-            for (int64_t j = 0; j < n[1]; ++j)
-                for (int64_t i = 0; i < n[0]; ++i) {
-                    const int64_t p = i + n[0] * (j + n[1] * k);
-                    const double g = gamma[p] / wre;
-                    double re = -m[p] * (w2r + w2i * g), im = -m[p] * (w2i - w2r * g);
-                    if (sommerfeld) {
-                        double sf = 0.0;
-                        const int64_t idx[3] = {i, j, k};
-                        for (int d = 0; d < dim; ++d) {
-                            const bool first = idx[d] == 0, last = idx[d] == n[d] - 1;
-                            const bool top = (d == dim - 1) && neumann_on_top;
-                            if ((first && !top) || last) sf += 2.0 / hsp[d];
-                        }
-                        im += wre * sf * std::sqrt(m[p]);
-                    }
-                    mr[p] = re;
-                    mi[p] = im;
-                }
-        const int NS = dim == 3 ? 27 : 9;
-        std::fill(coef_out, coef_out + (size_t)2 * NS * N, 0.0);
-        for (int64_t k = 0; k < n[2]; ++k)
-            for (int64_t j = 0; j < n[1]; ++j)
-                for (int64_t i = 0; i < n[0]; ++i) {
-                    const int64_t p = i + n[0] * (j + n[1] * k);
-                    for (int dk = (dim == 3 ? -1 : 0); dk <= (dim == 3 ? 1 : 0); ++dk)
-                        for (int dj = -1; dj <= 1; ++dj)
-                            for (int di = -1; di <= 1; ++di) {
-                                if (i + di < 0 || i + di >= n[0] || j + dj < 0 || j + dj >= n[1] || k + dk < 0 || k + dk >= n[2]) continue;
-                                const double I0 = di == 0, J0 = dj == 0, K0 = dk == 0;  // Kronecker deltas
-                                double lap, mm;
-                                if (dim == 2) {
-                                    lap = T[0][i][di + 1] * ((1.0 - bl) * A[1][j][dj + 1] + bl * J0) +
-                                          T[1][j][dj + 1] * ((1.0 - bl) * A[0][i][di + 1] + bl * I0);
-                                    mm = 0.5 * (B[1][j][dj + 1] * I0 + B[0][i][di + 1] * J0);
-                                } else {
-                                    const double a0 = A[0][i][di + 1], a1 = A[1][j][dj + 1], a2 = A[2][k][dk + 1];
-                                    lap = T[0][i][di + 1] * (bl * J0 * K0 + 0.5 * (1.0 - bl) * (a1 * K0 + J0 * a2)) +
-                                          T[1][j][dj + 1] * (bl * I0 * K0 + 0.5 * (1.0 - bl) * (a0 * K0 + I0 * a2)) +
-                                          T[2][k][dk + 1] * (bl * I0 * J0 + 0.5 * (1.0 - bl) * (a0 * J0 + I0 * a1));
-                                    mm = (1.0 / 3.0) * (B[1][j][dj + 1] * I0 * K0 + B[0][i][di + 1] * J0 * K0 + B[2][k][dk + 1] * I0 * J0);
-                                }
-                                const int64_t q = p + di + n[0] * (dj + n[1] * (int64_t)dk);  // column node: M * Diagonal(mass)
-                                const int s = (di + 1) + 3 * (dj + 1) + (dim == 3 ? 9 * (dk + 1) : 0);
-                                coef_out[2 * ((int64_t)s * N + p)] = lap + mm * mr[q];
-                                coef_out[2 * ((int64_t)s * N + p) + 1] = mm * mi[q];
-                            }
-                }
+        HH_REQUIRE(n_nodes && hsp && m && gamma && beta && coef_out, HH_ERR_ARG, "hh_ho_stencil: bad arguments");
+        build_ho_stencil(dim, n_nodes, hsp, m, gamma, wre, wim, neumann_on_top, sommerfeld, beta, coef_out);
         return HH_OK;
     });
 }
@@ -571,9 +495,41 @@ int hh_update_model(hh_handle_t h, const double* m, const double* gamma, double 
             const int64_t off = h->slab_mode ? ((int64_t)h->subs[i]->sgeo[0].koff - h->model_plane0) * h->pb.n[0] * h->pb.n[1] : 0;
             h->subs[i]->set_model(m + off, gamma + off, omega_re, omega_im);
             if (!h->lows.empty()) h->lows[i]->set_model(m + off, gamma + off, omega_re, omega_im);
+            for (SolverBase* sb : {h->subs[i].get(), h->lows.empty() ? (SolverBase*)nullptr : h->lows[i].get()})
+                if (sb && sb->ho) {  // the high-order stencil is rebuilt from these at the next hh_setup
+                    sb->ho_m.assign(m, m + h->pb.N());
+                    sb->ho_g.assign(gamma, gamma + h->pb.N());
+                }
         });
         h->pb.w_re = omega_re;
         h->pb.w_im = omega_im;
+        return HH_OK;
+    });
+}
+
+// GetHelmholtzOperatorHO as the operator of this handle (enable != 0) or back to the plain operator.  m and gamma are
+// the arrays hh_create was given (the library keeps Float64 host copies for the stencil construction at hh_setup).
+int hh_set_operator_ho(hh_handle_t h, int enable, const double* m, const double* gamma, const double* beta) {
+    if (!h) return HH_ERR_ARG;
+    return guarded(h, [&]() -> int {
+        HH_REQUIRE(h->slab_mode == 0, HH_ERR_UNSUPPORTED, "the high-order operator is not available on a slab handle");
+        HH_REQUIRE(!enable || (m && gamma && beta), HH_ERR_ARG, "hh_set_operator_ho: NULL array");
+        const int64_t N = h->pb.N();
+        for (auto* v : {&h->subs, &h->lows})
+            for (auto& sb : *v) {
+                HH_CUDA(cudaSetDevice(sb->device));
+                sb->clear();
+                sb->ho = enable != 0;
+                if (enable) {
+                    sb->ho_m.assign(m, m + N);
+                    sb->ho_g.assign(gamma, gamma + N);
+                    sb->ho_beta[0] = beta[0];
+                    sb->ho_beta[1] = h->pb.dim == 3 ? beta[1] : beta[0];
+                } else {
+                    sb->ho_m.clear();
+                    sb->ho_g.clear();
+                }
+            }
         return HH_OK;
     });
 }

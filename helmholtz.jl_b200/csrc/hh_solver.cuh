@@ -5,6 +5,7 @@
 // algorithms.
 #pragma once
 #include <algorithm>
+#include <array>
 #include <chrono>
 #include <cmath>
 #include <cstdio>
@@ -38,6 +39,91 @@ struct Error : std::runtime_error {
     do {                                                 \
         if (!(cond)) throw hh::Error((code), (msg));     \
     } while (0)
+
+// GetHelmholtzOperatorHO as a stored stencil, host side (see hh_ho_stencil in include/helmholtz_b200.h and the
+// derivation above its definition in hh_api.cu): coef_out[2*(s*N + node) + {0,1}], Float64.
+inline void build_ho_stencil(int dim, const int64_t* n_nodes, const double* hsp, const double* m, const double* gamma,
+                             double wre, double wim, int neumann_on_top, int sommerfeld, const double* beta,
+                             double* coef_out) {
+        HH_REQUIRE(dim == 2 || dim == 3, HH_ERR_ARG, "hh_ho_stencil: dim must be 2 or 3");
+        HH_REQUIRE(wre != 0.0, HH_ERR_ARG, "hh_ho_stencil: Re(omega) must be non-zero");
+        int64_t n[3] = {1, 1, 1};
+        for (int d = 0; d < dim; ++d) {
+            HH_REQUIRE(n_nodes[d] >= 2 && hsp[d] > 0.0, HH_ERR_ARG, "hh_ho_stencil: node counts must be >= 2, spacings positive");
+            n[d] = n_nodes[d];
+        }
+        const int64_t N = n[0] * n[1] * n[2];
+        const double bl = beta[0], bm = dim == 3 ? beta[1] : beta[0];
+        // 1-D tridiagonal tables, entry [i][o+1] couples node i with node i+o
+        auto tri = [&](int d, double diag_in, double diag_end, double off) {
+            std::vector<std::array<double, 3>> t((size_t)n[d]);
+            for (int64_t i = 0; i < n[d]; ++i) {
+                const bool end = (i == 0 || i == n[d] - 1);
+                t[i][1] = end ? diag_end : diag_in;
+                t[i][0] = i > 0 ? off : 0.0;
+                t[i][2] = i < n[d] - 1 ? off : 0.0;
+            }
+            return t;
+        };
+        std::vector<std::array<double, 3>> T[3], A[3], B[3];
+        for (int d = 0; d < dim; ++d) {
+            const double ih2 = 1.0 / (hsp[d] * hsp[d]);
+            T[d] = tri(d, 2.0 * ih2, ih2, -ih2);                      // ddxCN' * ddxCN
+            A[d] = tri(d, 0.5, 0.75, 0.25);                           // av3term(n, 1/2)
+            B[d] = tri(d, bm, 0.5 + 0.5 * bm, 0.5 * (1.0 - bm));      // av3term(n, beta_mass)
+        }
+        // mass = -w^2 m (1 - i gamma / Re w) - Sommerfeld   (GetHelmholtz.jl:62-68; getSommerfeldBC :222-247, BC = 2)
+        const double w2r = wre * wre - wim * wim, w2i = 2.0 * wre * wim;
+        std::vector<double> mr((size_t)N), mi((size_t)N);
+        for (int64_t k = 0; k < n[2]; ++k)
+            for (int64_t j = 0; j < n[1]; ++j)
+                for (int64_t i = 0; i < n[0]; ++i) {
+                    const int64_t p = i + n[0] * (j + n[1] * k);
+                    const double g = gamma[p] / wre;
+                    double re = -m[p] * (w2r + w2i * g), im = -m[p] * (w2i - w2r * g);
+                    if (sommerfeld) {
+                        double sf = 0.0;
+                        const int64_t idx[3] = {i, j, k};
+                        for (int d = 0; d < dim; ++d) {
+                            const bool first = idx[d] == 0, last = idx[d] == n[d] - 1;
+                            const bool top = (d == dim - 1) && neumann_on_top;
+                            if ((first && !top) || last) sf += 2.0 / hsp[d];
+                        }
+                        im += wre * sf * std::sqrt(m[p]);
+                    }
+                    mr[p] = re;
+                    mi[p] = im;
+                }
+        const int NS = dim == 3 ? 27 : 9;
+        std::fill(coef_out, coef_out + (size_t)2 * NS * N, 0.0);
+        for (int64_t k = 0; k < n[2]; ++k)
+            for (int64_t j = 0; j < n[1]; ++j)
+                for (int64_t i = 0; i < n[0]; ++i) {
+                    const int64_t p = i + n[0] * (j + n[1] * k);
+                    for (int dk = (dim == 3 ? -1 : 0); dk <= (dim == 3 ? 1 : 0); ++dk)
+                        for (int dj = -1; dj <= 1; ++dj)
+                            for (int di = -1; di <= 1; ++di) {
+                                if (i + di < 0 || i + di >= n[0] || j + dj < 0 || j + dj >= n[1] || k + dk < 0 || k + dk >= n[2]) continue;
+                                const double I0 = di == 0, J0 = dj == 0, K0 = dk == 0;  // Kronecker deltas
+                                double lap, mm;
+                                if (dim == 2) {
+                                    lap = T[0][i][di + 1] * ((1.0 - bl) * A[1][j][dj + 1] + bl * J0) +
+                                          T[1][j][dj + 1] * ((1.0 - bl) * A[0][i][di + 1] + bl * I0);
+                                    mm = 0.5 * (B[1][j][dj + 1] * I0 + B[0][i][di + 1] * J0);
+                                } else {
+                                    const double a0 = A[0][i][di + 1], a1 = A[1][j][dj + 1], a2 = A[2][k][dk + 1];
+                                    lap = T[0][i][di + 1] * (bl * J0 * K0 + 0.5 * (1.0 - bl) * (a1 * K0 + J0 * a2)) +
+                                          T[1][j][dj + 1] * (bl * I0 * K0 + 0.5 * (1.0 - bl) * (a0 * K0 + I0 * a2)) +
+                                          T[2][k][dk + 1] * (bl * I0 * J0 + 0.5 * (1.0 - bl) * (a0 * J0 + I0 * a1));
+                                    mm = (1.0 / 3.0) * (B[1][j][dj + 1] * I0 * K0 + B[0][i][di + 1] * J0 * K0 + B[2][k][dk + 1] * I0 * J0);
+                                }
+                                const int64_t q = p + di + n[0] * (dj + n[1] * (int64_t)dk);  // column node: M * Diagonal(mass)
+                                const int s = (di + 1) + 3 * (dj + 1) + (dim == 3 ? 9 * (dk + 1) : 0);
+                                coef_out[2 * ((int64_t)s * N + p)] = lap + mm * mr[q];
+                                coef_out[2 * ((int64_t)s * N + p) + 1] = mm * mi[q];
+                            }
+                }
+}
 
 }  // namespace hh
 #include "hh_slab.cuh"
@@ -228,6 +314,12 @@ struct SolverBase {
     // (B, X of hh_solve_device) hold the owned planes only.
     std::shared_ptr<SlabTransport> slab;
     std::vector<SlabLevel> sgeo;
+    // High-order / spread operator (GetHelmholtzOperatorHO, src/GetHelmholtz.jl:54-72): when set, the fine level is a
+    // stored 3^dim-point stencil built on the host (build_ho_stencil) from these Float64 copies of m and gamma, and
+    // every fine-level operation runs through the stored-stencil kernels of the coarse levels.
+    bool ho = false;
+    double ho_beta[2] = {1.0, 1.0};
+    std::vector<double> ho_m, ho_g;
     int64_t caller_N() const {
         return slab ? (int64_t)pb.n[0] * pb.n[1] * (sgeo[0].own1 - sgeo[0].own0) : pb.N();
     }
@@ -686,7 +778,7 @@ class Solver : public SolverBase {
         k_fine3d_tma_first<T, SECOND, KB, NS><<<g, 256, smem, stream>>>(op, mb, md, mc, b, out, out2, ld, nrhs, zchunk, groups);
     }
     bool can_fuse_first(const FineOp<T>& op, const C* b, int64_t ld) const {
-        return op.cdiag != nullptr && op.dinv != nullptr && tma_ok(op, ld) && ((uintptr_t)b % 16 == 0) && fuse_first;
+        return !ho && op.cdiag != nullptr && op.dinv != nullptr && tma_ok(op, ld) && ((uintptr_t)b % 16 == 0) && fuse_first;
     }
     // second == 0: out = x1, out2 = b - A x1;  second == 1: out = x2
     void fine_first(int second, const FineOp<T>& op0, const C* b, C* out, C* out2, int64_t ld, int nrhs) {
@@ -734,7 +826,7 @@ class Solver : public SolverBase {
         k_fine3d_tma_pro<T, KB, NS><<<g, 256, smem, stream>>>(op, mx, mb, mc, md, mxc, x, xc, out, ld, Cc.N, Cc.p0, Cc.n[1], nrhs, zchunk, groups);
     }
     bool can_fuse_prolong(const FineOp<T>& op, const C* x, const C* b, const Level& Cc, const C* xc, int64_t ld) const {
-        return fuse_first && op.cdiag != nullptr && op.dinv != nullptr && tma_ok(op, ld) && tma_ok_level(Cc) &&
+        return !ho && fuse_first && op.cdiag != nullptr && op.dinv != nullptr && tma_ok(op, ld) && tma_ok_level(Cc) &&
                ((uintptr_t)x % 16 == 0) && ((uintptr_t)b % 16 == 0) && ((uintptr_t)xc % 16 == 0);
     }
     void fine_prolong_jacobi(const FineOp<T>& op0, const C* x, const C* b, const Level& Cc, const C* xc, C* out, int64_t ld, int nrhs) {
@@ -847,7 +939,8 @@ class Solver : public SolverBase {
         return op;
     }
     void coarse_stencil(int mode, const Level& L, const C* x, const C* b, C* out, int nrhs) {
-        with_halos({{(int)(&L - levels.data()), x, 0}}, nrhs, L.zb, L.ze, [&](int z0, int z1) {
+        const int li = slab ? (int)(&L - levels.data()) : 0;
+        with_halos({{li, x, 0}}, nrhs, L.zb, L.ze, [&](int z0, int z1) {
             rz_b = z0;  // the launchers below read the plane range through zbeg / zend
             rz_e = z1;
             coarse_stencil_range(mode, L, x, b, out, nrhs);
@@ -986,6 +1079,7 @@ class Solver : public SolverBase {
 
     // ------------------------------------------------------------------ hierarchy (MGsetup)
     void clear() override {
+        hoH.coef.release();
         levels.clear();
         have_hierarchy = false;
         inv_dense.release();
@@ -997,6 +1091,57 @@ class Solver : public SolverBase {
     void level_nodes(int level, int64_t* out) const override {
         HH_REQUIRE(have_hierarchy && level >= 0 && level < (int)levels.size(), HH_ERR_ARG, "bad level");
         for (int d = 0; d < pb.dim; ++d) out[d] = levels[level].n[d];
+    }
+
+    // HO mode: host-built stencils -> device.  hoH gets the un-shifted operator (always: it is the Krylov operator);
+    // levels[0] gets the shifted one and damp/diag unless this solver only runs the Krylov method (mixed precision).
+    void build_ho_levels(const hh_mg_options& o) {
+        const int NS = pb.dim == 3 ? 27 : 9, center = pb.dim == 3 ? 13 : 4;
+        const int64_t Nd = pb.N();  // dense node count of the host stencil
+        HH_REQUIRE((int64_t)ho_m.size() == Nd && (int64_t)ho_g.size() == Nd, HH_ERR_STATE, "high-order operator: no model");
+        int64_t nn[3] = {pb.n[0], pb.n[1], pb.n[2]};
+        std::vector<double> host((size_t)2 * NS * Nd);
+        build_ho_stencil(pb.dim, nn, pb.h, ho_m.data(), ho_g.data(), pb.w_re, pb.w_im, pb.neumann_top, pb.sommerfeld, ho_beta,
+                         host.data());
+        const Level& L0 = levels[0];
+        auto upload = [&](DevBuf<C>& dst) {  // host Float64 dense -> device precision T in the level's row pitch
+            std::vector<C> tmp((size_t)NS * Nd);
+            for (size_t e = 0; e < tmp.size(); ++e) tmp[e] = mk<T>((T)host[2 * e], (T)host[2 * e + 1]);
+            dst.alloc((size_t)NS * L0.N);
+            if (L0.N == Nd) {
+                HH_CUDA(cudaMemcpyAsync(dst.p, tmp.data(), tmp.size() * sizeof(C), cudaMemcpyHostToDevice, stream));
+                HH_CUDA(cudaStreamSynchronize(stream));
+                return;
+            }
+            DevBuf<C> dense;
+            dense.alloc(tmp.size());
+            HH_CUDA(cudaMemcpyAsync(dense.p, tmp.data(), tmp.size() * sizeof(C), cudaMemcpyHostToDevice, stream));
+            HH_CUDA(cudaMemsetAsync(dst.p, 0, (size_t)NS * L0.N * sizeof(C), stream));  // ghost columns stay zero
+            const int64_t rows = (int64_t)pb.n[1] * pb.n[2];
+            launch(T_SETUP, 0, [&] {  // the NS coefficient arrays are repitched like NS right-hand sides
+                k_repitch<C><<<dim3(148, NS), 256, 0, stream>>>(dense.p, dst.p, pb.n[0], rows, pb.n[0], L0.p0, Nd, L0.N);
+            });
+            HH_CUDA(cudaStreamSynchronize(stream));
+        };
+        for (int d = 0; d < 3; ++d) hoH.n[d] = L0.n[d];
+        hoH.p0 = L0.p0;
+        hoH.N = L0.N;
+        hoH.Nlog = L0.Nlog;
+        hoH.zb = L0.zb;
+        hoH.ze = L0.ze;
+        hoH.koff = L0.koff;
+        hoH.n2g = L0.n2g;
+        upload(hoH.coef);
+        if (krylov_only) return;
+        // shifted operator of the hierarchy: + i shift Re(w)^2 m on the diagonal (GetHelmholtzShiftOP, GetHelmholtz.jl:81-83)
+        const double sw2 = o.shift[0] * pb.w_re * pb.w_re;
+        for (int64_t p = 0; p < Nd; ++p) host[2 * ((int64_t)center * Nd + p) + 1] += sw2 * ho_m[p];
+        Level& Lm = levels[0];
+        upload(Lm.coef);
+        Lm.dinv.alloc(Lm.N);
+        launch(T_SETUP, 0, [&] {
+            k_coarse_dinv<T><<<(unsigned)((Lm.N + 255) / 256), 256, 0, stream>>>(Lm.coef.p + (int64_t)center * Lm.N, Lm.dinv.p, Lm.N, (T)o.relax_param);
+        });
     }
 
     void set_level_planes(int l) {
@@ -1037,6 +1182,11 @@ class Solver : public SolverBase {
         levels[0].N = fineN();
         levels[0].Nlog = pb.N();
         set_level_planes(0);
+        if (ho) {
+            HH_REQUIRE(!slab, HH_ERR_UNSUPPORTED, "the high-order operator is not available on a slab handle");
+            HH_REQUIRE(!o.do_transpose, HH_ERR_UNSUPPORTED, "the high-order operator has no transposed solve yet");
+            build_ho_levels(o);
+        }
         if (krylov_only) {  // the cycle lives in another solver (prec_hook): only the fine-level geometry is needed
             have_hierarchy = true;
             setup_seconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
@@ -1063,7 +1213,9 @@ class Solver : public SolverBase {
             levels[l].N = (int64_t)levels[l].p0 * levels[l].n[1] * levels[l].n[2];
         }
         mg_fine = fine_op(o.shift[0], o.do_transpose, true);
-        if (o.levels > 1) precompute_diag(mg_fine, mg_cdiag, &mg_dinv, (T)o.relax_param);
+        // (HO mode: no matrix-free diagonal arrays, so the fused matrix-free kernels stay off and level 0 takes the
+        // generic stored-stencil path)
+        if (o.levels > 1 && !ho) precompute_diag(mg_fine, mg_cdiag, &mg_dinv, (T)o.relax_param);
         const int NS = pb.dim == 3 ? 27 : 9;
         const int center = pb.dim == 3 ? 13 : 4;
         for (int l = 1; l < o.levels; ++l) {
@@ -1076,7 +1228,7 @@ class Solver : public SolverBase {
             const unsigned nb = (unsigned)((tot + 127) / 128);
             if (slab && l >= 2) halo_exchange(l - 1, Lf.coef.p, NS, 0, HALO_LOWER);  // rows of the fine plane just below the slab
             launch(T_SETUP, 0, [&] {
-                if (l == 1) {
+                if (l == 1 && !ho) {
                     if (pb.dim == 3) {
                         FineCoef<T, 3> A{mg_fine};
                         k_galerkin<T, 3, FineCoef<T, 3>><<<nb, 128, 0, stream>>>(A, Lf.n[0], Lf.n[1], Lf.n[2], Lc.n[0], Lc.n[1], Lc.n[2], Lc.p0, Lc.N, Lc.coef.p,
@@ -1100,7 +1252,7 @@ class Solver : public SolverBase {
                 k_coarse_dinv<T><<<(unsigned)((Lc.N + 255) / 256), 256, 0, stream>>>(Lc.coef.p + (int64_t)center * Lc.N, Lc.dinv.p, Lc.N, (T)o.relax_param);
             });
         }
-        if (o.relax_type == HH_RELAX_JAC_GMRES || (o.levels == 1 && o.coarse_type == HH_COARSE_GMRES)) {
+        if (!ho && (o.relax_type == HH_RELAX_JAC_GMRES || (o.levels == 1 && o.coarse_type == HH_COARSE_GMRES))) {
             Level& L0 = levels[0];
             L0.dinv.alloc(L0.N);
             HH_CUDA(cudaMemsetAsync(L0.dinv.p, 0, (size_t)L0.N * sizeof(C), stream));
@@ -1154,7 +1306,7 @@ class Solver : public SolverBase {
     }
 
     void get_level_stencil(int level, void* out) override {
-        HH_REQUIRE(have_hierarchy && level >= 1 && level < (int)levels.size(), HH_ERR_ARG, "bad level");
+        HH_REQUIRE(have_hierarchy && level >= (ho && !krylov_only ? 0 : 1) && level < (int)levels.size(), HH_ERR_ARG, "bad level");
         HH_CUDA(cudaSetDevice(device));
         HH_CUDA(cudaStreamSynchronize(stream));
         const Level& L = levels[level];
@@ -1267,11 +1419,13 @@ class Solver : public SolverBase {
 
     // ------------------------------------------------------------------ generic operator access per level
     void level_apply(int l, int mode, const C* x, const C* b, C* out, int nrhs) {
-        if (l == 0) fine_stencil(mode, mg_fine, x, b, out, levels[0].N, nrhs, (T)opt.relax_param);
+        if (l == 0 && ho) coarse_stencil(mode, levels[0], x, b, out, nrhs);
+        else if (l == 0) fine_stencil(mode, mg_fine, x, b, out, levels[0].N, nrhs, (T)opt.relax_param);
         else coarse_stencil(mode, levels[l], x, b, out, nrhs);
     }
     void level_jacobi0(int l, const C* b, C* out, int nrhs) {
-        if (l == 0) fine_jacobi0(mg_fine, b, out, levels[0].N, nrhs, (T)opt.relax_param);
+        if (l == 0 && ho) diag_scale(T_COARSE_JACOBI0, levels[0].dinv.p, b, out, levels[0].N, nrhs);
+        else if (l == 0) fine_jacobi0(mg_fine, b, out, levels[0].N, nrhs, (T)opt.relax_param);
         else diag_scale(T_COARSE_JACOBI0, levels[l].dinv.p, b, out, levels[l].N, nrhs);
     }
 
@@ -1523,6 +1677,26 @@ class Solver : public SolverBase {
     void apply_device(const void* dX, void* dY, int64_t nrhs, int shifted, double shift, int transpose) override {
         HH_CUDA(cudaSetDevice(device));
         HH_REQUIRE(d_m.p != nullptr, HH_ERR_STATE, "no model set");
+        if (ho) {  // stored stencils exist for the un-shifted operator and for the hierarchy's shift only
+            HH_REQUIRE(have_hierarchy, HH_ERR_STATE, "high-order operator: hh_apply needs hh_setup first");
+            HH_REQUIRE(!transpose, HH_ERR_UNSUPPORTED, "high-order operator: transposed apply is not available");
+            HH_REQUIRE(!shifted || shift == 0.0 || (!krylov_only && shift == opt.shift[0]), HH_ERR_UNSUPPORTED,
+                       "high-order operator: hh_apply supports shift 0 and the shift given to hh_setup");
+            const Level& Lop = (shifted && shift != 0.0) ? levels[0] : hoH;
+            if (!padded()) {
+                coarse_stencil(MODE_APPLY, Lop, (const C*)dX, nullptr, (C*)dY, (int)nrhs);
+                HH_CUDA(cudaStreamSynchronize(stream));
+                return;
+            }
+            DevBuf<C> xi, yi;
+            alloc_zero(xi, (size_t)levels[0].N * nrhs);
+            alloc_zero(yi, (size_t)levels[0].N * nrhs);
+            repitch((const C*)dX, xi.p, (int)nrhs, true);
+            coarse_stencil(MODE_APPLY, Lop, xi.p, nullptr, yi.p, (int)nrhs);
+            repitch(yi.p, (C*)dY, (int)nrhs, false);
+            HH_CUDA(cudaStreamSynchronize(stream));
+            return;
+        }
         if (slab) {  // caller blocks hold the owned planes: go through blocks with halo planes
             HH_REQUIRE(have_hierarchy, HH_ERR_STATE, "slab decomposition: hh_apply needs hh_setup first");
             FineOp<T> op = fine_op(shifted ? shift : 0.0, transpose, true);
@@ -1563,6 +1737,12 @@ class Solver : public SolverBase {
         d_one.alloc(1);
         zc one = mk<double>(1.0, 0.0);
         HH_CUDA(cudaMemcpy(d_one.p, &one, sizeof(zc), cudaMemcpyHostToDevice));
+    }
+
+    // the un-shifted operator of the outer Krylov method: matrix-free 5/7-point stencil, or the stored HO stencil
+    void krylov_apply(int mode, const FineOp<T>& Hop, const C* x, const C* b, C* out, int64_t N, int nrhs) {
+        if (ho) coarse_stencil(mode, hoH, x, b, out, nrhs);
+        else fine_stencil(mode, Hop, x, b, out, N, nrhs, T(0));
     }
 
     // ------------------------------------------------------------------ outer Krylov
@@ -1663,7 +1843,7 @@ class Solver : public SolverBase {
         for (int cyc = 0; cyc < o.max_iter && !all_done; ++cyc) {
             for (int j = 0; j < m; ++j) {
                 precondition(V[j], Z[j], nrhs);
-                fine_stencil(MODE_APPLY, Hop, Z[j], nullptr, W[j + 1], N, nrhs, T(0));
+                krylov_apply(MODE_APPLY, Hop, Z[j], nullptr, W[j + 1], N, nrhs);
                 gmres_orthogonalise(outer, V.data(), j, W[j + 1], sp, nrhs, o.rel_tol);
                 all_done = fetch_done(outer.done.p, nrhs);
                 if (all_done) break;
@@ -1678,7 +1858,7 @@ class Solver : public SolverBase {
             if (all_done || cyc + 1 == o.max_iter) break;
             // restart: r = b - H x  (again used unscaled as the first basis vector)
             V[0] = W[0];
-            fine_stencil(MODE_RESID, Hop, X, B, W[0], N, nrhs, T(0));
+            krylov_apply(MODE_RESID, Hop, X, B, W[0], N, nrhs);
             gmres_begin(outer, W[0], sp, nrhs, false, o.rel_tol);
             all_done = fetch_done(outer.done.p, nrhs);
         }
@@ -1750,13 +1930,13 @@ class Solver : public SolverBase {
                 });
             }
             precondition(p, ph, nrhs);
-            fine_stencil(MODE_APPLY, Hop, ph, nullptr, v, N, nrhs, T(0));
+            krylov_apply(MODE_APPLY, Hop, ph, nullptr, v, N, nrhs);
             one[0] = rt;
             scalars(multidot(one, 1, v, sp, nrhs, false, d_partial.p), BICG_ALPHA);
             one[0] = v;  // s = r - alpha v  (in place in r)
             scalars(multiaxpy(one, 1, r, sp, nrhs, bicg.neg_alpha.p, 1, false, true, d_partial.p), BICG_HALF);
             precondition(r, sh, nrhs);
-            fine_stencil(MODE_APPLY, Hop, sh, nullptr, t, N, nrhs, T(0));
+            krylov_apply(MODE_APPLY, Hop, sh, nullptr, t, N, nrhs);
             one[0] = r;  // <s,t> and |t|^2
             scalars(multidot(one, 1, t, sp, nrhs, true, d_partial.p), BICG_OMEGA);
             one[0] = ph;
@@ -1788,6 +1968,7 @@ class Solver : public SolverBase {
     DevBuf<C> kry;
     int kry_cap = 0;
     DevBuf<zc> d_partial, d_one, d_red;
+    Level hoH;  // HO mode: the un-shifted operator H as a stored stencil on the fine grid (the outer Krylov operator)
     cudaStream_t comm_stream = nullptr;  // halo exchanges that overlap the interior planes (with_halos)
     cudaEvent_t ev_ready = nullptr, ev_landed = nullptr;
     bool halo_overlap = false;           // HH_HALO_OVERLAP=1: exchange on a second stream while the interior planes run

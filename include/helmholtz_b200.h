@@ -123,7 +123,7 @@ int hh_get_maximal_frequency(const double* m, int64_t n, int dim, const double* 
  * getSpreadNodalLaplacianAndMass, src/PlainNodalLaplacian.jl:106-141) as a stored stencil: coef_out[s*N + node] complex
  * (re,im) Float64, s = (d1+1)+3(d2+1)(+9(d3+1)) as in hh_get_level_stencil, 9 (2-D) or 27 (3-D) entries per node.
  * beta: 2-D beta[0] (Laplacian and mass); 3-D beta[0] Laplacian, beta[1] mass (the reference's beta == 1 is {1,1}).
- * Host-side set-up; the solver wiring of this operator is not built yet. */
+ * Host-side set-up (no device needed); hh_set_operator_ho runs the solver on this operator. */
 int hh_ho_stencil(int dim, const int64_t* n_nodes, const double* h, const double* m, const double* gamma, double omega_re,
                   double omega_im, int neumann_on_top, int sommerfeld, const double* beta, double* coef_out);
 /* loc2cs: 1-based subscripts -> 1-based linear index */
@@ -184,6 +184,15 @@ int hh_slab_level_stencil(hh_handle_t h, int slab, int level, int64_t* n_local_o
 int hh_set_stream(hh_handle_t h, void* cuda_stream);
 /* new model / frequency on the same grid: invalidates the hierarchy (clear! + new HelmholtzParam) */
 int hh_update_model(hh_handle_t h, const double* m, const double* gamma, double omega_re, double omega_im);
+
+/* GetHelmholtzOperatorHO (src/GetHelmholtz.jl:54-72) as the operator of this handle: the fine level becomes the stored
+ * stencil of hh_ho_stencil (built at hh_setup from Float64 copies of m and gamma, the arrays hh_create was given), the
+ * hierarchy is the Galerkin hierarchy of  H_HO + i*shift*w^2*diag(m)  (the matrix a reference caller passes to
+ * solveLinearSystem, :33,65) and the Krylov operator is H_HO.  enable = 0 returns to the plain operator.  Invalidates
+ * the hierarchy.  hh_apply then needs hh_setup first and supports shift 0 and the hierarchy's shift; transposed
+ * solves and slab handles are not supported with this operator.  hh_get_level_stencil(level 0) returns the shifted
+ * fine stencil. */
+int hh_set_operator_ho(hh_handle_t h, int enable, const double* m, const double* gamma, const double* beta);
 
 /* -------- multigrid hierarchy (MGsetup / clear!) -------- */
 int hh_setup(hh_handle_t h, const hh_mg_options* opts);

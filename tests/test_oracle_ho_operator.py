@@ -74,3 +74,23 @@ def test_library_ho_stencil_rejects_bad_input(pkg):
         pkg.GetHelmholtzOperatorHOStencil(mesh, m, 1.0, 0 * m, True, True, 0.7)   # 3-D needs (beta_Lap, beta_mass)
     with pytest.raises(ValueError):
         pkg.GetHelmholtzOperatorHOStencil(mesh, m[:4], 1.0, 0 * m, True, True, 1.0)
+
+
+@pytest.mark.parametrize("nodes,beta", [((9, 7), 2.0 / 3.0), ((6, 5, 4), [0.7, 0.9])])
+def test_host_operator_object_matches_the_oracle_matrix(pkg, ho, nodes, beta):
+    """GetHelmholtzOperatorHO(...) of the host mirror: H @ x, (H + shift) @ x and the adjoint view from the stored stencil"""
+    mesh, m, w, gamma = _problem(ho, nodes)
+    pmesh = pkg.getRegularMesh(list(mesh.domain), list(mesh.n))
+    H = ho.GetHelmholtzOperatorHO(mesh, m, w, gamma, True, True, beta)
+    SH = H + ho.GetHelmholtzShiftOP(m, w, 0.2)
+    Hp = pkg.GetHelmholtzOperatorHO(pmesh, m, w, gamma, True, True, beta)
+    SHp = Hp + pkg.GetHelmholtzShiftOP(m, w, 0.2)
+    rng = np.random.default_rng(0)
+    x = rng.standard_normal((H.shape[0], 2)) + 1j * rng.standard_normal((H.shape[0], 2))
+    scale = np.abs(H @ x).max()
+    assert np.abs(Hp @ x - H @ x).max() < 1e-13 * scale
+    assert np.abs(SHp @ x - SH @ x).max() < 1e-13 * scale
+    assert np.abs(SHp.H @ x - SH.conj().T @ x).max() < 1e-13 * scale
+    assert np.abs(Hp @ x[:, 0] - H @ x[:, 0]).max() < 1e-13 * scale
+    hp = pkg.HelmholtzParam(pmesh, gamma, m.ravel(order="F"), w, True, True)
+    assert np.abs(pkg.GetHelmholtzOperatorHO(hp, beta) @ x - H @ x).max() < 1e-13 * scale
