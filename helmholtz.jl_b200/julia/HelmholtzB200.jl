@@ -144,6 +144,26 @@ function SlabHandleNCCL(Mesh, m, omega, gamma, NeumannOnTop::Bool, Sommerfeld::B
     return hd
 end
 
+# ---- GetHelmholtzOperatorHO (src/GetHelmholtz.jl:54-72) ----
+# the explicit stencil coef[node, s] (s = offset index), ComplexF64; beta as in getSpreadNodalLaplacianAndMass
+function GetHelmholtzOperatorHOStencil(Mesh, m, omega, gamma, NeumannOnTop::Bool, Sommerfeld::Bool, beta = 1.0)
+    nodes = Int64.(Mesh.n .+ 1)
+    bb = Mesh.dim == 3 ? (beta == 1 ? [1.0, 1.0] : Float64.(beta)) : [Float64(beta), Float64(beta)]
+    coef = zeros(ComplexF64, prod(nodes), 3^Mesh.dim)
+    w = ComplexF64(omega)
+    check(ccall((:hh_ho_stencil, LIB), Cint,
+                (Cint, Ptr{Int64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Cdouble, Cdouble, Cint, Cint, Ptr{Float64}, Ptr{ComplexF64}),
+                Mesh.dim, nodes, Float64.(Mesh.h), vec(Float64.(m)), vec(Float64.(gamma)), real(w), imag(w), NeumannOnTop, Sommerfeld,
+                bb, coef))
+    return coef
+end
+# make GetHelmholtzOperatorHO the operator of a handle (before the first solve / hh_setup); enable = false goes back
+function setOperatorHO!(hd::Handle, m, gamma, beta; enable::Bool = true)
+    bb = length(beta) == 2 ? Float64.(beta) : [Float64(beta), Float64(beta)]
+    check(ccall((:hh_set_operator_ho, LIB), Cint, (Ptr{Cvoid}, Cint, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+                hd.ptr, enable, vec(Float64.(m)), vec(Float64.(gamma)), bb))
+end
+
 # ---- operator objects: matrix-free counterpart of the sparse H (src/GetHelmholtz.jl:33-50) ----
 struct HelmholtzShiftOP
     shift::Float64
