@@ -35,8 +35,8 @@ struct SlabLevel {
 };
 
 // Partition of an n3-plane grid with `levels` multigrid levels over `nranks` slabs.  The coarsest level's cells are
-// split as evenly as possible; finer levels follow by doubling, so that every slab owns the fine planes 2K-? its
-// coarse planes restrict from / interpolate to with a one-plane halo.  Below the owned range a slab keeps
+// split as evenly as possible; finer levels follow by doubling (a slab that owns coarse planes [K0,K1) owns fine planes
+// [2K0,2K1)), so that restriction and interpolation between a slab's own levels need a one-plane halo only.  Below the owned range a slab keeps
 // 2^(levels-1-l) planes on level l (only the top one is exchanged): that keeps local plane 0 of every level at an even
 // global index, i.e. local coarsening "z >> 1" agrees with the global one.  Returns false when a slab would be empty.
 inline bool slab_partition(int n3, int levels, int nranks, int rank, std::vector<SlabLevel>& out) {
