@@ -525,8 +525,6 @@ def solveLinearSystem_(ShiftedHT, B, X, param, doTranspose=0):
         raise ValueError("the shifted operator passed in does not carry solver.shift[1]")
     if isinstance(ShiftedHT, HelmholtzOperatorHO):
         # the reference builds its hierarchy from the matrix it is handed (:65): an HO matrix gives an HO hierarchy
-        if doTranspose:
-            raise NotImplementedError("transposed solves with the high-order operator")
         param.operatorHO = list(ShiftedHT.beta)
     MG = param.MG
     if param.doClear == 1:
@@ -779,3 +777,13 @@ def GetHelmholtzOperatorHO(*args):
     Msh, m, omega, gamma, neumann, somm = args[:6]
     beta = args[6] if len(args) > 6 else 1.0
     return HelmholtzOperatorHO(Msh, m, omega, gamma, neumann, somm, beta)
+
+
+def stencilAdjoint(nodes, coef):
+    """Conjugate transpose of an operator stored as coef[s, node] (hh_stencil_adjoint; host-side)."""
+    nodes = np.ascontiguousarray(np.asarray(nodes, dtype=np.int64))
+    cin = np.ascontiguousarray(np.asarray(coef, dtype=np.complex128))
+    out = np.empty_like(cin)
+    L.check(L.load().hh_stencil_adjoint(len(nodes), _ptr(nodes, C.c_int64), _ptr(cin.view(np.float64), C.c_double),
+                                        _ptr(out.view(np.float64), C.c_double)), None)
+    return out

@@ -302,6 +302,13 @@ extern "C" int hh_ho_stencil(int dim, const int64_t* n_nodes, const double* hsp,
     });
 }
 
+extern "C" int hh_stencil_adjoint(int dim, const int64_t* n_nodes, const double* coef_in, double* coef_out) {
+    return guarded(nullptr, [&]() -> int {
+        adjoint_stencil(dim, n_nodes, coef_in, coef_out);
+        return HH_OK;
+    });
+}
+
 // ---------------------------------------------------------------------------------------------
 // slab_mode 0: `ndev` replicas of the whole grid.  1: `ndev` slabs of one grid inside this process.  2: slab `rank` of
 // `nranks` on devices[0], NCCL communicator from `uid`.

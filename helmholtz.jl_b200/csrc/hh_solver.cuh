@@ -125,6 +125,33 @@ inline void build_ho_stencil(int dim, const int64_t* n_nodes, const double* hsp,
                 }
 }
 
+// Conjugate transpose of an operator stored as a 3^dim-point stencil on a dense column-major grid:
+// (A^H)[p, p+off] = conj(A[p+off, p]) = conj(coef[-off][p+off]).  Host side, Float64 (re,im) pairs.
+inline void adjoint_stencil(int dim, const int64_t* n_nodes, const double* in, double* out) {
+    HH_REQUIRE((dim == 2 || dim == 3) && n_nodes && in && out && in != out, HH_ERR_ARG, "hh_stencil_adjoint: bad arguments");
+    int64_t n[3] = {n_nodes[0], n_nodes[1], dim == 3 ? n_nodes[2] : 1};
+    const int64_t N = n[0] * n[1] * n[2];
+    const int NS = dim == 3 ? 27 : 9;
+    for (int s = 0; s < NS; ++s) {
+        const int di = s % 3 - 1, dj = (s / 3) % 3 - 1, dk = dim == 3 ? s / 9 - 1 : 0;
+        const int sm = NS - 1 - s;  // index of the opposite offset
+        for (int64_t k = 0; k < n[2]; ++k)
+            for (int64_t j = 0; j < n[1]; ++j)
+                for (int64_t i = 0; i < n[0]; ++i) {
+                    const int64_t p = i + n[0] * (j + n[1] * k);
+                    const bool inside = i + di >= 0 && i + di < n[0] && j + dj >= 0 && j + dj < n[1] && k + dk >= 0 && k + dk < n[2];
+                    if (!inside) {
+                        out[2 * ((int64_t)s * N + p)] = 0.0;
+                        out[2 * ((int64_t)s * N + p) + 1] = 0.0;
+                        continue;
+                    }
+                    const int64_t q = p + di + n[0] * (dj + n[1] * (int64_t)dk);
+                    out[2 * ((int64_t)s * N + p)] = in[2 * ((int64_t)sm * N + q)];
+                    out[2 * ((int64_t)s * N + p) + 1] = -in[2 * ((int64_t)sm * N + q) + 1];
+                }
+    }
+}
+
 }  // namespace hh
 #include "hh_slab.cuh"
 namespace hh {
@@ -1104,9 +1131,16 @@ class Solver : public SolverBase {
         build_ho_stencil(pb.dim, nn, pb.h, ho_m.data(), ho_g.data(), pb.w_re, pb.w_im, pb.neumann_top, pb.sommerfeld, ho_beta,
                          host.data());
         const Level& L0 = levels[0];
+        std::vector<double> adj;  // transposed hierarchy (doTranspose = 1): the same kernels on the adjoint stencils
         auto upload = [&](DevBuf<C>& dst) {  // host Float64 dense -> device precision T in the level's row pitch
+            const double* src = host.data();
+            if (o.do_transpose) {
+                adj.resize(host.size());
+                adjoint_stencil(pb.dim, nn, host.data(), adj.data());
+                src = adj.data();
+            }
             std::vector<C> tmp((size_t)NS * Nd);
-            for (size_t e = 0; e < tmp.size(); ++e) tmp[e] = mk<T>((T)host[2 * e], (T)host[2 * e + 1]);
+            for (size_t e = 0; e < tmp.size(); ++e) tmp[e] = mk<T>((T)src[2 * e], (T)src[2 * e + 1]);
             dst.alloc((size_t)NS * L0.N);
             if (L0.N == Nd) {
                 HH_CUDA(cudaMemcpyAsync(dst.p, tmp.data(), tmp.size() * sizeof(C), cudaMemcpyHostToDevice, stream));
@@ -1184,7 +1218,6 @@ class Solver : public SolverBase {
         set_level_planes(0);
         if (ho) {
             HH_REQUIRE(!slab, HH_ERR_UNSUPPORTED, "the high-order operator is not available on a slab handle");
-            HH_REQUIRE(!o.do_transpose, HH_ERR_UNSUPPORTED, "the high-order operator has no transposed solve yet");
             build_ho_levels(o);
         }
         if (krylov_only) {  // the cycle lives in another solver (prec_hook): only the fine-level geometry is needed
@@ -1679,7 +1712,8 @@ class Solver : public SolverBase {
         HH_REQUIRE(d_m.p != nullptr, HH_ERR_STATE, "no model set");
         if (ho) {  // stored stencils exist for the un-shifted operator and for the hierarchy's shift only
             HH_REQUIRE(have_hierarchy, HH_ERR_STATE, "high-order operator: hh_apply needs hh_setup first");
-            HH_REQUIRE(!transpose, HH_ERR_UNSUPPORTED, "high-order operator: transposed apply is not available");
+            HH_REQUIRE((transpose != 0) == (opt.do_transpose != 0), HH_ERR_UNSUPPORTED,
+                       "high-order operator: hh_apply applies the operator the hierarchy was built for (do_transpose of hh_setup)");
             HH_REQUIRE(!shifted || shift == 0.0 || (!krylov_only && shift == opt.shift[0]), HH_ERR_UNSUPPORTED,
                        "high-order operator: hh_apply supports shift 0 and the shift given to hh_setup");
             const Level& Lop = (shifted && shift != 0.0) ? levels[0] : hoH;

@@ -126,6 +126,10 @@ int hh_get_maximal_frequency(const double* m, int64_t n, int dim, const double* 
  * Host-side set-up (no device needed); hh_set_operator_ho runs the solver on this operator. */
 int hh_ho_stencil(int dim, const int64_t* n_nodes, const double* h, const double* m, const double* gamma, double omega_re,
                   double omega_im, int neumann_on_top, int sommerfeld, const double* beta, double* coef_out);
+/* conjugate transpose of a stored stencil (layout of hh_ho_stencil): (A^H)[p,p+off] = conj(A[p+off,p]).  Host-side;
+ * this is how the transposed hierarchy of the high-order operator is formed (doTranspose = 1,
+ * src/ShiftedLaplacianMultigridSolver.jl:68-70). */
+int hh_stencil_adjoint(int dim, const int64_t* n_nodes, const double* coef_in, double* coef_out);
 /* loc2cs: 1-based subscripts -> 1-based linear index */
 int64_t hh_point_source_index(int dim, const int64_t* n_nodes, const int64_t* sub);
 
@@ -189,8 +193,8 @@ int hh_update_model(hh_handle_t h, const double* m, const double* gamma, double 
  * stencil of hh_ho_stencil (built at hh_setup from Float64 copies of m and gamma, the arrays hh_create was given), the
  * hierarchy is the Galerkin hierarchy of  H_HO + i*shift*w^2*diag(m)  (the matrix a reference caller passes to
  * solveLinearSystem, :33,65) and the Krylov operator is H_HO.  enable = 0 returns to the plain operator.  Invalidates
- * the hierarchy.  hh_apply then needs hh_setup first and supports shift 0 and the hierarchy's shift; transposed
- * solves and slab handles are not supported with this operator.  hh_get_level_stencil(level 0) returns the shifted
+ * the hierarchy.  hh_apply then needs hh_setup first, supports shift 0 and the hierarchy's shift, and applies the
+ * operator the hierarchy was built for (do_transpose of hh_setup); slab handles are not supported with this operator.  hh_get_level_stencil(level 0) returns the shifted
  * fine stencil. */
 int hh_set_operator_ho(hh_handle_t h, int enable, const double* m, const double* gamma, const double* beta);
 

@@ -94,3 +94,15 @@ def test_host_operator_object_matches_the_oracle_matrix(pkg, ho, nodes, beta):
     assert np.abs(Hp @ x[:, 0] - H @ x[:, 0]).max() < 1e-13 * scale
     hp = pkg.HelmholtzParam(pmesh, gamma, m.ravel(order="F"), w, True, True)
     assert np.abs(pkg.GetHelmholtzOperatorHO(hp, beta) @ x - H @ x).max() < 1e-13 * scale
+
+
+@pytest.mark.parametrize("nodes,beta", [((9, 7), 2.0 / 3.0), ((6, 5, 4), [0.7, 0.9])])
+def test_stencil_adjoint_matches_the_oracle_matrix(pkg, ho, nodes, beta):
+    """hh_stencil_adjoint: how the transposed hierarchy of the high-order operator is formed (doTranspose = 1)"""
+    mesh, m, w, gamma = _problem(ho, nodes)
+    SH = ho.GetHelmholtzOperatorHO(mesh, m, w, gamma, True, True, beta) + ho.GetHelmholtzShiftOP(m, w, 0.2)
+    want = ho.csr_to_stencil(SH.conj().T.tocsr(), mesh.nodes)
+    got = pkg.stencilAdjoint(mesh.nodes, ho.csr_to_stencil(SH.tocsr(), mesh.nodes))
+    assert np.abs(got - want).max() <= 1e-15 * np.abs(want).max()
+    # an involution
+    assert np.array_equal(pkg.stencilAdjoint(mesh.nodes, got), ho.csr_to_stencil(SH.tocsr(), mesh.nodes))
