@@ -1,6 +1,5 @@
-"""doTranspose = 1 with GetHelmholtzOperatorHO (src/ShiftedLaplacianMultigridSolver.jl:68-70,78-80).  Kept in its own file,
-sorted after the other GPU tests: it was written after the round's GPU budget was spent, so its first run is the
-driver's (the host-side adjoint stencils it relies on are checked on CPU in tests/test_oracle_ho_operator.py)."""
+"""doTranspose = 1 with GetHelmholtzOperatorHO (src/ShiftedLaplacianMultigridSolver.jl:68-70,78-80): the hierarchy of
+the host-side adjoint stencils (checked on CPU in tests/test_oracle_ho_operator.py), the Krylov method on H^H."""
 import numpy as np
 import pytest
 import scipy.sparse.linalg as spla
