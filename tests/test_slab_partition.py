@@ -56,3 +56,43 @@ def test_single_slab_is_the_whole_grid(pkg):
         for l, g in enumerate(p):
             n = (n3 - 1) // (1 << l) + 1
             assert (g["own0"], g["own1"], g["koff"], g["nloc"], g["zb"], g["ze"], g["n2g"]) == (0, n, 0, n, 0, n, n)
+
+
+def test_partition_properties_randomised(pkg):
+    """the same invariants over many random (cells, levels, slabs): tiling, alignment, nesting, halo sufficiency"""
+    from hypothesis import given, settings
+    from hypothesis import strategies as st
+
+    @settings(max_examples=300, deadline=None)
+    @given(st.integers(1, 5), st.integers(1, 40), st.integers(1, 12))
+    def check(levels, coarse_cells, nranks):
+        n3 = coarse_cells * (1 << (levels - 1)) + 1
+        if coarse_cells < nranks:
+            with pytest.raises(ValueError):
+                pkg.slabPartition(n3, levels, nranks, 0)
+            return
+        parts = [pkg.slabPartition(n3, levels, nranks, r) for r in range(nranks)]
+        for l in range(levels):
+            n2g = (n3 - 1) // (1 << l) + 1
+            assert parts[0][l]["own0"] == 0 and parts[-1][l]["own1"] == n2g
+            for r, p in enumerate(parts):
+                g = p[l]
+                assert g["own1"] > g["own0"] and g["n2g"] == n2g
+                assert g["koff"] + g["zb"] == g["own0"] and g["ze"] - g["zb"] == g["own1"] - g["own0"]
+                assert 0 <= g["koff"] and g["koff"] + g["nloc"] <= n2g
+                if r + 1 < nranks:
+                    assert g["own1"] == parts[r + 1][l]["own0"] and g["nloc"] == g["ze"] + 1
+                if r > 0:
+                    assert g["zb"] >= 1
+                if l + 1 < levels:
+                    c = p[l + 1]
+                    assert g["koff"] == 2 * c["koff"] and g["own0"] == 2 * c["own0"]
+                    # fine planes read by the restriction to / written by the interpolation from the owned coarse planes
+                    lo_f = 2 * c["own0"] - (1 if c["own0"] > 0 else 0)
+                    hi_f = 2 * (c["own1"] - 1) + (1 if c["own1"] < c["n2g"] else 0)
+                    assert g["koff"] <= lo_f and hi_f <= g["koff"] + g["nloc"] - 1
+                    # coarse planes read by the interpolation to the owned fine planes
+                    hi_c = (g["own1"] - 1 + 1) // 2
+                    assert c["koff"] <= g["own0"] // 2 and hi_c <= c["koff"] + c["nloc"] - 1
+
+    check()
