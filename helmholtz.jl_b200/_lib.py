@@ -68,6 +68,8 @@ SIGNATURES = {
     "hh_point_source_index": (C.c_int64, [C.c_int, _i64p, _i64p]),
     "hh_ho_stencil": (C.c_int, [C.c_int, _i64p, _dp, _dp, _dp, C.c_double, C.c_double, C.c_int, C.c_int, _dp, _dp]),
     "hh_stencil_adjoint": (C.c_int, [C.c_int, _i64p, _dp, _dp]),
+    "hh_assemble_csc": (C.c_int, [C.c_int, _i64p, _dp, _dp, _dp, C.c_double, C.c_double, C.c_int, C.c_int, C.c_int, C.c_double,
+                                  _dp, _i64p, _i64p, _dp]),
     "hh_create": (C.c_int, [C.c_int, _i64p, _dp, _dp, _dp, C.c_double, C.c_double, C.c_int, C.c_int, C.c_int, C.c_int,
                             C.c_int, C.POINTER(_p)]),
     "hh_create_multi": (C.c_int, [C.c_int, _i64p, _dp, _dp, _dp, C.c_double, C.c_double, C.c_int, C.c_int, C.c_int,

@@ -787,3 +787,43 @@ def stencilAdjoint(nodes, coef):
     L.check(L.load().hh_stencil_adjoint(len(nodes), _ptr(nodes, C.c_int64), _ptr(cin.view(np.float64), C.c_double),
                                         _ptr(out.view(np.float64), C.c_double)), None)
     return out
+
+
+def GetHelmholtzMatrix(Msh, mNodal, omega, gamma, NeumannAtFirstDim, Sommerfeld, orderNeumannBC=2, shift=0.0, betaHO=None):
+    """The sparse matrix the reference's GetHelmholtzOperator (or, with betaHO, GetHelmholtzOperatorHO) returns, plus
+    GetHelmholtzShiftOP(m, omega, shift), as scipy.sparse.csc_matrix (hh_assemble_csc; host-side).  For code that uses
+    the matrix itself, e.g. the direct solves of test/HelmholtzTest.jl."""
+    import scipy.sparse as sp
+
+    nodes = (np.asarray(Msh.n, dtype=np.int64) + 1).copy()
+    dim = int(Msh.dim)
+    N = int(np.prod(nodes))
+    mm = np.ascontiguousarray(np.asarray(mNodal, dtype=np.float64).ravel(order="F"))
+    gg = np.ascontiguousarray(np.asarray(gamma, dtype=np.float64).ravel(order="F"))
+    if mm.size != N or gg.size != N:
+        raise ValueError(f"m and gamma must have prod(n+1) = {N} entries")
+    h = np.ascontiguousarray(np.asarray(Msh.h, dtype=np.float64))
+    w = complex(omega)
+    bb = None
+    if betaHO is not None:
+        if np.isscalar(betaHO):
+            if dim == 3 and betaHO != 1:
+                raise ValueError("getSpreadNodalLaplacianAndMass: in 3-D beta is a pair (Laplacian, mass)")
+            betaHO = [float(betaHO), float(betaHO)]
+        bb = np.ascontiguousarray(np.asarray(betaHO, dtype=np.float64))
+    colptr = np.zeros(N + 1, dtype=np.int64)
+    lib = L.load()
+
+    def call(rowval, nzval):
+        L.check(lib.hh_assemble_csc(dim, _ptr(nodes, C.c_int64), _ptr(h, C.c_double), _ptr(mm, C.c_double), _ptr(gg, C.c_double),
+                                    w.real, w.imag, int(bool(NeumannAtFirstDim)), int(bool(Sommerfeld)), int(orderNeumannBC),
+                                    float(shift), _ptr(bb, C.c_double) if bb is not None else None, _ptr(colptr, C.c_int64),
+                                    _ptr(rowval, C.c_int64) if rowval is not None else None,
+                                    _ptr(nzval.view(np.float64), C.c_double) if nzval is not None else None), None)
+
+    call(None, None)
+    nnz = int(colptr[N])
+    rowval = np.empty(nnz, dtype=np.int64)
+    nzval = np.empty(nnz, dtype=np.complex128)
+    call(rowval, nzval)
+    return sp.csc_matrix((nzval, rowval, colptr), shape=(N, N))

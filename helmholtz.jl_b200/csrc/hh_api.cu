@@ -302,6 +302,31 @@ extern "C" int hh_ho_stencil(int dim, const int64_t* n_nodes, const double* hsp,
     });
 }
 
+// GetHelmholtzOperator / GetHelmholtzOperatorHO as the sparse matrix the reference returns (SparseMatrixCSC, 0-based
+// here): call with rowval = nzval = NULL to get colptr and nnz = colptr[N], then again with arrays of that size.
+extern "C" int hh_assemble_csc(int dim, const int64_t* n_nodes, const double* hsp, const double* m, const double* gamma,
+                               double wre, double wim, int neumann_on_top, int sommerfeld, int order_bc, double shift,
+                               const double* ho_beta, int64_t* colptr, int64_t* rowval, double* nzval) {
+    return guarded(nullptr, [&]() -> int {
+        HH_REQUIRE(n_nodes && hsp && m && gamma && colptr && ((rowval == nullptr) == (nzval == nullptr)), HH_ERR_ARG,
+                   "hh_assemble_csc: bad arguments");
+        HH_REQUIRE(dim == 2 || dim == 3, HH_ERR_ARG, "hh_assemble_csc: dim must be 2 or 3");
+        int64_t N = 1;
+        for (int d = 0; d < dim; ++d) N *= n_nodes[d];
+        const int NS = dim == 3 ? 27 : 9;
+        std::vector<double> coef((size_t)2 * NS * N);
+        if (ho_beta) {
+            build_ho_stencil(dim, n_nodes, hsp, m, gamma, wre, wim, neumann_on_top, sommerfeld, ho_beta, coef.data());
+            const int center = dim == 3 ? 13 : 4;
+            for (int64_t p = 0; p < N; ++p) coef[2 * ((int64_t)center * N + p) + 1] += shift * wre * wre * m[p];
+        } else {
+            build_plain_stencil(dim, n_nodes, hsp, m, gamma, wre, wim, neumann_on_top, sommerfeld, order_bc, shift, coef.data());
+        }
+        stencil_to_csc(dim, n_nodes, coef.data(), colptr, rowval, nzval);
+        return HH_OK;
+    });
+}
+
 extern "C" int hh_stencil_adjoint(int dim, const int64_t* n_nodes, const double* coef_in, double* coef_out) {
     return guarded(nullptr, [&]() -> int {
         adjoint_stencil(dim, n_nodes, coef_in, coef_out);

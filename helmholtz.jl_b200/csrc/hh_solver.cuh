@@ -152,6 +152,82 @@ inline void adjoint_stencil(int dim, const int64_t* n_nodes, const double* in, d
     }
 }
 
+// GetHelmholtzOperator (src/GetHelmholtz.jl:33-50 on the Laplacian of src/PlainNodalLaplacian.jl:18-46) as a stored
+// stencil on the host, Float64: the same formulas the matrix-free kernels evaluate (fine_center / fine_w), for callers
+// that need the explicit matrix (hh_assemble_csc).  shift adds i*shift*Re(w)^2*m to the diagonal (GetHelmholtzShiftOP).
+inline void build_plain_stencil(int dim, const int64_t* n_nodes, const double* hsp, const double* m, const double* gamma,
+                                double wre, double wim, int neumann_on_top, int sommerfeld, int order_bc, double shift,
+                                double* coef_out) {
+    HH_REQUIRE(dim == 2 || dim == 3, HH_ERR_ARG, "dim must be 2 or 3");
+    HH_REQUIRE(order_bc == 1 || order_bc == 2, HH_ERR_ARG, "getNodalLaplacianMatrix: BC not supported");
+    HH_REQUIRE(wre != 0.0, HH_ERR_ARG, "Re(omega) must be non-zero");
+    int64_t n[3] = {1, 1, 1};
+    for (int d = 0; d < dim; ++d) {
+        HH_REQUIRE(n_nodes[d] >= 2 && hsp[d] > 0.0, HH_ERR_ARG, "node counts must be >= 2, spacings positive");
+        n[d] = n_nodes[d];
+    }
+    const int64_t N = n[0] * n[1] * n[2];
+    const int NS = dim == 3 ? 27 : 9;
+    const double BC = order_bc == 2 ? 2.0 : 1.0;
+    const double w2r = wre * wre - wim * wim, w2i = 2.0 * wre * wim;
+    std::fill(coef_out, coef_out + (size_t)2 * NS * N, 0.0);
+    const int center = dim == 3 ? 13 : 4;
+    const int64_t stride[3] = {1, 3, 9};
+    for (int64_t k = 0; k < n[2]; ++k)
+        for (int64_t j = 0; j < n[1]; ++j)
+            for (int64_t i = 0; i < n[0]; ++i) {
+                const int64_t p = i + n[0] * (j + n[1] * k);
+                const int64_t idx[3] = {i, j, k};
+                const double g = gamma[p] / wre;
+                double re = -m[p] * (w2r + w2i * g), im = -m[p] * (w2i - w2r * g) + shift * wre * wre * m[p];
+                double sf = 0.0;
+                for (int d = 0; d < dim; ++d) {
+                    const bool first = idx[d] == 0, last = idx[d] == n[d] - 1;
+                    const double ih2 = 1.0 / (hsp[d] * hsp[d]);
+                    re += ((first || last) ? BC : 2.0) * ih2;                         // dxxMat diagonal
+                    if (!first) coef_out[2 * ((center - stride[d]) * N + p)] = -(last ? BC : 1.0) * ih2;   // sub-diagonal
+                    if (!last) coef_out[2 * ((center + stride[d]) * N + p)] = -(first ? BC : 1.0) * ih2;   // super-diagonal
+                    const bool top = (d == dim - 1) && neumann_on_top;
+                    if (sommerfeld && ((first && !top) || last)) sf += 2.0 / hsp[d];  // getSommerfeldBC is called with BC = 2
+                }
+                im += wre * sf * std::sqrt(m[p]);
+                coef_out[2 * (center * N + p)] = re;
+                coef_out[2 * (center * N + p) + 1] = im;
+            }
+}
+
+// stored stencil -> compressed sparse column arrays (0-based), entries with a zero coefficient dropped.  Two passes:
+// rowval == nullptr only counts (colptr[N] = nnz).
+inline int64_t stencil_to_csc(int dim, const int64_t* n_nodes, const double* coef, int64_t* colptr, int64_t* rowval, double* nzval) {
+    int64_t n[3] = {n_nodes[0], n_nodes[1], dim == 3 ? n_nodes[2] : 1};
+    const int64_t N = n[0] * n[1] * n[2];
+    const int NS = dim == 3 ? 27 : 9;
+    int64_t nnz = 0;
+    for (int64_t kq = 0; kq < n[2]; ++kq)
+        for (int64_t jq = 0; jq < n[1]; ++jq)
+            for (int64_t iq = 0; iq < n[0]; ++iq) {
+                const int64_t q = iq + n[0] * (jq + n[1] * kq);
+                colptr[q] = nnz;
+                // rows p = q - off in ascending order: offsets from (+1,+1,+1) down to (-1,-1,-1)
+                for (int s = NS - 1; s >= 0; --s) {
+                    const int di = s % 3 - 1, dj = (s / 3) % 3 - 1, dk = dim == 3 ? s / 9 - 1 : 0;
+                    const int64_t ip = iq - di, jp = jq - dj, kp = kq - dk;
+                    if (ip < 0 || ip >= n[0] || jp < 0 || jp >= n[1] || kp < 0 || kp >= n[2]) continue;
+                    const int64_t p = ip + n[0] * (jp + n[1] * kp);
+                    const double re = coef[2 * ((int64_t)s * N + p)], im = coef[2 * ((int64_t)s * N + p) + 1];
+                    if (re == 0.0 && im == 0.0) continue;
+                    if (rowval) {
+                        rowval[nnz] = p;
+                        nzval[2 * nnz] = re;
+                        nzval[2 * nnz + 1] = im;
+                    }
+                    ++nnz;
+                }
+            }
+    colptr[N] = nnz;
+    return nnz;
+}
+
 }  // namespace hh
 #include "hh_slab.cuh"
 namespace hh {

@@ -13,6 +13,7 @@
 module HelmholtzB200
 
 using LinearAlgebra
+using SparseArrays
 
 export HelmholtzParam, getShiftedHelmholtzParam, GetHelmholtzOperator, GetHelmholtzShiftOP, getABL,
        getMaximalFrequency, getAcousticPointSource, loc2cs, getTopPointSrc, getMidPointSrc,
@@ -162,6 +163,26 @@ function setOperatorHO!(hd::Handle, m, gamma, beta; enable::Bool = true)
     bb = length(beta) == 2 ? Float64.(beta) : [Float64(beta), Float64(beta)]
     check(ccall((:hh_set_operator_ho, LIB), Cint, (Ptr{Cvoid}, Cint, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
                 hd.ptr, enable, vec(Float64.(m)), vec(Float64.(gamma)), bb))
+end
+
+# ---- the explicit SparseMatrixCSC of GetHelmholtzOperator / GetHelmholtzOperatorHO (for H \ q and the like) ----
+function GetHelmholtzMatrix(Mesh, m, omega, gamma, NeumannOnTop::Bool, Sommerfeld::Bool, orderNeumannBC::Int = 2;
+                            shift::Float64 = 0.0, betaHO = nothing)
+    nodes = Int64.(Mesh.n .+ 1)
+    N = prod(nodes)
+    w = ComplexF64(omega)
+    bb = betaHO === nothing ? Ptr{Float64}(C_NULL) : (length(betaHO) == 2 ? Float64.(betaHO) : [Float64(betaHO), Float64(betaHO)])
+    colptr = zeros(Int64, N + 1)
+    call(rowval, nzval) = check(ccall((:hh_assemble_csc, LIB), Cint,
+        (Cint, Ptr{Int64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Cdouble, Cdouble, Cint, Cint, Cint, Cdouble, Ptr{Float64},
+         Ptr{Int64}, Ptr{Int64}, Ptr{ComplexF64}),
+        Mesh.dim, nodes, Float64.(Mesh.h), vec(Float64.(m)), vec(Float64.(gamma)), real(w), imag(w), NeumannOnTop, Sommerfeld,
+        orderNeumannBC, shift, bb, colptr, rowval, nzval))
+    call(Ptr{Int64}(C_NULL), Ptr{ComplexF64}(C_NULL))
+    nnz = colptr[end]
+    rowval = zeros(Int64, nnz); nzval = zeros(ComplexF64, nnz)
+    call(rowval, nzval)
+    return SparseMatrixCSC(N, N, colptr .+ 1, rowval .+ 1, nzval)   # the library's indices are 0-based
 end
 
 # ---- operator objects: matrix-free counterpart of the sparse H (src/GetHelmholtz.jl:33-50) ----

@@ -126,6 +126,14 @@ int hh_get_maximal_frequency(const double* m, int64_t n, int dim, const double* 
  * Host-side set-up (no device needed); hh_set_operator_ho runs the solver on this operator. */
 int hh_ho_stencil(int dim, const int64_t* n_nodes, const double* h, const double* m, const double* gamma, double omega_re,
                   double omega_im, int neumann_on_top, int sommerfeld, const double* beta, double* coef_out);
+/* The explicit matrix the reference's GetHelmholtzOperator (src/GetHelmholtz.jl:33-50; ho_beta == NULL, order_neumann_bc
+ * in {1,2}) or GetHelmholtzOperatorHO (:54-72; ho_beta as in hh_ho_stencil) returns, plus i*shift*Re(w)^2*diag(m)
+ * (GetHelmholtzShiftOP), in compressed sparse column form with 0-based indices (SparseMatrixCSC minus one): for callers
+ * that use the matrix itself (H \ q in test/HelmholtzTest.jl:42).  Two calls: rowval = nzval = NULL fills colptr[N+1]
+ * (nnz = colptr[N]); the second call fills rowval[nnz] and nzval[2*nnz] (re,im).  Host-side, no device needed. */
+int hh_assemble_csc(int dim, const int64_t* n_nodes, const double* h, const double* m, const double* gamma, double omega_re,
+                    double omega_im, int neumann_on_top, int sommerfeld, int order_neumann_bc, double shift,
+                    const double* ho_beta, int64_t* colptr, int64_t* rowval, double* nzval);
 /* conjugate transpose of a stored stencil (layout of hh_ho_stencil): (A^H)[p,p+off] = conj(A[p+off,p]).  Host-side;
  * this is how the transposed hierarchy of the high-order operator is formed (doTranspose = 1,
  * src/ShiftedLaplacianMultigridSolver.jl:68-70). */

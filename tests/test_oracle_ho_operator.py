@@ -106,3 +106,29 @@ def test_stencil_adjoint_matches_the_oracle_matrix(pkg, ho, nodes, beta):
     assert np.abs(got - want).max() <= 1e-15 * np.abs(want).max()
     # an involution
     assert np.array_equal(pkg.stencilAdjoint(mesh.nodes, got), ho.csr_to_stencil(SH.tocsr(), mesh.nodes))
+
+
+@pytest.mark.parametrize("nodes", [(9, 7), (6, 5, 4)])
+def test_assembled_sparse_matrix_matches_the_oracle(pkg, ho, nodes):
+    """hh_assemble_csc: the SparseMatrixCSC the reference's GetHelmholtzOperator / GetHelmholtzOperatorHO return (for
+    callers that use the matrix itself, e.g. H \\ q in test/HelmholtzTest.jl:42): same pattern, same entries"""
+    import scipy.sparse.linalg as spla
+
+    mesh, m, w, gamma = _problem(ho, nodes)
+    pmesh = pkg.getRegularMesh(list(mesh.domain), list(mesh.n))
+    for neumann in (True, False):
+        for order in (1, 2):
+            for somm in (True, False):
+                H = (ho.GetHelmholtzOperator(mesh, m, w, gamma, neumann, somm, order) + ho.GetHelmholtzShiftOP(m, w, 0.2)).tocsc()
+                Hp = pkg.GetHelmholtzMatrix(pmesh, m, w, gamma, neumann, somm, order, 0.2)
+                assert Hp.nnz == H.nnz and Hp.has_sorted_indices
+                assert abs(Hp - H).max() <= 1e-15 * abs(H).max()
+    beta = 2.0 / 3.0 if len(nodes) == 2 else [0.7, 0.9]
+    wc = w * (1.0 - 0.02j)
+    H = ho.GetHelmholtzOperatorHO(mesh, m, wc, gamma, True, True, beta).tocsc()
+    Hp = pkg.GetHelmholtzMatrix(pmesh, m, wc, gamma, True, True, 2, 0.0, beta)
+    assert Hp.nnz == H.nnz and abs(Hp - H).max() <= 1e-15 * abs(H).max()
+    # the direct solve a caller would do with it
+    q = np.zeros(H.shape[0], dtype=complex)
+    q[H.shape[0] // 2] = 1.0
+    assert np.allclose(spla.spsolve(Hp, q), spla.spsolve(H, q), rtol=1e-10, atol=0)
