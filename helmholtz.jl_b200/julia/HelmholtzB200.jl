@@ -19,7 +19,9 @@ export HelmholtzParam, getShiftedHelmholtzParam, GetHelmholtzOperator, GetHelmho
        getMaximalFrequency, getAcousticPointSource, loc2cs, getTopPointSrc, getMidPointSrc,
        MGparam, getMGparam, hierarchyExists, ShiftedLaplacianMultigridSolver,
        getShiftedLaplacianMultigridSolver, copySolver, solveLinearSystem, solveLinearSystem!, clear!,
-       RegularMesh, getRegularMesh
+       RegularMesh, getRegularMesh,
+       GetHelmholtzMatrix, GetHelmholtzOperatorHOStencil, setOperatorHO!,
+       SlabHandle, SlabHandleNCCL, slabUniqueId, slabPartition
 
 const LIB = get(ENV, "HELMHOLTZ_B200_LIB", joinpath(@__DIR__, "..", "lib", "libhelmholtz_b200.so"))
 
