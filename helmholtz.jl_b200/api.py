@@ -186,6 +186,16 @@ class HelmholtzShiftOP:
         self.shift = float(shift)
         self.omega = float(omega)
 
+    def __neg__(self):
+        return HelmholtzShiftOP(-self.shift, self.omega)
+
+    def __mul__(self, a):
+        if np.isscalar(a) and np.isreal(a):
+            return HelmholtzShiftOP(float(a) * self.shift, self.omega)
+        return NotImplemented
+
+    __rmul__ = __mul__
+
 
 def GetHelmholtzShiftOP(mNodal, omega, shift):
     if np.iscomplexobj(omega):
@@ -827,3 +837,68 @@ def GetHelmholtzMatrix(Msh, mNodal, omega, gamma, NeumannAtFirstDim, Sommerfeld,
     nzval = np.empty(nnz, dtype=np.complex128)
     call(rowval, nzval)
     return sp.csc_matrix((nzval, rowval, colptr), shape=(N, N))
+
+
+# ------------------------------------------------------------------ remaining exports of the reference on this path
+def getSommerfeldBC(Msh, mNodal, omega, NeumannOnTop, orderNeumannBC=2):
+    """src/GetHelmholtz.jl:222-247: -i*omega*(BC/h_d)*sqrt(m) accumulated on every boundary face (edges and corners
+    add up), the first face of the last dimension skipped when NeumannOnTop.  Host-side set-up; the kernels evaluate the
+    same term in place (hh_get_diagonal returns it folded into the diagonal)."""
+    if orderNeumannBC not in (1, 2):
+        raise ValueError("getNodalLaplacianMatrix: BC not supported")
+    BC = 2.0 if orderNeumannBC == 2 else 1.0
+    nodes = tuple(int(v) + 1 for v in Msh.n)
+    m = np.asarray(mNodal, dtype=np.float64).reshape(nodes, order="F")
+    h = np.asarray(Msh.h, dtype=np.float64)
+    somm = np.zeros(nodes, dtype=np.complex128)
+    dim = len(nodes)
+    for d in range(dim):
+        for side in (0, -1):
+            if d == dim - 1 and side == 0 and NeumannOnTop:
+                continue
+            sl = [slice(None)] * dim
+            sl[d] = side
+            sl = tuple(sl)
+            somm[sl] += -1j * float(omega) * (BC / h[d]) * np.sqrt(m[sl])
+    return somm
+
+
+def getHelmholtzFun(ShiftedHelmholtzT, ShiftMat, y=None, numCores=1):
+    """src/GetHelmholtz.jl:85-95: the closure x -> ShiftedHelmholtzT' * x + ShiftMat * x.  The solver calls it with
+    ShiftMat = -GetHelmholtzShiftOP(m, omega, shift), which makes it x -> H x (ShiftedLaplacianMultigridSolver.jl:77-83).
+    ShiftedHelmholtzT is an operator object (its adjoint view is applied, as the reference's SpMatMul does), ShiftMat a
+    GetHelmholtzShiftOP object; y, when given, receives the result (the reference's preallocated work block)."""
+    op = ShiftedHelmholtzT.H + ShiftMat
+
+    def Hfun(x):
+        out = op.matvec(x)
+        if y is not None:
+            y[...] = np.asarray(out).reshape(y.shape, order="F") if not _is_torch_cuda(out) else out.reshape(y.shape)
+            return y
+        return out
+
+    return Hfun
+
+
+def getNodalLaplacianMatrix(Msh, orderNeumannBC=2):
+    """src/PlainNodalLaplacian.jl:32-46: -laplacian on the nodal grid with ghost-eliminated Neumann rows, as the sparse
+    matrix the reference returns (real CSC).  Host-side (hh_assemble_csc with a zero mass term)."""
+    nodes = tuple(int(v) + 1 for v in Msh.n)
+    z = np.zeros(nodes)
+    return GetHelmholtzMatrix(Msh, z, 1.0, z, True, False, orderNeumannBC).real.tocsc()
+
+
+def dxxMat(n, h, orderNeumannBC=2):
+    """src/PlainNodalLaplacian.jl:18-30: the 1-D factor of getNodalLaplacianMatrix (n nodes, spacing h)."""
+    import scipy.sparse as sp
+
+    if orderNeumannBC not in (1, 2):
+        raise ValueError("getNodalLaplacianMatrix: BC not supported")
+    BC = 2.0 if orderNeumannBC == 2 else 1.0
+    lo = -np.ones(n - 1)
+    lo[-1] = -BC
+    di = 2.0 * np.ones(n)
+    di[0] = di[-1] = BC
+    up = -np.ones(n - 1)
+    up[0] = -BC
+    return sp.diags([lo / h**2, di / h**2, up / h**2], [-1, 0, 1], format="csc")

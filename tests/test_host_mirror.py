@@ -75,3 +75,35 @@ def test_workloads_are_deterministic(pkg):
     vp = np.load(os.path.join(GOLDEN, "seg_salt_vp.npz"))["vp_ms"]
     c2 = pkg.workloads.config2(vp)
     assert c2["m"].shape == (257, 129) and abs(1 / np.sqrt(c2["m"].max()) - 1.5) < 1e-9
+
+
+def test_remaining_reference_exports_on_the_host(pkg, ho):
+    """getSommerfeldBC, getNodalLaplacianMatrix, dxxMat, getHelmholtzFun (src/GetHelmholtz.jl:2, PlainNodalLaplacian.jl:1):
+    host-side mirrors against the oracle's restatements; no device needed (the closure is exercised on the high-order
+    operator object, whose product is evaluated on the host)."""
+    rng = np.random.default_rng(9)
+    for nodes in ((9, 7), (6, 5, 4)):
+        nodes = np.array(nodes)
+        dom = sum([[0.0, (0.1 + 0.03 * d) * (nd - 1)] for d, nd in enumerate(nodes)], [])
+        om, pm = ho.getRegularMesh(dom, list(nodes - 1)), pkg.getRegularMesh(dom, list(nodes - 1))
+        m = 1.0 / (1.5 + rng.random(tuple(nodes))) ** 2
+        w = 3.0
+        for neumann in (True, False):
+            for order in (1, 2):
+                assert np.abs(pkg.getSommerfeldBC(pm, m, w, neumann, order) - ho.getSommerfeldBC(om, m, w, neumann, order)).max() < 1e-13
+        for order in (1, 2):
+            Lp, Lo = pkg.getNodalLaplacianMatrix(pm, order), ho.getNodalLaplacianMatrix(om, order)
+            assert Lp.nnz == Lo.nnz and abs(Lp - Lo).max() < 1e-12 * abs(Lo).max()
+            assert abs(pkg.dxxMat(7, 0.3, order) - ho.dxxMat(7, 0.3, order)).max() < 1e-13
+        # getHelmholtzFun as the solver uses it: Afun(x) = SH' ' x - ShiftOP x = H x
+        gamma = 0.05 * w * (1.0 + rng.random(tuple(nodes)))
+        beta = 2.0 / 3.0 if len(nodes) == 2 else [0.7, 0.9]
+        Hp = pkg.GetHelmholtzOperatorHO(pm, m, w, gamma, True, True, beta)
+        shiftop = pkg.GetHelmholtzShiftOP(m, w, 0.2)
+        SHT = (Hp + shiftop).H
+        x = rng.standard_normal((Hp.shape[0], 2)) + 1j * rng.standard_normal((Hp.shape[0], 2))
+        Afun = pkg.getHelmholtzFun(SHT, -shiftop)
+        Ho_ = ho.GetHelmholtzOperatorHO(om, m, w, gamma, True, True, beta)
+        assert np.abs(Afun(x) - Ho_ @ x).max() < 1e-12 * np.abs(Ho_ @ x).max()
+        y = np.zeros_like(x, order="F")
+        assert pkg.getHelmholtzFun(SHT, -1.0 * shiftop, y, 4)(x) is y and np.abs(y - Ho_ @ x).max() < 1e-12 * np.abs(y).max()
