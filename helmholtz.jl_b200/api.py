@@ -902,3 +902,22 @@ def dxxMat(n, h, orderNeumannBC=2):
     up = -np.ones(n - 1)
     up[0] = -BC
     return sp.diags([lo / h**2, di / h**2, up / h**2], [-1, 0, 1], format="csc")
+
+
+def Lap2DStencil(x1, x2, x3, x4, x5, h1invsq, h2invsq):
+    """src/PlainNodalLaplacian.jl:150-152: centre x1, dimension-1 neighbours x2/x3, dimension-2 neighbours x4/x5."""
+    return (2 * h1invsq + 2 * h2invsq) * x1 - h1invsq * (x2 + x3) - h2invsq * (x4 + x5)
+
+
+def multOpNeumann_(M, x, y, op=Lap2DStencil):
+    """src/PlainNodalLaplacian.jl:155-188 (`multOpNeumann!`): the reference's own matrix-free 2-D stencil apply, ghost
+    value = centre value (first-order Neumann); a no-op in 3-D, as in the reference.  Host-side, vectorised: `op` is
+    called once on whole arrays.  The device path of the same operator is hh_apply with orderNeumannBC = 1."""
+    if int(M.dim) != 2:
+        return y
+    n1, n2 = int(M.n[0]) + 1, int(M.n[1]) + 1
+    X = np.asarray(x).reshape((n1, n2), order="F")
+    P = np.pad(X, 1, mode="edge")  # ghost = centre of the boundary node
+    out = op(X, P[:-2, 1:-1], P[2:, 1:-1], P[1:-1, :-2], P[1:-1, 2:], 1.0 / float(M.h[0]) ** 2, 1.0 / float(M.h[1]) ** 2)
+    y[...] = np.asarray(out).reshape(np.shape(y), order="F")
+    return y

@@ -107,3 +107,16 @@ def test_remaining_reference_exports_on_the_host(pkg, ho):
         assert np.abs(Afun(x) - Ho_ @ x).max() < 1e-12 * np.abs(Ho_ @ x).max()
         y = np.zeros_like(x, order="F")
         assert pkg.getHelmholtzFun(SHT, -1.0 * shiftop, y, 4)(x) is y and np.abs(y - Ho_ @ x).max() < 1e-12 * np.abs(y).max()
+
+
+def test_multOpNeumann_is_the_first_order_neumann_laplacian(pkg, ho):
+    """src/PlainNodalLaplacian.jl:150-188 == getNodalLaplacianMatrix(M, 1) * x (the reference's matrix-free precedent)"""
+    rng = np.random.default_rng(1)
+    om, pm = ho.getRegularMesh([0, 1.2, 0, 0.7], [11, 8]), pkg.getRegularMesh([0, 1.2, 0, 0.7], [11, 8])
+    x = rng.standard_normal(12 * 9)
+    y = np.zeros_like(x)
+    assert pkg.multOpNeumann_(pm, x, y, pkg.Lap2DStencil) is y
+    assert np.abs(y - ho.getNodalLaplacianMatrix(om, 1) @ x).max() < 1e-11
+    m3 = pkg.getRegularMesh([0, 1, 0, 1, 0, 1], [2, 2, 2])
+    z = np.ones(27)
+    assert np.array_equal(pkg.multOpNeumann_(m3, np.ones(27), z), np.ones(27))  # the reference's 3-D branch is empty
