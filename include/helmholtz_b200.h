@@ -21,6 +21,9 @@
  *   solveLinearSystem                    src/ShiftedLaplacianMultigridSolver.jl:33-102 -> hh_solve / hh_solve_device
  *   clear!                               src/ShiftedLaplacianMultigridSolver.jl:105-109 -> hh_clear
  *   copySolver                           src/ShiftedLaplacianMultigridSolver.jl:18-22  -> hh_create on the same model (no hierarchy)
+ *   GetHelmholtzOperatorHO               src/GetHelmholtz.jl:54-72                     -> hh_ho_stencil / hh_set_operator_ho
+ *   the returned SparseMatrixCSC itself  src/GetHelmholtz.jl:49,71                     -> hh_assemble_csc (host; for H \ q callers)
+ *   (no counterpart: one grid over several GPUs)                                       -> hh_create_slab_local / hh_create_slab_nccl
  *
  * Memory layout: all arrays are Julia `Array`s: column-major, node (i,j,k) (0-based here)
  * at i + j*n1 + k*n1*n2; B and X are N x nrhs column-major (each right-hand side
