@@ -105,6 +105,7 @@ class _Handle:
         common = (self.dim, _ptr(nodes, C.c_int64), _ptr(h, C.c_double), _ptr(mm, C.c_double), _ptr(gg, C.c_double),
                   w.real, w.imag, int(bool(NeumannOnTop)), int(bool(Sommerfeld)), int(orderNeumannBC), prec)
         self.slabs = slabs
+        self.order = int(orderNeumannBC)
         self.planes = (0, int(nodes[-1]))  # planes of the last dimension the caller's B / X hold
         if slabs is None:
             rc = lib.hh_create_multi(*common, _ptr(devs, C.c_int), len(devs), C.byref(out))
@@ -167,6 +168,27 @@ def _as_block(x, N, dtype):
     if a.dtype != dtype or not a.flags.f_contiguous:
         a = np.asfortranarray(a, dtype=dtype)
     return a
+
+
+def _torch_rows(x, hd, what):
+    """CUDA tensor -> (rows, layout): `rows` is the (nrhs, N) contiguous block the library works on (every right-hand
+    side contiguous = Julia's column-major N x nrhs).  Accepted shapes, as the numpy path and the reference:
+    (N,), (N, nrhs) [layout "cols": copied transposed], and the zero-copy (nrhs, N) with rows = right-hand sides
+    [layout "rows"].  An N x N block is read as (N, nrhs) like the reference's."""
+    import torch
+
+    if x.device.index != hd.devices[0]:
+        raise ValueError(f"{what} lives on cuda:{x.device.index} but the solver handle was created on cuda:{hd.devices[0]} "
+                         "(set solver.devices = [B.device.index] before the first solve)")
+    want = torch.complex128 if hd.dtype == np.complex128 else torch.complex64
+    N = hd.N
+    if x.dim() == 1 and x.shape[0] == N:
+        return x.to(want).reshape(1, N).contiguous(), "vec"
+    if x.dim() == 2 and x.shape[0] == N:
+        return x.to(want).t().contiguous(), "cols"
+    if x.dim() == 2 and x.shape[1] == N:
+        return x.to(want).contiguous(), "rows"
+    raise ValueError(f"{what} has shape {tuple(x.shape)}; expected ({N},), ({N}, nrhs) or the zero-copy (nrhs, {N})")
 
 
 def _is_torch_cuda(x):
@@ -234,13 +256,11 @@ class HelmholtzOperator:
         if _is_torch_cuda(x):
             import torch
 
-            want = torch.complex128 if hd.dtype == np.complex128 else torch.complex64
-            xx = x.to(want).reshape(-1, hd.N) if x.dim() > 1 else x.to(want).reshape(1, hd.N)
-            xx = xx.contiguous()
+            xx, layout = _torch_rows(x, hd, "x")
             y = torch.empty_like(xx)
             L.check(hd.lib.hh_apply_device(hd.h, xx.data_ptr(), y.data_ptr(), xx.shape[0], int(self.shift != 0.0),
                                            self.shift, int(self.adjoint)), hd.h)
-            return y.reshape(x.shape)
+            return y.t() if layout == "cols" else y.reshape(x.shape)
         vec = np.ndim(x) == 1
         X = _as_block(x, hd.N, hd.dtype)
         Y = np.empty_like(X, order="F")
@@ -485,6 +505,8 @@ def copySolver(s):
     s2.devices = s.devices
     s2.slabs = s.slabs
     s2.operatorHO = s.operatorHO
+    if hasattr(s, "orderNeumannBC"):
+        s2.orderNeumannBC = s.orderNeumannBC
     return s2
 
 
@@ -498,7 +520,8 @@ def _ensure_hierarchy(param, doTranspose):
             (MG._hd.slabs is not getattr(param, "slabs", None) or MG._hd.levels != MG.levels):
         clear(MG)  # the slab partition depends on the number of levels
     if MG._hd is None:
-        MG._hd = _Handle(hp.Mesh, hp.m, hp.omega, hp.gamma, hp.NeumannOnTop, hp.Sommerfeld, 2, MG.VAL, param.devices,
+        MG._hd = _Handle(hp.Mesh, hp.m, hp.omega, hp.gamma, hp.NeumannOnTop, hp.Sommerfeld,
+                         getattr(param, "orderNeumannBC", 2), MG.VAL, param.devices,
                          MG.cyclePrecision, getattr(param, "slabs", None), MG.levels)
         MG._hd.cycle_precision = MG.cyclePrecision
         MG._hd.levels = MG.levels
@@ -537,9 +560,22 @@ def solveLinearSystem_(ShiftedHT, B, X, param, doTranspose=0):
         # the reference builds its hierarchy from the matrix it is handed (:65): an HO matrix gives an HO hierarchy
         param.operatorHO = list(ShiftedHT.beta)
     MG = param.MG
+    if isinstance(ShiftedHT, HelmholtzOperator):
+        # ... and so does the Neumann order of the operator it is handed (GetHelmholtzOperator(Hparam, orderNeumannBC))
+        if ShiftedHT._hd.N != int(np.prod(np.asarray(param.helmParam.Mesh.n) + 1)):
+            raise ValueError("the operator passed in lives on another mesh than solver.helmParam")
+        if getattr(param, "orderNeumannBC", 2) != ShiftedHT._hd.order:
+            param.orderNeumannBC = ShiftedHT._hd.order
+            clear(MG)
+    elif ShiftedHT is not None and hasattr(ShiftedHT, "shape") and not isinstance(ShiftedHT, HelmholtzOperatorHO):
+        Nn = int(np.prod(np.asarray(param.helmParam.Mesh.n) + 1))
+        if tuple(ShiftedHT.shape) != (Nn, Nn):
+            raise ValueError(f"the matrix passed in is {tuple(ShiftedHT.shape)}, the solver's mesh has {Nn} nodes")
     if param.doClear == 1:
         clear(MG)
     torch_in = _is_torch_cuda(B)
+    if torch_in and param.devices is None and MG._hd is None:
+        param.devices = [B.device.index]  # the handle is created where the right-hand sides live
     # one process per slab: this process sees its planes of B only, the library detects zero columns after the all-reduce
     local_view = (getattr(param, "slabs", None) or {}).get("mode") == "nccl"
     if local_view:
@@ -570,15 +606,21 @@ def solveLinearSystem_(ShiftedHT, B, X, param, doTranspose=0):
     if torch_in:
         import torch
 
-        want = torch.complex128 if hd.dtype == np.complex128 else torch.complex64
-        Bt = B.to(want).reshape(-1, hd.N).contiguous()  # rows = right-hand sides (column-major N x nrhs)
-        Xt = X.reshape(-1, hd.N)
-        assert Xt.dtype == want and Xt.is_contiguous()
+        # (N,), (N, nrhs) as the reference, or the zero-copy (nrhs, N) block with rows = right-hand sides
+        Bt, layout = _torch_rows(B, hd, "B")
+        if not (isinstance(X, torch.Tensor) and X.is_cuda and X.shape == B.shape and X.dtype == Bt.dtype):
+            raise ValueError("solveLinearSystem!: X must be a CUDA tensor with the shape of B and the solver's precision")
+        if X.device != B.device:
+            raise ValueError("solveLinearSystem!: X and B live on different devices")
+        direct = layout != "cols" and X.is_contiguous()
+        Xt = X.reshape(-1, hd.N) if direct else torch.empty_like(Bt)
         nrhs = Bt.shape[0]
         iters = np.zeros(nrhs, dtype=np.int32)
         relres = np.zeros(nrhs, dtype=np.float64)
         rc = L.check(hd.lib.hh_solve_device(hd.h, Bt.data_ptr(), Xt.data_ptr(), nrhs, C.byref(so),
                                             _ptr(iters, C.c_int32), _ptr(relres, C.c_double)), hd.h)
+        if not direct:
+            X.copy_(Xt.t() if layout == "cols" else Xt.reshape(X.shape))
     else:
         Bm = _as_block(B, hd.N, hd.dtype)
         nrhs = Bm.shape[1]

@@ -669,14 +669,17 @@ int hh_apply_device(hh_handle_t h, const void* dX, void* dY, int64_t nrhs, int s
 // right-hand sides replica i can hold at once next to its work vectors (and its ComplexF32 companion's, if mixed)
 static int64_t batch_limit(hh_handle_t h, int i, const hh_solve_options& o) {
     SolverBase* s = h->subs[i].get();
-    if (h->lows.empty()) return s->max_rhs_per_batch(o);
+    // the staging slots of earlier hh_solve calls are kept and reused: they count as available
+    double staged = 0.0;
+    for (int q = 0; q < 2; ++q) staged += (double)h->stages[i]->db[q].n + (double)h->stages[i]->dx[q].n;
+    if (h->lows.empty()) return s->max_rhs_per_batch(o, staged);
     SolverBase* lo = h->lows[i].get();
     HH_CUDA(cudaSetDevice(s->device));
     size_t fr = 0, tot = 0;
     HH_CUDA(cudaMemGetInfo(&fr, &tot));
     const double staging = 2.0 * (double)lo->internal_ld() * sizeof(cx<float>);
     const double per = s->per_rhs_bytes(o) + lo->cycle_bytes_per_rhs() + staging;
-    const double held = s->held_bytes() + lo->held_bytes() + (double)(h->lo_b[i]->n + h->lo_z[i]->n) * sizeof(cx<float>);
+    const double held = s->held_bytes() + lo->held_bytes() + (double)(h->lo_b[i]->n + h->lo_z[i]->n) * sizeof(cx<float>) + staged;
     return std::max<int64_t>((int64_t)std::floor(0.90 * ((double)fr + held) / per), 0);
 }
 

@@ -1,6 +1,8 @@
 // hh_common.cuh -- shared types, complex arithmetic and reduction helpers.
 #pragma once
 #include <cuda_runtime.h>
+#include <limits.h>
+#include <math.h>
 #include <stdint.h>
 
 namespace hh {
@@ -31,11 +33,17 @@ template <typename T>
 __host__ __device__ __forceinline__ cx<T> operator*(T s, cx<T> a) { return mk<T>(s * a.x, s * a.y); }
 template <typename T>
 __host__ __device__ __forceinline__ cx<T> conj(cx<T> a) { return mk<T>(a.x, -a.y); }
-// acc += a*b
+__host__ __device__ __forceinline__ double fma_t(double a, double b, double c) { return fma(a, b, c); }
+__host__ __device__ __forceinline__ float fma_t(float a, float b, float c) { return fmaf(a, b, c); }
+// acc += a*b as FOUR chained fused multiply-adds.  Written out because `acc.x += a.x*b.x - a.y*b.y` compiles to
+// DMUL + DFMA + DADD per component (the compiler may not re-associate), i.e. 6 instead of 4 FP64 instructions per
+// complex multiply-add: the 27-point kernels are bound by exactly that pipe.
 template <typename T>
 __host__ __device__ __forceinline__ void cfma(cx<T>& acc, cx<T> a, cx<T> b) {
-    acc.x += a.x * b.x - a.y * b.y;
-    acc.y += a.x * b.y + a.y * b.x;
+    acc.x = fma_t(a.x, b.x, acc.x);
+    acc.x = fma_t(-a.y, b.y, acc.x);
+    acc.y = fma_t(a.x, b.y, acc.y);
+    acc.y = fma_t(a.y, b.x, acc.y);
 }
 // acc += s*b (s real)
 template <typename T>

@@ -375,6 +375,10 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         "r"(parity)
         : "memory");
 }
+// Orders this thread's earlier generic-proxy accesses to shared memory before later async-proxy (TMA) accesses to the
+// same bytes.  Needed wherever threads WRITE a staged tile that the TMA engine refills later (k_fine3d_tma_pro);
+// executed by the writers, followed by the CTA barrier the issuing thread waits on.
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 // 4-D / 3-D tiled TMA loads (cp.async.bulk.tensor, SASS UTMALDG): one instruction moves a whole box,
 // out-of-range coordinates are zero-filled by the hardware (that is how tile halos at the domain
 // boundary and surplus RHS slots are handled).
@@ -680,6 +684,7 @@ __global__ void __launch_bounds__(256) k_fine3d_tma_pro(FineOp<T> op, const __gr
             xv[q] = v;
         }
         if (hoff >= 0) xs[hoff] = xs[hoff] + interp(c0, hcoff, hpar, ok);
+        fence_proxy_async();  // these generic stores precede the TMA refill of this stage (after a CTA barrier)
     };
     if (threadIdx.x == 0) {
         for (int s = 0; s < NS; ++s) mbar_init(&bars[s], 1);
@@ -883,7 +888,7 @@ __global__ void __launch_bounds__(256) k_fine3d_tma_first(FineOp<T> op, const __
 
 // ---------------------------------------------------------------------------------------------
 // Coarse levels, 3-D, TMA production form: 27-point stencil with stored Galerkin coefficients.
-// A CTA (128 threads) owns a 32 x 4 tile of (i,j) columns and walks a chunk of z planes in the
+// A CTA owns a TX x TY tile of (i,j) columns (TX*TY <= 128) and walks a chunk of z planes in the
 // scatter form of k_coarse3d_zmarch (three rolling accumulators per right-hand side).  Each
 // iteration consumes one stage staged by the TMA engine: the x tile of input plane zi with a
 // one-node halo for all KB right-hand sides, the three 9-coefficient sets that plane feeds (dk = -1
@@ -891,10 +896,20 @@ __global__ void __launch_bounds__(256) k_fine3d_tma_first(FineOp<T> op, const __
 // that completes in this iteration.  Out-of-range planes, halos and surplus RHS slots are zero-filled
 // by the hardware, so the loop has no boundary cases.  The 27 coefficients of a node are read once
 // per KB (up to 8) right-hand sides.
+//
+// The kernel is bound by the FP64 pipe and the shared-memory pipe together (108 DFMA and ~12 LDS.128
+// per node and right-hand side), not by HBM, unless both pipes stay busy: with KB >= 2 the CTA runs
+// TWO warpgroups of 128 threads on the same staged tile, each taking KB/2 right-hand sides -- 8 warps
+// per SM (2 per scheduler) instead of 4, half the accumulator registers per thread -- and the tile
+// shape is a launch-time choice (hh_solver.cuh: coarse_tile) so that 2^k+1 grids do not leave most of
+// the last tile column idle (129 = 4*32+1 wastes 19 % of a 32-wide tiling, 9 % of an 11-wide one).
 // ---------------------------------------------------------------------------------------------
-template <typename T, int MODE, int KB>
+template <typename T, int MODE, int KB, int TX_, int TY_>
 struct CoarseTmaCfg {
-    static constexpr int TX = 32, TY = 4;
+    static constexpr int TX = TX_, TY = TY_;
+    static constexpr int NWG = KB >= 2 ? 2 : 1;   // warpgroups (128 threads each) working on one staged tile
+    static constexpr int KH = KB / NWG;           // right-hand sides per warpgroup
+    static constexpr int THREADS = 128 * NWG;
     static constexpr int HX = sizeof(T) == 4 ? 2 : 1;  // see FineTmaCfg
     static constexpr int PX = TX + 2 * HX;
     static constexpr int XT = (TY + 2) * PX;
@@ -909,29 +924,60 @@ struct CoarseTmaCfg {
     static constexpr int STAGE_BYTES = OFF_D + (MODE == MODE_JACOBI ? al(BT * ES) : 0);
     static constexpr uint32_t TX_BYTES = KB * XT * ES + 27 * BT * ES + (MODE != MODE_APPLY ? KB * BT * ES : 0) +
                                          (MODE == MODE_JACOBI ? BT * ES : 0);
-    static constexpr int NS = 2;
+    static constexpr int NS = (3 * STAGE_BYTES + 64 <= 227 * 1024) ? 3 : 2;
+    static_assert(TX * TY <= 128, "a warpgroup covers the tile with one thread per column");
+    static_assert((TX * ES) % 16 == 0 && (PX * ES) % 16 == 0, "TMA box rows are 16-byte multiples");
+    static_assert(2 * STAGE_BYTES + 64 <= 227 * 1024, "two stages must fit in shared memory");
 };
 
-template <typename T, int MODE, int KB>
-__global__ void __launch_bounds__(128) k_coarse3d_tma(const __grid_constant__ TmaDesc tm_x,
-                                                      const __grid_constant__ TmaDesc tm_c,
-                                                      const __grid_constant__ TmaDesc tm_b,
-                                                      const __grid_constant__ TmaDesc tm_d, cx<T>* __restrict__ out,
-                                                      int n0, int n1, int n2, int sy, int64_t ld, int nrhs,
-                                                      int zchunk, int groups, int zb, int ze) {
-    typedef CoarseTmaCfg<T, MODE, KB> Cfg;
-    constexpr int TX = Cfg::TX, TY = Cfg::TY, PX = Cfg::PX, NS = Cfg::NS;
+// one input plane scattered into the three rolling accumulators: acc[2] += c(dk=-1) x, acc[1] += c(dk=0) x,
+// acc[0] += c(dk=+1) x over the 3 x 3 in-plane neighbourhood (sx, cm, c0, cp already point at this thread's entries)
+template <typename T, int KH, int XT, int BT, int PX, bool UM, bool U0, bool UP>
+__device__ __forceinline__ void coarse_scatter(cx<T> (&acc)[3][KH], const cx<T>* __restrict__ sx, const cx<T>* __restrict__ cm,
+                                               const cx<T>* __restrict__ c0, const cx<T>* __restrict__ cp) {
+#pragma unroll
+    for (int dj = -1; dj <= 1; ++dj) {
+#pragma unroll
+        for (int di = -1; di <= 1; ++di) {
+            const int sxy = (di + 1) + 3 * (dj + 1);
+            cx<T> fm, f0, fp;
+            if (UM) fm = cm[sxy * BT];
+            if (U0) f0 = c0[sxy * BT];
+            if (UP) fp = cp[sxy * BT];
+#pragma unroll
+            for (int q = 0; q < KH; ++q) {
+                const cx<T> xv = sx[q * XT + di + dj * PX];
+                if (UM) cfma(acc[2][q], fm, xv);
+                if (U0) cfma(acc[1][q], f0, xv);
+                if (UP) cfma(acc[0][q], fp, xv);
+            }
+        }
+    }
+}
+
+template <typename T, int MODE, int KB, int TX_, int TY_>
+__global__ void __launch_bounds__(CoarseTmaCfg<T, MODE, KB, TX_, TY_>::THREADS, 1)
+    k_coarse3d_tma(const __grid_constant__ TmaDesc tm_x, const __grid_constant__ TmaDesc tm_c,
+                   const __grid_constant__ TmaDesc tm_b, const __grid_constant__ TmaDesc tm_d, cx<T>* __restrict__ out,
+                   int n0, int n1, int n2, int sy, int64_t ld, int nrhs, int zchunk, int groups, int zb, int ze) {
+    typedef CoarseTmaCfg<T, MODE, KB, TX_, TY_> Cfg;
+    constexpr int TX = Cfg::TX, TY = Cfg::TY, PX = Cfg::PX, NS = Cfg::NS, KH = Cfg::KH;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + (size_t)NS * Cfg::STAGE_BYTES);
-    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int wg = threadIdx.x >> 7;                     // warpgroup: right-hand sides q0 .. q0+KH-1 of the group
+    const int lt = threadIdx.x & 127;
+    const bool lane_ok = lt < TX * TY;                    // tiles smaller than 128 columns leave the last lanes idle
+    const int lc = lane_ok ? lt : 0;
+    const int tx = lc % TX, ty = lc / TX;
     const int i0 = (blockIdx.x / groups) * TX, j0 = blockIdx.y * TY;
     const int i = i0 + tx, j = j0 + ty;
     const int r0 = (blockIdx.x % groups) * KB;
+    const int q0 = wg * KH;
     const int z0 = zb + blockIdx.z * zchunk;
     const int z1 = min(ze, z0 + zchunk);
     (void)n2;
     const int niter = z1 - z0 + 2;  // input planes z0-1 .. z1
-    const bool active = (i < n0) && (j < n1);
+    const bool active = lane_ok && (i < n0) && (j < n1);
     auto issue = [&](int s, int zi) {
         unsigned char* st = smem_raw + (size_t)s * Cfg::STAGE_BYTES;
         mbar_expect_tx(&bars[s], Cfg::TX_BYTES);
@@ -949,9 +995,9 @@ __global__ void __launch_bounds__(128) k_coarse3d_tma(const __grid_constant__ Tm
     }
     __syncthreads();
     const cx<T> zero = mk<T>(T(0), T(0));
-    cx<T> acc[3][KB], xprev[KB];
+    cx<T> acc[3][KH], xprev[KH];
 #pragma unroll
-    for (int q = 0; q < KB; ++q) {
+    for (int q = 0; q < KH; ++q) {
         acc[0][q] = acc[1][q] = acc[2][q] = zero;
         xprev[q] = zero;
     }
@@ -965,38 +1011,25 @@ __global__ void __launch_bounds__(128) k_coarse3d_tma(const __grid_constant__ Tm
         const int s = it % NS;
         const unsigned char* st = smem_raw + (size_t)s * Cfg::STAGE_BYTES;
         mbar_wait(&bars[s], (uint32_t)((it / NS) & 1));
-        const cx<T>* sx = reinterpret_cast<const cx<T>*>(st + Cfg::OFF_X);
+        const cx<T>* sx = reinterpret_cast<const cx<T>*>(st + Cfg::OFF_X) + q0 * Cfg::XT;
         const cx<T>* cm = reinterpret_cast<const cx<T>*>(st + Cfg::OFF_C);
         const cx<T>* c0 = reinterpret_cast<const cx<T>*>(st + Cfg::OFF_C + Cfg::CSET);
         const cx<T>* cp = reinterpret_cast<const cx<T>*>(st + Cfg::OFF_C + 2 * Cfg::CSET);
-#pragma unroll
-        for (int dj = -1; dj <= 1; ++dj) {
-#pragma unroll
-            for (int di = -1; di <= 1; ++di) {
-                const int sxy = (di + 1) + 3 * (dj + 1);
-                const cx<T> fm = cm[sxy * Cfg::BT + bidx];
-                const cx<T> f0 = c0[sxy * Cfg::BT + bidx];
-                const cx<T> fp = cp[sxy * Cfg::BT + bidx];
-#pragma unroll
-                for (int q = 0; q < KB; ++q) {
-                    const cx<T> xv = sx[q * Cfg::XT + cidx + di + dj * PX];
-                    cfma(acc[2][q], fm, xv);
-                    cfma(acc[1][q], f0, xv);
-                    cfma(acc[0][q], fp, xv);
-                }
-            }
-        }
+        // the first / last input plane of a chunk feeds one output plane only: skip the other two coefficient sets
+        if (it == 0) coarse_scatter<T, KH, Cfg::XT, Cfg::BT, PX, true, false, false>(acc, sx + cidx, cm + bidx, c0 + bidx, cp + bidx);
+        else if (it == niter - 1) coarse_scatter<T, KH, Cfg::XT, Cfg::BT, PX, false, false, true>(acc, sx + cidx, cm + bidx, c0 + bidx, cp + bidx);
+        else coarse_scatter<T, KH, Cfg::XT, Cfg::BT, PX, true, true, true>(acc, sx + cidx, cm + bidx, c0 + bidx, cp + bidx);
         // output plane zi-1 is complete
         const int zo = zi - 1;
         if (active && zo >= z0 && zo < z1) {
             const int64_t p = pxy + (int64_t)zo * sz;
-            const cx<T>* sb = reinterpret_cast<const cx<T>*>(st + Cfg::OFF_B);
+            const cx<T>* sb = reinterpret_cast<const cx<T>*>(st + Cfg::OFF_B) + q0 * Cfg::BT;
             cx<T> dv = zero;
             if (MODE == MODE_JACOBI) dv = reinterpret_cast<const cx<T>*>(st + Cfg::OFF_D)[bidx];
 #pragma unroll
-            for (int q = 0; q < KB; ++q) {
-                if (r0 + q < nrhs) {
-                    const int64_t o = (int64_t)(r0 + q) * ld + p;
+            for (int q = 0; q < KH; ++q) {
+                if (r0 + q0 + q < nrhs) {
+                    const int64_t o = (int64_t)(r0 + q0 + q) * ld + p;
                     if (MODE == MODE_APPLY) {
                         out[o] = acc[0][q];
                     } else {
@@ -1008,7 +1041,7 @@ __global__ void __launch_bounds__(128) k_coarse3d_tma(const __grid_constant__ Tm
             }
         }
 #pragma unroll
-        for (int q = 0; q < KB; ++q) {
+        for (int q = 0; q < KH; ++q) {
             acc[0][q] = acc[1][q];
             acc[1][q] = acc[2][q];
             acc[2][q] = zero;
@@ -1017,6 +1050,26 @@ __global__ void __launch_bounds__(128) k_coarse3d_tma(const __grid_constant__ Tm
         __syncthreads();
         if (threadIdx.x == 0 && it + NS < niter) issue(s, zi + NS);
     }
+}
+
+// Column-scaled copy of a stored stencil: As[s][p] = A[s][p] * dinv[p + off(s)], i.e. As = A * diag(dinv).  With it the
+// right-preconditioned Jacobi-GMRES of a level (inexact coarsest solve, Jac-GMRES smoother) applies w = (A D^-1) v in
+// ONE stencil pass instead of z = D^-1 v followed by w = A z (saves a 2S pass and a launch per GMRES step).
+template <typename T, int DIM>
+__global__ void __launch_bounds__(256) k_scale_columns(CoarseOp<T> op, cx<T>* __restrict__ scaled) {
+    const int NS = (DIM == 3) ? 27 : 9;
+    const int64_t nodes = (int64_t)op.n[0] * op.n[1] * op.n[2];
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nodes * NS) return;
+    const int s = (int)(t / nodes);
+    const int64_t q = t - (int64_t)s * nodes;
+    const int i = (int)(q % op.n[0]), j = (int)((q / op.n[0]) % op.n[1]), k = (int)(q / ((int64_t)op.n[0] * op.n[1]));
+    const int di = s % 3 - 1, dj = (s / 3) % 3 - 1, dk = (DIM == 3) ? (s / 9 - 1) : 0;
+    const int64_t p = i + (int64_t)op.sy * j + (int64_t)op.sy * op.n[1] * k;
+    cx<T> v = mk<T>(T(0), T(0));
+    if ((unsigned)(i + di) < (unsigned)op.n[0] && (unsigned)(j + dj) < (unsigned)op.n[1] && (unsigned)(k + dk) < (unsigned)op.n[2])
+        v = op.coef[(int64_t)s * op.N + p] * op.dinv[p + di + (int64_t)op.sy * dj + (int64_t)op.sy * op.n[1] * dk];
+    scaled[(int64_t)s * op.N + p] = v;
 }
 
 // centre coefficient (incl. Laplacian diagonal) and damp/centre as arrays, for the TMA-staged kernels
@@ -1362,11 +1415,20 @@ __global__ void k_band_fill(CoarseOp<T> op, zc* __restrict__ band, int bw) {
 }
 
 // right-looking banded LU, one CTA (set-up only).  L (unit lower) and U overwrite the band.
-__global__ void __launch_bounds__(1024) k_band_lu(zc* __restrict__ band, int64_t N, int bw) {
+// The factorisation does not pivot (see above); with shift == 0 and no attenuation the coarse operator is indefinite
+// and a pivot can collapse.  flag[0] is set to 1 + the row of the first pivot that is not finite or smaller than
+// 1e-13 x the largest pivot seen so far; the host turns that into HH_ERR_UNSUPPORTED instead of returning Inf/NaN.
+__global__ void __launch_bounds__(1024) k_band_lu(zc* __restrict__ band, int64_t N, int bw, int* __restrict__ flag) {
     const int64_t W = 2 * (int64_t)bw + 1;
+    double pmax = 0.0;
     for (int64_t k = 0; k < N; ++k) {
         const int nrow = (int)min((int64_t)bw, N - 1 - k);
         const zc piv = band[k * W + bw];
+        {
+            const double pa = fabs(piv.x) + fabs(piv.y);
+            if (threadIdx.x == 0 && flag[0] == 0 && !(pa > 1e-13 * pmax && pa < 1e300 && pa > 0.0)) flag[0] = (int)min(k + 1, (int64_t)INT_MAX);
+            pmax = fmax(pmax, pa);
+        }
         for (int t = threadIdx.x; t < nrow; t += blockDim.x) {
             const int64_t i = k + 1 + t;
             zc* e = &band[i * W + (k - i + bw)];

@@ -397,7 +397,7 @@ struct SolverBase {
     virtual void cycle_device(const void* dB, void* dZ, int64_t nrhs) = 0;
     virtual int solve_device(const void* dB, void* dX, int64_t nrhs, const hh_solve_options& o, int32_t* iters,
                              double* relres) = 0;
-    virtual int64_t max_rhs_per_batch(const hh_solve_options& o) = 0;
+    virtual int64_t max_rhs_per_batch(const hh_solve_options& o, double reusable_bytes = 0.0) = 0;
     virtual size_t elem_size() const = 0;
     virtual void scatter_point_sources(void* dB, const int64_t* idx0, const double* val, int64_t nrhs) = 0;
     // ---- mixed precision (HH_C64_MIXED): a ComplexF64 Krylov solver whose preconditioner is the multigrid cycle of a
@@ -464,6 +464,7 @@ class Solver : public SolverBase {
         int zb = 0, ze = 1;         // planes computed by the kernels (slab: the owned planes; else 0, n[2])
         int koff = 0, n2g = 1;      // slab: global index of local plane 0, global plane count (else 0, n[2])
         DevBuf<C> coef, dinv;       // l >= 1 (dinv also on l = 0 when Jac-GMRES is used)
+        DevBuf<C> scoef;            // coef * diag(dinv) on the levels that run a Jacobi-preconditioned GMRES
         DevBuf<C> x, b, t;          // work vectors N x kcap (l >= 1); l = 0 owns only t
         SmallWs gs;                 // Jac-GMRES smoother / inexact coarsest solve (Jacobi-preconditioned)
         SmallWs ks;                 // K-cycle: 2 steps of FGMRES preconditioned by the recursive cycle
@@ -484,6 +485,11 @@ class Solver : public SolverBase {
         // opt-in: measured slower than exchange-then-compute on 8 B200 (profiles/bench_r01_config5_slab_n8_513_ab.jsonl)
         const char* ho = getenv("HH_HALO_OVERLAP");
         halo_overlap = ho && ho[0] == '1';
+        const char* ct = getenv("HH_COARSE_TILE");
+        if (ct && !strcmp(ct, "16x8")) force_tile = 0;
+        if (ct && !strcmp(ct, "alt")) force_tile = 1;
+        const char* sc = getenv("HH_SCALED_GMRES");  // A/B switch of the one-pass (A D^-1) apply (default on)
+        scaled_gmres = !(sc && sc[0] == '0');
         const char* hs = getenv("HH_HALO_SPLIT");
         split_always = hs && hs[0] == '1';
         use_pitch = sizeof(T) == 4 && pb.dim == 3 && fine_kernel == FK_TMA;
@@ -962,40 +968,67 @@ class Solver : public SolverBase {
         const int64_t es = 2 * sizeof(T);
         return (es * L.p0) % 16 == 0 && (es * L.p0 * L.n[1]) % 16 == 0 && (es * L.N) % 16 == 0;
     }
-    template <int MODE, int KB>
-    void coarse_tma_launch(const Level& L, const C* x, const C* b, C* out, int nrhs) {
-        typedef CoarseTmaCfg<T, MODE, KB> Cfg;
+    // ---- 27-point TMA kernel: tile shape and z-chunking ------------------------------------------------------------
+    // Tile shapes (TX x TY columns per CTA): 16 x 8, or the "alternative" 11 x 11 (ComplexF64) / 12 x 10 (ComplexF32,
+    // whose TMA rows must be 16-byte multiples), which wastes far fewer lanes on the small 2^k+1 grids (65 = 4*16+1
+    // fills 73 % of a 16 x 8 tiling, 92 % of an 11 x 11 one) at the price of two-way bank conflicts on rows that a
+    // quarter-warp straddles.  HH_COARSE_TILE=16x8|alt forces one.
+    static constexpr int ALT_TX = sizeof(T) == 8 ? 11 : 12, ALT_TY = sizeof(T) == 8 ? 11 : 10;
+    int coarse_tile(const Level& L) const {
+        if (force_tile >= 0) return force_tile;
+        const double t16 = (double)((L.n[0] + 15) / 16) * ((L.n[1] + 7) / 8);
+        const double talt = (double)((L.n[0] + ALT_TX - 1) / ALT_TX) * ((L.n[1] + ALT_TY - 1) / ALT_TY);
+        return talt < 0.90 * t16 ? 1 : 0;
+    }
+    // z-chunks of equal length such that the waves of one-CTA-per-SM CTAs are full and the two extra input planes a
+    // chunk stages (which cost a third of a plane each) stay a small share: minimise waves x (chunk + 2/3)
+    static void balanced_chunks(int nz, int64_t ctas_per_chunk, int& zchunk, int& nzc) {
+        double best = 1e300;
+        zchunk = nz;
+        nzc = 1;
+        for (int c = 1; c <= nz; ++c) {
+            const int zc = (nz + c - 1) / c, cc = (nz + zc - 1) / zc;
+            if (cc != c) continue;  // same chunk length as a smaller count
+            const double waves = std::ceil((double)ctas_per_chunk * cc / 148.0);
+            const double cost = waves * (zc + 0.67) + 0.02 * cc;  // tie-break: fewer, longer chunks
+            if (cost < best) best = cost, zchunk = zc, nzc = cc;
+            if (zc <= 2) break;
+        }
+    }
+    template <int MODE, int KB, int TX, int TY>
+    void coarse_tma_launch(const Level& L, const C* coef, const C* x, const C* b, C* out, int nrhs) {
+        typedef CoarseTmaCfg<T, MODE, KB, TX, TY> Cfg;
         constexpr size_t smem = (size_t)Cfg::NS * Cfg::STAGE_BYTES + Cfg::NS * sizeof(uint64_t);
         static bool attr_set = false;
         if (!attr_set) {
-            HH_CUDA(cudaFuncSetAttribute(k_coarse3d_tma<T, MODE, KB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            HH_CUDA(cudaFuncSetAttribute(k_coarse3d_tma<T, MODE, KB, TX, TY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             attr_set = true;
         }
         const int groups = (nrhs + KB - 1) / KB;
-        const int tx = (L.n[0] + Cfg::TX - 1) / Cfg::TX, ty = (L.n[1] + Cfg::TY - 1) / Cfg::TY;
+        const int tx = (L.n[0] + TX - 1) / TX, ty = (L.n[1] + TY - 1) / TY;
         int zchunk, nzc;
-        const int nz = zend(L) - zbeg(L);
-        zchunks(nz, tx * ty, groups, 32, zchunk, nzc);
-        // one CTA per SM is resident: aim for a few waves, not for many tiny chunks
-        while (nzc > 1 && (int64_t)tx * ty * groups * nzc > 148 * 6) {
-            zchunk = std::min(nz, zchunk * 2);
-            nzc = (nz + zchunk - 1) / zchunk;
-        }
+        balanced_chunks(zend(L) - zbeg(L), (int64_t)tx * ty * groups, zchunk, nzc);
         dim3 g(tx * groups, ty, nzc);
-        TmaDesc mx = make_tmap_g(x, L.n, L.p0, L.N, Cfg::PX, Cfg::TY + 2, KB, nrhs);
-        TmaDesc mc = make_tmap_g(L.coef.p, L.n, L.p0, L.N, Cfg::TX, Cfg::TY, 9, 27);
-        TmaDesc mb = (MODE != MODE_APPLY) ? make_tmap_g(b, L.n, L.p0, L.N, Cfg::TX, Cfg::TY, KB, nrhs) : mx;
-        TmaDesc md = (MODE == MODE_JACOBI) ? make_tmap_g(L.dinv.p, L.n, L.p0, L.N, Cfg::TX, Cfg::TY, 1, 0) : mx;
-        k_coarse3d_tma<T, MODE, KB><<<g, 128, smem, stream>>>(mx, mc, mb, md, out, L.n[0], L.n[1], L.n[2], L.p0, L.N, nrhs, zchunk, groups, zbeg(L), zend(L));
+        TmaDesc mx = make_tmap_g(x, L.n, L.p0, L.N, Cfg::PX, TY + 2, KB, nrhs);
+        TmaDesc mc = make_tmap_g(coef, L.n, L.p0, L.N, TX, TY, 9, 27);
+        TmaDesc mb = (MODE != MODE_APPLY) ? make_tmap_g(b, L.n, L.p0, L.N, TX, TY, KB, nrhs) : mx;
+        TmaDesc md = (MODE == MODE_JACOBI) ? make_tmap_g(L.dinv.p, L.n, L.p0, L.N, TX, TY, 1, 0) : mx;
+        k_coarse3d_tma<T, MODE, KB, TX, TY><<<g, Cfg::THREADS, smem, stream>>>(mx, mc, mb, md, out, L.n[0], L.n[1], L.n[2], L.p0, L.N, nrhs,
+                                                                                zchunk, groups, zbeg(L), zend(L));
+    }
+    template <int MODE, int KB>
+    void coarse_tma_tile(const Level& L, const C* coef, const C* x, const C* b, C* out, int nrhs) {
+        if (coarse_tile(L) == 1) coarse_tma_launch<MODE, KB, ALT_TX, ALT_TY>(L, coef, x, b, out, nrhs);
+        else coarse_tma_launch<MODE, KB, 16, 8>(L, coef, x, b, out, nrhs);
     }
     template <int MODE>
-    void coarse_tma_mode(const Level& L, const C* x, const C* b, C* out, int nrhs) {
+    void coarse_tma_mode(const Level& L, const C* coef, const C* x, const C* b, C* out, int nrhs) {
         int kb = 1;
         while (kb * 2 <= nrhs && kb * 2 <= 8) kb *= 2;
-        if (kb == 8) coarse_tma_launch<MODE, 8>(L, x, b, out, nrhs);
-        else if (kb == 4) coarse_tma_launch<MODE, 4>(L, x, b, out, nrhs);
-        else if (kb == 2) coarse_tma_launch<MODE, 2>(L, x, b, out, nrhs);
-        else coarse_tma_launch<MODE, 1>(L, x, b, out, nrhs);
+        if (kb == 8) coarse_tma_tile<MODE, 8>(L, coef, x, b, out, nrhs);
+        else if (kb == 4) coarse_tma_tile<MODE, 4>(L, coef, x, b, out, nrhs);
+        else if (kb == 2) coarse_tma_tile<MODE, 2>(L, coef, x, b, out, nrhs);
+        else coarse_tma_tile<MODE, 1>(L, coef, x, b, out, nrhs);
     }
     static int coarse_kb(int nrhs) {
         const int pref = sizeof(T) == 8 ? 4 : 8;
@@ -1032,7 +1065,7 @@ class Solver : public SolverBase {
     }
     CoarseOp<T> coarse_op(const Level& L) const {
         CoarseOp<T> op;
-        op.coef = L.coef.p;
+        op.coef = (use_scaled && L.scoef.p) ? L.scoef.p : L.coef.p;  // scaled: A diag(dinv), see k_scale_columns
         op.dinv = L.dinv.p;
         for (int d = 0; d < 3; ++d) op.n[d] = L.n[d];
         op.sy = L.p0;
@@ -1041,14 +1074,18 @@ class Solver : public SolverBase {
         op.ze = zend(L);
         return op;
     }
-    void coarse_stencil(int mode, const Level& L, const C* x, const C* b, C* out, int nrhs) {
+    // scaled: apply the column-scaled copy A diag(dinv) of the level's operator (right-preconditioned Jacobi-GMRES)
+    void coarse_stencil(int mode, const Level& L, const C* x, const C* b, C* out, int nrhs, bool scaled = false) {
         const int li = slab ? (int)(&L - levels.data()) : 0;
+        HH_REQUIRE(!scaled || L.scoef.p != nullptr, HH_ERR_STATE, "no scaled operator on this level");
+        use_scaled = scaled;
         with_halos({{li, x, 0}}, nrhs, L.zb, L.ze, [&](int z0, int z1) {
             rz_b = z0;  // the launchers below read the plane range through zbeg / zend
             rz_e = z1;
             coarse_stencil_range(mode, L, x, b, out, nrhs);
             rz_b = rz_e = -1;
         });
+        use_scaled = false;
     }
     void coarse_stencil_range(int mode, const Level& L, const C* x, const C* b, C* out, int nrhs) {
         dim3 g, blk;
@@ -1061,7 +1098,10 @@ class Solver : public SolverBase {
             KB = 1;
             while (KB * 2 <= nrhs && KB * 2 <= 8) KB *= 2;
         }
-        const double coefb = NS * S * N * ((nrhs + KB - 1) / KB);
+        // algorithmic bytes: the 3^dim coefficients of a node once per launch (k = the whole batch shares
+        // one read; re-reads by further RHS groups are L2 traffic the kernel has to earn, not algorithmic bytes)
+        (void)KB;
+        const double coefb = NS * S * N;
         double bytes;
         int tag;
         if (mode == MODE_APPLY) bytes = 2 * S * N * nrhs + coefb, tag = T_COARSE_APPLY;
@@ -1071,9 +1111,9 @@ class Solver : public SolverBase {
         const int64_t ld = L.N;
         if (use_tma) {
             launch(tag, bytes, [&] {
-                if (mode == MODE_APPLY) coarse_tma_mode<MODE_APPLY>(L, x, b, out, nrhs);
-                else if (mode == MODE_RESID) coarse_tma_mode<MODE_RESID>(L, x, b, out, nrhs);
-                else coarse_tma_mode<MODE_JACOBI>(L, x, b, out, nrhs);
+                if (mode == MODE_APPLY) coarse_tma_mode<MODE_APPLY>(L, op.coef, x, b, out, nrhs);
+                else if (mode == MODE_RESID) coarse_tma_mode<MODE_RESID>(L, op.coef, x, b, out, nrhs);
+                else coarse_tma_mode<MODE_JACOBI>(L, op.coef, x, b, out, nrhs);
             });
             return;
         }
@@ -1361,6 +1401,22 @@ class Solver : public SolverBase {
                 k_coarse_dinv<T><<<(unsigned)((Lc.N + 255) / 256), 256, 0, stream>>>(Lc.coef.p + (int64_t)center * Lc.N, Lc.dinv.p, Lc.N, (T)o.relax_param);
             });
         }
+        // levels whose Jacobi-preconditioned GMRES (smoother or inexact coarsest solve) runs on a stored stencil
+        for (int l = (ho ? 0 : 1); l < o.levels && scaled_gmres; ++l) {
+            const bool gm = (o.relax_type == HH_RELAX_JAC_GMRES && l < o.levels - 1) ||
+                            (l == o.levels - 1 && o.coarse_type == HH_COARSE_GMRES);
+            if (!gm) continue;
+            Level& L = levels[l];
+            if (slab) halo_exchange(l, L.dinv.p, 1, 0, HALO_BOTH);  // columns on the halo planes are scaled by the neighbour's dinv
+            L.scoef.alloc((size_t)NS * L.N);
+            HH_CUDA(cudaMemsetAsync(L.scoef.p, 0, (size_t)NS * L.N * sizeof(C), stream));
+            const int64_t tot = (int64_t)L.n[0] * L.n[1] * L.n[2] * NS;
+            CoarseOp<T> op = coarse_op(L);
+            launch(T_SETUP, 0, [&] {
+                if (pb.dim == 3) k_scale_columns<T, 3><<<(unsigned)((tot + 255) / 256), 256, 0, stream>>>(op, L.scoef.p);
+                else k_scale_columns<T, 2><<<(unsigned)((tot + 255) / 256), 256, 0, stream>>>(op, L.scoef.p);
+            });
+        }
         if (!ho && (o.relax_type == HH_RELAX_JAC_GMRES || (o.levels == 1 && o.coarse_type == HH_COARSE_GMRES))) {
             Level& L0 = levels[0];
             L0.dinv.alloc(L0.N);
@@ -1403,7 +1459,19 @@ class Solver : public SolverBase {
             if (pb.dim == 3) k_band_fill<T, 3><<<nb, 256, 0, stream>>>(op, band.p, bw);
             else k_band_fill<T, 2><<<nb, 256, 0, stream>>>(op, band.p, bw);
         });
-        launch(T_SETUP, 0, [&] { k_band_lu<<<1, 1024, 0, stream>>>(band.p, N, bw); });
+        DevBuf<int> lu_flag;
+        lu_flag.alloc(1);
+        HH_CUDA(cudaMemsetAsync(lu_flag.p, 0, sizeof(int), stream));
+        launch(T_SETUP, 0, [&] { k_band_lu<<<1, 1024, 0, stream>>>(band.p, N, bw, lu_flag.p); });
+        {
+            int bad = 0;
+            HH_CUDA(cudaMemcpyAsync(&bad, lu_flag.p, sizeof(int), cudaMemcpyDeviceToHost, stream));
+            HH_CUDA(cudaStreamSynchronize(stream));
+            HH_REQUIRE(bad == 0, HH_ERR_UNSUPPORTED,
+                       "exact coarsest solve: the LU factorisation (no pivoting) met a vanishing pivot at row " + std::to_string(bad - 1) +
+                           "; the coarse operator is (nearly) singular or indefinite (shift = 0 without attenuation?) -- use a positive "
+                           "shift or coarse_type GMRES");
+        }
         for (int64_t c0 = 0; c0 < N; c0 += 32768) {
             const unsigned nc = (unsigned)std::min<int64_t>(32768, N - c0);
             launch(T_SETUP, 0, [&] { k_band_inverse<<<nc, 256, 0, stream>>>(band.p, N, bw, c0, inv.p); });
@@ -1587,6 +1655,12 @@ class Solver : public SolverBase {
         gmres_begin(g, V[0], sp, nrhs, true, 0.0);
         for (int j = 0; j < nsteps; ++j) {
             C* z;
+            if (prec == 0 && L.scoef.p != nullptr) {
+                // Jacobi, stored stencil: w = (A D^-1) v_j in one pass over the column-scaled coefficients
+                coarse_stencil(MODE_APPLY, L, V[j], nullptr, W[j + 1], nrhs, true);
+                gmres_orthogonalise(g, V.data(), j, W[j + 1], sp, nrhs, 0.0);
+                continue;
+            }
             if (prec == 0) {
                 z = L.pt;  // Jacobi: z = dinv .* v_j (not stored: x += dinv .* (V y) at the end)
                 diag_scale(l == 0 ? T_FINE_JACOBI0 : T_COARSE_JACOBI0, L.dinv.p, V[j], z, N, nrhs);
@@ -1859,11 +1933,12 @@ class Solver : public SolverBase {
     int krylov_vectors(const hh_solve_options& o) const {
         return o.krylov == HH_KRYLOV_GMRES ? (2 * o.inner + 1) : 7;
     }
-    int64_t max_rhs_per_batch(const hh_solve_options& o) override {
+    // reusable_bytes: device memory the caller already holds and will reuse for this solve (host staging slots)
+    int64_t max_rhs_per_batch(const hh_solve_options& o, double reusable_bytes = 0.0) override {
         HH_CUDA(cudaSetDevice(device));
         size_t fr = 0, tot = 0;
         HH_CUDA(cudaMemGetInfo(&fr, &tot));
-        double avail = (double)fr;
+        double avail = (double)fr + reusable_bytes;
         // memory we already hold for work vectors counts as available for re-use
         avail += (double)kcap * level_bytes_per_rhs() + (double)kry.n * sizeof(C);
         const int64_t Nf = have_hierarchy ? levels[0].N : pb.N();
@@ -1871,13 +1946,15 @@ class Solver : public SolverBase {
         int64_t k = (int64_t)std::floor(0.90 * avail / per);
         return std::max<int64_t>(k, 0);
     }
+    // The arena is addressed with the vector stride N * kry_cap (fgmres, bicgstab, the padded B / X blocks), so what
+    // must fit is vectors x N x kry_cap -- not x nrhs: Krylov method and restart length are per-call options, and a
+    // later solve with more vectors but fewer right-hand sides would otherwise write past the end.
     void ensure_krylov_memory(const hh_solve_options& o, int nrhs) {
-        const size_t need = (size_t)(krylov_vectors(o) + (padded() ? 2 : 0)) * levels[0].N * nrhs;
-        if (need > kry.n || nrhs > kry_cap) {
-            kry.release();
-            alloc_zero(kry, need);
-            kry_cap = nrhs;
-        }
+        const size_t nvec = (size_t)(krylov_vectors(o) + (padded() ? 2 : 0));
+        if (nrhs <= kry_cap && nvec * levels[0].N * kry_cap <= kry.n) return;
+        kry.release();
+        alloc_zero(kry, nvec * levels[0].N * nrhs);
+        kry_cap = nrhs;
     }
 
     int solve_device(const void* dB, void* dX, int64_t nrhs64, const hh_solve_options& o, int32_t* iters,
@@ -2084,6 +2161,9 @@ class Solver : public SolverBase {
     bool halo_overlap = false;           // HH_HALO_OVERLAP=1: exchange on a second stream while the interior planes run
     bool split_always = false;
     int rz_b = -1, rz_e = -1;            // plane range override of the coarse launchers (with_halos)
+    bool use_scaled = false;             // coarse_op() hands out the column-scaled coefficients (coarse_stencil)
+    int force_tile = -1;                 // HH_COARSE_TILE: 0 = 16x8, 1 = alternative tile (coarse_tile)
+    bool scaled_gmres = true;
     GmresMem outer;
     int outer_cap = 0;
     BicgMem bicg;

@@ -1,0 +1,115 @@
+"""Regression tests for defects found in review of round 1: Krylov arena sizing across calls with different
+Krylov options, layout of CUDA tensors handed to solveLinearSystem, the un-pivoted exact coarsest solve on an
+indefinite / singular coarse operator, the Neumann order of the operator the solver is handed."""
+import numpy as np
+import pytest
+import scipy.sparse.linalg as spla
+
+from conftest import rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def _problem(pkg, n=17, seed=9):
+    cfg = pkg.workloads.config4(n=n, sigma=2.0, seed=seed, pad=3)
+    mesh = pkg.getRegularMesh(cfg["domain"], cfg["n_cells"])
+    m = cfg["m"]
+    w = pkg.getMaximalFrequency(m, mesh)
+    gamma = 0.01 * w * np.ones(m.shape) + pkg.getABL(mesh.n + 1, True, cfg["pad"], w)
+    return cfg, mesh, m, w, gamma
+
+
+def test_krylov_arena_follows_per_call_options(gpu_pkg, ho):
+    """Krylov method and restart length are per-call options on a live hierarchy: BiCGSTAB with 2 RHS (7 vectors)
+    followed by GMRES(20) with 1 RHS (41 vectors, stride N*capacity), GMRES(5) with 16 RHS followed by GMRES(20) with
+    4 -- sequences that used to address the arena past its end."""
+    pkg = gpu_pkg
+    cfg, mesh, m, w, gamma = _problem(pkg)
+    omesh = ho.getRegularMesh(cfg["domain"], cfg["n_cells"])
+    H = ho.GetHelmholtzOperator(omesh, m, w, gamma, True, True)
+    lu = spla.splu(H.tocsc())
+    rng = np.random.default_rng(1)
+    N = 17**3
+    B = np.asfortranarray(rng.standard_normal((N, 16)) + 1j * rng.standard_normal((N, 16)))
+    Xt = lu.solve(B)
+    hp = pkg.HelmholtzParam(mesh, gamma, m.ravel(order="F"), w, True, True)
+    MG = pkg.getMGparam(pkg.ComplexF64, pkg.Int64, 2, 1, 80, 1e-10, "Jac", 0.8, 2, 2, "V", "NoMUMPS")
+    A = pkg.getShiftedLaplacianMultigridSolver(hp, MG, 0.2, "BiCGSTAB", 0)
+    for kry, inner, cols in (("BiCGSTAB", 0, 2), ("GMRES", 20, 1), ("GMRES", 5, 16), ("GMRES", 20, 4), ("BiCGSTAB", 0, 16),
+                             ("GMRES", 30, 3)):
+        A.Krylov, A.inner = kry, inner
+        X, A = pkg.solveLinearSystem(None, B[:, :cols].copy(order="F"), A)
+        assert rel_err(np.reshape(X, (N, -1)), Xt[:, :cols]) < 1e-7, (kry, inner, cols)
+
+
+def test_torch_tensor_layouts(gpu_pkg, ho):
+    """(N,), (N, nrhs) as the reference and the numpy path, or the zero-copy (nrhs, N); anything else is an error."""
+    import torch
+
+    pkg = gpu_pkg
+    cfg, mesh, m, w, gamma = _problem(pkg)
+    rng = np.random.default_rng(2)
+    N = 17**3
+    B = np.asfortranarray(rng.standard_normal((N, 3)) + 1j * rng.standard_normal((N, 3)))
+    hp = pkg.HelmholtzParam(mesh, gamma, m.ravel(order="F"), w, True, True)
+    MG = pkg.getMGparam(pkg.ComplexF64, pkg.Int64, 2, 1, 30, 1e-8, "Jac", 0.8, 2, 2, "V", "NoMUMPS")
+    A = pkg.getShiftedLaplacianMultigridSolver(hp, MG, 0.2, "GMRES", 5)
+    Xh, A = pkg.solveLinearSystem(None, B, A)
+    Bc = torch.as_tensor(B, device="cuda")  # (N, nrhs), the reference's layout
+    assert Bc.shape == (N, 3)
+    Xc, A = pkg.solveLinearSystem(None, Bc, A)
+    assert Xc.shape == (N, 3) and rel_err(Xc.cpu().numpy(), Xh) < 1e-13
+    Xr, A = pkg.solveLinearSystem(None, Bc.t().contiguous(), A)  # (nrhs, N) zero-copy
+    assert Xr.shape == (3, N) and rel_err(Xr.cpu().numpy().T, Xh) < 1e-13
+    Xv, A = pkg.solveLinearSystem(None, Bc[:, 1].contiguous(), A)
+    assert Xv.shape == (N,) and rel_err(Xv.cpu().numpy(), Xh[:, 1]) < 1e-12
+    Hop = pkg.HelmholtzOperator(A.MG._hd)
+    assert rel_err((Hop @ Bc).cpu().numpy(), Hop @ B) < 1e-14
+    with pytest.raises(ValueError):
+        pkg.solveLinearSystem(None, Bc[: N - 1], A)
+    with pytest.raises(ValueError):
+        pkg.solveLinearSystem_(None, Bc, torch.empty((3, N), dtype=torch.complex128, device="cuda"), A)
+
+
+def test_exact_coarse_solve_reports_vanishing_pivot(gpu_pkg):
+    """The exact coarsest solve factorises without pivoting.  A singular coarse operator (pure Neumann Laplacian: m = 0,
+    no shift, no attenuation, no Sommerfeld) must be reported, not returned as Inf/NaN; shift = 0 with attenuation
+    (the reference's getAfun branch) still works."""
+    pkg = gpu_pkg
+    n = 9
+    mesh = pkg.getRegularMesh([0.0, 0.8, 0.0, 0.8, 0.0, 0.8], [n - 1] * 3)
+    zero = np.zeros((n, n, n))
+    MG = pkg.getMGparam(pkg.ComplexF64, pkg.Int64, 2, 1, 5, 1e-6, "Jac", 0.8, 2, 2, "V", "NoMUMPS")
+    hp = pkg.HelmholtzParam(mesh, zero, zero, 1.0, True, False)
+    A = pkg.getShiftedLaplacianMultigridSolver(hp, MG, 0.0, "GMRES", 5)
+    b = np.zeros(n**3, dtype=np.complex128)
+    b[0] = 1.0
+    with pytest.raises(pkg._lib.HelmholtzB200Error) as e:
+        pkg.solveLinearSystem(None, b, A)
+    assert "pivot" in str(e.value)
+    cfg, mesh, m, w, gamma = _problem(pkg)
+    MG = pkg.getMGparam(pkg.ComplexF64, pkg.Int64, 2, 1, 60, 1e-8, "Jac", 0.8, 2, 2, "V", "NoMUMPS")
+    hp = pkg.HelmholtzParam(mesh, gamma + 0.3 * w, m.ravel(order="F"), w, True, True)
+    A = pkg.getShiftedLaplacianMultigridSolver(hp, MG, 0.0, "GMRES", 10)
+    q = np.zeros(17**3, dtype=np.complex128)
+    q[17 * 17 * 3 + 100] = 1.0
+    x, A = pkg.solveLinearSystem(None, q, A)
+    assert A.relres[0] <= 1e-8
+
+
+def test_solver_follows_neumann_order_of_the_operator(gpu_pkg, ho):
+    """solveLinearSystem builds its hierarchy from the operator it is handed (ShiftedLaplacianMultigridSolver.jl:65):
+    GetHelmholtzOperator(Hparam, 1) + shift solves the first-order-Neumann system."""
+    pkg = gpu_pkg
+    cfg, mesh, m, w, gamma = _problem(pkg)
+    omesh = ho.getRegularMesh(cfg["domain"], cfg["n_cells"])
+    hp = pkg.HelmholtzParam(mesh, gamma, m.ravel(order="F"), w, True, True)
+    q = np.zeros(17**3, dtype=np.complex128)
+    q[17 * 17 * 2 + 40] = 1.0
+    for order in (1, 2):
+        H1 = pkg.GetHelmholtzOperator(hp, order)
+        MG = pkg.getMGparam(pkg.ComplexF64, pkg.Int64, 2, 1, 60, 1e-9, "Jac", 0.8, 2, 2, "V", "NoMUMPS")
+        A = pkg.getShiftedLaplacianMultigridSolver(hp, MG, 0.2, "GMRES", 10)
+        x, A = pkg.solveLinearSystem((H1 + pkg.GetHelmholtzShiftOP(m, w, 0.2)).H, q, A)
+        Ho = ho.GetHelmholtzOperator(omesh, m, w, gamma, True, True, order)
+        assert np.linalg.norm(Ho @ x - q) / np.linalg.norm(q) < 1e-8, order
