@@ -662,6 +662,12 @@ def solveLinearSystem(ShiftedHT, B, param, doTranspose=0):
 def solvePointSources(param, srcs, amplitudes=None, doTranspose=0):
     """Solve for point sources without materialising a dense B on the host (hh_solve_point_sources).
     srcs: list of 1-based subscripts; amplitude default 1/||h||^2 as getAcousticPointSource."""
+    return solvePointSources_(param, srcs, None, amplitudes, doTranspose)
+
+
+def solvePointSources_(param, srcs, X, amplitudes=None, doTranspose=0):
+    """In-place form: X is an N x nrhs column-major host block of the solver's precision (e.g. a pinned buffer) that
+    receives the solutions; None allocates one."""
     hd = _ensure_hierarchy(param, doTranspose)
     MG = param.MG
     Mesh = param.helmParam.Mesh
@@ -677,7 +683,10 @@ def solvePointSources(param, srcs, amplitudes=None, doTranspose=0):
     so.max_iter = MG.maxOuterIter
     so.do_transpose = int(doTranspose)
     so.rel_tol = MG.relativeTol
-    X = np.empty((hd.N, nrhs), dtype=hd.dtype, order="F")
+    if X is None:
+        X = np.empty((hd.N, nrhs), dtype=hd.dtype, order="F")
+    elif not (isinstance(X, np.ndarray) and X.dtype == hd.dtype and X.shape == (hd.N, nrhs) and X.flags.f_contiguous):
+        raise ValueError(f"X must be a column-major {hd.N} x {nrhs} numpy block of dtype {hd.dtype}")
     iters = np.zeros(nrhs, dtype=np.int32)
     relres = np.zeros(nrhs, dtype=np.float64)
     t0 = time.perf_counter()

@@ -21,6 +21,14 @@ pytestmark = pytest.mark.gpu
 N1 = 257
 
 
+def _log(msg):
+    """numbers for profiles/: printed, and appended to $HH_TEST_LOG when set"""
+    print(msg)
+    if os.environ.get("HH_TEST_LOG"):
+        with open(os.environ["HH_TEST_LOG"], "a") as f:
+            f.write(msg + "\n")
+
+
 @pytest.fixture(scope="module")
 def truth(gpu_pkg, ho):
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
@@ -65,7 +73,7 @@ def test_config4_solution_matches_cpu_port(gpu_pkg, truth):
     x9, A = pkg.solveLinearSystem(None, truth["b"], A)
     assert int(A.iterations[0]) == truth["it9"]
     err = rel_err(x9, truth["x"])
-    print(f"257^3: iterations {truth['it6']} (1e-6) / {truth['it9']} (1e-9), GPU vs CPU-port solution error {err:.2e}, "
+    _log(f"257^3: iterations {truth['it6']} (1e-6) / {truth['it9']} (1e-9), GPU vs CPU-port solution error {err:.2e}, "
           f"error of the 1e-6 solve {rel_err(x6, truth['x']):.2e}")
     assert err <= 1e-6
     pkg.clear(A.MG)
@@ -78,11 +86,24 @@ def test_config5_style_slabs_match_cpu_port(gpu_pkg, truth):
     A = _solver(pkg, truth, pkg.ComplexF64, 1e-9, slabs=4)
     x, A = pkg.solveLinearSystem(None, truth["b"], A)
     assert int(A.iterations[0]) == truth["it9"]
+    _log(f"257^3 in 4 slabs: iterations {int(A.iterations[0])}, solution error vs CPU port {rel_err(x, truth['x']):.2e}")
     assert rel_err(x, truth["x"]) <= 1e-6
     pkg.clear(A.MG)
 
 
-@pytest.mark.parametrize("prec,tol,bound", [("c128", 1e-9, 1e-6), ("c64", 1e-5, 1e-4)])
+def test_complexf32_solution_within_1e_4(gpu_pkg, truth):
+    """north_star: <= 1e-4 in ComplexF32 against the CPU solve (bench settings; ComplexF32 reaches a ~1.5e-6 true
+    residual, so the solve runs to 2e-6)."""
+    pkg = gpu_pkg
+    A = _solver(pkg, truth, pkg.ComplexF32, 2e-6)
+    x, A = pkg.solveLinearSystem(None, truth["b"].astype(np.complex64), A)
+    err = rel_err(x.astype(np.complex128), truth["x"])
+    _log(f"257^3 ComplexF32, bench settings: iterations {int(A.iterations[0])}, relres {A.relres[0]:.2e}, solution error {err:.2e}")
+    assert err <= 1e-4
+    pkg.clear(A.MG)
+
+
+@pytest.mark.parametrize("prec,tol,bound", [("c128", 1e-9, 1e-6), ("c64", 2e-6, 1e-4)])
 def test_reference_production_multigrid_at_scale(gpu_pkg, truth, prec, tol, bound):
     """SURVEY 8(f2) at the headline size: 5 levels (257 -> 17), K-cycle, Jac-GMRES smoother with nu(l) = l+1 sweeps,
     inexact GMRES coarsest solve, FGMRES(5): ComplexF64 to 1e-9 and the paper runs' ComplexF32 / 1e-5
@@ -93,7 +114,7 @@ def test_reference_production_multigrid_at_scale(gpu_pkg, truth, prec, tol, boun
                 coarse_iters=10, maxit=50)
     x, A = pkg.solveLinearSystem(None, truth["b"].astype(P), A)
     err = rel_err(x.astype(np.complex128), truth["x"])
-    print(f"production MG {prec}: iterations {int(A.iterations[0])}, relres {A.relres[0]:.2e}, solution error {err:.2e}")
+    _log(f"production MG {prec}: iterations {int(A.iterations[0])}, relres {A.relres[0]:.2e}, solution error {err:.2e}")
     assert A.relres[0] <= tol
     assert err <= bound
     pkg.clear(A.MG)
