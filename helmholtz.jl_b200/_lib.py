@@ -85,6 +85,9 @@ SIGNATURES = {
     "hh_slab_level_stencil": (C.c_int, [_p, C.c_int, C.c_int, _i64p, _p]),
     "hh_set_stream": (C.c_int, [_p, _p]),
     "hh_update_model": (C.c_int, [_p, _dp, _dp, C.c_double, C.c_double]),
+    "hh_set_frequency_abl": (C.c_int, [_p, C.c_double, C.c_double, C.c_double, _i64p, C.c_double]),
+    "hh_get_gamma": (C.c_int, [_p, _dp]),
+    "hh_get_maximal_frequency_device": (C.c_int, [_p, _dp]),
     "hh_set_operator_ho": (C.c_int, [_p, C.c_int, _dp, _dp, _dp]),
     "hh_setup": (C.c_int, [_p, C.POINTER(hh_mg_options)]),
     "hh_clear": (C.c_int, [_p]),

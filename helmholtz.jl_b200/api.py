@@ -702,6 +702,45 @@ def solvePointSources_(param, srcs, X, amplitudes=None, doTranspose=0):
     return X, param
 
 
+# ------------------------------------------------------------------ device-side set-up (frequency sweeps)
+def setFrequencyABL(param, omega, gamma_const, ABLpad, ABLamp, fetch_gamma=True):
+    """New frequency on the model the solver's handle already holds: omega is replaced and
+    gamma <- gamma_const + getABL(n+1, NeumannOnTop, ABLpad, ABLamp) is evaluated ON THE DEVICE (hh_set_frequency_abl;
+    the 9-argument GetHelmholtzOperator of src/GetHelmholtz.jl:22-31 without a host pass over the grid or an upload).
+    The hierarchy is invalidated; the next solve rebuilds it.  param.helmParam follows (gamma is read back unless
+    fetch_gamma is False, in which case param.helmParam.gamma is left stale and only the live handle is valid)."""
+    if np.iscomplexobj(omega) and complex(omega).imag != 0.0:
+        raise TypeError("setFrequencyABL: the shifted-Laplacian solver needs a real omega")
+    MG = param.MG
+    if MG._hd is None:
+        _ensure_hierarchy(param, MG.doTranspose)
+    hd = MG._hd
+    nodes = hd.nodes
+    pad = np.ascontiguousarray(np.asarray(ABLpad, dtype=np.int64).ravel())
+    if pad.size == 1:
+        pad = np.repeat(pad, nodes.size)
+    L.check(hd.lib.hh_set_frequency_abl(hd.h, float(np.real(omega)), 0.0, float(gamma_const), _ptr(pad, C.c_int64), float(ABLamp)), hd.h)
+    MG._built_for = None
+    hp = param.helmParam
+    gamma = hp.gamma
+    if fetch_gamma:
+        g = np.empty(hd.N, dtype=np.float64)
+        L.check(hd.lib.hh_get_gamma(hd.h, _ptr(g, C.c_double)), hd.h)
+        gamma = g.reshape(np.shape(hp.gamma), order="F") if np.size(hp.gamma) == hd.N else g
+    param.helmParam = HelmholtzParam(hp.Mesh, gamma, hp.m, float(np.real(omega)), hp.NeumannOnTop, hp.Sommerfeld)
+    return param
+
+
+def getMaximalFrequencyDevice(param):
+    """getMaximalFrequency (src/GetHelmholtz.jl:75-79) from the model resident on the device."""
+    MG = param.MG
+    if MG._hd is None:
+        _ensure_hierarchy(param, MG.doTranspose)
+    out = C.c_double()
+    L.check(MG._hd.lib.hh_get_maximal_frequency_device(MG._hd.h, C.byref(out)), MG._hd.h)
+    return out.value
+
+
 # ------------------------------------------------------------------ slab decomposition helpers
 def slabUniqueId():
     """128-byte NCCL communicator id (call on one rank, broadcast to the others)."""

@@ -152,72 +152,30 @@ int hh_device_count(int* count) {
 int hh_get_abl(int dim, const int64_t* n, int neumann_on_top, const int64_t* pad, double amp, double* gamma) {
     return guarded(nullptr, [&]() -> int {
         HH_REQUIRE((dim == 2 || dim == 3) && n && pad && gamma, HH_ERR_ARG, "hh_get_abl: bad arguments");
-        for (int d = 0; d < dim; ++d)
-            HH_REQUIRE(n[d] >= 2 && pad[d] >= 1 && pad[d] <= n[d], HH_ERR_ARG, "hh_get_abl: pad must be in 1..n");
+        std::vector<double> tab[4];
+        abl_tables(dim, n, neumann_on_top, pad, tab);  // the 1-D ramps (shared with the device-side hh_set_frequency_abl)
         if (dim == 2) {
-            const int64_t n1 = n[0], n2 = n[1], p1 = pad[0], p2 = pad[1];
-            std::vector<double> a1(n1, 0.0), a2(n2, 0.0);
-            // a1: ramp ((p1..1)/p1)^2 on the first p1 nodes, ((1..p1)/p1)^2 on the last p1; later writes add
-            for (int64_t t = 0; t < p1; ++t) {
-                const double bwd = (double)((p1 - t) * (p1 - t)) / (double)(p1 * p1);
-                const double fwd = (double)((t + 1) * (t + 1)) / (double)(p1 * p1);
-                a1[t] += bwd;
-                a1[n1 - p1 + t] += fwd;
-            }
-            std::vector<double> top(n2, 0.0), bot(n2, 0.0);
-            for (int64_t t = 0; t < p2; ++t) {
-                top[t] = (double)((p2 - t) * (p2 - t)) / (double)(p2 * p2);
-                bot[n2 - p2 + t] = (double)((t + 1) * (t + 1)) / (double)(p2 * p2);
-            }
             // the reference adds the side ramps over all columns and subtracts the corner products only where
             // the side ramp meets the dim-2 ramp (first p1 / last p1 rows separately, GetHelmholtz.jl:152-161)
-            std::vector<double> l1(n1, 0.0), r1(n1, 0.0);
-            for (int64_t t = 0; t < p1; ++t) {
-                l1[t] = (double)((p1 - t) * (p1 - t)) / (double)(p1 * p1);
-                r1[n1 - p1 + t] = (double)((t + 1) * (t + 1)) / (double)(p1 * p1);
-            }
-            for (int64_t j = 0; j < n2; ++j) {
-                for (int64_t i = 0; i < n1; ++i) {
-                    double g = 0.0;
-                    if (!neumann_on_top) g += top[j] - l1[i] * top[j] - r1[i] * top[j];
+            const std::vector<double>&l1 = tab[0], &r1 = tab[1], &top = tab[2], &bot = tab[3];
+            for (int64_t j = 0; j < n[1]; ++j)
+                for (int64_t i = 0; i < n[0]; ++i) {
+                    double g = top[j] - l1[i] * top[j] - r1[i] * top[j];
                     g += bot[j];
                     g += l1[i];
                     g += r1[i];
                     g -= l1[i] * bot[j];
                     g -= r1[i] * bot[j];
-                    gamma[i + n1 * j] = g * amp;
+                    gamma[i + n[0] * j] = g * amp;
                 }
-            }
-            (void)a1;
-            (void)a2;
             return HH_OK;
         }
-        const int64_t nn[3] = {n[0], n[1], n[2]};
-        std::vector<double> g[3];
-        for (int d = 0; d < 3; ++d) {
-            const int64_t nd = nn[d], p = pad[d];
-            const double x0 = d < 2 ? -1.0 : 0.0, x1 = 1.0;
-            std::vector<double> x(nd);
-            // Julia range(a, stop=b, length=n): a + i*(b-a)/(n-1) (evaluated like LinRange: lerp)
-            for (int64_t i = 0; i < nd; ++i) {
-                const double t = nd > 1 ? (double)i / (double)(nd - 1) : 0.0;
-                x[i] = (1.0 - t) * x0 + t * x1;
-            }
-            g[d].assign(nd, 0.0);
-            const bool left = !(d == 2 && neumann_on_top);
-            if (left)
-                for (int64_t i = 0; i < p; ++i) g[d][i] += (x[i] - x[p - 1]) * (x[i] - x[p - 1]);
-            for (int64_t i = nd - p; i < nd; ++i) g[d][i] += (x[i] - x[nd - p]) * (x[i] - x[nd - p]);
-            double mx = 0.0;
-            for (int64_t i = 0; i < nd; ++i) mx = std::max(mx, g[d][i]);
-            for (int64_t i = 0; i < nd; ++i) g[d][i] /= (mx + 1e-5);
-        }
-        for (int64_t k = 0; k < nn[2]; ++k)
-            for (int64_t j = 0; j < nn[1]; ++j)
-                for (int64_t i = 0; i < nn[0]; ++i) {
-                    double v = (g[0][i] + g[1][j] + g[2][k]) * amp;
+        for (int64_t k = 0; k < n[2]; ++k)
+            for (int64_t j = 0; j < n[1]; ++j)
+                for (int64_t i = 0; i < n[0]; ++i) {
+                    double v = (tab[0][i] + tab[1][j] + tab[2][k]) * amp;
                     if (v >= amp) v = amp;
-                    gamma[i + nn[0] * (j + nn[1] * k)] = v;
+                    gamma[i + n[0] * (j + n[1] * k)] = v;
                 }
         return HH_OK;
     });
@@ -535,6 +493,57 @@ int hh_update_model(hh_handle_t h, const double* m, const double* gamma, double 
         });
         h->pb.w_re = omega_re;
         h->pb.w_im = omega_im;
+        return HH_OK;
+    });
+}
+
+// Frequency sweep on a resident model: omega replaced and gamma <- gamma_const + getABL(n, NeumannOnTop, pad, amp)
+// evaluated on the device from the 1-D ramps (GetHelmholtz.jl:22-31 with :97-220); m is kept.  Invalidates the hierarchy.
+int hh_set_frequency_abl(hh_handle_t h, double omega_re, double omega_im, double gamma_const, const int64_t* pad, double amp) {
+    if (!h) return HH_ERR_ARG;
+    return guarded(h, [&]() -> int {
+        HH_REQUIRE(pad && omega_re != 0.0, HH_ERR_ARG, "hh_set_frequency_abl: bad arguments");
+        int64_t ng[3] = {h->pb.n[0], h->pb.n[1], h->pb.n[2]};
+        for_each_sub(h, [&](int i) {
+            h->subs[i]->set_frequency_abl(omega_re, omega_im, gamma_const, ng, pad, amp);
+            if (!h->lows.empty()) h->lows[i]->set_frequency_abl(omega_re, omega_im, gamma_const, ng, pad, amp);
+        });
+        h->pb.w_re = omega_re;
+        h->pb.w_im = omega_im;
+        return HH_OK;
+    });
+}
+
+// gamma as the device holds it (Float64 copy): whole grid, or the planes own0 <= k < own1 of an NCCL slab handle
+int hh_get_gamma(hh_handle_t h, double* gamma_out) {
+    if (!h || !gamma_out) return HH_ERR_ARG;
+    return guarded(h, [&]() -> int {
+        if (h->slab_mode == 0) {
+            h->subs[0]->get_gamma(gamma_out);
+            return HH_OK;
+        }
+        const int64_t plane = (int64_t)h->pb.n[0] * h->pb.n[1];
+        for (auto& sb : h->subs) {
+            const SlabLevel& g = sb->sgeo[0];
+            std::vector<double> loc((size_t)plane * g.nloc);
+            sb->get_gamma(loc.data());
+            const int64_t dst0 = h->slab_mode == 1 ? g.own0 : 0;
+            std::memcpy(gamma_out + plane * dst0, loc.data() + plane * g.zb, sizeof(double) * plane * (g.own1 - g.own0));
+        }
+        return HH_OK;
+    });
+}
+
+// getMaximalFrequency (src/GetHelmholtz.jl:75-79) from the model the handle holds on the device.  With NCCL slabs the
+// maximum is over this rank's planes (halo planes included): all-reduce it with MAX over the ranks.
+int hh_get_maximal_frequency_device(hh_handle_t h, double* omega_max) {
+    if (!h || !omega_max) return HH_ERR_ARG;
+    return guarded(h, [&]() -> int {
+        double mm = 0.0;
+        for (auto& sb : h->subs) mm = std::max(mm, sb->max_m());
+        double hm = h->pb.h[0];
+        for (int d = 1; d < h->pb.dim; ++d) hm = std::max(hm, h->pb.h[d]);
+        *omega_max = (0.1 * 2 * M_PI) / (hm * std::sqrt(mm));
         return HH_OK;
     });
 }

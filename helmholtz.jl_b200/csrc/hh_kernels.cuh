@@ -1072,6 +1072,171 @@ __global__ void __launch_bounds__(256) k_scale_columns(CoarseOp<T> op, cx<T>* __
     scaled[(int64_t)s * op.N + p] = v;
 }
 
+// ---------------------------------------------------------------------------------------------
+// 2-D grids (BASELINE configs 1-2): the marching dimension of the TMA ring is the RIGHT-HAND SIDE.  A CTA owns a
+// 32 x 8 tile of nodes and a chunk of the RHS block; every thread evaluates the coefficients of its node once --
+// the matrix-free 5-point row (centre with mass / absorbing layer / Sommerfeld / shift, four weights) on the fine
+// level, the 9 stored Galerkin coefficients on a coarse level -- and keeps them in registers while the x tiles
+// (one-node halo) and b tiles of KB right-hand sides at a time stream through an NS-deep mbarrier ring.  Halos at
+// the domain boundary and surplus RHS slots are zero-filled by the TMA unit.  With 64 sources per batch (config 2)
+// the coefficient work is amortised 64 times and a sweep moves exactly 3S per node and right-hand side.
+// ---------------------------------------------------------------------------------------------
+template <typename T, int MODE, int KB>
+struct Rhs2dCfg {
+    static constexpr int TX = 32, TY = 8;
+    static constexpr int HX = sizeof(T) == 4 ? 2 : 1;  // see FineTmaCfg
+    static constexpr int PX = TX + 2 * HX;
+    static constexpr int XT = (TY + 2) * PX;
+    static constexpr int BT = TY * TX;
+    static constexpr int ES = (int)sizeof(cx<T>);
+    static constexpr int al(int b) { return (b + 127) / 128 * 128; }
+    static constexpr int OFF_X = 0;
+    static constexpr int OFF_B = al(KB * XT * ES);
+    static constexpr int STAGE_BYTES = OFF_B + (MODE != MODE_APPLY ? al(KB * BT * ES) : 0);
+    static constexpr uint32_t TX_BYTES = KB * XT * ES + (MODE != MODE_APPLY ? KB * BT * ES : 0);
+    static constexpr int NS = 4;
+};
+
+// COARSE = false: matrix-free fine operator `fop`; COARSE = true: stored 9-point stencil `cop` (+ cop.dinv)
+template <typename T, int MODE, int KB, bool COARSE>
+__global__ void __launch_bounds__(256) k_stencil2d_tma(FineOp<T> fop, CoarseOp<T> cop, const __grid_constant__ TmaDesc tm_x,
+                                                       const __grid_constant__ TmaDesc tm_b, cx<T>* __restrict__ out,
+                                                       int64_t ld, int nrhs, int rchunk, T damp) {
+    typedef Rhs2dCfg<T, MODE, KB> Cfg;
+    constexpr int TX = Cfg::TX, TY = Cfg::TY, PX = Cfg::PX, NS = Cfg::NS;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + (size_t)NS * Cfg::STAGE_BYTES);
+    const int n0 = COARSE ? cop.n[0] : fop.n[0], n1 = COARSE ? cop.n[1] : fop.n[1];
+    const int sy = COARSE ? cop.sy : fop.sy;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int i0 = blockIdx.x * TX, j0 = blockIdx.y * TY;
+    const int i = i0 + tx, j = j0 + ty;
+    const int rb = blockIdx.z * rchunk, re = min(nrhs, rb + rchunk);
+    const int niter = (re - rb + KB - 1) / KB;
+    const bool active = (i < n0) && (j < n1);
+    auto issue = [&](int s, int it) {
+        unsigned char* st = smem_raw + (size_t)s * Cfg::STAGE_BYTES;
+        mbar_expect_tx(&bars[s], Cfg::TX_BYTES);
+        tma_load_4d(st + Cfg::OFF_X, &tm_x, 2 * (i0 - Cfg::HX), j0 - 1, 0, rb + it * KB, &bars[s]);
+        if (MODE != MODE_APPLY) tma_load_4d(st + Cfg::OFF_B, &tm_b, 2 * i0, j0, 0, rb + it * KB, &bars[s]);
+    };
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < NS; ++s) mbar_init(&bars[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        for (int s = 0; s < NS && s < niter; ++s) issue(s, s);
+    }
+    __syncthreads();
+    const int ic = active ? i : 0, jc = active ? j : 0;
+    const int64_t p = ic + (int64_t)sy * jc;
+    // the row of this node, in registers for every right-hand side of the chunk
+    cx<T> cf[9];
+    cx<T> dinv = mk<T>(T(0), T(0));
+    if (COARSE) {
+#pragma unroll
+        for (int s9 = 0; s9 < 9; ++s9) cf[s9] = cop.coef[(int64_t)s9 * cop.N + p];  // absent neighbours hold 0
+        if (MODE == MODE_JACOBI) dinv = cop.dinv[p];
+    } else {
+        const cx<T> c = fine_center<T, 2>(fop, p, ic, jc, 0);
+#pragma unroll
+        for (int s9 = 0; s9 < 9; ++s9) cf[s9] = mk<T>(T(0), T(0));
+        cf[4] = c;
+        cf[3] = mk<T>(-fine_w(fop, 0, 0, ic, n0), T(0));
+        cf[5] = mk<T>(-fine_w(fop, 0, 1, ic, n0), T(0));
+        cf[1] = mk<T>(-fine_w(fop, 1, 0, jc, n1), T(0));
+        cf[7] = mk<T>(-fine_w(fop, 1, 1, jc, n1), T(0));
+        if (MODE == MODE_JACOBI) dinv = rdiv(damp, c);
+    }
+    const int cidx = (ty + 1) * PX + (tx + Cfg::HX);
+    const int bidx = ty * TX + tx;
+#pragma unroll 1
+    for (int it = 0; it < niter; ++it) {
+        const int s = it % NS;
+        const unsigned char* st = smem_raw + (size_t)s * Cfg::STAGE_BYTES;
+        mbar_wait(&bars[s], (uint32_t)((it / NS) & 1));
+        if (active) {
+            const cx<T>* sx = reinterpret_cast<const cx<T>*>(st + Cfg::OFF_X) + cidx;
+            const cx<T>* sb = reinterpret_cast<const cx<T>*>(st + Cfg::OFF_B) + bidx;
+#pragma unroll
+            for (int q = 0; q < KB; ++q) {
+                const int r = rb + it * KB + q;
+                const cx<T>* xt = sx + q * Cfg::XT;
+                const cx<T> xc = xt[0];
+                cx<T> a = cf[4] * xc;
+                if (COARSE) {
+                    cfma(a, cf[0], xt[-PX - 1]);
+                    cfma(a, cf[1], xt[-PX]);
+                    cfma(a, cf[2], xt[-PX + 1]);
+                    cfma(a, cf[3], xt[-1]);
+                    cfma(a, cf[5], xt[1]);
+                    cfma(a, cf[6], xt[PX - 1]);
+                    cfma(a, cf[7], xt[PX]);
+                    cfma(a, cf[8], xt[PX + 1]);
+                } else {
+                    rfma(a, cf[3].x, xt[-1]);
+                    rfma(a, cf[5].x, xt[1]);
+                    rfma(a, cf[1].x, xt[-PX]);
+                    rfma(a, cf[7].x, xt[PX]);
+                }
+                if (r < re) {
+                    const int64_t o = (int64_t)r * ld + p;
+                    if (MODE == MODE_APPLY) {
+                        out[o] = a;
+                    } else {
+                        const cx<T> bv = sb[q * Cfg::BT];
+                        if (MODE == MODE_RESID) out[o] = bv - a;
+                        else out[o] = xc + dinv * (bv - a);
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x == 0 && it + NS < niter) issue(s, it + NS);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Device-side set-up: gamma <- gamma0 + getABL(n, NeumannAtFirstDim, ABLpad, ABLamp) evaluated from
+// the separable 1-D profiles of src/GetHelmholtz.jl:141-218 (tables built on the host in Float64: they are O(n)).
+//   3-D (:164-218): gamma = min(amp (g0[i] + g1[j] + g2[k]), amp), g_d already normalised by (max + 1e-5)
+//   2-D (:141-163): gamma = amp ( [top[j] (1 - l[i] - r[i])] + bot[j] + l[i] + r[i] - l[i] bot[j] - r[i] bot[j] )
+//                   with tab0 = l, tab1 = r (dim 1 ramps), tab2 = top (zero when Neumann), tab3 = bot
+// koff: global index of local plane 0 (slab decomposition).
+// ---------------------------------------------------------------------------------------------
+template <typename T, int DIM>
+__global__ void __launch_bounds__(256) k_gamma_abl(T* __restrict__ g, int n0, int n1, int n2, int koff, double gamma0, double amp,
+                                                   const double* __restrict__ tab0, const double* __restrict__ tab1,
+                                                   const double* __restrict__ tab2, const double* __restrict__ tab3) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = blockIdx.y * blockDim.y + threadIdx.y;
+    const int k = (DIM == 3) ? blockIdx.z * blockDim.z + threadIdx.z : 0;
+    if (i >= n0 || j >= n1 || k >= n2) return;
+    double v;
+    if (DIM == 3) {
+        v = (tab0[i] + tab1[j] + tab2[k + koff]) * amp;
+        if (v >= amp) v = amp;
+    } else {
+        const double l = tab0[i], r = tab1[i], top = tab2[j], bot = tab3[j];
+        v = (top - l * top - r * top + bot + l + r - l * bot - r * bot) * amp;
+    }
+    g[i + (int64_t)n0 * (j + (int64_t)n1 * k)] = (T)(gamma0 + v);
+}
+
+// max of a real array (getMaximalFrequency, src/GetHelmholtz.jl:75-79): per-block maxima, finished on the host
+template <typename T>
+__global__ void __launch_bounds__(256) k_max_partial(const T* __restrict__ a, int64_t n, double* __restrict__ out) {
+    __shared__ double sm[32];
+    double v = -1e300;
+    for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < n; p += (int64_t)gridDim.x * blockDim.x) v = fmax(v, (double)a[p]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < (int)(blockDim.x >> 5); ++w) v = fmax(v, sm[w]);
+        out[blockIdx.x] = v;
+    }
+}
+
 // centre coefficient (incl. Laplacian diagonal) and damp/centre as arrays, for the TMA-staged kernels
 template <typename T, int DIM>
 __global__ void __launch_bounds__(256) k_fine_precompute(FineOp<T> op, cx<T>* __restrict__ cdiag, cx<T>* __restrict__ dinv,
@@ -1235,6 +1400,100 @@ __global__ void __launch_bounds__(256) k_restrict(const cx<T>* __restrict__ r, c
             }
         }
         bc[(int64_t)q * ldc + pc] = acc;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K3 (3-D production form): full-weighting restriction with the fine planes staged by TMA.
+// A CTA owns a CTX x CTY tile of coarse columns and marches over a chunk of coarse planes; every fine plane it
+// touches (2K-1, 2K, 2K+1) is loaded once, as one box of (2 CTX + 1) x (2 CTY + 1) nodes per right-hand side, into an
+// NS-deep mbarrier ring; a thread forms the in-plane restriction s(z) of its column from the staged tile and rolls
+// bc(K) = 1/4 s(2K-1) + 1/2 s(2K) + 1/4 s(2K+1) in registers.  Rows, columns and planes outside the grid are
+// zero-filled by the hardware, which IS the truncated boundary stencil of R = 2^-3 P^T.  Replaces one thread per
+// coarse node doing 27 stride-2 global loads (3.4 TB/s, latency-bound) by coalesced bulk loads.
+// ---------------------------------------------------------------------------------------------
+template <typename T, int KB>
+struct RestrictCfg {
+    static constexpr int CTX = 16, CTY = 8;
+    static constexpr int HX = sizeof(T) == 4 ? 2 : 1;          // the box starts HX fine nodes left of 2*I0 (16-byte aligned start)
+    static constexpr int FX = 2 * CTX + 1 + (HX - 1);          // 33 (ComplexF64) / 34 (ComplexF32: even width)
+    static constexpr int FY = 2 * CTY + 1;
+    static constexpr int FT = FX * FY;
+    static constexpr int ES = (int)sizeof(cx<T>);
+    static constexpr int al(int b) { return (b + 127) / 128 * 128; }
+    static constexpr int STAGE_BYTES = al(KB * FT * ES);
+    static constexpr uint32_t TX_BYTES = KB * FT * ES;
+    static constexpr int NS = 6;
+    static_assert((FX * ES) % 16 == 0, "TMA box rows are 16-byte multiples");
+};
+
+template <typename T, int KB>
+__global__ void __launch_bounds__(128) k_restrict3d_tma(const __grid_constant__ TmaDesc tm_r, cx<T>* __restrict__ bc,
+                                                        int nc0, int nc1, int csy, int64_t ldc, int nrhs, int kchunk,
+                                                        int groups, int Kb, int Ke) {
+    typedef RestrictCfg<T, KB> Cfg;
+    constexpr int NS = Cfg::NS, FX = Cfg::FX;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + (size_t)NS * Cfg::STAGE_BYTES);
+    const int tx = threadIdx.x % Cfg::CTX, ty = threadIdx.x / Cfg::CTX;
+    const int I0 = (blockIdx.x / groups) * Cfg::CTX, J0 = blockIdx.y * Cfg::CTY;
+    const int r0 = (blockIdx.x % groups) * KB;
+    const int K0 = Kb + blockIdx.z * kchunk, K1 = min(Ke, K0 + kchunk);
+    const int zf0 = 2 * K0 - 1;                 // first fine plane of the chunk (may be -1: zero-filled)
+    const int niter = 2 * (K1 - K0) + 1;        // fine planes 2K0-1 .. 2K1-1
+    const int I = I0 + tx, J = J0 + ty;
+    const bool active = I < nc0 && J < nc1;
+    auto issue = [&](int s, int z) {
+        mbar_expect_tx(&bars[s], Cfg::TX_BYTES);
+        tma_load_4d(smem_raw + (size_t)s * Cfg::STAGE_BYTES, &tm_r, 2 * (2 * I0 - Cfg::HX), 2 * J0 - 1, z, r0, &bars[s]);
+    };
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < NS; ++s) mbar_init(&bars[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        for (int s = 0; s < NS && s < niter; ++s) issue(s, zf0 + s);
+    }
+    __syncthreads();
+    const cx<T> zero = mk<T>(T(0), T(0));
+    cx<T> cur[KB], nxt[KB];  // bc(K) being accumulated, and the quarter of the odd plane that belongs to bc(K+1)
+#pragma unroll
+    for (int q = 0; q < KB; ++q) cur[q] = nxt[q] = zero;
+    const int cidx = (2 * ty + 1) * FX + (2 * tx + Cfg::HX);  // the node (2I, 2J) inside the staged tile
+    const int64_t pc = (active ? I : 0) + (int64_t)csy * (active ? J : 0);
+    const int64_t csz = (int64_t)csy * nc1;
+#pragma unroll 1
+    for (int it = 0; it < niter; ++it) {
+        const int s = it % NS;
+        mbar_wait(&bars[s], (uint32_t)((it / NS) & 1));
+        const cx<T>* t = reinterpret_cast<const cx<T>*>(smem_raw + (size_t)s * Cfg::STAGE_BYTES) + cidx;
+        const bool odd = (it & 1) == 0;  // fine plane zf0 + it is odd when it is even
+#pragma unroll
+        for (int q = 0; q < KB; ++q) {
+            const cx<T>* tq = t + q * Cfg::FT;
+            cx<T> a = tq[0];                                                     // 1/2 * 1/2
+            cx<T> e = (tq[-1] + tq[1]) + (tq[-FX] + tq[FX]);                      // 1/2 * 1/4
+            cx<T> c = (tq[-FX - 1] + tq[-FX + 1]) + (tq[FX - 1] + tq[FX + 1]);    // 1/4 * 1/4
+            cx<T> sxy = T(0.25) * a + T(0.125) * e + T(0.0625) * c;
+            if (odd) {
+                cur[q] = cur[q] + T(0.25) * sxy;   // closes bc(K) of the plane below ... (K = (z-1)/2)
+                nxt[q] = T(0.25) * sxy;            // ... and opens bc(K+1)
+            } else {
+                cur[q] = cur[q] + T(0.5) * sxy;
+            }
+        }
+        if (odd && it > 0) {  // plane 2K+1 done: bc(K) complete, K = K0 + it/2 - 1
+            const int K = K0 + (it >> 1) - 1;
+            if (active) {
+#pragma unroll
+                for (int q = 0; q < KB; ++q)
+                    if (r0 + q < nrhs) bc[(int64_t)(r0 + q) * ldc + pc + (int64_t)K * csz] = cur[q];
+            }
+        }
+        if (odd) {
+#pragma unroll
+            for (int q = 0; q < KB; ++q) cur[q] = nxt[q];
+        }
+        __syncthreads();
+        if (threadIdx.x == 0 && it + NS < niter) issue(s, zf0 + it + NS);
     }
 }
 
@@ -1416,18 +1675,20 @@ __global__ void k_band_fill(CoarseOp<T> op, zc* __restrict__ band, int bw) {
 
 // right-looking banded LU, one CTA (set-up only).  L (unit lower) and U overwrite the band.
 // The factorisation does not pivot (see above); with shift == 0 and no attenuation the coarse operator is indefinite
-// and a pivot can collapse.  flag[0] is set to 1 + the row of the first pivot that is not finite or smaller than
-// 1e-13 x the largest pivot seen so far; the host turns that into HH_ERR_UNSUPPORTED instead of returning Inf/NaN.
-__global__ void __launch_bounds__(1024) k_band_lu(zc* __restrict__ band, int64_t N, int bw, int* __restrict__ flag) {
+// and a pivot can collapse.  flag[0] is set to 1 + the row of the first pivot that is not finite or has lost ten digits
+// against the diagonal entry it started from (diag0, scratch of N doubles); the host turns that into
+// HH_ERR_UNSUPPORTED instead of returning Inf/NaN.
+__global__ void __launch_bounds__(1024) k_band_lu(zc* __restrict__ band, int64_t N, int bw, int* __restrict__ flag,
+                                                  double* __restrict__ diag0) {
     const int64_t W = 2 * (int64_t)bw + 1;
-    double pmax = 0.0;
+    for (int64_t k = threadIdx.x; k < N; k += blockDim.x) diag0[k] = fabs(band[k * W + bw].x) + fabs(band[k * W + bw].y);
+    __syncthreads();
     for (int64_t k = 0; k < N; ++k) {
         const int nrow = (int)min((int64_t)bw, N - 1 - k);
         const zc piv = band[k * W + bw];
         {
             const double pa = fabs(piv.x) + fabs(piv.y);
-            if (threadIdx.x == 0 && flag[0] == 0 && !(pa > 1e-13 * pmax && pa < 1e300 && pa > 0.0)) flag[0] = (int)min(k + 1, (int64_t)INT_MAX);
-            pmax = fmax(pmax, pa);
+            if (threadIdx.x == 0 && flag[0] == 0 && !(pa > 1e-10 * diag0[k] && pa < 1e300 && pa > 0.0)) flag[0] = (int)min(k + 1, (int64_t)INT_MAX);
         }
         for (int t = threadIdx.x; t < nrow; t += blockDim.x) {
             const int64_t i = k + 1 + t;

@@ -384,9 +384,54 @@ struct Problem {
     int64_t N() const { return (int64_t)n[0] * n[1] * n[2]; }
 };
 
+// 1-D profiles of getABL (src/GetHelmholtz.jl:141-218), Float64 on the host: tab[0..3] as k_gamma_abl reads them
+// (n = GLOBAL node counts).  The whole-array form hh_get_abl and the device-side hh_set_frequency_abl share them.
+inline void abl_tables(int dim, const int64_t* n, int neumann_on_top, const int64_t* pad, std::vector<double> tab[4]) {
+    HH_REQUIRE((dim == 2 || dim == 3) && n && pad, HH_ERR_ARG, "getABL: bad arguments");
+    for (int d = 0; d < dim; ++d) HH_REQUIRE(n[d] >= 2 && pad[d] >= 1 && pad[d] <= n[d], HH_ERR_ARG, "getABL: pad must be in 1..n");
+    if (dim == 2) {
+        const int64_t n1 = n[0], n2 = n[1], p1 = pad[0], p2 = pad[1];
+        tab[0].assign(n1, 0.0);  // left ramp of dim 1: ((p1..1)/p1)^2
+        tab[1].assign(n1, 0.0);  // right ramp: ((1..p1)/p1)^2
+        tab[2].assign(n2, 0.0);  // top ramp of dim 2 (absent under NeumannAtFirstDim)
+        tab[3].assign(n2, 0.0);  // bottom ramp
+        for (int64_t t = 0; t < p1; ++t) {
+            tab[0][t] = (double)((p1 - t) * (p1 - t)) / (double)(p1 * p1);
+            tab[1][n1 - p1 + t] = (double)((t + 1) * (t + 1)) / (double)(p1 * p1);
+        }
+        for (int64_t t = 0; t < p2; ++t) {
+            if (!neumann_on_top) tab[2][t] = (double)((p2 - t) * (p2 - t)) / (double)(p2 * p2);
+            tab[3][n2 - p2 + t] = (double)((t + 1) * (t + 1)) / (double)(p2 * p2);
+        }
+        return;
+    }
+    for (int d = 0; d < 3; ++d) {
+        const int64_t nd = n[d], p = pad[d];
+        const double x0 = d < 2 ? -1.0 : 0.0, x1 = 1.0;
+        std::vector<double> x(nd);
+        // Julia range(a, stop=b, length=n): a + i*(b-a)/(n-1) (evaluated like LinRange: lerp)
+        for (int64_t i = 0; i < nd; ++i) {
+            const double t = nd > 1 ? (double)i / (double)(nd - 1) : 0.0;
+            x[i] = (1.0 - t) * x0 + t * x1;
+        }
+        tab[d].assign(nd, 0.0);
+        const bool left = !(d == 2 && neumann_on_top);
+        if (left)
+            for (int64_t i = 0; i < p; ++i) tab[d][i] += (x[i] - x[p - 1]) * (x[i] - x[p - 1]);
+        for (int64_t i = nd - p; i < nd; ++i) tab[d][i] += (x[i] - x[nd - p]) * (x[i] - x[nd - p]);
+        double mx = 0.0;
+        for (int64_t i = 0; i < nd; ++i) mx = std::max(mx, tab[d][i]);
+        for (int64_t i = 0; i < nd; ++i) tab[d][i] /= (mx + 1e-5);
+    }
+    tab[3].assign(1, 0.0);
+}
+
 struct SolverBase {
     virtual ~SolverBase() {}
     virtual void set_model(const double* m, const double* gamma, double wre, double wim) = 0;
+    virtual void set_frequency_abl(double wre, double wim, double gamma0, const int64_t* n_global, const int64_t* pad, double amp) = 0;
+    virtual void get_gamma(double* out) = 0;
+    virtual double max_m() = 0;
     virtual void setup(const hh_mg_options& o) = 0;
     virtual void clear() = 0;
     virtual bool hierarchy_exists() const = 0;
@@ -490,6 +535,8 @@ class Solver : public SolverBase {
         if (ct && !strcmp(ct, "alt")) force_tile = 1;
         const char* sc = getenv("HH_SCALED_GMRES");  // A/B switch of the one-pass (A D^-1) apply (default on)
         scaled_gmres = !(sc && sc[0] == '0');
+        const char* tr = getenv("HH_TMA_RESTRICT");
+        tma_restrict = !(tr && tr[0] == '0');
         const char* hs = getenv("HH_HALO_SPLIT");
         split_always = hs && hs[0] == '1';
         use_pitch = sizeof(T) == 4 && pb.dim == 3 && fine_kernel == FK_TMA;
@@ -522,19 +569,70 @@ class Solver : public SolverBase {
         }
         HH_CUDA(cudaMemcpy(d_m.p, hm.data(), N * sizeof(T), cudaMemcpyHostToDevice));
         HH_CUDA(cudaMemcpy(d_g.p, hg.data(), N * sizeof(T), cudaMemcpyHostToDevice));
-        if (fine_sy() != pb.n[0]) {  // pitched copies for the kernels that work on the internal (padded) vectors
-            const int64_t Np = fineN();
-            d_mp.alloc(Np);
-            d_gp.alloc(Np);
-            HH_CUDA(cudaMemsetAsync(d_mp.p, 0, Np * sizeof(T), stream));
-            HH_CUDA(cudaMemsetAsync(d_gp.p, 0, Np * sizeof(T), stream));
-            const int64_t rows = (int64_t)pb.n[1] * pb.n[2];
-            k_repitch<T><<<dim3(592, 1), 256, 0, stream>>>(d_m.p, d_mp.p, pb.n[0], rows, pb.n[0], fine_sy(), 0, 0);
-            k_repitch<T><<<dim3(592, 1), 256, 0, stream>>>(d_g.p, d_gp.p, pb.n[0], rows, pb.n[0], fine_sy(), 0, 0);
-            HH_CUDA(cudaStreamSynchronize(stream));
-        }
+        refresh_pitched();  // pitched copies for the kernels that work on the internal (padded) vectors
         h_op_valid[0] = h_op_valid[1] = false;
         clear();
+    }
+
+    // copies of m / gamma in the row pitch of the internal vectors (only when that differs from the dense one)
+    void refresh_pitched() {
+        if (fine_sy() == pb.n[0]) return;
+        const int64_t Np = fineN();
+        if (d_mp.n != (size_t)Np) {
+            d_mp.alloc(Np);
+            d_gp.alloc(Np);
+        }
+        HH_CUDA(cudaMemsetAsync(d_mp.p, 0, Np * sizeof(T), stream));
+        HH_CUDA(cudaMemsetAsync(d_gp.p, 0, Np * sizeof(T), stream));
+        const int64_t rows = (int64_t)pb.n[1] * pb.n[2];
+        k_repitch<T><<<dim3(592, 1), 256, 0, stream>>>(d_m.p, d_mp.p, pb.n[0], rows, pb.n[0], fine_sy(), 0, 0);
+        k_repitch<T><<<dim3(592, 1), 256, 0, stream>>>(d_g.p, d_gp.p, pb.n[0], rows, pb.n[0], fine_sy(), 0, 0);
+        HH_CUDA(cudaStreamSynchronize(stream));
+    }
+    // Frequency sweep on a resident model: omega replaced, gamma <- gamma0 + getABL(...) evaluated on the
+    // device (k_gamma_abl); m stays where it is.  Invalidates the hierarchy like set_model.
+    void set_frequency_abl(double wre, double wim, double gamma0, const int64_t* n_global, const int64_t* pad, double amp) override {
+        HH_CUDA(cudaSetDevice(device));
+        HH_REQUIRE(d_m.p != nullptr, HH_ERR_STATE, "no model set");
+        HH_REQUIRE(!ho, HH_ERR_UNSUPPORTED, "hh_set_frequency_abl: not available with the high-order operator (it keeps host copies of gamma)");
+        std::vector<double> tab[4];
+        abl_tables(pb.dim, n_global, pb.neumann_top, pad, tab);
+        DevBuf<double> dt[4];
+        for (int q = 0; q < 4; ++q) {
+            dt[q].alloc(std::max<size_t>(tab[q].size(), 1));
+            if (!tab[q].empty()) HH_CUDA(cudaMemcpyAsync(dt[q].p, tab[q].data(), tab[q].size() * sizeof(double), cudaMemcpyHostToDevice, stream));
+        }
+        dim3 g, blk;
+        grid3(pb.n, pb.dim, g, blk);
+        const int koff = slab ? sgeo[0].koff : 0;
+        launch(T_SETUP, 0, [&] {
+            if (pb.dim == 3) k_gamma_abl<T, 3><<<g, blk, 0, stream>>>(d_g.p, pb.n[0], pb.n[1], pb.n[2], koff, gamma0, amp, dt[0].p, dt[1].p, dt[2].p, dt[3].p);
+            else k_gamma_abl<T, 2><<<g, blk, 0, stream>>>(d_g.p, pb.n[0], pb.n[1], 1, 0, gamma0, amp, dt[0].p, dt[1].p, dt[2].p, dt[3].p);
+        });
+        HH_CUDA(cudaStreamSynchronize(stream));
+        pb.w_re = wre;
+        pb.w_im = wim;
+        refresh_pitched();
+        h_op_valid[0] = h_op_valid[1] = false;
+        clear();
+    }
+    void get_gamma(double* out) override {
+        HH_CUDA(cudaSetDevice(device));
+        const int64_t N = pb.N();
+        std::vector<T> hg(N);
+        HH_CUDA(cudaMemcpy(hg.data(), d_g.p, N * sizeof(T), cudaMemcpyDeviceToHost));
+        for (int64_t i = 0; i < N; ++i) out[i] = (double)hg[i];
+    }
+    double max_m() override {  // over the planes this solver holds
+        HH_CUDA(cudaSetDevice(device));
+        const int nb = 296;
+        DevBuf<double> part;
+        part.alloc(nb);
+        launch(T_SETUP, 0, [&] { k_max_partial<T><<<nb, 256, 0, stream>>>(d_m.p, pb.N(), part.p); });
+        std::vector<double> h(nb);
+        HH_CUDA(cudaMemcpyAsync(h.data(), part.p, nb * sizeof(double), cudaMemcpyDeviceToHost, stream));
+        HH_CUDA(cudaStreamSynchronize(stream));
+        return *std::max_element(h.begin(), h.end());
     }
 
     // Row pitch of the internal fine-level arrays.  TMA needs 16-byte multiples for every global stride: always
@@ -758,6 +856,10 @@ class Solver : public SolverBase {
             launch(tag, bytes, [&] { fine3d_dispatch(mode, op, x, b, out, ld, nrhs, damp); });
             return;
         }
+        if (tma2d_ok(op.sy, op.n[1], ld, x, b, mode)) {
+            launch(tag, bytes, [&] { stencil2d_dispatch<false>(mode, op, CoarseOp<T>{}, op.n, op.sy, x, b, out, ld, nrhs, damp); });
+            return;
+        }
         launch(tag, bytes, [&] {
             if (pb.dim == 3) {
                 if (mode == MODE_APPLY) k_fine_stencil<T, 3, MODE_APPLY, 2><<<g, blk, 0, stream>>>(op, x, b, out, ld, nrhs, damp);
@@ -978,7 +1080,7 @@ class Solver : public SolverBase {
         if (force_tile >= 0) return force_tile;
         const double t16 = (double)((L.n[0] + 15) / 16) * ((L.n[1] + 7) / 8);
         const double talt = (double)((L.n[0] + ALT_TX - 1) / ALT_TX) * ((L.n[1] + ALT_TY - 1) / ALT_TY);
-        return talt < 0.90 * t16 ? 1 : 0;
+        return talt < 0.96 * t16 ? 1 : 0;
     }
     // z-chunks of equal length such that the waves of one-CTA-per-SM CTAs are full and the two extra input planes a
     // chunk stages (which cost a third of a plane each) stay a small share: minimise waves x (chunk + 2/3)
@@ -1054,6 +1156,46 @@ class Solver : public SolverBase {
         else if (kb == 2) coarse3d_launch<MODE, 2>(L, x, b, out, nrhs);
         else coarse3d_launch<MODE, 1>(L, x, b, out, nrhs);
     }
+    // ---- 2-D grids: RHS-marching TMA kernel (k_stencil2d_tma) ----------------------------------------------------
+    bool tma2d_ok(int sy, int n1, int64_t ld, const C* x, const C* b, int mode) const {
+        if (pb.dim != 2 || fine_kernel != FK_TMA) return false;
+        const int64_t es = 2 * sizeof(T);
+        return (es * sy) % 16 == 0 && (es * ld) % 16 == 0 && ((uintptr_t)x % 16 == 0) && (mode == MODE_APPLY || (uintptr_t)b % 16 == 0) &&
+               n1 >= 1;
+    }
+    template <int MODE, int KB, bool COARSE>
+    void stencil2d_launch(const FineOp<T>& fop, const CoarseOp<T>& cop, const int* n, int sy, const C* x, const C* b, C* out,
+                          int64_t ld, int nrhs, T damp) {
+        typedef Rhs2dCfg<T, MODE, KB> Cfg;
+        constexpr size_t smem = (size_t)Cfg::NS * Cfg::STAGE_BYTES + Cfg::NS * sizeof(uint64_t);
+        static bool attr_set = false;
+        if (!attr_set) {
+            HH_CUDA(cudaFuncSetAttribute(k_stencil2d_tma<T, MODE, KB, COARSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            attr_set = true;
+        }
+        const int tx = (n[0] + Cfg::TX - 1) / Cfg::TX, ty = (n[1] + Cfg::TY - 1) / Cfg::TY;
+        // chunks of the RHS block (multiples of KB) so that small grids still fill the SMs
+        int nch = std::max(1, std::min((nrhs + KB - 1) / KB, (2 * 148 + tx * ty - 1) / (tx * ty)));
+        int rchunk = ((nrhs + nch - 1) / nch + KB - 1) / KB * KB;
+        nch = (nrhs + rchunk - 1) / rchunk;
+        const int nn[3] = {n[0], n[1], 1};
+        TmaDesc mx = make_tmap_g(x, nn, sy, ld, Cfg::PX, Cfg::TY + 2, KB, nrhs);
+        TmaDesc mb = (MODE != MODE_APPLY) ? make_tmap_g(b, nn, sy, ld, Cfg::TX, Cfg::TY, KB, nrhs) : mx;
+        k_stencil2d_tma<T, MODE, KB, COARSE><<<dim3(tx, ty, nch), 256, smem, stream>>>(fop, cop, mx, mb, out, ld, nrhs, rchunk, damp);
+    }
+    template <bool COARSE>
+    void stencil2d_dispatch(int mode, const FineOp<T>& fop, const CoarseOp<T>& cop, const int* n, int sy, const C* x, const C* b,
+                            C* out, int64_t ld, int nrhs, T damp) {
+        if (nrhs >= 2) {
+            if (mode == MODE_APPLY) stencil2d_launch<MODE_APPLY, 2, COARSE>(fop, cop, n, sy, x, b, out, ld, nrhs, damp);
+            else if (mode == MODE_RESID) stencil2d_launch<MODE_RESID, 2, COARSE>(fop, cop, n, sy, x, b, out, ld, nrhs, damp);
+            else stencil2d_launch<MODE_JACOBI, 2, COARSE>(fop, cop, n, sy, x, b, out, ld, nrhs, damp);
+        } else {
+            if (mode == MODE_APPLY) stencil2d_launch<MODE_APPLY, 1, COARSE>(fop, cop, n, sy, x, b, out, ld, nrhs, damp);
+            else if (mode == MODE_RESID) stencil2d_launch<MODE_RESID, 1, COARSE>(fop, cop, n, sy, x, b, out, ld, nrhs, damp);
+            else stencil2d_launch<MODE_JACOBI, 1, COARSE>(fop, cop, n, sy, x, b, out, ld, nrhs, damp);
+        }
+    }
     void fine_jacobi0(const FineOp<T>& op, const C* b, C* out, int64_t ld, int nrhs, T damp) {
         dim3 g, blk;
         grid3(pb.n, pb.dim, g, blk);
@@ -1117,6 +1259,10 @@ class Solver : public SolverBase {
             });
             return;
         }
+        if (tma2d_ok(L.p0, L.n[1], ld, x, b, mode)) {
+            launch(tag, bytes, [&] { stencil2d_dispatch<true>(mode, FineOp<T>{}, op, L.n, L.p0, x, b, out, ld, nrhs, T(0)); });
+            return;
+        }
         if (pb.dim == 3 && fine_kernel != FK_SIMPLE) {
             launch(tag, bytes, [&] {
                 if (mode == MODE_APPLY) coarse3d_mode<MODE_APPLY>(L, x, b, out, nrhs);
@@ -1142,10 +1288,37 @@ class Solver : public SolverBase {
             k_diag_scale<T><<<(unsigned)((N + 255) / 256), 256, 0, stream>>>(dinv, b, out, N, N, nrhs);
         });
     }
+    template <int KB>
+    void restrict_tma_launch(const Level& F, const Level& Cc, const C* r, C* bc, int nrhs) {
+        typedef RestrictCfg<T, KB> Cfg;
+        constexpr size_t smem = (size_t)Cfg::NS * Cfg::STAGE_BYTES + Cfg::NS * sizeof(uint64_t);
+        static bool attr_set = false;
+        if (!attr_set) {
+            HH_CUDA(cudaFuncSetAttribute(k_restrict3d_tma<T, KB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            attr_set = true;
+        }
+        const int groups = (nrhs + KB - 1) / KB;
+        const int tx = (Cc.n[0] + Cfg::CTX - 1) / Cfg::CTX, ty = (Cc.n[1] + Cfg::CTY - 1) / Cfg::CTY;
+        // two CTAs per SM: chunks of coarse planes such that the grid is a few waves of 296
+        const int nk = Cc.ze - Cc.zb;
+        int nzc = (int)std::max<int64_t>(1, std::min<int64_t>(nk, (4 * 296 + (int64_t)tx * ty * groups - 1) / ((int64_t)tx * ty * groups)));
+        int kchunk = (nk + nzc - 1) / nzc;
+        nzc = (nk + kchunk - 1) / kchunk;
+        dim3 g(tx * groups, ty, nzc);
+        TmaDesc mr = make_tmap_g(r, F.n, F.p0, F.N, Cfg::FX, Cfg::FY, KB, nrhs);
+        k_restrict3d_tma<T, KB><<<g, 128, smem, stream>>>(mr, bc, Cc.n[0], Cc.n[1], Cc.p0, Cc.N, nrhs, kchunk, groups, Cc.zb, Cc.ze);
+    }
     void restrict_to(const Level& F, const Level& Cc, const C* r, C* bc, int nrhs) {
         dim3 g, blk;
         grid3z(Cc.n, pb.dim, Cc.zb, Cc.ze, g, blk);
         halo_exchange((int)(&F - levels.data()), r, nrhs, 0, HALO_LOWER);
+        if (pb.dim == 3 && tma_restrict && tma_ok_level(F) && ((uintptr_t)r % 16 == 0)) {
+            launch(T_RESTRICT, S * ((double)F.Nlog + (double)Cc.Nlog) * nrhs, [&] {
+                if (nrhs >= 2) restrict_tma_launch<2>(F, Cc, r, bc, nrhs);
+                else restrict_tma_launch<1>(F, Cc, r, bc, nrhs);
+            });
+            return;
+        }
         launch(T_RESTRICT, S * ((double)F.Nlog + (double)Cc.Nlog) * nrhs, [&] {
             if (pb.dim == 3)
                 k_restrict<T, 3><<<g, blk, 0, stream>>>(r, bc, F.n[0], F.n[1], F.n[2], Cc.n[0], Cc.n[1], Cc.n[2], F.p0, Cc.p0, F.N, Cc.N, nrhs,
@@ -1462,7 +1635,9 @@ class Solver : public SolverBase {
         DevBuf<int> lu_flag;
         lu_flag.alloc(1);
         HH_CUDA(cudaMemsetAsync(lu_flag.p, 0, sizeof(int), stream));
-        launch(T_SETUP, 0, [&] { k_band_lu<<<1, 1024, 0, stream>>>(band.p, N, bw, lu_flag.p); });
+        DevBuf<double> diag0;
+        diag0.alloc((size_t)N);
+        launch(T_SETUP, 0, [&] { k_band_lu<<<1, 1024, 0, stream>>>(band.p, N, bw, lu_flag.p, diag0.p); });
         {
             int bad = 0;
             HH_CUDA(cudaMemcpyAsync(&bad, lu_flag.p, sizeof(int), cudaMemcpyDeviceToHost, stream));
@@ -2164,6 +2339,7 @@ class Solver : public SolverBase {
     bool use_scaled = false;             // coarse_op() hands out the column-scaled coefficients (coarse_stencil)
     int force_tile = -1;                 // HH_COARSE_TILE: 0 = 16x8, 1 = alternative tile (coarse_tile)
     bool scaled_gmres = true;
+    bool tma_restrict = true;            // HH_TMA_RESTRICT=0: the one-thread-per-coarse-node restriction (A/B baseline)
     GmresMem outer;
     int outer_cap = 0;
     BicgMem bicg;

@@ -15,13 +15,37 @@ module HelmholtzB200
 using LinearAlgebra
 using SparseArrays
 
+# ---- jInv plug-in conformance -----------------------------------------------------------------------------------
+# The reference's solver is a jInv linear-solver plug-in: it subtypes jInv.LinearSolvers.AbstractSolver and EXTENDS
+# jInv's generic functions (src/Helmholtz.jl:4-8; src/ShiftedLaplacianMultigridSolver.jl:4,17,32,104), so that jInv's
+# forward-modelling / inversion code dispatches into it (`solveLinearSystem(A, B, param::AbstractSolver, doTranspose)`,
+# `copySolver(param)` per worker, `clear!(param)`).  When jInv is installed this module does exactly the same -- the
+# import lines below are the reference's own -- and takes RegularMesh / getRegularMesh from jInv.Mesh.  Without jInv
+# (stand-alone use, CI) it defines stand-ins with the same names so that the rest of the file is identical.
+const HAVE_JINV = Base.find_package("jInv") !== nothing
+@static if HAVE_JINV
+    using jInv.Mesh                                   # RegularMesh, getRegularMesh        (src/Helmholtz.jl:4)
+    using jInv.LinearSolvers                          #                                    (src/Helmholtz.jl:5)
+    import jInv.Utils.clear!                          #                                    (src/Helmholtz.jl:6)
+    import jInv.LinearSolvers.AbstractSolver          #                                    (src/Helmholtz.jl:7)
+    import jInv.LinearSolvers.solveLinearSystem       #                                    (src/Helmholtz.jl:8)
+    import jInv.LinearSolvers.solveLinearSystem!      # in-place variant jInv callers use (test/Elastic/...DDElasticHelmholtz.jl:57-58)
+    import jInv.LinearSolvers.copySolver              #                                    (src/ShiftedLaplacianMultigridSolver.jl:17)
+else
+    abstract type AbstractSolver end
+    function clear! end
+    function solveLinearSystem end
+    function solveLinearSystem! end
+    function copySolver end
+end
+
 export HelmholtzParam, getShiftedHelmholtzParam, GetHelmholtzOperator, GetHelmholtzShiftOP, getABL,
        getMaximalFrequency, getAcousticPointSource, loc2cs, getTopPointSrc, getMidPointSrc,
        MGparam, getMGparam, hierarchyExists, ShiftedLaplacianMultigridSolver,
        getShiftedLaplacianMultigridSolver, copySolver, solveLinearSystem, solveLinearSystem!, clear!,
        RegularMesh, getRegularMesh,
        GetHelmholtzMatrix, GetHelmholtzOperatorHOStencil, setOperatorHO!,
-       SlabHandle, SlabHandleNCCL, slabUniqueId, slabPartition
+       SlabHandle, SlabHandleNCCL, slabUniqueId, slabPartition, setFrequencyABL!, getGamma
 
 const LIB = get(ENV, "HELMHOLTZ_B200_LIB", joinpath(@__DIR__, "..", "lib", "libhelmholtz_b200.so"))
 
@@ -44,24 +68,31 @@ function check(rc::Integer, h::Ptr{Cvoid} = C_NULL)
     return rc
 end
 
-# ---- jInv.Mesh.RegularMesh: only domain / n / h / dim cross the ABI.  With jInv loaded, pass its mesh instead. ----
-struct RegularMesh
-    domain::Vector{Float64}
-    n::Vector{Int64}
-    h::Vector{Float64}
-    dim::Int
+# ---- jInv.Mesh.RegularMesh: only domain / n / h / dim cross the ABI.  With jInv loaded this is jInv's own type. ----
+@static if !HAVE_JINV
+    struct RegularMesh
+        domain::Vector{Float64}
+        n::Vector{Int64}
+        h::Vector{Float64}
+        dim::Int
+    end
+    getRegularMesh(domain, n) = (d = vec(Float64.(domain)); nn = vec(Int64.(n));
+                                 RegularMesh(d, nn, (d[2:2:end] .- d[1:2:end]) ./ nn, length(nn)))
+    clear!(M::RegularMesh) = nothing                  # jInv clears the mesh's cached operators; the stand-in has none
 end
-getRegularMesh(domain, n) = (d = vec(Float64.(domain)); nn = vec(Int64.(n));
-                             RegularMesh(d, nn, (d[2:2:end] .- d[1:2:end]) ./ nn, length(nn)))
 
 # ---- src/Helmholtz.jl:13-20 ----
 mutable struct HelmholtzParam
-    Mesh
+    Mesh::RegularMesh
     gamma::Array{Float64}
     m::Array{Float64}
     omega::Union{Float64,ComplexF64}
     NeumannOnTop::Bool
     Sommerfeld::Bool
+end
+function clear!(HP::HelmholtzParam)                   # src/Helmholtz.jl:25-30
+    clear!(HP.Mesh)
+    return
 end
 getShiftedHelmholtzParam(p::HelmholtzParam, s::Float64) =
     HelmholtzParam(p.Mesh, p.gamma .+ s * real(p.omega), p.m, p.omega, p.NeumannOnTop, p.Sommerfeld)
@@ -145,6 +176,22 @@ function SlabHandleNCCL(Mesh, m, omega, gamma, NeumannOnTop::Bool, Sommerfeld::B
     hd = Handle(out[], Int(nodes[1] * nodes[2] * (o1[] - o0[])), VAL)  # N = nodes of the owned planes
     finalizer(x -> (x.ptr != C_NULL && ccall((:hh_destroy, LIB), Cint, (Ptr{Cvoid},), x.ptr); x.ptr = C_NULL), hd)
     return hd
+end
+
+# ---- device-side set-up for frequency sweeps: gamma <- gamma_const + getABL(...) on the device, omega replaced ----
+function setFrequencyABL!(hd::Handle, omega::Float64, gamma_const::Float64, ABLpad::Array{Int64}, ABLamp::Float64)
+    check(ccall((:hh_set_frequency_abl, LIB), Cint, (Ptr{Cvoid}, Cdouble, Cdouble, Cdouble, Ptr{Int64}, Cdouble),
+                hd.ptr, omega, 0.0, gamma_const, ABLpad, ABLamp), hd.ptr)
+end
+function getGamma(hd::Handle)
+    g = zeros(Float64, hd.N)
+    check(ccall((:hh_get_gamma, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}), hd.ptr, g), hd.ptr)
+    return g
+end
+function getMaximalFrequency(hd::Handle)
+    out = Ref{Cdouble}(0.0)
+    check(ccall((:hh_get_maximal_frequency_device, LIB), Cint, (Ptr{Cvoid}, Ref{Cdouble}), hd.ptr, out), hd.ptr)
+    return out[]
 end
 
 # ---- GetHelmholtzOperatorHO (src/GetHelmholtz.jl:54-72) ----
@@ -295,7 +342,7 @@ function mg_options(MG::MGparam, shift::Vector{Float64}, doTranspose::Int)
 end
 
 # ---- src/ShiftedLaplacianMultigridSolver.jl:4-30 ----
-mutable struct ShiftedLaplacianMultigridSolver
+mutable struct ShiftedLaplacianMultigridSolver <: AbstractSolver   # jInv.LinearSolvers.AbstractSolver when jInv is loaded
     helmParam::HelmholtzParam
     MG::MGparam
     shift::Array{Float64}
@@ -314,7 +361,8 @@ getShiftedLaplacianMultigridSolver(helmParam::HelmholtzParam, MG::MGparam, shift
                                    inner::Int64 = 5, verbose::Bool = false) =
     getShiftedLaplacianMultigridSolver(helmParam, MG, ones(MG.levels) * shift, Krylov, inner, verbose)
 
-function copySolver(s::ShiftedLaplacianMultigridSolver)  # :18-22 -- settings only, no hierarchy
+function copySolver(s::ShiftedLaplacianMultigridSolver)  # :18-22 -- settings only, no hierarchy (a method of jInv's copySolver)
+    clear!(s.helmParam.Mesh)                             # :20
     MG = s.MG
     MG2 = MGparam(MG.VAL, MG.levels, MG.numCores, MG.maxOuterIter, MG.relativeTol, MG.relaxType, MG.relaxParam, MG.relaxPre,
                   MG.relaxPost, MG.cycleType, MG.coarseSolveType, MG.coarseIters, 0, nothing, nothing)
@@ -328,8 +376,9 @@ function clear!(MG::MGparam)
     end
     MG.hd = nothing; MG.builtFor = nothing
 end
-function clear!(s::ShiftedLaplacianMultigridSolver)  # :105-109
+function clear!(s::ShiftedLaplacianMultigridSolver)  # :105-109 (a method of jInv.Utils.clear!)
     clear!(s.MG)
+    clear!(s.helmParam)
     s.doClear = 0
 end
 
@@ -348,7 +397,7 @@ function ensureHierarchy(param::ShiftedLaplacianMultigridSolver, doTranspose::In
     return MG.hd
 end
 
-# in-place variant (jInv.LinearSolvers.solveLinearSystem!)
+# in-place variant: a method of jInv.LinearSolvers.solveLinearSystem!(A, B, X, param::AbstractSolver, doTranspose)
 function solveLinearSystem!(ShiftedHT, B, X, param::ShiftedLaplacianMultigridSolver, doTranspose::Int64 = 0)
     param.helmParam.omega isa ComplexF64 && imag(param.helmParam.omega) != 0 &&
         throw(MethodError(GetHelmholtzShiftOP, (param.helmParam.m, param.helmParam.omega, param.shift[1])))  # :77
@@ -380,6 +429,8 @@ function solveLinearSystem!(ShiftedHT, B, X, param::ShiftedLaplacianMultigridSol
     return X, param
 end
 
+# a method of jInv.LinearSolvers.solveLinearSystem (src/ShiftedLaplacianMultigridSolver.jl:32-33): jInv's callers reach it
+# by dispatch on the solver type; ShiftedHT (the adjoint of the shifted matrix in the reference) is accepted and unused
 function solveLinearSystem(ShiftedHT, B, param::ShiftedLaplacianMultigridSolver, doTranspose::Int64 = 0)
     if size(B, 2) == 1
         B = vec(B)                                     # :34-36

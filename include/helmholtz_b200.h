@@ -14,7 +14,8 @@
  *   getHelmholtzFun (Afun closure)       src/GetHelmholtz.jl:85-95         -> hh_apply(shifted=0)
  *   getABL                               src/GetHelmholtz.jl:97-220        -> hh_get_abl
  *   getSommerfeldBC                      src/GetHelmholtz.jl:222-247       -> computed in-kernel; hh_get_diagonal exposes it
- *   getMaximalFrequency                  src/GetHelmholtz.jl:75-79         -> hh_get_maximal_frequency
+ *   getMaximalFrequency                  src/GetHelmholtz.jl:75-79         -> hh_get_maximal_frequency[_device]
+ *   getABL inside GetHelmholtzOperator   src/GetHelmholtz.jl:22-31          -> hh_set_frequency_abl (device-side)
  *   getAcousticPointSource / loc2cs      src/getPointSource.jl:82-112      -> hh_point_source_index / hh_solve_point_sources
  *   Multigrid.getMGparam / MGsetup       (un-vendored; call sites test/ShiftedLaplacianTest.jl:63-64,
  *                                         src/ShiftedLaplacianMultigridSolver.jl:65)   -> hh_mg_options / hh_setup
@@ -199,6 +200,16 @@ int hh_slab_level_stencil(hh_handle_t h, int slab, int level, int64_t* n_local_o
 int hh_set_stream(hh_handle_t h, void* cuda_stream);
 /* new model / frequency on the same grid: invalidates the hierarchy (clear! + new HelmholtzParam) */
 int hh_update_model(hh_handle_t h, const double* m, const double* gamma, double omega_re, double omega_im);
+
+/* Device-side set-up for frequency sweeps on a resident model: replaces omega and sets
+ * gamma <- gamma_const + getABL(n, NeumannOnTop, pad, amp) on the device (the 9-argument GetHelmholtzOperator,
+ * src/GetHelmholtz.jl:22-31, with getABL :97-220 evaluated from its separable 1-D ramps); m is kept.  Invalidates the
+ * hierarchy like hh_update_model.  Not available with the high-order operator. */
+int hh_set_frequency_abl(hh_handle_t h, double omega_re, double omega_im, double gamma_const, const int64_t* pad, double amp);
+/* gamma as the device holds it, Float64[N] (NCCL slab handle: the planes the caller's B / X hold) */
+int hh_get_gamma(hh_handle_t h, double* gamma_out);
+/* getMaximalFrequency (src/GetHelmholtz.jl:75-79) of the model the handle holds on the device */
+int hh_get_maximal_frequency_device(hh_handle_t h, double* omega_max);
 
 /* GetHelmholtzOperatorHO (src/GetHelmholtz.jl:54-72) as the operator of this handle: the fine level becomes the stored
  * stencil of hh_ho_stencil (built at hh_setup from Float64 copies of m and gamma, the arrays hh_create was given), the

@@ -103,7 +103,7 @@ def test_complexf32_solution_within_1e_4(gpu_pkg, truth):
     pkg.clear(A.MG)
 
 
-@pytest.mark.parametrize("prec,tol,bound", [("c128", 1e-9, 1e-6), ("c64", 2e-6, 1e-4)])
+@pytest.mark.parametrize("prec,tol,bound", [("c128", 1e-9, 1e-6), ("c64", 1.8e-6, 1e-4)])
 def test_reference_production_multigrid_at_scale(gpu_pkg, truth, prec, tol, bound):
     """SURVEY 8(f2) at the headline size: 5 levels (257 -> 17), K-cycle, Jac-GMRES smoother with nu(l) = l+1 sweeps,
     inexact GMRES coarsest solve, FGMRES(5): ComplexF64 to 1e-9 and the paper runs' ComplexF32 / 1e-5

@@ -113,3 +113,42 @@ def test_solver_follows_neumann_order_of_the_operator(gpu_pkg, ho):
         x, A = pkg.solveLinearSystem((H1 + pkg.GetHelmholtzShiftOP(m, w, 0.2)).H, q, A)
         Ho = ho.GetHelmholtzOperator(omesh, m, w, gamma, True, True, order)
         assert np.linalg.norm(Ho @ x - q) / np.linalg.norm(q) < 1e-8, order
+
+
+@pytest.mark.parametrize("dim,neumann,prec,slabs", [(2, True, np.complex128, 0), (2, False, np.complex128, 0),
+                                                    (3, True, np.complex128, 0), (3, False, np.complex64, 0),
+                                                    (3, True, np.complex128, 3)])
+def test_device_side_abl_and_frequency_sweep(gpu_pkg, ho, dim, neumann, prec, slabs):
+    """hh_set_frequency_abl evaluates gamma0 + getABL on the device for a new frequency; the result equals
+    the oracle's getABL (src/GetHelmholtz.jl:97-220) and the solve equals that of a fresh handle built from host arrays."""
+    pkg = gpu_pkg
+    rng = np.random.default_rng(5)
+    nodes = [33, 25] if dim == 2 else [17, 13, 33]
+    dom = sum([[0.0, 0.1 * (n - 1)] for n in nodes], [])
+    mesh = pkg.getRegularMesh(dom, np.array(nodes) - 1)
+    m = 1.0 / (1.5 + 2.0 * rng.random(nodes)) ** 2
+    w0 = pkg.getMaximalFrequency(m, mesh)
+    pad = [4, 3] if dim == 2 else [3, 3, 4]
+    g0 = 0.01 * w0 * np.ones(nodes) + ho.getABL(nodes, neumann, pad, w0)
+    lv = 2 if dim == 2 else 3
+    MG = pkg.getMGparam(prec, pkg.Int64, lv, 1, 60, 1e-8 if prec == np.complex128 else 1e-5, "Jac", 0.8, 2, 2, "V", "GMRES", coarseIters=10)
+    hp = pkg.HelmholtzParam(mesh, g0, m.ravel(order="F"), w0, neumann, True)
+    A = pkg.getShiftedLaplacianMultigridSolver(hp, MG, 0.2, "GMRES", 5)
+    if slabs:
+        A.slabs = {"mode": "local", "devices": [0] * slabs}
+    q = np.zeros(int(np.prod(nodes)), dtype=prec)
+    q[int(np.prod(nodes)) // 2 + 3] = 1.0
+    x0, A = pkg.solveLinearSystem(None, q, A)
+    assert abs(pkg.getMaximalFrequencyDevice(A) - w0) <= (1e-12 if prec == np.complex128 else 1e-6) * w0
+    w1 = 0.8 * w0
+    A = pkg.setFrequencyABL(A, w1, 0.02 * w1, pad, w1)
+    g1 = 0.02 * w1 + ho.getABL(nodes, neumann, pad, w1)
+    assert np.abs(A.helmParam.gamma.reshape(nodes, order="F") - g1).max() <= (1e-13 if prec == np.complex128 else 1e-6) * g1.max()
+    assert not pkg.hierarchyExists(A.MG)
+    x1, A = pkg.solveLinearSystem(None, q, A)
+    MG2 = pkg.getMGparam(prec, pkg.Int64, lv, 1, 60, MG.relativeTol, "Jac", 0.8, 2, 2, "V", "GMRES", coarseIters=10)
+    hp2 = pkg.HelmholtzParam(mesh, g1, m.ravel(order="F"), w1, neumann, True)
+    A2 = pkg.getShiftedLaplacianMultigridSolver(hp2, MG2, 0.2, "GMRES", 5)
+    x2, A2 = pkg.solveLinearSystem(None, q, A2)
+    assert rel_err(x1, x2) < (1e-9 if prec == np.complex128 else 2e-4)
+    assert rel_err(x1, x0) > 1e-3  # really the new frequency
