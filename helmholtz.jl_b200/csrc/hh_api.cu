@@ -933,14 +933,31 @@ static int solve_host(hh_handle_t h, const void* B, const int64_t* idx, const do
         kmax = std::min<int64_t>(std::max<int64_t>(kmax, 1), ncols);
         const char* pe = getenv("HH_HOST_PIPELINE");
         const bool pipeline = !(pe && pe[0] == '0');
-        int64_t kb = kmax;
-        if (pipeline && ncols >= 8 && kmax >= (ncols + 1) / 2) kb = (ncols + 1) / 2;
+        // Sub-batches.  Only the H2D copy of the FIRST and the D2H copy of the LAST sub-batch are exposed (the others
+        // overlap a solve), so a block of >= 16 columns is cut as quarter / half / quarter: the exposed copies shrink
+        // to a quarter of the block each while the half in the middle keeps the coefficient reuse of a large batch
+        // (a batch of 4 costs ~5 % more per column than one of 16, a batch of 2 ~45 %).  Smaller blocks: two halves.
+        std::vector<int64_t> sizes;
+        if (pipeline && ncols >= 16 && kmax >= (ncols + 1) / 2) {
+            const int64_t q = std::max<int64_t>(4, (ncols / 4) / 4 * 4);
+            sizes = {q, ncols - 2 * q, q};
+        } else if (pipeline && ncols >= 8 && kmax >= (ncols + 1) / 2) {
+            sizes = {(ncols + 1) / 2, ncols / 2};
+        } else {
+            for (int64_t c = 0; c < ncols; c += kmax) sizes.push_back(std::min(kmax, ncols - c));
+        }
+        int64_t kb = 0;
+        std::vector<int64_t> start(sizes.size());
+        for (size_t q = 0; q < sizes.size(); ++q) {
+            start[q] = q ? start[q - 1] + sizes[q - 1] : c0;
+            kb = std::max(kb, sizes[q]);
+        }
         hs.ensure((size_t)N * kb * es);
-        const int64_t nb = (ncols + kb - 1) / kb;
+        const int64_t nb = (int64_t)sizes.size();
         std::vector<int64_t> idx0;
         auto stage_in = [&](int64_t bidx) {  // enqueue the right-hand sides of sub-batch bidx into its slot
             const int slot = (int)(bidx & 1);
-            const int64_t c = c0 + bidx * kb, k = std::min(kb, c1 - c);
+            const int64_t c = start[bidx], k = sizes[bidx];
             if (idx) {
                 idx0.resize(k);
                 for (int64_t r = 0; r < k; ++r) idx0[r] = idx[c + r] - 1;
@@ -954,7 +971,7 @@ static int solve_host(hh_handle_t h, const void* B, const int64_t* idx, const do
         stage_in(0);
         for (int64_t bidx = 0; bidx < nb; ++bidx) {
             const int slot = (int)(bidx & 1);
-            const int64_t c = c0 + bidx * kb, k = std::min(kb, c1 - c);
+            const int64_t c = start[bidx], k = sizes[bidx];
             // prefetch the next sub-batch: its B slot was last read by solve(bidx-1), which has returned
             if (bidx + 1 < nb) stage_in(bidx + 1);
             if (!idx) HH_CUDA(cudaStreamWaitEvent(s->stream, hs.h2d[slot], 0));

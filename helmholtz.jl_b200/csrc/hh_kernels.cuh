@@ -1263,7 +1263,7 @@ __global__ void __launch_bounds__(256) k_fine_jacobi0(FineOp<T> op, const cx<T>*
     if (i >= n0 || j >= n1 || k >= n2) return;
     const int64_t p = i + (int64_t)op.sy * j + (int64_t)op.sy * n1 * k;
     const cx<T> dinv = rdiv(damp, fine_center<T, DIM>(op, p, i, j, k));
-    for (int r = 0; r < nrhs; ++r) out[(int64_t)r * ld + p] = dinv * b[(int64_t)r * ld + p];
+    for (int r = (DIM == 2 ? blockIdx.z : 0); r < nrhs; r += (DIM == 2 ? gridDim.z : 1)) out[(int64_t)r * ld + p] = dinv * b[(int64_t)r * ld + p];
 }
 
 // complex diagonal c_p (without the Laplacian part) in double, for hh_get_diagonal
@@ -1346,7 +1346,7 @@ __global__ void __launch_bounds__(256) k_diag_scale(const cx<T>* __restrict__ di
     const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= N) return;
     const cx<T> d = dinv[p];
-    for (int r = 0; r < nrhs; ++r) out[(int64_t)r * ld + p] = d * b[(int64_t)r * ld + p];
+    for (int r = blockIdx.y; r < nrhs; r += gridDim.y) out[(int64_t)r * ld + p] = d * b[(int64_t)r * ld + p];
 }
 
 // fine-level damp/diag as an explicit array (used by Jac-GMRES on the fine level)
@@ -1380,7 +1380,8 @@ __global__ void __launch_bounds__(256) k_restrict(const cx<T>* __restrict__ r, c
     const int64_t sy = fsy, sz = (int64_t)fsy * nf1;
     const int64_t pc = I + (int64_t)csy * J + (int64_t)csy * nc1 * K;
     const int fi = 2 * I, fj = 2 * J, fk = (DIM == 3) ? 2 * K : 0;
-    for (int q = 0; q < nrhs; ++q) {
+    // 2-D: the grid's z dimension strides over the right-hand sides (a 2-D grid alone cannot fill the SMs)
+    for (int q = (DIM == 2 ? blockIdx.z : 0); q < nrhs; q += (DIM == 2 ? gridDim.z : 1)) {
         const cx<T>* rr = r + (int64_t)q * ldf;
         cx<T> acc = mk<T>(T(0), T(0));
 #pragma unroll
@@ -1515,7 +1516,7 @@ __global__ void __launch_bounds__(256) k_prolong_add(cx<T>* __restrict__ x, cons
     const int oi = i & 1, oj = j & 1, ok = (DIM == 3) ? (k & 1) : 0;
     const T w = T(1) / T((1 << oi) * (1 << oj) * (1 << ok));
     const int64_t base = I0 + cy * J0 + cz * K0;
-    for (int q = 0; q < nrhs; ++q) {
+    for (int q = (DIM == 2 ? blockIdx.z : 0); q < nrhs; q += (DIM == 2 ? gridDim.z : 1)) {
         const cx<T>* c = xc + (int64_t)q * ldc + base;
         cx<T> acc = mk<T>(T(0), T(0));
 #pragma unroll

@@ -820,6 +820,11 @@ class Solver : public SolverBase {
             g = dim3((n[0] + 31) / 32, (n[1] + 7) / 8, 1);
         }
     }
+    // 2-D grids: how many slices of the RHS block the z dimension of a one-thread-per-node grid strides over
+    static unsigned rhs_slices(const dim3& g, int nrhs) {
+        const int64_t ctas = (int64_t)g.x * g.y;
+        return (unsigned)std::max<int64_t>(1, std::min<int64_t>(nrhs, (4 * 148 + ctas - 1) / ctas));
+    }
     static int vec_blocks(int64_t N, int nrhs) {
         int64_t nb = (N + 2047) / 2048;  // 8 elements per thread
         int64_t cap = std::max<int64_t>(1, (148 * 8 + nrhs - 1) / nrhs);
@@ -1202,7 +1207,7 @@ class Solver : public SolverBase {
         const double N = (double)pb.N();
         launch(T_FINE_JACOBI0, 2 * S * N * nrhs + 2.0 * CR * N, [&] {
             if (pb.dim == 3) k_fine_jacobi0<T, 3><<<g, blk, 0, stream>>>(op, b, out, ld, nrhs, damp);
-            else k_fine_jacobi0<T, 2><<<g, blk, 0, stream>>>(op, b, out, ld, nrhs, damp);
+            else k_fine_jacobi0<T, 2><<<dim3(g.x, g.y, rhs_slices(g, nrhs)), blk, 0, stream>>>(op, b, out, ld, nrhs, damp);
         });
     }
     CoarseOp<T> coarse_op(const Level& L) const {
@@ -1285,7 +1290,9 @@ class Solver : public SolverBase {
     }
     void diag_scale(int tag, const C* dinv, const C* b, C* out, int64_t N, int nrhs) {
         launch(tag, 2 * S * (double)N * nrhs + S * (double)N, [&] {
-            k_diag_scale<T><<<(unsigned)((N + 255) / 256), 256, 0, stream>>>(dinv, b, out, N, N, nrhs);
+            const unsigned nb = (unsigned)((N + 255) / 256);
+            const unsigned ny = (unsigned)std::max<int64_t>(1, std::min<int64_t>(nrhs, (4 * 148 + nb - 1) / nb));
+            k_diag_scale<T><<<dim3(nb, ny), 256, 0, stream>>>(dinv, b, out, N, N, nrhs);
         });
     }
     template <int KB>
@@ -1324,7 +1331,8 @@ class Solver : public SolverBase {
                 k_restrict<T, 3><<<g, blk, 0, stream>>>(r, bc, F.n[0], F.n[1], F.n[2], Cc.n[0], Cc.n[1], Cc.n[2], F.p0, Cc.p0, F.N, Cc.N, nrhs,
                                                         Cc.zb, Cc.ze, F.koff, F.n2g);
             else
-                k_restrict<T, 2><<<g, blk, 0, stream>>>(r, bc, F.n[0], F.n[1], 1, Cc.n[0], Cc.n[1], 1, F.p0, Cc.p0, F.N, Cc.N, nrhs, 0, 1, 0, 1);
+                k_restrict<T, 2><<<dim3(g.x, g.y, rhs_slices(g, nrhs)), blk, 0, stream>>>(r, bc, F.n[0], F.n[1], 1, Cc.n[0], Cc.n[1], 1, F.p0, Cc.p0, F.N,
+                                                                                        Cc.N, nrhs, 0, 1, 0, 1);
         });
     }
     void prolong_add(const Level& F, const Level& Cc, C* x, const C* xc, int nrhs) {
@@ -1335,7 +1343,8 @@ class Solver : public SolverBase {
             if (pb.dim == 3)
                 k_prolong_add<T, 3><<<g, blk, 0, stream>>>(x, xc, F.n[0], F.n[1], F.n[2], F.p0, Cc.p0, Cc.n[1], F.N, Cc.N, nrhs, F.zb, F.ze);
             else
-                k_prolong_add<T, 2><<<g, blk, 0, stream>>>(x, xc, F.n[0], F.n[1], 1, F.p0, Cc.p0, Cc.n[1], F.N, Cc.N, nrhs, 0, 1);
+                k_prolong_add<T, 2><<<dim3(g.x, g.y, rhs_slices(g, nrhs)), blk, 0, stream>>>(x, xc, F.n[0], F.n[1], 1, F.p0, Cc.p0, Cc.n[1], F.N, Cc.N, nrhs,
+                                                                                           0, 1);
         });
     }
 

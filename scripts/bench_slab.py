@@ -22,6 +22,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import __graft_entry__ as graft  # noqa: E402
+from bench import ClockSampler  # noqa: E402  (NVML clock / throttle-reason sampling during the timed region)
 
 
 def main():
@@ -124,13 +125,16 @@ def run_variant(a, pkg, lib, torch, dist, rank, world, local, mesh, nodes, w, hp
     lib.hh_profile_reset(hd.h)
     l0 = C.c_int64()
     lib.hh_get_counters(hd.h, None, None, None, C.byref(l0))
+    sampler = ClockSampler(local)
     barrier()
+    sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     for _ in range(a.steps):
         pkg.solveLinearSystem_(None, B, X, A)
     ev1.record()
     barrier()
+    sampler.stop_flag.set()
     ms = ev0.elapsed_time(ev1)
     l1 = C.c_int64()
     lib.hh_get_counters(hd.h, None, None, None, C.byref(l1))
@@ -181,6 +185,7 @@ def run_variant(a, pkg, lib, torch, dist, rank, world, local, mesh, nodes, w, hp
             "e2e": {"value": a.nrhs / float(tmax[1]), "unit": "RHS/s", "h2d_bytes_per_step": int(Nown * a.nrhs * es),
                     "d2h_bytes_per_step": int(Nown * a.nrhs * es), "note": "bytes of rank 0; every rank copies its own planes"},
             "gpu_launches": int(l1.value - l0.value),
+            "clocks": sampler.result(),
             "per_kernel_rank0": {d["kernel"]: {"launches": d["launches"], "share": round(d["ms"] / tot, 4),
                                                "avg_ms": round(d["ms"] / d["launches"], 4),
                                                "gbs": round(d["bytes"] / d["ms"] / 1e6, 1) if d["bytes"] else None} for d in tags},
