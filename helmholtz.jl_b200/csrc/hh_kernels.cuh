@@ -756,6 +756,265 @@ __global__ void __launch_bounds__(256) k_fine3d_tma_pro(FineOp<T> op, const __gr
 }
 
 // ---------------------------------------------------------------------------------------------
+// Fused coarse-grid correction + TWO post-smoothing sweeps on the fine level (3-D, TMA form):
+//   x' = x + P xc ;  x1 = x' + dinv .* (b - A x') ;  out = x1 + dinv .* (b - A x1)
+// Neither x' nor x1 touches HBM: per node and right-hand side the pass reads x, b (and xc/8) and writes x2 --
+// 3.125 S instead of the 6.125 S of k_fine3d_tma_pro followed by k_fine3d_tma<JACOBI>.  The price is a two-node
+// halo: the x tile is staged with two halo nodes per side, corrected in shared memory (all 36 x 12 entries), x1 is
+// formed on the tile plus a one-node ring (the ring nodes by the first 84*KB threads) into a two-slot plane buffer in
+// shared memory, and x2 on the tile proper.  In z the kernel runs three planes deep: when plane p arrives it
+// completes x'(p), x1(p-1) and x2(p-2); a chunk of output planes [z0,z1) therefore stages planes z0-2 .. z1+1.
+// The z-neighbours of a column (x' and x1 of the planes before) ride in registers, b / c / dinv of the plane a
+// thread has just used for x1 are carried in registers for its x2 one iteration later, so only two stages are
+// live at a time.  Not used under slab decomposition (the halo planes are one deep there).
+// ---------------------------------------------------------------------------------------------
+template <typename T, int KB>
+struct FinePro2Cfg {
+    static constexpr int TX = 32, TY = 8;
+    static constexpr int H2 = 2;                        // halo of the x tile (even: 16-byte aligned box start in both precisions)
+    static constexpr int PX2 = TX + 2 * H2, PY2 = TY + 2 * H2, XT2 = PX2 * PY2;
+    static constexpr int H1 = sizeof(T) == 4 ? 2 : 1;   // x halo of the b / c / dinv tiles and of the x1 plane buffer
+    static constexpr int PX1 = TX + 2 * H1, PY1 = TY + 2, ET1 = PX1 * PY1;
+    static constexpr int CH = sizeof(T) == 4 ? 2 : 1;   // the coarse tile starts CH coarse nodes left of i0/2
+    static constexpr int CTX = TX / 2 + 2 + CH, CTY = TY / 2 + 3, CT = CTX * CTY;
+    static constexpr int ES = (int)sizeof(cx<T>);
+    static constexpr int al(int b) { return (b + 127) / 128 * 128; }
+    static constexpr int OFF_X = 0;
+    static constexpr int OFF_B = al(KB * XT2 * ES);
+    static constexpr int OFF_C = OFF_B + al(KB * ET1 * ES);
+    static constexpr int OFF_D = OFF_C + al(ET1 * ES);
+    static constexpr int OFF_XC = OFF_D + al(ET1 * ES);
+    static constexpr int XC_PLANE = al(KB * CT * ES);
+    static constexpr int STAGE_BYTES = OFF_XC + 2 * XC_PLANE;
+    static constexpr uint32_t TX_BYTES = KB * XT2 * ES + KB * ET1 * ES + 2 * ET1 * ES + 2 * KB * CT * ES;
+    static constexpr int X1_SLOT = al(KB * ET1 * ES);   // x1 of one plane on the tile + ring
+    static constexpr int NS = (4 * STAGE_BYTES + 2 * X1_SLOT + 64 <= 227 * 1024) ? 4 : 3;
+    static constexpr int NCORR = (KB * XT2 + 255) / 256;  // entries of the x tile each thread corrects
+    static constexpr int RING = 2 * (TX + 2) + 2 * TY;    // nodes of the one-node ring (84)
+    static_assert((PX2 * ES) % 16 == 0 && (PX1 * ES) % 16 == 0 && (CTX * ES) % 16 == 0, "TMA box rows are 16-byte multiples");
+    static_assert(RING * KB <= 256, "one thread per ring node and right-hand side");
+};
+
+template <typename T, int KB>
+__global__ void __launch_bounds__(256, 1) k_fine3d_tma_pro2(FineOp<T> op, const __grid_constant__ TmaDesc tm_x,
+                                                            const __grid_constant__ TmaDesc tm_b,
+                                                            const __grid_constant__ TmaDesc tm_c,
+                                                            const __grid_constant__ TmaDesc tm_d,
+                                                            const __grid_constant__ TmaDesc tm_xc, cx<T>* __restrict__ out,
+                                                            int64_t ld, int nrhs, int zchunk, int groups) {
+    typedef FinePro2Cfg<T, KB> Cfg;
+    constexpr int TX = Cfg::TX, TY = Cfg::TY, PX2 = Cfg::PX2, PX1 = Cfg::PX1, NS = Cfg::NS, H1 = Cfg::H1, H2 = Cfg::H2;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    unsigned char* x1buf = smem_raw + (size_t)NS * Cfg::STAGE_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(x1buf + 2 * Cfg::X1_SLOT);
+    const int n0 = op.n[0], n1 = op.n[1], n2 = op.n[2];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int i0 = (blockIdx.x / groups) * TX, j0 = blockIdx.y * TY;
+    const int i = i0 + tx, j = j0 + ty;
+    const int r0 = (blockIdx.x % groups) * KB;
+    const int z0 = op.zb + blockIdx.z * zchunk;
+    const int z1 = min(op.ze, z0 + zchunk);
+    const int pf = z0 - 2, pl = z1 + 1;  // first / last staged plane
+    const int64_t sy = op.sy, sz = (int64_t)op.sy * n1;
+    const bool active = (i < n0) && (j < n1);
+    const int Is = (i0 >> 1) - Cfg::CH, Js = (j0 >> 1) - 1;  // origin of the coarse tile
+    auto issue = [&](int s, int p) {
+        unsigned char* st = smem_raw + (size_t)s * Cfg::STAGE_BYTES;
+        mbar_expect_tx(&bars[s], Cfg::TX_BYTES);
+        tma_load_4d(st + Cfg::OFF_X, &tm_x, 2 * (i0 - H2), j0 - H2, p, r0, &bars[s]);
+        tma_load_4d(st + Cfg::OFF_B, &tm_b, 2 * (i0 - H1), j0 - 1, p, r0, &bars[s]);
+        tma_load_3d(st + Cfg::OFF_C, &tm_c, 2 * (i0 - H1), j0 - 1, p, &bars[s]);
+        tma_load_3d(st + Cfg::OFF_D, &tm_d, 2 * (i0 - H1), j0 - 1, p, &bars[s]);
+        tma_load_4d(st + Cfg::OFF_XC, &tm_xc, 2 * Is, Js, p >> 1, r0, &bars[s]);
+        tma_load_4d(st + Cfg::OFF_XC + Cfg::XC_PLANE, &tm_xc, 2 * Is, Js, (p >> 1) + 1, r0, &bars[s]);
+    };
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < NS; ++s) mbar_init(&bars[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        for (int s = 0; s < NS && pf + s <= pl; ++s) issue(s, pf + s);
+    }
+    // ---- correction geometry of the x-tile entries this thread owns (z-invariant) ----
+    int coff[Cfg::NCORR], cinfo[Cfg::NCORR];  // x-tile offset (or -1), coarse-tile offset << 2 | parity bits
+#pragma unroll
+    for (int k = 0; k < Cfg::NCORR; ++k) {
+        const int e = threadIdx.x + 256 * k;
+        coff[k] = -1;
+        cinfo[k] = 0;
+        if (e < KB * Cfg::XT2) {
+            const int q = e / Cfg::XT2, r = e - q * Cfg::XT2;
+            const int row = r / PX2, col = r - row * PX2;
+            const int fi = i0 - H2 + col, fj = j0 - H2 + row;
+            if ((unsigned)fi < (unsigned)n0 && (unsigned)fj < (unsigned)n1) {
+                coff[k] = e;
+                cinfo[k] = ((q * Cfg::CT + ((fj >> 1) - Js) * Cfg::CTX + ((fi >> 1) - Is)) << 2) | (fi & 1) | ((fj & 1) << 1);
+            }
+        }
+    }
+    auto interp = [&](const cx<T>* c0, int info, int ok) -> cx<T> {
+        const int oi = info & 1, oj = (info >> 1) & 1;
+        const cx<T>* p0 = c0 + (info >> 2);
+        cx<T> acc = p0[0];
+        if (oi) acc = acc + p0[1];
+        if (oj) {
+            acc = acc + p0[Cfg::CTX];
+            if (oi) acc = acc + p0[Cfg::CTX + 1];
+        }
+        if (ok) {
+            const cx<T>* p1 = p0 + Cfg::XC_PLANE / Cfg::ES;
+            acc = acc + p1[0];
+            if (oi) acc = acc + p1[1];
+            if (oj) {
+                acc = acc + p1[Cfg::CTX];
+                if (oi) acc = acc + p1[Cfg::CTX + 1];
+            }
+        }
+        return (T(1) / T(1 << (oi + oj + ok))) * acc;
+    };
+    // ---- the ring node of this thread (threads < 84*KB): one node of the one-node ring, one right-hand side ----
+    const bool ring_thread = threadIdx.x < Cfg::RING * KB;
+    int rq = 0, ri = 0, rj = 0, rrow = 0, rcol = 0;  // RHS slot, fine coordinates, position relative to (i0-1, j0-1)
+    if (ring_thread) {
+        rq = threadIdx.x / Cfg::RING;
+        const int u = threadIdx.x - rq * Cfg::RING;
+        constexpr int RW = TX + 2;
+        if (u < RW) {
+            rrow = 0;
+            rcol = u;
+        } else if (u < 2 * RW) {
+            rrow = TY + 1;
+            rcol = u - RW;
+        } else if (u < 2 * RW + TY) {
+            rrow = 1 + (u - 2 * RW);
+            rcol = 0;
+        } else {
+            rrow = 1 + (u - 2 * RW - TY);
+            rcol = TX + 1;
+        }
+        ri = i0 - 1 + rcol;
+        rj = j0 - 1 + rrow;
+    }
+    const bool ring_ok = ring_thread && (unsigned)ri < (unsigned)n0 && (unsigned)rj < (unsigned)n1;
+    // offsets of the two roles inside an x tile (two-node halo) and inside an E1 tile (b, c, dinv, x1 buffer)
+    const int xi_c = (ty + H2) * PX2 + (tx + H2), e1_c = (ty + 1) * PX1 + (tx + H1);
+    const int xi_r = (rrow + H2 - 1) * PX2 + (rcol + H2 - 1) + rq * Cfg::XT2, e1_r = rrow * PX1 + (rcol + H1 - 1);
+    const int ic = active ? i : 0, jc = active ? j : 0;
+    const T wxm = fine_w(op, 0, 0, ic, n0), wxp = fine_w(op, 0, 1, ic, n0);
+    const T wym = fine_w(op, 1, 0, jc, n1), wyp = fine_w(op, 1, 1, jc, n1);
+    const int ir = ring_ok ? ri : 0, jr = ring_ok ? rj : 0;
+    const T rwxm = fine_w(op, 0, 0, ir, n0), rwxp = fine_w(op, 0, 1, ir, n0);
+    const T rwym = fine_w(op, 1, 0, jr, n1), rwyp = fine_w(op, 1, 1, jr, n1);
+    const int64_t pxy = ic + sy * jc;
+    const cx<T> zero = mk<T>(T(0), T(0));
+    cx<T> xa[KB], xb[KB], y3[KB], y2[KB], b2[KB];  // x'(p-2), x'(p-1); x1(p-3), x1(p-2); b(p-2) of the own column
+    cx<T> c2 = zero, d2 = zero;                    // c(p-2), dinv(p-2)
+    cx<T> ra = zero, rb = zero;                    // x'(p-2), x'(p-1) of the ring node
+#pragma unroll
+    for (int q = 0; q < KB; ++q) xa[q] = xb[q] = y3[q] = y2[q] = b2[q] = zero;
+    __syncthreads();
+#pragma unroll 1
+    for (int p = pf; p <= pl; ++p) {
+        const int it = p - pf;
+        const int s = it % NS;
+        unsigned char* st = smem_raw + (size_t)s * Cfg::STAGE_BYTES;
+        const unsigned char* stm = smem_raw + (size_t)((it + NS - 1) % NS) * Cfg::STAGE_BYTES;  // stage of plane p-1
+        mbar_wait(&bars[s], (uint32_t)((it / NS) & 1));
+        // (1) x'(p) = x(p) + (P xc)(p) on the whole staged tile (planes outside the grid stay zero)
+        cx<T>* xs = reinterpret_cast<cx<T>*>(st + Cfg::OFF_X);
+        if ((unsigned)p < (unsigned)n2) {
+            const cx<T>* cc = reinterpret_cast<const cx<T>*>(st + Cfg::OFF_XC);
+            const int ok = p & 1;
+#pragma unroll
+            for (int k = 0; k < Cfg::NCORR; ++k)
+                if (coff[k] >= 0) xs[coff[k]] = xs[coff[k]] + interp(cc, cinfo[k], ok);
+        }
+        fence_proxy_async();  // generic stores into a stage the TMA engine refills later
+        __syncthreads();
+        // (2) x1(p-1) on the tile and its ring, from x'(p-2) [registers], x'(p-1) [stage p-1], x'(p) [stage p]
+        cx<T> y1[KB];
+#pragma unroll
+        for (int q = 0; q < KB; ++q) y1[q] = zero;
+        cx<T> bn[KB], cn = zero, dn = zero;  // b, c, dinv of plane p-1 at the own node
+#pragma unroll
+        for (int q = 0; q < KB; ++q) bn[q] = zero;
+        cx<T>* x1w = reinterpret_cast<cx<T>*>(x1buf + (size_t)((p - 1) & 1) * Cfg::X1_SLOT);
+        if (it >= 2) {  // planes p-2, p-1, p are all staged
+            const cx<T>* xm1 = reinterpret_cast<const cx<T>*>(stm + Cfg::OFF_X);
+            const cx<T>* sb = reinterpret_cast<const cx<T>*>(stm + Cfg::OFF_B);
+            const cx<T>* sc = reinterpret_cast<const cx<T>*>(stm + Cfg::OFF_C);
+            const cx<T>* sd = reinterpret_cast<const cx<T>*>(stm + Cfg::OFF_D);
+            const T wzm = fine_wz(op, 0, p - 1), wzp = fine_wz(op, 1, p - 1);
+            cn = sc[e1_c];
+            dn = sd[e1_c];
+#pragma unroll
+            for (int q = 0; q < KB; ++q) {
+                const cx<T>* xt = xm1 + q * Cfg::XT2 + xi_c;
+                bn[q] = sb[q * Cfg::ET1 + e1_c];
+                cx<T> a = cn * xb[q];
+                rfma(a, -wxm, xt[-1]);
+                rfma(a, -wxp, xt[1]);
+                rfma(a, -wym, xt[-PX2]);
+                rfma(a, -wyp, xt[PX2]);
+                rfma(a, -wzm, xa[q]);
+                rfma(a, -wzp, xs[q * Cfg::XT2 + xi_c]);
+                y1[q] = xb[q] + dn * (bn[q] - a);
+                x1w[q * Cfg::ET1 + e1_c] = y1[q];
+            }
+            if (ring_thread) {
+                cx<T> v = zero;
+                if (ring_ok) {
+                    const cx<T>* xt = xm1 + xi_r;
+                    cx<T> a = sc[e1_r] * rb;
+                    rfma(a, -rwxm, xt[-1]);
+                    rfma(a, -rwxp, xt[1]);
+                    rfma(a, -rwym, xt[-PX2]);
+                    rfma(a, -rwyp, xt[PX2]);
+                    rfma(a, -wzm, ra);
+                    rfma(a, -wzp, xs[xi_r]);
+                    v = rb + sd[e1_r] * (sb[rq * Cfg::ET1 + e1_r] - a);
+                }
+                x1w[rq * Cfg::ET1 + e1_r] = v;
+            }
+        }
+        // (3) x2(p-2) on the tile, from x1(p-3), x1(p-2) [registers; neighbours in the other x1 slot], x1(p-1)
+        const int zo = p - 2;
+        if (active && zo >= z0 && zo < z1) {
+            const cx<T>* x1r = reinterpret_cast<const cx<T>*>(x1buf + (size_t)(zo & 1) * Cfg::X1_SLOT) + e1_c;
+            const T wzm = fine_wz(op, 0, zo), wzp = fine_wz(op, 1, zo);
+            const int64_t pn = pxy + (int64_t)zo * sz;
+#pragma unroll
+            for (int q = 0; q < KB; ++q) {
+                const cx<T>* yt = x1r + q * Cfg::ET1;
+                cx<T> a = c2 * y2[q];
+                rfma(a, -wxm, yt[-1]);
+                rfma(a, -wxp, yt[1]);
+                rfma(a, -wym, yt[-PX1]);
+                rfma(a, -wyp, yt[PX1]);
+                rfma(a, -wzm, y3[q]);
+                rfma(a, -wzp, y1[q]);
+                if (r0 + q < nrhs) out[(int64_t)(r0 + q) * ld + pn] = y2[q] + d2 * (b2[q] - a);
+            }
+        }
+        // roll the registers
+#pragma unroll
+        for (int q = 0; q < KB; ++q) {
+            xa[q] = xb[q];
+            xb[q] = xs[q * Cfg::XT2 + xi_c];
+            y3[q] = y2[q];
+            y2[q] = y1[q];
+            b2[q] = bn[q];
+        }
+        c2 = cn;
+        d2 = dn;
+        if (ring_thread) {
+            ra = rb;
+            rb = xs[xi_r];
+        }
+        __syncthreads();  // stage of plane p-1 and the x1 slot just read are free
+        if (threadIdx.x == 0 && it >= 1 && p - 1 + NS <= pl) issue((it + NS - 1) % NS, p - 1 + NS);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Fused start of a cycle on the fine level (3-D, TMA form): the first Jacobi sweep from a zero guess,
 // x1 = dinv .* b, is never written and re-read -- the kernel stages b and dinv WITH halo, forms x1 on
 // the fly at the centre and the six neighbours, and directly produces

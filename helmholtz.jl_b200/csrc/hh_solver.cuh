@@ -241,6 +241,7 @@ enum Tag {
     T_FINE_FIRST_RESID,
     T_FINE_FIRST_JACOBI,
     T_FINE_PROLONG_JACOBI,
+    T_FINE_PROLONG_JACOBI2,
     T_COARSE_APPLY,
     T_COARSE_RESID,
     T_COARSE_JACOBI,
@@ -258,7 +259,7 @@ enum Tag {
     T_NTAGS
 };
 static const char* const kTagNames[T_NTAGS] = {
-    "fine_apply",   "fine_resid",   "fine_jacobi",    "fine_jacobi0", "fine_first_resid", "fine_first_jacobi", "fine_prolong_jacobi",
+    "fine_apply",   "fine_resid",   "fine_jacobi",    "fine_jacobi0", "fine_first_resid", "fine_first_jacobi", "fine_prolong_jacobi", "fine_prolong_jacobi2",
     "coarse_apply", "coarse_resid",
     "coarse_jacobi", "coarse_jacobi0", "restrict",    "prolong",      "coarsest_dense", "krylov_dot",
     "krylov_axpy",  "copy",           "scalar",       "setup",        "halo_exchange", "allreduce"};
@@ -535,6 +536,8 @@ class Solver : public SolverBase {
         if (ct && !strcmp(ct, "alt")) force_tile = 1;
         const char* sc = getenv("HH_SCALED_GMRES");  // A/B switch of the one-pass (A D^-1) apply (default on)
         scaled_gmres = !(sc && sc[0] == '0');
+        const char* fp = getenv("HH_FUSE_POST2");
+        fuse_post2 = !(fp && fp[0] == '0');
         const char* tr = getenv("HH_TMA_RESTRICT");
         tma_restrict = !(tr && tr[0] == '0');
         const char* hs = getenv("HH_HALO_SPLIT");
@@ -1058,6 +1061,52 @@ class Solver : public SolverBase {
         launch(T_FINE_PROLONG_JACOBI, (3.0 * N + 0.125 * N) * S * nrhs + 2.0 * S * N, [&] {
             if (nrhs >= 2) tma3d_pro_launch<2>(op, x, b, Cc, xc, out, ld, nrhs);
             else tma3d_pro_launch<1>(op, x, b, Cc, xc, out, ld, nrhs);
+        });
+    }
+    // fused coarse-grid correction + two post-smoothing sweeps; see k_fine3d_tma_pro2 (whole grids only: two-node halo)
+    template <int KB>
+    void tma3d_pro2_launch(const FineOp<T>& op, const C* x, const C* b, const Level& Cc, const C* xc, C* out, int64_t ld, int nrhs) {
+        typedef FinePro2Cfg<T, KB> Cfg;
+        constexpr size_t smem = (size_t)Cfg::NS * Cfg::STAGE_BYTES + 2 * Cfg::X1_SLOT + Cfg::NS * sizeof(uint64_t);
+        static bool attr_set = false;
+        if (!attr_set) {
+            HH_CUDA(cudaFuncSetAttribute(k_fine3d_tma_pro2<T, KB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            attr_set = true;
+        }
+        const int groups = (nrhs + KB - 1) / KB;
+        const int tx = (pb.n[0] + Cfg::TX - 1) / Cfg::TX, ty = (pb.n[1] + Cfg::TY - 1) / Cfg::TY;
+        // one CTA per SM, four extra planes per chunk: long, equal chunks in whole waves
+        int zchunk, nzc;
+        {
+            const int nz = op.ze - op.zb;
+            const int64_t per = (int64_t)tx * ty * groups;
+            double best = 1e300;
+            zchunk = nz;
+            nzc = 1;
+            for (int c = 1; c <= nz; ++c) {
+                const int zc = (nz + c - 1) / c, cc = (nz + zc - 1) / zc;
+                if (cc != c) continue;
+                const double cost = std::ceil((double)per * cc / 148.0) * (zc + 4.0);
+                if (cost < best) best = cost, zchunk = zc, nzc = cc;
+                if (zc <= 8) break;
+            }
+        }
+        dim3 g(tx * groups, ty, nzc);
+        TmaDesc mx = make_tmap_n(x, op.sy, ld, Cfg::PX2, Cfg::PY2, KB, nrhs);
+        TmaDesc mb = make_tmap_n(b, op.sy, ld, Cfg::PX1, Cfg::PY1, KB, nrhs);
+        TmaDesc mc = make_tmap_n(op.cdiag, op.sy, ld, Cfg::PX1, Cfg::PY1, 1, 0);
+        TmaDesc md = make_tmap_n(op.dinv, op.sy, ld, Cfg::PX1, Cfg::PY1, 1, 0);
+        TmaDesc mxc = make_tmap_g(xc, Cc.n, Cc.p0, Cc.N, Cfg::CTX, Cfg::CTY, KB, nrhs);
+        k_fine3d_tma_pro2<T, KB><<<g, 256, smem, stream>>>(op, mx, mb, mc, md, mxc, out, ld, nrhs, zchunk, groups);
+    }
+    bool can_fuse_post2(const FineOp<T>& op, const C* x, const C* b, const Level& Cc, const C* xc, int64_t ld) const {
+        return fuse_post2 && !slab && can_fuse_prolong(op, x, b, Cc, xc, ld);
+    }
+    void fine_prolong_jacobi2(const FineOp<T>& op, const C* x, const C* b, const Level& Cc, const C* xc, C* out, int64_t ld, int nrhs) {
+        const double N = (double)pb.N();
+        launch(T_FINE_PROLONG_JACOBI2, (3.0 * N + 0.125 * N) * S * nrhs + 2.0 * S * N, [&] {
+            if (nrhs >= 2) tma3d_pro2_launch<2>(op, x, b, Cc, xc, out, ld, nrhs);
+            else tma3d_pro2_launch<1>(op, x, b, Cc, xc, out, ld, nrhs);
         });
     }
     template <int MODE>
@@ -1937,20 +1986,29 @@ class Solver : public SolverBase {
         C* xx = x;
         C* tt = F.pt;
         const int npre = opt.relax_pre[l];
+        const int npost = opt.relax_post[l];
+        // Fused correction + two post-smoothing sweeps (k_fine3d_tma_pro2) reads the iterate from one buffer and writes the
+        // result to another, and the result must land in the caller's x: the pre-smoothed iterate then lives in the
+        // level's scratch vector and the residual (dead after the restriction) borrows x.
+        bool post2 = false;
         if (l == 0 && x_is_zero && opt.relax_type == HH_RELAX_JAC && npre >= 1 && can_fuse_first(mg_fine, b, F.N)) {
+            post2 = npost >= 2 && (npost % 2) == 0 && can_fuse_post2(mg_fine, tt, b, Cc, Cc.px, F.N) && ((uintptr_t)xx % 16 == 0);
+            C* itb = post2 ? tt : xx;  // the iterate after pre-smoothing
+            C* rsb = post2 ? xx : tt;  // the residual
             if (npre == 1) {
-                fine_first(0, mg_fine, b, xx, tt, F.N, nrhs);  // x1 and r = b - A x1 in one pass
+                fine_first(0, mg_fine, b, itb, rsb, F.N, nrhs);  // x1 and r = b - A x1 in one pass
             } else {
-                // first two sweeps in one pass, written so that the remaining npre-2 ping-pong sweeps end in xx
-                C* cur = ((npre - 2) % 2 == 0) ? xx : tt;
-                C* oth = (cur == xx) ? tt : xx;
+                // first two sweeps in one pass, written so that the remaining npre-2 ping-pong sweeps end in itb
+                C* cur = ((npre - 2) % 2 == 0) ? itb : rsb;
+                C* oth = (cur == itb) ? rsb : itb;
                 fine_first(1, mg_fine, b, cur, nullptr, F.N, nrhs);
                 for (int sw = 2; sw < npre; ++sw) {
                     level_apply(l, MODE_JACOBI, cur, b, oth, nrhs);
                     std::swap(cur, oth);
                 }
-                level_apply(l, MODE_RESID, xx, b, tt, nrhs);
+                level_apply(l, MODE_RESID, itb, b, rsb, nrhs);
             }
+            if (post2) std::swap(xx, tt);  // from here on: xx = iterate (the scratch vector), tt = residual (the caller's x)
         } else {
             smooth(l, npre, b, xx, tt, x_is_zero, false, nrhs);
             level_apply(l, MODE_RESID, xx, b, tt, nrhs);
@@ -1966,7 +2024,17 @@ class Solver : public SolverBase {
         } else {
             small_gmres(l + 1, 2, 1, Cc.pb, Cc.px, true, nrhs);
         }
-        const int npost = opt.relax_post[l];
+        if (post2) {
+            // x2 = J(J(x + P xc)) in one pass, into the caller's x (tt here); further pairs of sweeps ping-pong back to it
+            C* cur = tt;
+            C* oth = xx;
+            fine_prolong_jacobi2(mg_fine, xx, b, Cc, Cc.px, tt, F.N, nrhs);
+            for (int sw = 2; sw < npost; ++sw) {
+                level_apply(l, MODE_JACOBI, cur, b, oth, nrhs);
+                std::swap(cur, oth);
+            }
+            return;  // npost is even: the last sweep wrote the caller's x
+        }
         if (l == 0 && opt.relax_type == HH_RELAX_JAC && npost >= 1 && can_fuse_prolong(mg_fine, xx, b, Cc, Cc.px, F.N)) {
             // x' = x + P xc and the first post-smoothing sweep in one pass (x' never touches HBM)
             C* cur = tt;
@@ -2349,6 +2417,7 @@ class Solver : public SolverBase {
     int force_tile = -1;                 // HH_COARSE_TILE: 0 = 16x8, 1 = alternative tile (coarse_tile)
     bool scaled_gmres = true;
     bool tma_restrict = true;            // HH_TMA_RESTRICT=0: the one-thread-per-coarse-node restriction (A/B baseline)
+    bool fuse_post2 = true;              // HH_FUSE_POST2=0: correction + first sweep fused, second sweep separate (A/B baseline)
     GmresMem outer;
     int outer_cap = 0;
     BicgMem bicg;

@@ -20,6 +20,8 @@ def classify(name):
     m = re.search(r"k_fine3d_tma_first<\w+, (\d)", name)
     if m:
         return "fine_first_resid" if m.group(1) == "0" else "fine_first_jacobi"
+    if "k_fine3d_tma_pro2<" in name:
+        return "fine_prolong_jacobi2"
     if "k_fine3d_tma_pro<" in name:
         return "fine_prolong_jacobi"
     m = re.search(r"k_fine3d_(?:tma|zmarch)<\w+, (\d)", name)

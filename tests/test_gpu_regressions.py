@@ -152,3 +152,41 @@ def test_device_side_abl_and_frequency_sweep(gpu_pkg, ho, dim, neumann, prec, sl
     x2, A2 = pkg.solveLinearSystem(None, q, A2)
     assert rel_err(x1, x2) < (1e-9 if prec == np.complex128 else 2e-4)
     assert rel_err(x1, x0) > 1e-3  # really the new frequency
+
+
+@pytest.mark.parametrize("prec,tol", [(np.complex128, 1e-13), (np.complex64, 2e-5)])
+@pytest.mark.parametrize("nodes,pre,post,cyc,nrhs", [((33, 33, 33), 2, 2, "V", 2), ((65, 49, 37), 1, 2, "W", 3), ((41, 25, 33), 1, 4, "V", 1),
+                                                      ((97, 17, 21), 2, 2, "W", 5)])
+def test_fused_two_sweep_post_smoothing_equals_separate_sweeps(gpu_pkg, prec, tol, nodes, pre, post, cyc, nrhs):
+    """k_fine3d_tma_pro2 (correction + two post-sweeps in one pass, x' and x1 never in HBM) against the same cycle with the
+    second sweep as its own kernel (HH_FUSE_POST2=0), on grids with partial tiles in every direction."""
+    import os
+
+    pkg = gpu_pkg
+    rng = np.random.default_rng(17)
+    n = np.array(nodes)
+    dom = sum([[0.0, 0.1 * (v - 1)] for v in n], [])
+    mesh = pkg.getRegularMesh(dom, list(n - 1))
+    m = 1.0 / (1.5 + 2.0 * rng.random(tuple(n))) ** 2
+    w = 0.8 * pkg.getMaximalFrequency(m, mesh)
+    gamma = 0.02 * w * (1.0 + rng.random(tuple(n))) + pkg.getABL(n, True, [3, 3, 4], w)
+    N = int(np.prod(n))
+    B = np.asfortranarray((rng.standard_normal((N, nrhs)) + 1j * rng.standard_normal((N, nrhs))).astype(prec))
+    out = {}
+    for flag in ("1", "0"):
+        os.environ["HH_FUSE_POST2"] = flag
+        try:
+            MG = pkg.getMGparam(prec, pkg.Int64, 3, 1, 30, 1e-6, "Jac", 0.8, pre, post, cyc, "GMRES", coarseIters=6)
+            hp = pkg.HelmholtzParam(mesh, gamma, m.ravel(order="F"), w, True, True)
+            A = pkg.getShiftedLaplacianMultigridSolver(hp, MG, 0.2, "GMRES", 5)
+            hd = pkg.api._ensure_hierarchy(A, 0)
+        finally:
+            del os.environ["HH_FUSE_POST2"]
+        Z = np.empty_like(B, order="F")
+        pkg._lib.check(hd.lib.hh_cycle(hd.h, B.ctypes.data, Z.ctypes.data, nrhs), hd.h)
+        X, A = pkg.solveLinearSystem(None, B, A)
+        out[flag] = (Z, X, A.iterations.copy())
+        pkg.clear(MG)
+    assert rel_err(out["1"][0], out["0"][0]) < tol
+    assert np.array_equal(out["1"][2], out["0"][2])
+    assert rel_err(out["1"][1], out["0"][1]) < 100 * tol
