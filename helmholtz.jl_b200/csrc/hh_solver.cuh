@@ -536,8 +536,11 @@ class Solver : public SolverBase {
         if (ct && !strcmp(ct, "alt")) force_tile = 1;
         const char* sc = getenv("HH_SCALED_GMRES");  // A/B switch of the one-pass (A D^-1) apply (default on)
         scaled_gmres = !(sc && sc[0] == '0');
+        // opt-in: measured SLOWER than the two kernels it replaces (7.4 ms against 3.4 + 2.3 ms per cycle at 257^3 x 16 RHS,
+        // profiles/r02_rejected_experiments.md): half the HBM bytes, but twice the shared-memory traffic behind two CTA
+        // barriers per plane at one CTA per SM
         const char* fp = getenv("HH_FUSE_POST2");
-        fuse_post2 = !(fp && fp[0] == '0');
+        fuse_post2 = fp && fp[0] == '1';
         const char* tr = getenv("HH_TMA_RESTRICT");
         tma_restrict = !(tr && tr[0] == '0');
         const char* hs = getenv("HH_HALO_SPLIT");
@@ -2417,7 +2420,7 @@ class Solver : public SolverBase {
     int force_tile = -1;                 // HH_COARSE_TILE: 0 = 16x8, 1 = alternative tile (coarse_tile)
     bool scaled_gmres = true;
     bool tma_restrict = true;            // HH_TMA_RESTRICT=0: the one-thread-per-coarse-node restriction (A/B baseline)
-    bool fuse_post2 = true;              // HH_FUSE_POST2=0: correction + first sweep fused, second sweep separate (A/B baseline)
+    bool fuse_post2 = false;             // HH_FUSE_POST2=1: correction + BOTH post-sweeps in one pass (k_fine3d_tma_pro2; slower, see ctor)
     GmresMem outer;
     int outer_cap = 0;
     BicgMem bicg;
