@@ -541,6 +541,8 @@ class Solver : public SolverBase {
         // barriers per plane at one CTA per SM
         const char* fp = getenv("HH_FUSE_POST2");
         fuse_post2 = fp && fp[0] == '1';
+        const char* k16 = getenv("HH_COARSE_KB16");
+        kb16_apply = !(k16 && k16[0] == '0');
         const char* tr = getenv("HH_TMA_RESTRICT");
         tma_restrict = !(tr && tr[0] == '0');
         const char* hs = getenv("HH_HALO_SPLIT");
@@ -1184,6 +1186,12 @@ class Solver : public SolverBase {
     void coarse_tma_mode(const Level& L, const C* coef, const C* x, const C* b, C* out, int nrhs) {
         int kb = 1;
         while (kb * 2 <= nrhs && kb * 2 <= 8) kb *= 2;
+        // the plain apply (the matvec of the coarsest Jacobi-GMRES) stages no b / dinv tiles: 16 right-hand sides fit in
+        // one stage, so the 27 coefficient tiles are fetched once per node instead of once per group of 8
+        if (MODE == MODE_APPLY && nrhs >= 16 && kb16_apply) {
+            coarse_tma_tile<MODE_APPLY, 16>(L, coef, x, b, out, nrhs);
+            return;
+        }
         if (kb == 8) coarse_tma_tile<MODE, 8>(L, coef, x, b, out, nrhs);
         else if (kb == 4) coarse_tma_tile<MODE, 4>(L, coef, x, b, out, nrhs);
         else if (kb == 2) coarse_tma_tile<MODE, 2>(L, coef, x, b, out, nrhs);
@@ -2420,6 +2428,7 @@ class Solver : public SolverBase {
     int force_tile = -1;                 // HH_COARSE_TILE: 0 = 16x8, 1 = alternative tile (coarse_tile)
     bool scaled_gmres = true;
     bool tma_restrict = true;            // HH_TMA_RESTRICT=0: the one-thread-per-coarse-node restriction (A/B baseline)
+    bool kb16_apply = true;              // HH_COARSE_KB16=0: groups of 8 right-hand sides in the 27-point apply as well (A/B)
     bool fuse_post2 = false;             // HH_FUSE_POST2=1: correction + BOTH post-sweeps in one pass (k_fine3d_tma_pro2; slower, see ctor)
     GmresMem outer;
     int outer_cap = 0;
