@@ -1170,7 +1170,13 @@ struct CoarseTmaCfg {
     static constexpr int KH = KB / NWG;           // right-hand sides per warpgroup
     static constexpr int THREADS = 128 * NWG;
     static constexpr int HX = sizeof(T) == 4 ? 2 : 1;  // see FineTmaCfg
-    static constexpr int PX = TX + 2 * HX;
+    // Row pitch of the staged x tile.  Threads are numbered row-major over the TX-wide tile, so a quarter-warp (the unit
+    // of a 16-byte shared load) that straddles two tile rows is conflict-free only if the pitch exceeds TX by a multiple
+    // of 8 entries (128 bytes): the 11-wide ComplexF64 tile pads its rows from 13 to 19 entries (the box simply fetches
+    // six more columns; ncu showed 26 % of the shared wavefronts of the unpadded tile were bank conflicts and the shared
+    // pipe at 77 % -- the binding pipe of this kernel).
+    static constexpr int PADX = (sizeof(T) == 8 && (TX % 8) != 0) ? (8 - (2 * HX) % 8) % 8 : 0;
+    static constexpr int PX = TX + 2 * HX + PADX;
     static constexpr int XT = (TY + 2) * PX;
     static constexpr int BT = TY * TX;
     static constexpr int ES = (int)sizeof(cx<T>);

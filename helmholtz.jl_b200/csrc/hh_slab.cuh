@@ -13,6 +13,7 @@
 #include <dlfcn.h>
 #include <nccl.h>
 
+#include <algorithm>
 #include <condition_variable>
 #include <memory>
 #include <mutex>
@@ -182,6 +183,32 @@ struct ThreadGroup {
             throw hh::Error(HH_ERR_CUDA, std::string("NCCL: ") + #call + ": " + NcclApi::get().GetErrorString(r__)); \
     } while (0)
 
+// Gather the outgoing planes of all segments into the two contiguous send blocks (pack) / scatter the two received blocks
+// into the halo planes (unpack): ONE launch each instead of two strided cudaMemcpy2DAsync per direction -- the exchange is
+// latency-bound (thousands of exchanges of 2-34 MB per batch), so every launch around the ncclSend/ncclRecv pair counts.
+// Segment r starts at base + r*stride; block layout: segment-major, `bytes` (a multiple of 16) per segment.
+__global__ void __launch_bounds__(256) k_halo_copy(char* __restrict__ base, size_t stride, int nseg, size_t bytes, char* __restrict__ blk_a,
+                                                   size_t off_a, char* __restrict__ blk_b, size_t off_b, int to_block) {
+    // blk_a <-> base + off_a (if blk_a), blk_b <-> base + off_b (if blk_b); to_block: planes -> blocks, else blocks -> planes
+    const size_t n16 = bytes / 16;
+    const size_t tot = n16 * nseg;
+    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < tot; t += (size_t)gridDim.x * blockDim.x) {
+        const size_t r = t / n16, e = t - r * n16;
+        if (blk_a) {
+            uint4* pl = reinterpret_cast<uint4*>(base + r * stride + off_a) + e;
+            uint4* bk = reinterpret_cast<uint4*>(blk_a + r * bytes) + e;
+            if (to_block) *bk = *pl;
+            else *pl = *bk;
+        }
+        if (blk_b) {
+            uint4* pl = reinterpret_cast<uint4*>(base + r * stride + off_b) + e;
+            uint4* bk = reinterpret_cast<uint4*>(blk_b + r * bytes) + e;
+            if (to_block) *bk = *pl;
+            else *pl = *bk;
+        }
+    }
+}
+
 struct NcclTransport : SlabTransport {
     ncclComm_t comm = nullptr;
     NcclTransport(int rank_, int nranks_, const void* unique_id) {
@@ -224,16 +251,29 @@ struct NcclTransport : SlabTransport {
                 stage_bytes = 4 * blk;
             }
             char *o_up = stage, *o_dn = stage + blk, *i_dn = stage + 2 * blk, *i_up = stage + 3 * blk;
-            if (s_up) HH_CUDA(cudaMemcpy2DAsync(o_up, bytes, base + send_up, stride, bytes, nseg, cudaMemcpyDeviceToDevice, st));
-            if (s_dn) HH_CUDA(cudaMemcpy2DAsync(o_dn, bytes, base + send_dn, stride, bytes, nseg, cudaMemcpyDeviceToDevice, st));
+            const bool fast = (bytes % 16 == 0) && (stride % 16 == 0) && ((uintptr_t)base % 16 == 0) && (send_up % 16 == 0) &&
+                              (send_dn % 16 == 0) && (recv_up % 16 == 0) && (recv_dn % 16 == 0);
+            const unsigned nb = (unsigned)std::min<size_t>(296, (blk / 16 + 255) / 256);
+            if (fast) {
+                if (s_up || s_dn)
+                    k_halo_copy<<<nb, 256, 0, st>>>(base, stride, nseg, bytes, s_up ? o_up : nullptr, send_up, s_dn ? o_dn : nullptr, send_dn, 1);
+            } else {
+                if (s_up) HH_CUDA(cudaMemcpy2DAsync(o_up, bytes, base + send_up, stride, bytes, nseg, cudaMemcpyDeviceToDevice, st));
+                if (s_dn) HH_CUDA(cudaMemcpy2DAsync(o_dn, bytes, base + send_dn, stride, bytes, nseg, cudaMemcpyDeviceToDevice, st));
+            }
             HH_NCCL(api.GroupStart());
             if (s_up) HH_NCCL(api.Send(o_up, blk, ncclChar, rank + 1, comm, st));
             if (r_dn) HH_NCCL(api.Recv(i_dn, blk, ncclChar, rank - 1, comm, st));
             if (s_dn) HH_NCCL(api.Send(o_dn, blk, ncclChar, rank - 1, comm, st));
             if (r_up) HH_NCCL(api.Recv(i_up, blk, ncclChar, rank + 1, comm, st));
             HH_NCCL(api.GroupEnd());
-            if (r_dn) HH_CUDA(cudaMemcpy2DAsync(base + recv_dn, stride, i_dn, bytes, bytes, nseg, cudaMemcpyDeviceToDevice, st));
-            if (r_up) HH_CUDA(cudaMemcpy2DAsync(base + recv_up, stride, i_up, bytes, bytes, nseg, cudaMemcpyDeviceToDevice, st));
+            if (fast) {
+                if (r_dn || r_up)
+                    k_halo_copy<<<nb, 256, 0, st>>>(base, stride, nseg, bytes, r_dn ? i_dn : nullptr, recv_dn, r_up ? i_up : nullptr, recv_up, 0);
+            } else {
+                if (r_dn) HH_CUDA(cudaMemcpy2DAsync(base + recv_dn, stride, i_dn, bytes, bytes, nseg, cudaMemcpyDeviceToDevice, st));
+                if (r_up) HH_CUDA(cudaMemcpy2DAsync(base + recv_up, stride, i_up, bytes, bytes, nseg, cudaMemcpyDeviceToDevice, st));
+            }
             return;
         }
         HH_NCCL(api.GroupStart());

@@ -541,8 +541,6 @@ class Solver : public SolverBase {
         // barriers per plane at one CTA per SM
         const char* fp = getenv("HH_FUSE_POST2");
         fuse_post2 = fp && fp[0] == '1';
-        const char* k16 = getenv("HH_COARSE_KB16");
-        kb16_apply = !(k16 && k16[0] == '0');
         const char* tr = getenv("HH_TMA_RESTRICT");
         tma_restrict = !(tr && tr[0] == '0');
         const char* hs = getenv("HH_HALO_SPLIT");
@@ -750,12 +748,15 @@ class Solver : public SolverBase {
     int zend(const Level& L) const { return rz_e >= 0 ? rz_e : L.ze; }
     // Sum the nblk partials of each of the nq quantities, all-reduce over the slabs and leave the result in `partial`
     // in the layout of nblk = 1 (which is returned).  No-op without slabs.
+    // The scalar kernels that consume the sums read them from `red_out` (the partial buffer itself, or the all-reduced
+    // block: no copy back).
     int slab_reduce(zc* partial, int nq, int nblk) {
+        red_out = partial;
         if (!slab || slab->nranks == 1) return nblk;
         if (d_red.n < (size_t)nq) d_red.alloc((size_t)std::max(nq, 4096));
         launch(T_SCALAR, 0, [&] { k_sum_partials<<<(nq + 7) / 8, 256, 0, stream>>>(partial, nq, nblk, d_red.p); });
         launch(T_ALLREDUCE, 16.0 * nq, [&] { slab->allreduce(stream, (double*)d_red.p, 2 * nq, false); });
-        HH_CUDA(cudaMemcpyAsync(partial, d_red.p, (size_t)nq * sizeof(zc), cudaMemcpyDeviceToDevice, stream));
+        red_out = d_red.p;
         return 1;
     }
     // range of a level's vectors that the Krylov / reduction kernels work on (slab: the owned planes)
@@ -1186,12 +1187,6 @@ class Solver : public SolverBase {
     void coarse_tma_mode(const Level& L, const C* coef, const C* x, const C* b, C* out, int nrhs) {
         int kb = 1;
         while (kb * 2 <= nrhs && kb * 2 <= 8) kb *= 2;
-        // the plain apply (the matvec of the coarsest Jacobi-GMRES) stages no b / dinv tiles: 16 right-hand sides fit in
-        // one stage, so the 27 coefficient tiles are fetched once per node instead of once per group of 8
-        if (MODE == MODE_APPLY && nrhs >= 16 && kb16_apply) {
-            coarse_tma_tile<MODE_APPLY, 16>(L, coef, x, b, out, nrhs);
-            return;
-        }
         if (kb == 8) coarse_tma_tile<MODE, 8>(L, coef, x, b, out, nrhs);
         else if (kb == 4) coarse_tma_tile<MODE, 4>(L, coef, x, b, out, nrhs);
         else if (kb == 2) coarse_tma_tile<MODE, 2>(L, coef, x, b, out, nrhs);
@@ -1859,7 +1854,7 @@ class Solver : public SolverBase {
             const int nv = std::min(HH_MAXV, j + 1 - i0);
             for (int i = 0; i < nv; ++i) vv[i] = V[i0 + i];
             const int nblk = multidot(vv, nv, w, N, nrhs, i0 == 0, d_partial.p);
-            launch(T_SCALAR, 0, [&] { k_gmres_hcol<<<nrhs, 32, 0, stream>>>(g.st, d_partial.p, nblk, j, i0, nv); });
+            launch(T_SCALAR, 0, [&] { k_gmres_hcol<<<nrhs, 32, 0, stream>>>(g.st, red_out, nblk, j, i0, nv); });
         }
         int nblk = 0;
         for (int i0 = 0; i0 <= j; i0 += HH_MAXV) {
@@ -1869,11 +1864,11 @@ class Solver : public SolverBase {
             nblk = multiaxpy(vv, nv, w, N, nrhs, g.hcol.p + i0, g.st.m + 1, true, last, d_partial.p,
                              last ? g.scale.p : nullptr);
         }
-        launch(T_SCALAR, 0, [&] { k_gmres_givens<<<nrhs, 32, 0, stream>>>(g.st, d_partial.p, nblk, j, tol); });
+        launch(T_SCALAR, 0, [&] { k_gmres_givens<<<nrhs, 32, 0, stream>>>(g.st, red_out, nblk, j, tol); });
     }
     void gmres_begin(GmresMem& g, const C* r, const Span& N, int nrhs, bool first, double tol) {
         const int nblk = multidot(nullptr, 0, r, N, nrhs, true, d_partial.p);
-        launch(T_SCALAR, 0, [&] { k_gmres_begin<<<nrhs, 32, 0, stream>>>(g.st, d_partial.p, nblk, first ? 1 : 0, tol); });
+        launch(T_SCALAR, 0, [&] { k_gmres_begin<<<nrhs, 32, 0, stream>>>(g.st, red_out, nblk, first ? 1 : 0, tol); });
     }
     void gmres_solve_y(GmresMem& g, int nrhs) {
         launch(T_SCALAR, 0, [&] { k_gmres_solve_y<<<(nrhs + 63) / 64, 64, 0, stream>>>(g.st, nrhs); });
@@ -2360,7 +2355,7 @@ class Solver : public SolverBase {
         C* sh = kry.p + 6 * vs;
         const FineOp<T> Hop = krylov_op(o.do_transpose);
         auto scalars = [&](int nblk, int stage) {
-            launch(T_SCALAR, 0, [&] { k_bicg_scalars<<<nrhs, 32, 0, stream>>>(bicg.st, d_partial.p, nblk, stage, o.rel_tol); });
+            launch(T_SCALAR, 0, [&] { k_bicg_scalars<<<nrhs, 32, 0, stream>>>(bicg.st, red_out, nblk, stage, o.rel_tol); });
         };
         zero_vec(X, N, nrhs);
         copy_vec(B, r, N, nrhs);
@@ -2418,6 +2413,7 @@ class Solver : public SolverBase {
     DevBuf<C> kry;
     int kry_cap = 0;
     DevBuf<zc> d_partial, d_one, d_red;
+    const zc* red_out = nullptr;         // where the last multidot / multiaxpy left its (all-reduced) sums: see slab_reduce
     Level hoH;  // HO mode: the un-shifted operator H as a stored stencil on the fine grid (the outer Krylov operator)
     cudaStream_t comm_stream = nullptr;  // halo exchanges that overlap the interior planes (with_halos)
     cudaEvent_t ev_ready = nullptr, ev_landed = nullptr;
@@ -2428,7 +2424,6 @@ class Solver : public SolverBase {
     int force_tile = -1;                 // HH_COARSE_TILE: 0 = 16x8, 1 = alternative tile (coarse_tile)
     bool scaled_gmres = true;
     bool tma_restrict = true;            // HH_TMA_RESTRICT=0: the one-thread-per-coarse-node restriction (A/B baseline)
-    bool kb16_apply = true;              // HH_COARSE_KB16=0: groups of 8 right-hand sides in the 27-point apply as well (A/B)
     bool fuse_post2 = false;             // HH_FUSE_POST2=1: correction + BOTH post-sweeps in one pass (k_fine3d_tma_pro2; slower, see ctor)
     GmresMem outer;
     int outer_cap = 0;
