@@ -938,7 +938,9 @@ static int solve_host(hh_handle_t h, const void* B, const int64_t* idx, const do
         // to a quarter of the block each while the half in the middle keeps the coefficient reuse of a large batch
         // (a batch of 4 costs ~5 % more per column than one of 16, a batch of 2 ~45 %).  Smaller blocks: two halves.
         std::vector<int64_t> sizes;
-        if (pipeline && ncols >= 16 && kmax >= (ncols + 1) / 2) {
+        const char* hc = getenv("HH_HOST_CHUNKS");  // A/B: 2 = two halves, 3 = quarter / half / quarter (default)
+        const bool three = !(hc && hc[0] == '2');
+        if (pipeline && three && ncols >= 16 && kmax >= (ncols + 1) / 2) {
             const int64_t q = std::max<int64_t>(4, (ncols / 4) / 4 * 4);
             sizes = {q, ncols - 2 * q, q};
         } else if (pipeline && ncols >= 8 && kmax >= (ncols + 1) / 2) {
