@@ -329,6 +329,10 @@ def run_b200(a):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     pkg = graft.load_package()
     lib = pkg._lib.load()
+    # pinned staging buffers of the e2e legs on the GPU's own NUMA node (PCIe copies of 8 ranks crossing the socket link
+    # were the e2e limiter at 8 GPUs in round 1)
+    all_cpus = os.sched_getaffinity(0)
+    numa = pkg.sharding.bind_to_gpu_numa_node(local)
     wl = workload(a, pkg.workloads, pkg)
     s = wl["settings"]
     mesh = wl["mesh"]
@@ -486,6 +490,7 @@ def run_b200(a):
         cpu = None
         if not a.no_cpu_baseline and world == 1:
             try:
+                os.sched_setaffinity(0, all_cpus)  # the CPU arm uses every host core
                 blk = a.cpu_rhs or 2
                 wl_cpu = cpu_arm_inputs(a)  # built by the oracle, independent of the product's host helpers
                 secs, itc, rrc, oc = cpu_full_solve(wl_cpu, [(7 * c) % nsrc for c in range(blk)])
@@ -505,7 +510,7 @@ def run_b200(a):
                        "parallelism": f"rhs-sharding x{world} (independent columns, no data-path collective)",
                        "l2": "inputs larger than L2: every vector block is %.0f MB, no flush needed" % (N * a.nrhs * es / 1e6),
                        "rel_tol": a.tol, "iterations_mean": float(its.mean()), "iterations_max": int(its.max()),
-                       "true_relres_max_last_step": true_res},
+                       "true_relres_max_last_step": true_res, "host_numa_binding_rank0": numa},
             "e2e": e2e,
             "e2e_point_sources": e2e_ps,
             "gpu_launches": launches,

@@ -934,12 +934,13 @@ static int solve_host(hh_handle_t h, const void* B, const int64_t* idx, const do
         const char* pe = getenv("HH_HOST_PIPELINE");
         const bool pipeline = !(pe && pe[0] == '0');
         // Sub-batches.  Only the H2D copy of the FIRST and the D2H copy of the LAST sub-batch are exposed (the others
-        // overlap a solve), so a block of >= 16 columns is cut as quarter / half / quarter: the exposed copies shrink
-        // to a quarter of the block each while the half in the middle keeps the coefficient reuse of a large batch
-        // (a batch of 4 costs ~5 % more per column than one of 16, a batch of 2 ~45 %).  Smaller blocks: two halves.
+        // overlap a solve): a block of >= 8 columns is cut in two halves (a batch of 8 costs ~2 % more per column than
+        // one of 16, a batch of 4 ~5 %, a batch of 2 ~45 %: finer cuts lose more than the shorter exposed copies gain).
         std::vector<int64_t> sizes;
-        const char* hc = getenv("HH_HOST_CHUNKS");  // A/B: 2 = two halves, 3 = quarter / half / quarter (default)
-        const bool three = !(hc && hc[0] == '2');
+        // HH_HOST_CHUNKS=3: quarter / half / quarter instead of two halves.  Measured (profiles/bench_r02_n8_c128*.json): no gain
+        // at 1 GPU and 2-4 % slower at 8 GPUs -- the two extra small batches cost what the shorter exposed copies save.
+        const char* hc = getenv("HH_HOST_CHUNKS");
+        const bool three = hc && hc[0] == '3';
         if (pipeline && three && ncols >= 16 && kmax >= (ncols + 1) / 2) {
             const int64_t q = std::max<int64_t>(4, (ncols / 4) / 4 * 4);
             sizes = {q, ncols - 2 * q, q};

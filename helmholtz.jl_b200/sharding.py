@@ -59,3 +59,37 @@ def gather_planes(X_local, planes, nodes, dst=0):
     if not np.all(seen == 1):
         raise ValueError("the ranks' plane ranges do not tile the grid")
     return X
+
+
+# ---- host placement: keep a rank's pinned staging buffers on the NUMA node its GPU hangs off -----------------------------
+def bind_to_gpu_numa_node(device_index: int):
+    """Restrict the calling process to the CPUs of the NUMA node the GPU `device_index` is attached to (Linux sysfs), so
+    that pinned host buffers allocated afterwards are first-touched on that node and PCIe copies do not cross the
+    inter-socket link.  Call before allocating host buffers.  Returns {"gpu_numa_node", "cpus"} or None when the
+    topology is not exposed (no NUMA information, non-Linux, restricted sysfs) -- placement is then left to the OS."""
+    import os
+
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(int(device_index))
+        bus = pynvml.nvmlDeviceGetPciInfo(h).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        bus = bus.lower()
+        if len(bus.split(":")[0]) == 8:  # NVML prints an 8-digit domain, sysfs a 4-digit one
+            bus = bus[4:]
+        node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read().strip())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return {"gpu_numa_node": node, "cpus": len(cpus)}
+    except Exception:
+        return None
