@@ -416,6 +416,7 @@ def run_b200(a):
     R = Hop.matvec(X) - B
     true_res = float((torch.linalg.vector_norm(R, dim=1) / torch.linalg.vector_norm(B, dim=1)).max())
     del R
+    torch.cuda.empty_cache()  # the library allocates with cudaMalloc: hand torch's cached blocks back before the e2e legs
     # per-kernel-class device time (CUDA events on the launching stream, recorded during the timed region)
     tags = profile_tables(lib, hd)
     lib.hh_profile_enable(hd.h, 0)
@@ -430,12 +431,21 @@ def run_b200(a):
     e2e = None
     e2e_ps = None
     if not a.no_e2e:
-        Bh = torch.zeros((a.nrhs, N), dtype=tdt).pin_memory()
-        Xh_t = torch.empty((a.nrhs, N), dtype=tdt).pin_memory()
+        # pinned B and X of one call; every rank of the node pins its own pair, so the block of one call is halved until the
+        # node's free host memory holds all of them twice over (the device-resident `value` above is not affected)
+        ne = a.nrhs
+        try:
+            avail = next(int(l.split()[1]) * 1024 for l in open("/proc/meminfo") if l.startswith("MemAvailable"))
+            while ne > 1 and 2.0 * (2 * N * ne * es) * world > 0.8 * avail:
+                ne //= 2
+        except Exception:
+            pass
+        Bh = torch.zeros((ne, N), dtype=tdt, pin_memory=True)
+        Xh_t = torch.empty((ne, N), dtype=tdt, pin_memory=True)
         Bh_np, Xh = Bh.numpy().T, Xh_t.numpy().T  # N x nrhs column-major views of the pinned buffers
         t_e2e, t_ps = [], []
         for k in range(1 + a.e2e_steps):
-            cols = step_sources(1000 + k)
+            cols = step_sources(1000 + k)[:ne]
             Bh.zero_()
             for c, sidx in enumerate(cols):
                 Bh[c, all_idx[sidx]] = amp
@@ -450,7 +460,7 @@ def run_b200(a):
             assert np.isfinite(chk)
             barrier()
             t0 = time.perf_counter()
-            pkg.solvePointSources_(Ainv, [wl["srcs"][sidx] for sidx in cols], Xh, np.full(a.nrhs, amp))
+            pkg.solvePointSources_(Ainv, [wl["srcs"][sidx] for sidx in cols], Xh, np.full(ne, amp))
             chk = float(abs(Xh[all_idx[cols[0]], 0]))
             torch.cuda.synchronize()
             dt = time.perf_counter() - t0
@@ -460,11 +470,11 @@ def run_b200(a):
         te = torch.tensor([float(np.mean(t_e2e)), float(np.mean(t_ps))], dtype=torch.float64, device="cuda")
         if world > 1:
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
-        e2e = {"value": a.nrhs * world / float(te[0]), "unit": UNIT, "h2d_bytes_per_step": int(N * a.nrhs * es),
-               "d2h_bytes_per_step": int(N * a.nrhs * es), "steps": a.e2e_steps,
+        e2e = {"value": ne * world / float(te[0]), "unit": UNIT, "h2d_bytes_per_step": int(N * ne * es),
+               "d2h_bytes_per_step": int(N * ne * es), "steps": a.e2e_steps, "rhs_per_call_per_gpu": ne,
                "api": "solveLinearSystem!(A, B_host, X_host, Ainv) -> hh_solve (pinned host B and X)"}
-        e2e_ps = {"value": a.nrhs * world / float(te[1]), "unit": UNIT, "h2d_bytes_per_step": int(a.nrhs * 24),
-                  "d2h_bytes_per_step": int(N * a.nrhs * es), "steps": a.e2e_steps,
+        e2e_ps = {"value": ne * world / float(te[1]), "unit": UNIT, "h2d_bytes_per_step": int(ne * 24),
+                  "d2h_bytes_per_step": int(N * ne * es), "steps": a.e2e_steps, "rhs_per_call_per_gpu": ne,
                   "api": "solvePointSources!(Ainv, srcs, X_host) -> hh_solve_point_sources (no dense B; pinned host X)"}
         del Bh, Xh_t
 

@@ -937,10 +937,12 @@ static int solve_host(hh_handle_t h, const void* B, const int64_t* idx, const do
         // overlap a solve): a block of >= 8 columns is cut in two halves (a batch of 8 costs ~2 % more per column than
         // one of 16, a batch of 4 ~5 %, a batch of 2 ~45 %: finer cuts lose more than the shorter exposed copies gain).
         std::vector<int64_t> sizes;
-        // HH_HOST_CHUNKS=3: quarter / half / quarter instead of two halves.  Measured (profiles/bench_r02_n8_c128*.json): no gain
-        // at 1 GPU and 2-4 % slower at 8 GPUs -- the two extra small batches cost what the shorter exposed copies save.
+        // Quarter / half / quarter instead of two halves: for a block of 16 columns measured as no gain at 1 GPU and 2-4 %
+        // slower at 8 GPUs (profiles/bench_r02_n8_c128*.json: two batches of 4 cost what the shorter exposed copies save);
+        // from 32 columns on the quarters are batches of >= 8 (~2 % dearer per column) and it is the default.
+        // HH_HOST_CHUNKS=2 / 3 force either cut.
         const char* hc = getenv("HH_HOST_CHUNKS");
-        const bool three = hc && hc[0] == '3';
+        const bool three = hc ? hc[0] == '3' : ncols >= 32;
         if (pipeline && three && ncols >= 16 && kmax >= (ncols + 1) / 2) {
             const int64_t q = std::max<int64_t>(4, (ncols / 4) / 4 * 4);
             sizes = {q, ncols - 2 * q, q};

@@ -2077,7 +2077,7 @@ __global__ void __launch_bounds__(256) k_dense_apply(const cx<T>* __restrict__ i
 // K7: batched Krylov vector kernels.  Vectors are N x nrhs (leading dimension ld); every
 // right-hand side has its own scalars (batched, not block, Krylov).
 // ---------------------------------------------------------------------------------------------
-#define HH_MAXV 8
+#define HH_MAXV 10
 template <typename T>
 struct VecList {
     const cx<T>* v[HH_MAXV];
@@ -2143,6 +2143,30 @@ __global__ void __launch_bounds__(256) k_multiaxpy(VecList<T> V, cx<T>* __restri
     if (WITH_NORM) {
         const double s = block_sum(nrm, sm);
         if (threadIdx.x == 0) partial[(int64_t)r * nblk + blockIdx.x] = mk<double>(s, 0.0);
+    }
+}
+
+// x (+)= dinv .* sum_i coef[r*cstride + i] * V_i   (i < NV): the solution update of a Jacobi-preconditioned GMRES of a
+// level, x = x0 + D^-1 (V y), in one pass (instead of zero + multiaxpy + diagonal scaling [+ axpy]).  dinv has one
+// entry per node (shared by the right-hand sides).  ACCUM: add to x, else overwrite.
+template <typename T, int NV, bool ACCUM>
+__global__ void __launch_bounds__(256) k_combine(VecList<T> V, const cx<T>* __restrict__ dinv, cx<T>* __restrict__ x,
+                                                 int64_t N, int64_t ld, const zc* __restrict__ coef, int cstride) {
+    const int r = blockIdx.y, nblk = gridDim.x;
+    const int64_t base = (int64_t)r * ld;
+    cx<T> c[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        const zc cc = coef[(int64_t)r * cstride + i];
+        c[i] = mk<T>((T)cc.x, (T)cc.y);
+    }
+    for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < N; p += (int64_t)nblk * blockDim.x) {
+        cx<T> acc = mk<T>(T(0), T(0));
+#pragma unroll
+        for (int i = 0; i < NV; ++i) cfma(acc, c[i], V.v[i][base + p]);
+        acc = dinv[p] * acc;
+        if (ACCUM) acc = x[base + p] + acc;
+        x[base + p] = acc;
     }
 }
 
@@ -2232,9 +2256,10 @@ struct GmresState {
     double* acc; // [r][2]: ||w||^2 and sum |g_i|^2/d_i^2 of the current column
 };
 
-// after a multidot group: g_i = <v~_i, w>, i0 <= i < i0+nv (<= j); the first group also carries ||w||^2
-__global__ void k_gmres_hcol(GmresState st, const zc* __restrict__ partial, int nblk, int j, int i0, int nv) {
-    const int r = blockIdx.x, nrhs = gridDim.x;
+// after a multidot group: g_i = <v~_i, w>, i0 <= i < i0+nv (<= j); the first group also carries ||w||^2.
+// Called by every lane of the warp that owns right-hand side r (lane 0 writes).
+__device__ __forceinline__ void gmres_hcol_dev(const GmresState& st, const zc* __restrict__ partial, int nblk, int r, int nrhs,
+                                               int j, int i0, int nv) {
     const int ldh = st.m + 1;
     const bool lead = (threadIdx.x & 31) == 0;
     double sumsq = 0.0;
@@ -2264,12 +2289,18 @@ __global__ void k_gmres_hcol(GmresState st, const zc* __restrict__ partial, int 
         st.scale[r] = mk<double>((st.done[r] || !(be2 > 0.0)) ? 0.0 : 1.0 / sqrt(be2), 0.0);
     }
 }
+__global__ void k_gmres_hcol(GmresState st, const zc* __restrict__ partial, int nblk, int j, int i0, int nv) {
+    gmres_hcol_dev(st, partial, nblk, blockIdx.x, gridDim.x, j, i0, nv);
+}
 
-// after the orthogonalisation pass: d_{j+1} = ||v~_{j+1}||, h_{j+1,j}, Givens rotations, residual estimate
-__global__ void k_gmres_givens(GmresState st, const zc* __restrict__ partial, int nblk, int j, double tol) {
-    const int r = blockIdx.x;
-    const zc nn = reduce_partials(partial, r, nblk);
-    if ((threadIdx.x & 31) != 0) return;
+// after the orthogonalisation pass: d_{j+1} = ||v~_{j+1}||, h_{j+1,j}, Givens rotations, residual estimate.
+// One thread per right-hand side.  nn2 = ||v~_{j+1}||^2 as measured by the update pass.
+// est != 0: the update pass was NOT run (the last column of a cycle: v_{j+1} is never used, only h_{j+1,j} is) and
+// h_{j+1,j} = ||w - sum <v_i,w> v_i|| / d_j comes from the dot pass alone: ||w||^2 - sum |g_i|^2/d_i^2 (orthonormal v_i).
+// The cancellation error of that difference is ~1e-15 ||w||^2, i.e. relative 1e-15 (||w||/h)^2 in h^2; the floor keeps a
+// near-breakdown column (h < 1e-6 ||w||, the Krylov space already holds the solution) from reading as h = 0, which would
+// report a zero residual: the estimate errs towards "not converged" and the restart's true residual decides.
+__device__ __forceinline__ void gmres_givens_dev(const GmresState& st, int r, int j, double tol, double nn2, int est) {
     const int m = st.m, ldh = m + 1;
     if (st.done[r]) return;
     zc* Hc = st.H + (int64_t)r * ldh * m + (int64_t)j * ldh;
@@ -2277,10 +2308,20 @@ __global__ void k_gmres_givens(GmresState st, const zc* __restrict__ partial, in
     zc* sn = st.sn + (int64_t)r * m;
     zc* s = st.s + (int64_t)r * ldh;
     double* d = st.d + (int64_t)r * ldh;
-    const double dn = sqrt(nn.x);
-    d[j + 1] = dn;
-    const double sc = st.scale[r].x;
-    const double hn = (sc > 0.0 && d[j] > 0.0) ? dn / (sc * d[j]) : 0.0;
+    double hn;
+    if (est) {
+        const double* acc = st.acc + 2 * (int64_t)r;
+        double be2 = acc[0] - acc[1];
+        const double floor2 = 1e-12 * acc[0];
+        if (!(be2 > floor2)) be2 = floor2;
+        d[j + 1] = 0.0;  // no stored vector
+        hn = (d[j] > 0.0) ? sqrt(be2) / d[j] : 0.0;
+    } else {
+        const double dn = sqrt(nn2);
+        d[j + 1] = dn;
+        const double sc = st.scale[r].x;
+        hn = (sc > 0.0 && d[j] > 0.0) ? dn / (sc * d[j]) : 0.0;
+    }
     Hc[j + 1] = mk<double>(hn, 0.0);
     for (int k = 0; k < j; ++k) {
         const zc t = cs[k].x * Hc[k] + sn[k] * Hc[k + 1];
@@ -2316,6 +2357,185 @@ __global__ void k_gmres_givens(GmresState st, const zc* __restrict__ partial, in
     st.nprec[r] += 1;
     if (!(err > tol)) st.done[r] = 1;  // also catches NaN -> stops; host checks for NaN separately
     if (err != err) st.done[r] = 2;
+}
+__global__ void k_gmres_givens(GmresState st, const zc* __restrict__ partial, int nblk, int j, double tol, int est) {
+    const int r = blockIdx.x;
+    zc nn = mk<double>(0.0, 0.0);
+    if (!est) nn = reduce_partials(partial, r, nblk);
+    if ((threadIdx.x & 31) != 0) return;
+    gmres_givens_dev(st, r, j, tol, nn.x, est);
+}
+
+// One scalar kernel per step of the fixed-length GMRES of a level (smoother / coarsest solve / K-cycle: no
+// convergence test, so the Givens update of a column can wait for the next column's dot sums):
+//   flags & 1: column j-1's update pass has run; its ||v~_j||^2 partials are in `norm` -> Givens of column j-1
+//   then the Gram-Schmidt coefficients of column j from `dots` (one multidot group with ||w||^2, nv = j+1)
+//   flags & 2: column j is the last one -> its Givens update from the estimate (no update pass follows)
+__global__ void k_gmres_small_step(GmresState st, const zc* __restrict__ dots, int nblk_d, const zc* __restrict__ norm,
+                                   int nblk_n, int j, int flags) {
+    const int r = blockIdx.x, nrhs = gridDim.x;
+    const bool lead = (threadIdx.x & 31) == 0;
+    if (flags & 1) {
+        const zc nn = reduce_partials(norm, r, nblk_n);
+        if (lead) gmres_givens_dev(st, r, j - 1, 0.0, nn.x, 0);
+    }
+    __syncwarp();
+    gmres_hcol_dev(st, dots, nblk_d, r, nrhs, j, 0, j + 1);
+    if ((flags & 2) && lead) gmres_givens_dev(st, r, j, 0.0, 0.0, 1);
+}
+
+// ---- latency-lean forms of the scalar kernels --------------------------------------------------------------------
+// The one-warp kernels above spend their ~15-20 us in chains of dependent global loads (one quantity after the other,
+// then one Givens rotation after the other).  Here one warp per QUANTITY sums its block partials (all loads in flight at
+// once), and warp 0 then does the per-RHS algebra with lane-parallel loads of the Hessenberg column and the stored
+// rotations (lane k holds entry k; the serial recurrences read them by shuffle).  Same arithmetic, same order.
+__device__ __forceinline__ zc shfl_zc(zc v, int src) {
+    return mk<double>(__shfl_sync(0xffffffffu, v.x, src), __shfl_sync(0xffffffffu, v.y, src));
+}
+// warp 0, all lanes: Gram-Schmidt coefficients of column j from the sums g[0..nv) (g[nv] = ||w||^2 when i0 == 0)
+__device__ __forceinline__ void gmres_hcol_w0(const GmresState& st, const zc* g, int r, int j, int i0, int nv) {
+    const int lane = threadIdx.x & 31;
+    const int ldh = st.m + 1;
+    const int done = st.done[r];
+    const double dj = st.d[(int64_t)r * ldh + j];
+    double term = 0.0;
+    if (lane < nv) {
+        const double di = st.d[(int64_t)r * ldh + i0 + lane];
+        const zc gi = g[lane];
+        const bool ok = !done && di > 0.0 && dj > 0.0;
+        st.hcol[(int64_t)r * ldh + i0 + lane] = ok ? (1.0 / (di * di)) * gi : mk<double>(0.0, 0.0);
+        st.H[(int64_t)r * ldh * st.m + (int64_t)j * ldh + i0 + lane] = ok ? (1.0 / (di * dj)) * gi : mk<double>(0.0, 0.0);
+        if (ok) term = (gi.x * gi.x + gi.y * gi.y) / (di * di);
+    }
+    double sumsq = 0.0;
+    for (int i = 0; i < nv; ++i) sumsq += __shfl_sync(0xffffffffu, term, i);  // the order of the one-thread version
+    if (lane != 0) return;
+    double* acc = st.acc + 2 * (int64_t)r;
+    double a0 = acc[0], a1 = acc[1];
+    if (i0 == 0) {
+        a0 = g[nv].x;
+        a1 = 0.0;
+    }
+    a1 += sumsq;
+    acc[0] = a0;
+    acc[1] = a1;
+    if (i0 + nv == j + 1) {
+        double be2 = a0 - a1;
+        const double floor2 = 1e-6 * a0;
+        if (!(be2 > floor2)) be2 = floor2;
+        st.scale[r] = mk<double>((done || !(be2 > 0.0)) ? 0.0 : 1.0 / sqrt(be2), 0.0);
+    }
+}
+// warp 0, all lanes (uniform control flow): the Givens update of column j (see gmres_givens_dev)
+__device__ __forceinline__ void gmres_givens_w0(const GmresState& st, int r, int j, double tol, double nn2, int est) {
+    const int lane = threadIdx.x & 31;
+    const int m = st.m, ldh = m + 1;
+    if (j + 1 > 32) {  // restart lengths beyond a warp: the one-thread form
+        if (lane == 0) gmres_givens_dev(st, r, j, tol, nn2, est);
+        return;
+    }
+    if (st.done[r]) return;
+    zc* Hc = st.H + (int64_t)r * ldh * m + (int64_t)j * ldh;
+    zc* cs = st.cs + (int64_t)r * m;
+    zc* sn = st.sn + (int64_t)r * m;
+    zc* s = st.s + (int64_t)r * ldh;
+    double* d = st.d + (int64_t)r * ldh;
+    // every load of the update, issued together
+    const zc hk = lane <= j ? Hc[lane] : mk<double>(0.0, 0.0);
+    const double ck = lane < j ? cs[lane].x : 0.0;
+    const zc sk = lane < j ? sn[lane] : mk<double>(0.0, 0.0);
+    const double dj = d[j];
+    const zc sj = s[j];
+    const double bn = st.bnorm[r];
+    const double sc = st.scale[r].x;
+    const double a0 = st.acc[2 * (int64_t)r], a1 = st.acc[2 * (int64_t)r + 1];
+    const int np0 = st.nprec[r];
+    double hn, dn1;
+    if (est) {
+        double be2 = a0 - a1;
+        const double floor2 = 1e-12 * a0;
+        if (!(be2 > floor2)) be2 = floor2;
+        dn1 = 0.0;  // no stored vector
+        hn = (dj > 0.0) ? sqrt(be2) / dj : 0.0;
+    } else {
+        dn1 = sqrt(nn2);
+        hn = (sc > 0.0 && dj > 0.0) ? dn1 / (sc * dj) : 0.0;
+    }
+    zc cur = shfl_zc(hk, 0);
+    for (int k = 0; k < j; ++k) {
+        const zc nxt = shfl_zc(hk, k + 1);
+        const double c = __shfl_sync(0xffffffffu, ck, k);
+        const zc sg = shfl_zc(sk, k);
+        const zc t = c * cur + sg * nxt;
+        cur = c * nxt - conj(sg) * cur;
+        if (lane == 0) Hc[k] = t;
+    }
+    if (lane != 0) return;
+    d[j + 1] = dn1;
+    const zc a = cur;
+    const double aa = sqrt(a.x * a.x + a.y * a.y);
+    const double den = sqrt(aa * aa + hn * hn);
+    double c;
+    zc sgn;
+    if (den == 0.0) {
+        c = 1.0;
+        sgn = mk<double>(0.0, 0.0);
+    } else if (aa == 0.0) {
+        c = 0.0;
+        sgn = mk<double>(1.0, 0.0);
+    } else {
+        c = aa / den;
+        sgn = (hn / (den * aa)) * a;
+    }
+    cs[j] = mk<double>(c, 0.0);
+    sn[j] = sgn;
+    Hc[j] = c * a + hn * sgn;
+    Hc[j + 1] = mk<double>(0.0, 0.0);
+    const zc s1 = mk<double>(0.0, 0.0) - conj(sgn) * sj;
+    s[j + 1] = s1;
+    s[j] = c * sj;
+    const double err = sqrt(s1.x * s1.x + s1.y * s1.y) / bn;
+    st.err[r] = err;
+    st.jdone[r] = j + 1;
+    st.nprec[r] = np0 + 1;
+    if (!(err > tol)) st.done[r] = 1;
+    if (err != err) st.done[r] = 2;
+}
+// grid nrhs, block 32*(nv+1) [i0 == 0] or 32*nv threads: warp w sums quantity w of the multidot group
+__global__ void __launch_bounds__(32 * (HH_MAXV + 2)) k_gmres_hcol_mw(GmresState st, const zc* __restrict__ partial, int nblk, int j, int i0,
+                                                                     int nv) {
+    __shared__ zc g[HH_MAXV + 2];
+    const int r = blockIdx.x, nrhs = gridDim.x, w = threadIdx.x >> 5;
+    const zc v = reduce_partials(partial, (int64_t)w * nrhs + r, nblk);
+    if ((threadIdx.x & 31) == 0) g[w] = v;
+    __syncthreads();
+    if (w == 0) gmres_hcol_w0(st, g, r, j, i0, nv);
+}
+// grid nrhs, block 32 threads
+__global__ void k_gmres_givens_mw(GmresState st, const zc* __restrict__ partial, int nblk, int j, double tol, int est) {
+    const int r = blockIdx.x;
+    zc nn = mk<double>(0.0, 0.0);
+    if (!est) nn = reduce_partials(partial, r, nblk);
+    gmres_givens_w0(st, r, j, tol, nn.x, est);
+}
+// k_gmres_small_step with one warp per quantity: grid nrhs, block 32*(j+3) threads -- warps 0..j the dots of column j,
+// warp j+1 its ||w||^2, warp j+2 the pending ||v~_j||^2 of column j-1 (idle when flags & 1 == 0)
+__global__ void __launch_bounds__(32 * (HH_MAXV + 2)) k_gmres_small_step_mw(GmresState st, const zc* __restrict__ dots, int nblk_d,
+                                                                           const zc* __restrict__ norm, int nblk_n, int j, int flags) {
+    __shared__ zc g[HH_MAXV + 2];
+    const int r = blockIdx.x, nrhs = gridDim.x, w = threadIdx.x >> 5;
+    const int nv = j + 1;
+    zc v = mk<double>(0.0, 0.0);
+    if (w <= nv) v = reduce_partials(dots, (int64_t)w * nrhs + r, nblk_d);
+    else if (flags & 1) v = reduce_partials(norm, r, nblk_n);
+    if ((threadIdx.x & 31) == 0) g[w] = v;
+    __syncthreads();
+    if (w != 0) return;
+    if (flags & 1) gmres_givens_w0(st, r, j - 1, 0.0, g[nv + 1].x, 0);
+    __syncwarp();
+    gmres_hcol_w0(st, g, r, j, 0, nv);
+    __syncwarp();
+    if (flags & 2) gmres_givens_w0(st, r, j, 0.0, 0.0, 1);
 }
 
 // y = H(1:jd,1:jd) \ s(1:jd); stored as y_i/d_i (coefficients of the stored z~_i), zero beyond jd

@@ -40,89 +40,146 @@ struct Error : std::runtime_error {
         if (!(cond)) throw hh::Error((code), (msg));     \
     } while (0)
 
-// GetHelmholtzOperatorHO as a stored stencil, host side (see hh_ho_stencil in include/helmholtz_b200.h and the
-// derivation above its definition in hh_api.cu): coef_out[2*(s*N + node) + {0,1}], Float64.
+// GetHelmholtzOperatorHO (src/GetHelmholtz.jl:54-72 with getSpreadNodalLaplacianAndMass, src/PlainNodalLaplacian.jl:106-141)
+// as a stored stencil.  The Kronecker construction collapses to sums of tensor products of 1-D tridiagonals, so ONE
+// entry of the operator is a closed form of the row node, the offset and the model at the column node: ho_coef below is
+// that closed form, compiled for the host (hh_ho_stencil, hh_assemble_csc: pinned against the oracle's Kronecker
+// assembly by the CPU tests) and for the device (k_ho_stencil: the solver's own set-up).
+struct HoGeom {
+    int dim;
+    int n[3];
+    double ih2[3];   // 1/h_d^2
+    double hs[3];    // h_d
+    double bl, bm;   // beta of the Laplacian spread and of the mass average
+    double wre, w2r, w2i;
+    int neumann_top, sommerfeld;
+};
+inline HoGeom ho_geom(int dim, const int64_t* n_nodes, const double* hsp, double wre, double wim, int neumann_on_top, int sommerfeld,
+                      const double* beta) {
+    HoGeom g{};
+    g.dim = dim;
+    for (int d = 0; d < 3; ++d) {
+        g.n[d] = d < dim ? (int)n_nodes[d] : 1;
+        g.ih2[d] = d < dim ? 1.0 / (hsp[d] * hsp[d]) : 0.0;
+        g.hs[d] = d < dim ? hsp[d] : 1.0;
+    }
+    g.bl = beta[0];
+    g.bm = dim == 3 ? beta[1] : beta[0];
+    g.wre = wre;
+    g.w2r = wre * wre - wim * wim;
+    g.w2i = 2.0 * wre * wim;
+    g.neumann_top = neumann_on_top;
+    g.sommerfeld = sommerfeld;
+    return g;
+}
+// entry of a 1-D tridiagonal table that couples node i with node i+o (o in {-1,0,1}); zero when i+o is outside
+__host__ __device__ __forceinline__ double ho_tri(int i, int n, int o, double diag_in, double diag_end, double off) {
+    if (o == 0) return (i == 0 || i == n - 1) ? diag_end : diag_in;
+    if (o < 0) return i > 0 ? off : 0.0;
+    return i < n - 1 ? off : 0.0;
+}
+// mass = -w^2 m (1 - i gamma / Re w) - Sommerfeld at node (i,j,k)   (GetHelmholtz.jl:62-68; getSommerfeldBC :222-247, BC = 2)
+__host__ __device__ __forceinline__ void ho_mass(const HoGeom& g, double mp, double gp, int i, int j, int k, double& re, double& im) {
+    const double gg = gp / g.wre;
+    re = -mp * (g.w2r + g.w2i * gg);
+    im = -mp * (g.w2i - g.w2r * gg);
+    if (g.sommerfeld) {
+        double sf = 0.0;
+        const int idx[3] = {i, j, k};
+        for (int d = 0; d < g.dim; ++d) {
+            const bool first = idx[d] == 0, last = idx[d] == g.n[d] - 1;
+            const bool top = (d == g.dim - 1) && g.neumann_top;
+            if ((first && !top) || last) sf += 2.0 / g.hs[d];
+        }
+        im += g.wre * sf * sqrt(mp);
+    }
+}
+// H_HO[(i,j,k), (i+di,j+dj,k+dk)] (+ i*shift_w2*m on the diagonal); m / gamma are dense column-major arrays.
+// Returns false (entry zero) when the column node is outside the grid.
+__host__ __device__ __forceinline__ bool ho_coef(const HoGeom& g, const double* __restrict__ m, const double* __restrict__ gam, int i,
+                                                 int j, int k, int di, int dj, int dk, double shift_w2, double& re, double& im) {
+    re = im = 0.0;
+    const int n0 = g.n[0], n1 = g.n[1], n2 = g.n[2];
+    if (i + di < 0 || i + di >= n0 || j + dj < 0 || j + dj >= n1 || k + dk < 0 || k + dk >= n2) return false;
+    const double I0 = di == 0, J0 = dj == 0, K0 = dk == 0;  // Kronecker deltas
+    const double bl = g.bl, bm = g.bm;
+    // T = ddxCN' * ddxCN, A = av3term(n, 1/2), B = av3term(n, beta_mass)
+    const double t0 = ho_tri(i, n0, di, 2.0 * g.ih2[0], g.ih2[0], -g.ih2[0]);
+    const double t1 = ho_tri(j, n1, dj, 2.0 * g.ih2[1], g.ih2[1], -g.ih2[1]);
+    const double a0 = ho_tri(i, n0, di, 0.5, 0.75, 0.25), a1 = ho_tri(j, n1, dj, 0.5, 0.75, 0.25);
+    const double b0 = ho_tri(i, n0, di, bm, 0.5 + 0.5 * bm, 0.5 * (1.0 - bm));
+    const double b1 = ho_tri(j, n1, dj, bm, 0.5 + 0.5 * bm, 0.5 * (1.0 - bm));
+    double lap, mm;
+    if (g.dim == 2) {
+        lap = t0 * ((1.0 - bl) * a1 + bl * J0) + t1 * ((1.0 - bl) * a0 + bl * I0);
+        mm = 0.5 * (b1 * I0 + b0 * J0);
+    } else {
+        const double t2 = ho_tri(k, n2, dk, 2.0 * g.ih2[2], g.ih2[2], -g.ih2[2]);
+        const double a2 = ho_tri(k, n2, dk, 0.5, 0.75, 0.25);
+        const double b2 = ho_tri(k, n2, dk, bm, 0.5 + 0.5 * bm, 0.5 * (1.0 - bm));
+        lap = t0 * (bl * J0 * K0 + 0.5 * (1.0 - bl) * (a1 * K0 + J0 * a2)) +
+              t1 * (bl * I0 * K0 + 0.5 * (1.0 - bl) * (a0 * K0 + I0 * a2)) +
+              t2 * (bl * I0 * J0 + 0.5 * (1.0 - bl) * (a0 * J0 + I0 * a1));
+        mm = (1.0 / 3.0) * (b1 * I0 * K0 + b0 * J0 * K0 + b2 * I0 * J0);
+    }
+    const int64_t q = (int64_t)(i + di) + (int64_t)n0 * ((j + dj) + (int64_t)n1 * (k + dk));  // column node: M * Diagonal(mass)
+    double mr, mi;
+    ho_mass(g, m[q], gam[q], i + di, j + dj, k + dk, mr, mi);
+    re = lap + mm * mr;
+    im = mm * mi;
+    if (di == 0 && dj == 0 && dk == 0) im += shift_w2 * m[q];
+    return true;
+}
+// host side (hh_ho_stencil in include/helmholtz_b200.h): coef_out[2*(s*N + node) + {0,1}], Float64
 inline void build_ho_stencil(int dim, const int64_t* n_nodes, const double* hsp, const double* m, const double* gamma,
                              double wre, double wim, int neumann_on_top, int sommerfeld, const double* beta,
                              double* coef_out) {
-        HH_REQUIRE(dim == 2 || dim == 3, HH_ERR_ARG, "hh_ho_stencil: dim must be 2 or 3");
-        HH_REQUIRE(wre != 0.0, HH_ERR_ARG, "hh_ho_stencil: Re(omega) must be non-zero");
-        int64_t n[3] = {1, 1, 1};
-        for (int d = 0; d < dim; ++d) {
-            HH_REQUIRE(n_nodes[d] >= 2 && hsp[d] > 0.0, HH_ERR_ARG, "hh_ho_stencil: node counts must be >= 2, spacings positive");
-            n[d] = n_nodes[d];
-        }
-        const int64_t N = n[0] * n[1] * n[2];
-        const double bl = beta[0], bm = dim == 3 ? beta[1] : beta[0];
-        // 1-D tridiagonal tables, entry [i][o+1] couples node i with node i+o
-        auto tri = [&](int d, double diag_in, double diag_end, double off) {
-            std::vector<std::array<double, 3>> t((size_t)n[d]);
-            for (int64_t i = 0; i < n[d]; ++i) {
-                const bool end = (i == 0 || i == n[d] - 1);
-                t[i][1] = end ? diag_end : diag_in;
-                t[i][0] = i > 0 ? off : 0.0;
-                t[i][2] = i < n[d] - 1 ? off : 0.0;
+    HH_REQUIRE(dim == 2 || dim == 3, HH_ERR_ARG, "hh_ho_stencil: dim must be 2 or 3");
+    HH_REQUIRE(wre != 0.0, HH_ERR_ARG, "hh_ho_stencil: Re(omega) must be non-zero");
+    for (int d = 0; d < dim; ++d)
+        HH_REQUIRE(n_nodes[d] >= 2 && hsp[d] > 0.0, HH_ERR_ARG, "hh_ho_stencil: node counts must be >= 2, spacings positive");
+    const HoGeom g = ho_geom(dim, n_nodes, hsp, wre, wim, neumann_on_top, sommerfeld, beta);
+    const int64_t N = (int64_t)g.n[0] * g.n[1] * g.n[2];
+    const int NS = dim == 3 ? 27 : 9;
+    for (int s = 0; s < NS; ++s) {
+        const int di = s % 3 - 1, dj = (s / 3) % 3 - 1, dk = dim == 3 ? s / 9 - 1 : 0;
+        for (int k = 0; k < g.n[2]; ++k)
+            for (int j = 0; j < g.n[1]; ++j)
+                for (int i = 0; i < g.n[0]; ++i) {
+                    const int64_t p = i + (int64_t)g.n[0] * (j + (int64_t)g.n[1] * k);
+                    double re, im;
+                    ho_coef(g, m, gamma, i, j, k, di, dj, dk, 0.0, re, im);
+                    coef_out[2 * ((int64_t)s * N + p)] = re;
+                    coef_out[2 * ((int64_t)s * N + p) + 1] = im;
+                }
+    }
+}
+
+// device side (the solver's own set-up): one thread per node writes its 9 / 27 entries into the level's arrays (row
+// pitch p0, leading dimension ldN per coefficient array, precision T).  adjoint != 0 writes the conjugate transpose,
+// (A^H)[p, p+off] = conj(A[p+off, p]): the entry of row p+off at offset -off (doTranspose = 1).
+template <typename T>
+__global__ void __launch_bounds__(256) k_ho_stencil(HoGeom g, const double* __restrict__ m, const double* __restrict__ gam,
+                                                    double shift_w2, int adjoint, int p0, int64_t ldN, cx<T>* __restrict__ coef) {
+    const int64_t Nd = (int64_t)g.n[0] * g.n[1] * g.n[2];
+    const int NS = g.dim == 3 ? 27 : 9;
+    for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < Nd; p += (int64_t)gridDim.x * blockDim.x) {
+        const int i = (int)(p % g.n[0]);
+        const int64_t t = p / g.n[0];
+        const int j = (int)(t % g.n[1]), k = (int)(t / g.n[1]);
+        const int64_t dst = i + (int64_t)p0 * (j + (int64_t)g.n[1] * k);
+        for (int s = 0; s < NS; ++s) {
+            const int di = s % 3 - 1, dj = (s / 3) % 3 - 1, dk = g.dim == 3 ? s / 9 - 1 : 0;
+            double re = 0.0, im = 0.0;
+            if (!adjoint) {
+                ho_coef(g, m, gam, i, j, k, di, dj, dk, shift_w2, re, im);
+            } else if (i + di >= 0 && i + di < g.n[0] && j + dj >= 0 && j + dj < g.n[1] && k + dk >= 0 && k + dk < g.n[2]) {
+                ho_coef(g, m, gam, i + di, j + dj, k + dk, -di, -dj, -dk, shift_w2, re, im);
+                im = -im;
             }
-            return t;
-        };
-        std::vector<std::array<double, 3>> T[3], A[3], B[3];
-        for (int d = 0; d < dim; ++d) {
-            const double ih2 = 1.0 / (hsp[d] * hsp[d]);
-            T[d] = tri(d, 2.0 * ih2, ih2, -ih2);                      // ddxCN' * ddxCN
-            A[d] = tri(d, 0.5, 0.75, 0.25);                           // av3term(n, 1/2)
-            B[d] = tri(d, bm, 0.5 + 0.5 * bm, 0.5 * (1.0 - bm));      // av3term(n, beta_mass)
+            coef[(int64_t)s * ldN + dst] = mk<T>((T)re, (T)im);
         }
-        // mass = -w^2 m (1 - i gamma / Re w) - Sommerfeld   (GetHelmholtz.jl:62-68; getSommerfeldBC :222-247, BC = 2)
-        const double w2r = wre * wre - wim * wim, w2i = 2.0 * wre * wim;
-        std::vector<double> mr((size_t)N), mi((size_t)N);
-        for (int64_t k = 0; k < n[2]; ++k)
-            for (int64_t j = 0; j < n[1]; ++j)
-                for (int64_t i = 0; i < n[0]; ++i) {
-                    const int64_t p = i + n[0] * (j + n[1] * k);
-                    const double g = gamma[p] / wre;
-                    double re = -m[p] * (w2r + w2i * g), im = -m[p] * (w2i - w2r * g);
-                    if (sommerfeld) {
-                        double sf = 0.0;
-                        const int64_t idx[3] = {i, j, k};
-                        for (int d = 0; d < dim; ++d) {
-                            const bool first = idx[d] == 0, last = idx[d] == n[d] - 1;
-                            const bool top = (d == dim - 1) && neumann_on_top;
-                            if ((first && !top) || last) sf += 2.0 / hsp[d];
-                        }
-                        im += wre * sf * std::sqrt(m[p]);
-                    }
-                    mr[p] = re;
-                    mi[p] = im;
-                }
-        const int NS = dim == 3 ? 27 : 9;
-        std::fill(coef_out, coef_out + (size_t)2 * NS * N, 0.0);
-        for (int64_t k = 0; k < n[2]; ++k)
-            for (int64_t j = 0; j < n[1]; ++j)
-                for (int64_t i = 0; i < n[0]; ++i) {
-                    const int64_t p = i + n[0] * (j + n[1] * k);
-                    for (int dk = (dim == 3 ? -1 : 0); dk <= (dim == 3 ? 1 : 0); ++dk)
-                        for (int dj = -1; dj <= 1; ++dj)
-                            for (int di = -1; di <= 1; ++di) {
-                                if (i + di < 0 || i + di >= n[0] || j + dj < 0 || j + dj >= n[1] || k + dk < 0 || k + dk >= n[2]) continue;
-                                const double I0 = di == 0, J0 = dj == 0, K0 = dk == 0;  // Kronecker deltas
-                                double lap, mm;
-                                if (dim == 2) {
-                                    lap = T[0][i][di + 1] * ((1.0 - bl) * A[1][j][dj + 1] + bl * J0) +
-                                          T[1][j][dj + 1] * ((1.0 - bl) * A[0][i][di + 1] + bl * I0);
-                                    mm = 0.5 * (B[1][j][dj + 1] * I0 + B[0][i][di + 1] * J0);
-                                } else {
-                                    const double a0 = A[0][i][di + 1], a1 = A[1][j][dj + 1], a2 = A[2][k][dk + 1];
-                                    lap = T[0][i][di + 1] * (bl * J0 * K0 + 0.5 * (1.0 - bl) * (a1 * K0 + J0 * a2)) +
-                                          T[1][j][dj + 1] * (bl * I0 * K0 + 0.5 * (1.0 - bl) * (a0 * K0 + I0 * a2)) +
-                                          T[2][k][dk + 1] * (bl * I0 * J0 + 0.5 * (1.0 - bl) * (a0 * J0 + I0 * a1));
-                                    mm = (1.0 / 3.0) * (B[1][j][dj + 1] * I0 * K0 + B[0][i][di + 1] * J0 * K0 + B[2][k][dk + 1] * I0 * J0);
-                                }
-                                const int64_t q = p + di + n[0] * (dj + n[1] * (int64_t)dk);  // column node: M * Diagonal(mass)
-                                const int s = (di + 1) + 3 * (dj + 1) + (dim == 3 ? 9 * (dk + 1) : 0);
-                                coef_out[2 * ((int64_t)s * N + p)] = lap + mm * mr[q];
-                                coef_out[2 * ((int64_t)s * N + p) + 1] = mm * mi[q];
-                            }
-                }
+    }
 }
 
 // Conjugate transpose of an operator stored as a 3^dim-point stencil on a dense column-major grid:
@@ -501,6 +558,7 @@ class Solver : public SolverBase {
         DevBuf<C> v, z;  // (steps+1) basis vectors; `steps` preconditioned vectors when flexible
         int steps = 0;
         GmresMem g;
+        DevBuf<zc> np;   // ||v~_{j+1}||^2 partials of the last update pass, consumed by the next step's scalar kernel
     };
     struct Level {
         int n[3] = {1, 1, 1};
@@ -545,6 +603,15 @@ class Solver : public SolverBase {
         tma_restrict = !(tr && tr[0] == '0');
         const char* hs = getenv("HH_HALO_SPLIT");
         split_always = hs && hs[0] == '1';
+        // A/B switches of the round-2 Krylov savings (default on): the last column of a GMRES cycle skips its update pass
+        // (HH_SKIP_LAST_UPDATE), the fixed-length GMRES of a level runs one scalar kernel / one all-reduce per step and a
+        // one-pass solution update (HH_SMALL_FUSED)
+        const char* sl = getenv("HH_SKIP_LAST_UPDATE");
+        skip_last_update = !(sl && sl[0] == '0');
+        const char* sf = getenv("HH_SMALL_FUSED");
+        small_fused = !(sf && sf[0] == '0');
+        const char* sq = getenv("HH_SCALAR_FAST");  // one warp per reduced quantity + lane-parallel Givens (default on)
+        scalar_fast = sq && sq[0] == '1';  // TODO(verify on B200): default on once the GPU suite has run with it
         use_pitch = sizeof(T) == 4 && pb.dim == 3 && fine_kernel == FK_TMA;
     }
     ~Solver() override {
@@ -1415,6 +1482,11 @@ class Solver : public SolverBase {
     }
     // partial sums of conj(V_i).w (i<nv) [+ |w|^2 if with_norm]; returns nblk
     int multidot(const C* const* V, int nv, const C* w, const Span& sp, int nrhs, bool with_norm, zc* partial) {
+        const int nblk = multidot_launch(V, nv, w, sp, nrhs, with_norm, partial);
+        return slab_reduce(partial, (nv + (with_norm ? 1 : 0)) * nrhs, nblk);
+    }
+    // the kernel only: the block partials stay in `partial` (layout of k_multidot), nblk is returned
+    int multidot_launch(const C* const* V, int nv, const C* w, const Span& sp, int nrhs, bool with_norm, zc* partial) {
         HH_REQUIRE(nv >= 0 && nv <= HH_MAXV, HH_ERR_ARG, "multidot: too many vectors");
         const int64_t N = sp.len, ld = sp.ld;
         const int nblk = vec_blocks(N, nrhs);
@@ -1430,14 +1502,19 @@ class Solver : public SolverBase {
         else k_multidot<T, NV, false><<<g, 256, 0, stream>>>(L, w, N, ld, partial);            \
         break;
             switch (nv) {
-                HH_MD(0) HH_MD(1) HH_MD(2) HH_MD(3) HH_MD(4) HH_MD(5) HH_MD(6) HH_MD(7) HH_MD(8)
+                HH_MD(0) HH_MD(1) HH_MD(2) HH_MD(3) HH_MD(4) HH_MD(5) HH_MD(6) HH_MD(7) HH_MD(8) HH_MD(9) HH_MD(10)
             }
 #undef HH_MD
         });
-        return slab_reduce(partial, (nv + (with_norm ? 1 : 0)) * nrhs, nblk);
+        return nblk;
     }
     int multiaxpy(const C* const* V, int nv, C* w, const Span& sp, int nrhs, const zc* coef, int cstride, bool negate,
                   bool with_norm, zc* partial, const zc* post = nullptr) {
+        const int nblk = multiaxpy_launch(V, nv, w, sp, nrhs, coef, cstride, negate, with_norm, partial, post);
+        return with_norm ? slab_reduce(partial, nrhs, nblk) : nblk;
+    }
+    int multiaxpy_launch(const C* const* V, int nv, C* w, const Span& sp, int nrhs, const zc* coef, int cstride, bool negate,
+                         bool with_norm, zc* partial, const zc* post = nullptr) {
         HH_REQUIRE(nv >= 1 && nv <= HH_MAXV, HH_ERR_ARG, "multiaxpy: bad vector count");
         const int64_t N = sp.len, ld = sp.ld;
         const int nblk = vec_blocks(N, nrhs);
@@ -1451,10 +1528,29 @@ class Solver : public SolverBase {
         if (with_norm) k_multiaxpy<T, NV, true><<<g, 256, 0, stream>>>(L, w, N, ld, coef, cstride, negate, post, partial); \
         else k_multiaxpy<T, NV, false><<<g, 256, 0, stream>>>(L, w, N, ld, coef, cstride, negate, post, partial);          \
         break;
-            switch (nv) { HH_MA(1) HH_MA(2) HH_MA(3) HH_MA(4) HH_MA(5) HH_MA(6) HH_MA(7) HH_MA(8) }
+            switch (nv) { HH_MA(1) HH_MA(2) HH_MA(3) HH_MA(4) HH_MA(5) HH_MA(6) HH_MA(7) HH_MA(8) HH_MA(9) HH_MA(10) }
 #undef HH_MA
         });
-        return with_norm ? slab_reduce(partial, nrhs, nblk) : nblk;
+        return nblk;
+    }
+    // x (+)= dinv .* sum_{i<nv} coef[r*cstride + i] V_i on the span (k_combine)
+    void combine(const C* const* V, int nv, const C* dinv, C* x, const Span& sp, int nrhs, const zc* coef, int cstride,
+                 bool accumulate, int tag) {
+        HH_REQUIRE(nv >= 1 && nv <= HH_MAXV, HH_ERR_ARG, "combine: bad vector count");
+        const int64_t N = sp.len, ld = sp.ld;
+        const int nblk = vec_blocks(N, nrhs);
+        VecList<T> L;
+        for (int i = 0; i < HH_MAXV; ++i) L.v[i] = i < nv ? V[i] + sp.off : nullptr;
+        dim3 g(nblk, nrhs);
+        launch(tag, S * (double)N * (nrhs * (nv + (accumulate ? 2 : 1)) + 1), [&] {
+#define HH_CB(NV)                                                                                                      \
+    case NV:                                                                                                           \
+        if (accumulate) k_combine<T, NV, true><<<g, 256, 0, stream>>>(L, dinv + sp.off, x + sp.off, N, ld, coef, cstride); \
+        else k_combine<T, NV, false><<<g, 256, 0, stream>>>(L, dinv + sp.off, x + sp.off, N, ld, coef, cstride);           \
+        break;
+            switch (nv) { HH_CB(1) HH_CB(2) HH_CB(3) HH_CB(4) HH_CB(5) HH_CB(6) HH_CB(7) HH_CB(8) HH_CB(9) HH_CB(10) }
+#undef HH_CB
+        });
     }
 
     // ------------------------------------------------------------------ hierarchy (MGsetup)
@@ -1473,17 +1569,58 @@ class Solver : public SolverBase {
         for (int d = 0; d < pb.dim; ++d) out[d] = levels[level].n[d];
     }
 
-    // HO mode: host-built stencils -> device.  hoH gets the un-shifted operator (always: it is the Krylov operator);
-    // levels[0] gets the shifted one and damp/diag unless this solver only runs the Krylov method (mixed precision).
+    // HO mode.  hoH gets the un-shifted operator (always: it is the Krylov operator); levels[0] gets the shifted one and
+    // damp/diag unless this solver only runs the Krylov method (mixed precision).  The stencils are evaluated on the
+    // device from Float64 copies of m and gamma (k_ho_stencil: the closed form the host export hh_ho_stencil uses);
+    // HH_HO_BUILD=host keeps the round-1 path (host loop + upload of 27 N coefficients) as an A/B.
     void build_ho_levels(const hh_mg_options& o) {
         const int NS = pb.dim == 3 ? 27 : 9, center = pb.dim == 3 ? 13 : 4;
-        const int64_t Nd = pb.N();  // dense node count of the host stencil
+        const int64_t Nd = pb.N();  // dense node count of the caller's model arrays
         HH_REQUIRE((int64_t)ho_m.size() == Nd && (int64_t)ho_g.size() == Nd, HH_ERR_STATE, "high-order operator: no model");
         int64_t nn[3] = {pb.n[0], pb.n[1], pb.n[2]};
+        const Level& L0 = levels[0];
+        for (int d = 0; d < 3; ++d) hoH.n[d] = L0.n[d];
+        hoH.p0 = L0.p0;
+        hoH.N = L0.N;
+        hoH.Nlog = L0.Nlog;
+        hoH.zb = L0.zb;
+        hoH.ze = L0.ze;
+        hoH.koff = L0.koff;
+        hoH.n2g = L0.n2g;
+        const double sw2 = o.shift[0] * pb.w_re * pb.w_re;
+        const char* hb = getenv("HH_HO_BUILD");
+        if (hb && !strcmp(hb, "device")) {  // TODO(verify on B200): default once test_gpu_ho*.py have run with it
+            HH_REQUIRE(pb.w_re != 0.0, HH_ERR_ARG, "high-order operator: Re(omega) must be non-zero");
+            const HoGeom g = ho_geom(pb.dim, nn, pb.h, pb.w_re, pb.w_im, pb.neumann_top, pb.sommerfeld, ho_beta);
+            DevBuf<double> dm, dg;
+            dm.alloc((size_t)Nd);
+            dg.alloc((size_t)Nd);
+            HH_CUDA(cudaMemcpyAsync(dm.p, ho_m.data(), (size_t)Nd * sizeof(double), cudaMemcpyHostToDevice, stream));
+            HH_CUDA(cudaMemcpyAsync(dg.p, ho_g.data(), (size_t)Nd * sizeof(double), cudaMemcpyHostToDevice, stream));
+            auto build = [&](DevBuf<C>& dst, double shift_w2) {
+                dst.alloc((size_t)NS * L0.N);
+                if (L0.N != Nd) HH_CUDA(cudaMemsetAsync(dst.p, 0, (size_t)NS * L0.N * sizeof(C), stream));  // ghost columns stay zero
+                const unsigned nb = (unsigned)std::min<int64_t>((Nd + 255) / 256, 148 * 16);
+                launch(T_SETUP, 0, [&] {
+                    k_ho_stencil<T><<<nb, 256, 0, stream>>>(g, dm.p, dg.p, shift_w2, o.do_transpose ? 1 : 0, L0.p0, L0.N, dst.p);
+                });
+            };
+            build(hoH.coef, 0.0);
+            if (!krylov_only) {
+                // shifted operator of the hierarchy: + i shift Re(w)^2 m on the diagonal (GetHelmholtzShiftOP, GetHelmholtz.jl:81-83)
+                Level& Lm = levels[0];
+                build(Lm.coef, sw2);
+                Lm.dinv.alloc(Lm.N);
+                launch(T_SETUP, 0, [&] {
+                    k_coarse_dinv<T><<<(unsigned)((Lm.N + 255) / 256), 256, 0, stream>>>(Lm.coef.p + (int64_t)center * Lm.N, Lm.dinv.p, Lm.N, (T)o.relax_param);
+                });
+            }
+            HH_CUDA(cudaStreamSynchronize(stream));  // dm / dg are released on return
+            return;
+        }
         std::vector<double> host((size_t)2 * NS * Nd);
         build_ho_stencil(pb.dim, nn, pb.h, ho_m.data(), ho_g.data(), pb.w_re, pb.w_im, pb.neumann_top, pb.sommerfeld, ho_beta,
                          host.data());
-        const Level& L0 = levels[0];
         std::vector<double> adj;  // transposed hierarchy (doTranspose = 1): the same kernels on the adjoint stencils
         auto upload = [&](DevBuf<C>& dst) {  // host Float64 dense -> device precision T in the level's row pitch
             const double* src = host.data();
@@ -1510,18 +1647,9 @@ class Solver : public SolverBase {
             });
             HH_CUDA(cudaStreamSynchronize(stream));
         };
-        for (int d = 0; d < 3; ++d) hoH.n[d] = L0.n[d];
-        hoH.p0 = L0.p0;
-        hoH.N = L0.N;
-        hoH.Nlog = L0.Nlog;
-        hoH.zb = L0.zb;
-        hoH.ze = L0.ze;
-        hoH.koff = L0.koff;
-        hoH.n2g = L0.n2g;
         upload(hoH.coef);
         if (krylov_only) return;
         // shifted operator of the hierarchy: + i shift Re(w)^2 m on the diagonal (GetHelmholtzShiftOP, GetHelmholtz.jl:81-83)
-        const double sw2 = o.shift[0] * pb.w_re * pb.w_re;
         for (int64_t p = 0; p < Nd; ++p) host[2 * ((int64_t)center * Nd + p) + 1] += sw2 * ho_m[p];
         Level& Lm = levels[0];
         upload(Lm.coef);
@@ -1798,12 +1926,14 @@ class Solver : public SolverBase {
             if (gs > 0) {
                 alloc_zero(L.gs.v, (size_t)(gs + 1) * L.N * nrhs);
                 alloc_gmres_state(L.gs.g, gs, nrhs);
+                L.gs.np.alloc((size_t)std::max(nrhs, 1) * (148 * 8 + 8));
             }
             L.ks.steps = kcycle_level(l) ? 2 : 0;
             if (L.ks.steps) {
                 alloc_zero(L.ks.v, (size_t)3 * L.N * nrhs);
                 alloc_zero(L.ks.z, (size_t)2 * L.N * nrhs);
                 alloc_gmres_state(L.ks.g, 2, nrhs);
+                L.ks.np.alloc((size_t)std::max(nrhs, 1) * (148 * 8 + 8));
             }
         }
         kcap = nrhs;
@@ -1848,13 +1978,26 @@ class Solver : public SolverBase {
     // Orthogonalise w against V_0..V_j (classical Gram-Schmidt in one fused pass over the vectors),
     // then the Givens update.  Leaves 1/||w|| in st.scale.
     // V[0..j] are the stored (scaled) basis vectors, w = A z~_j on entry, the next basis vector on exit.
-    void gmres_orthogonalise(GmresMem& g, const C* const* V, int j, C* w, const Span& N, int nrhs, double tol) {
+    // last_column: w is the last column of its cycle -- v_{j+1} would never be read, so the update pass over the vectors
+    // is skipped and h_{j+1,j} comes from the dot pass alone (gmres_givens_dev, est).
+    void gmres_orthogonalise(GmresMem& g, const C* const* V, int j, C* w, const Span& N, int nrhs, double tol,
+                             bool last_column = false) {
         const C* vv[HH_MAXV];
         for (int i0 = 0; i0 <= j; i0 += HH_MAXV) {
             const int nv = std::min(HH_MAXV, j + 1 - i0);
             for (int i = 0; i < nv; ++i) vv[i] = V[i0 + i];
             const int nblk = multidot(vv, nv, w, N, nrhs, i0 == 0, d_partial.p);
-            launch(T_SCALAR, 0, [&] { k_gmres_hcol<<<nrhs, 32, 0, stream>>>(g.st, red_out, nblk, j, i0, nv); });
+            launch(T_SCALAR, 0, [&] {
+                if (scalar_fast) k_gmres_hcol_mw<<<nrhs, 32 * (nv + (i0 == 0 ? 1 : 0)), 0, stream>>>(g.st, red_out, nblk, j, i0, nv);
+                else k_gmres_hcol<<<nrhs, 32, 0, stream>>>(g.st, red_out, nblk, j, i0, nv);
+            });
+        }
+        if (last_column && skip_last_update) {
+            launch(T_SCALAR, 0, [&] {
+                if (scalar_fast) k_gmres_givens_mw<<<nrhs, 32, 0, stream>>>(g.st, nullptr, 0, j, tol, 1);
+                else k_gmres_givens<<<nrhs, 32, 0, stream>>>(g.st, nullptr, 0, j, tol, 1);
+            });
+            return;
         }
         int nblk = 0;
         for (int i0 = 0; i0 <= j; i0 += HH_MAXV) {
@@ -1864,7 +2007,41 @@ class Solver : public SolverBase {
             nblk = multiaxpy(vv, nv, w, N, nrhs, g.hcol.p + i0, g.st.m + 1, true, last, d_partial.p,
                              last ? g.scale.p : nullptr);
         }
-        launch(T_SCALAR, 0, [&] { k_gmres_givens<<<nrhs, 32, 0, stream>>>(g.st, red_out, nblk, j, tol); });
+        launch(T_SCALAR, 0, [&] {
+            if (scalar_fast) k_gmres_givens_mw<<<nrhs, 32, 0, stream>>>(g.st, red_out, nblk, j, tol, 0);
+            else k_gmres_givens<<<nrhs, 32, 0, stream>>>(g.st, red_out, nblk, j, tol, 0);
+        });
+    }
+    // One step of a level's fixed-length GMRES with ONE scalar kernel and (slabs) ONE all-reduce: the Givens update of
+    // column j-1 waits for the dot sums of column j (k_gmres_small_step); `pending` = nblk of the update pass of column
+    // j-1 whose norm partials sit in ws.np (0: none).  The last column skips its update pass.
+    void gmres_step_fused(SmallWs& ws, const C* const* V, int j, C* w, const Span& N, int nrhs, bool last_column, int& pending) {
+        GmresMem& g = ws.g;
+        const int nv = j + 1;
+        const int nblk = multidot_launch(V, nv, w, N, nrhs, true, d_partial.p);
+        const zc* dots = d_partial.p;
+        const zc* norms = ws.np.p;
+        int nb_d = nblk, nb_n = pending;
+        if (slab && slab->nranks > 1) {
+            const int nq = (nv + 1) * nrhs, nq2 = pending ? nrhs : 0;
+            if (d_red.n < (size_t)(nq + nq2)) d_red.alloc((size_t)std::max(nq + nq2, 4096));
+            launch(T_SCALAR, 0, [&] {
+                k_sum_partials<<<(nq + 7) / 8, 256, 0, stream>>>(d_partial.p, nq, nblk, d_red.p);
+                if (nq2) k_sum_partials<<<(nq2 + 7) / 8, 256, 0, stream>>>(ws.np.p, nq2, pending, d_red.p + nq);
+            });
+            launch(T_ALLREDUCE, 16.0 * (nq + nq2), [&] { slab->allreduce(stream, (double*)d_red.p, 2 * (nq + nq2), false); });
+            dots = d_red.p;
+            norms = d_red.p + nq;
+            nb_d = nb_n = 1;
+        }
+        const int flags = (pending ? 1 : 0) | (last_column ? 2 : 0);
+        launch(T_SCALAR, 0, [&] {
+            if (scalar_fast) k_gmres_small_step_mw<<<nrhs, 32 * (j + 3), 0, stream>>>(g.st, dots, nb_d, norms, nb_n, j, flags);
+            else k_gmres_small_step<<<nrhs, 32, 0, stream>>>(g.st, dots, nb_d, norms, nb_n, j, flags);
+        });
+        pending = 0;
+        if (!last_column)
+            pending = multiaxpy_launch(V, nv, w, N, nrhs, g.hcol.p, g.st.m + 1, true, true, ws.np.p, g.scale.p);
     }
     void gmres_begin(GmresMem& g, const C* r, const Span& N, int nrhs, bool first, double tol) {
         const int nblk = multidot(nullptr, 0, r, N, nrhs, true, d_partial.p);
@@ -1892,12 +2069,18 @@ class Solver : public SolverBase {
         if (x_is_zero) V[0] = b;  // r0 = b: used in place, unscaled (d_0 = ||b||)
         else level_apply(l, MODE_RESID, x, b, W[0], nrhs);
         gmres_begin(g, V[0], sp, nrhs, true, 0.0);
+        const bool fused = small_fused && nsteps <= HH_MAXV && ws.np.p != nullptr;
+        int pending = 0;
+        auto orthogonalise = [&](int j) {
+            if (fused) gmres_step_fused(ws, V.data(), j, W[j + 1], sp, nrhs, j == nsteps - 1, pending);
+            else gmres_orthogonalise(g, V.data(), j, W[j + 1], sp, nrhs, 0.0, j == nsteps - 1);
+        };
         for (int j = 0; j < nsteps; ++j) {
             C* z;
             if (prec == 0 && L.scoef.p != nullptr) {
                 // Jacobi, stored stencil: w = (A D^-1) v_j in one pass over the column-scaled coefficients
                 coarse_stencil(MODE_APPLY, L, V[j], nullptr, W[j + 1], nrhs, true);
-                gmres_orthogonalise(g, V.data(), j, W[j + 1], sp, nrhs, 0.0);
+                orthogonalise(j);
                 continue;
             }
             if (prec == 0) {
@@ -1908,11 +2091,15 @@ class Solver : public SolverBase {
                 cycle(l, V[j], z, true, nrhs);
             }
             level_apply(l, MODE_APPLY, z, nullptr, W[j + 1], nrhs);
-            gmres_orthogonalise(g, V.data(), j, W[j + 1], sp, nrhs, 0.0);
+            orthogonalise(j);
         }
         gmres_solve_y(g, nrhs);
         const C* vv[HH_MAXV];
-        if (prec == 0) {
+        if (prec == 0 && fused) {
+            // x (+)= dinv .* (V y) in one pass
+            for (int i = 0; i < nsteps; ++i) vv[i] = V[i];
+            combine(vv, nsteps, L.dinv.p, x, sp, nrhs, g.y.p, g.st.m, !x_is_zero, T_AXPY);
+        } else if (prec == 0) {
             // t = sum_j y_j v_j  (accumulated into the last slot, free now), then x (+)= dinv .* t
             C* t = W[nsteps];
             zero_vec(t, N, nrhs);
@@ -2289,7 +2476,7 @@ class Solver : public SolverBase {
             for (int j = 0; j < m; ++j) {
                 precondition(V[j], Z[j], nrhs);
                 krylov_apply(MODE_APPLY, Hop, Z[j], nullptr, W[j + 1], N, nrhs);
-                gmres_orthogonalise(outer, V.data(), j, W[j + 1], sp, nrhs, o.rel_tol);
+                gmres_orthogonalise(outer, V.data(), j, W[j + 1], sp, nrhs, o.rel_tol, j == m - 1);
                 all_done = fetch_done(outer.done.p, nrhs);
                 if (all_done) break;
             }
@@ -2424,6 +2611,9 @@ class Solver : public SolverBase {
     int force_tile = -1;                 // HH_COARSE_TILE: 0 = 16x8, 1 = alternative tile (coarse_tile)
     bool scaled_gmres = true;
     bool tma_restrict = true;            // HH_TMA_RESTRICT=0: the one-thread-per-coarse-node restriction (A/B baseline)
+    bool skip_last_update = true;        // HH_SKIP_LAST_UPDATE=0: orthogonalise the last column of a cycle like the others
+    bool scalar_fast = true;             // HH_SCALAR_FAST=0: the one-warp, one-thread forms of the GMRES scalar kernels
+    bool small_fused = true;             // HH_SMALL_FUSED=0: two scalar kernels / two reductions per step of a level's GMRES
     bool fuse_post2 = false;             // HH_FUSE_POST2=1: correction + BOTH post-sweeps in one pass (k_fine3d_tma_pro2; slower, see ctor)
     GmresMem outer;
     int outer_cap = 0;

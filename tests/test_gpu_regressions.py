@@ -190,3 +190,56 @@ def test_fused_two_sweep_post_smoothing_equals_separate_sweeps(gpu_pkg, prec, to
     assert rel_err(out["1"][0], out["0"][0]) < tol
     assert np.array_equal(out["1"][2], out["0"][2])
     assert rel_err(out["1"][1], out["0"][1]) < 100 * tol
+
+
+@pytest.mark.parametrize("prec,tol", [(np.complex128, 1e-9), (np.complex64, 2e-4)])
+@pytest.mark.parametrize("levels,relax,cyc,coarse,citers,pre,post", [
+    (3, "Jac", "W", "GMRES", 10, 1, 2),          # the bench's cycle: coarsest Jacobi-GMRES(10)
+    (3, "Jac-GMRES", "K", "GMRES", 5, 2, 2),     # Jac-GMRES smoother on every level + K-cycle FGMRES(2)
+    (2, "Jac", "V", "GMRES", 13, 2, 2),          # more steps than one vector group: the un-fused path with the skipped last pass
+])
+def test_skipped_last_update_and_fused_level_gmres_match_plain_path(gpu_pkg, prec, tol, levels, relax, cyc, coarse, citers, pre, post):
+    """Round-2 Krylov savings against the plain path (HH_SKIP_LAST_UPDATE=0 HH_SMALL_FUSED=0): the last column of every
+    GMRES cycle takes h_{j+1,j} from the dot pass instead of a pass that writes a vector nobody reads, and the
+    fixed-length GMRES of a level runs one scalar kernel per step with the Givens update deferred, plus a one-pass
+    x (+)= D^-1 V y.  One cycle, the full solve and the iteration counts must agree."""
+    import os
+
+    pkg = gpu_pkg
+    rng = np.random.default_rng(23)
+    n = np.array((33, 41, 25))
+    dom = sum([[0.0, 0.1 * (v - 1)] for v in n], [])
+    mesh = pkg.getRegularMesh(dom, list(n - 1))
+    m = 1.0 / (1.5 + 2.0 * rng.random(tuple(n))) ** 2
+    w = 0.8 * pkg.getMaximalFrequency(m, mesh)
+    gamma = 0.02 * w * (1.0 + rng.random(tuple(n))) + pkg.getABL(n, True, [3, 3, 4], w)
+    N = int(np.prod(n))
+    nrhs = 3
+    B = np.asfortranarray((rng.standard_normal((N, nrhs)) + 1j * rng.standard_normal((N, nrhs))).astype(prec))
+    B[:, 1] = 0  # a zero right-hand side rides along (frozen column)
+    out = {}
+    for flag in ("1", "0"):
+        os.environ["HH_SKIP_LAST_UPDATE"] = flag
+        os.environ["HH_SMALL_FUSED"] = flag
+        try:
+            MG = pkg.getMGparam(prec, pkg.Int64, levels, 1, 40, 1e-6 if prec == np.complex128 else 1e-4, relax, 0.8, pre, post, cyc,
+                                coarse, coarseIters=citers)
+            hp = pkg.HelmholtzParam(mesh, gamma, m.ravel(order="F"), w, True, True)
+            A = pkg.getShiftedLaplacianMultigridSolver(hp, MG, 0.2, "GMRES", 5)
+            hd = pkg.api._ensure_hierarchy(A, 0)
+        finally:
+            del os.environ["HH_SKIP_LAST_UPDATE"]
+            del os.environ["HH_SMALL_FUSED"]
+        Z = np.empty_like(B, order="F")
+        pkg._lib.check(hd.lib.hh_cycle(hd.h, B.ctypes.data, Z.ctypes.data, nrhs), hd.h)
+        X, A = pkg.solveLinearSystem(None, B, A)
+        out[flag] = (Z, np.reshape(X, (N, nrhs)).copy(), A.iterations.copy())
+        pkg.clear(MG)
+    assert np.all(out["1"][0][:, 1] == 0) and np.all(out["1"][1][:, 1] == 0)
+    assert rel_err(out["1"][0], out["0"][0]) < tol
+    if prec == np.complex128:
+        assert np.array_equal(out["1"][2], out["0"][2])
+    else:
+        assert np.abs(out["1"][2].astype(int) - out["0"][2].astype(int)).max() <= 1
+    # both solves stop at the same residual tolerance: they agree to a small multiple of it
+    assert rel_err(out["1"][1], out["0"][1]) < (2e-5 if prec == np.complex128 else 5e-3)
