@@ -756,6 +756,221 @@ __global__ void __launch_bounds__(256) k_fine3d_tma_pro(FineOp<T> op, const __gr
 }
 
 // ---------------------------------------------------------------------------------------------
+// The same fusion when the iterate that is corrected is the FIRST sweep from zero, x1 = dinv .* b (pre-smoothing count 1,
+// the bench's W(1,2) / V(1,*) cycles):   x' = dinv .* b + P xc ;  out = x' + dinv .* (b - A x')
+// x1 is recomputed from b and dinv (both staged WITH halo, as k_fine3d_tma_first stages them) instead of being written
+// by the first kernel and read back here: the cycle start writes only the residual (2S instead of 3S per node and
+// right-hand side) and this pass reads b once instead of x and b (2S + S/8 instead of 3S + S/8).  The staged b tile
+// becomes the x' tile in place (the centre thread keeps b and dinv of its column in registers for the Jacobi update),
+// the stage is 27 KB instead of 34 KB, so the ring is 4 deep at two CTAs per SM.  Values are those of the two-kernel
+// path: x1 is formed by the same multiplication.
+// ---------------------------------------------------------------------------------------------
+template <typename T, int KB>
+struct FineProBCfg {
+    static constexpr int TX = 32, TY = 8;
+    static constexpr int HX = sizeof(T) == 4 ? 2 : 1;  // see FineTmaCfg
+    static constexpr int PX = TX + 2 * HX;
+    static constexpr int XT = (TY + 2) * PX;
+    static constexpr int BT = TY * TX;
+    static constexpr int CH = sizeof(T) == 4 ? 2 : 1;
+    static constexpr int CTX = sizeof(T) == 4 ? TX / 2 + 4 : TX / 2 + 2, CTY = TY / 2 + 2, CT = CTX * CTY;
+    static constexpr int ES = (int)sizeof(cx<T>);
+    static constexpr int al(int b) { return (b + 127) / 128 * 128; }
+    static constexpr int OFF_B = 0;                            // b tiles with halo (become the x' tiles), KB right-hand sides
+    static constexpr int OFF_D = al(KB * XT * ES);             // dinv tile with halo
+    static constexpr int OFF_C = OFF_D + al(XT * ES);          // centre coefficient tile
+    static constexpr int OFF_XC = OFF_C + al(BT * ES);         // two coarse planes, KB right-hand sides each
+    static constexpr int XC_PLANE = al(KB * CT * ES);
+    static constexpr int STAGE_BYTES = OFF_XC + 2 * XC_PLANE;
+    static constexpr uint32_t TX_BYTES = KB * XT * ES + XT * ES + BT * ES + 2 * KB * CT * ES;
+};
+
+template <typename T, int KB, int NS>
+__global__ void __launch_bounds__(256) k_fine3d_tma_prob(FineOp<T> op, const __grid_constant__ TmaDesc tm_b,
+                                                         const __grid_constant__ TmaDesc tm_d,
+                                                         const __grid_constant__ TmaDesc tm_c,
+                                                         const __grid_constant__ TmaDesc tm_xc,
+                                                         const cx<T>* __restrict__ b, const cx<T>* __restrict__ xcg,
+                                                         cx<T>* __restrict__ out, int64_t ld, int64_t ldc, int csy,
+                                                         int nc1, int nrhs, int zchunk, int groups) {
+    typedef FineProBCfg<T, KB> Cfg;
+    constexpr int TX = Cfg::TX, TY = Cfg::TY, PX = Cfg::PX;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + (size_t)NS * Cfg::STAGE_BYTES);
+    const int n0 = op.n[0], n1 = op.n[1], n2 = op.n[2];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int i0 = (blockIdx.x / groups) * TX, j0 = blockIdx.y * TY;
+    const int i = i0 + tx, j = j0 + ty;
+    const int r0 = (blockIdx.x % groups) * KB;
+    const int z0 = op.zb + blockIdx.z * zchunk;
+    const int z1 = min(op.ze, z0 + zchunk);
+    const int zl = min(z1, n2 - 1);
+    const int64_t sy = op.sy, sz = (int64_t)op.sy * n1;
+    const bool active = (i < n0) && (j < n1);
+    const int Is = (i0 >> 1) - Cfg::CH, Js = (j0 >> 1) - 1;  // origin of the coarse tile
+    auto issue = [&](int s, int z) {
+        unsigned char* st = smem_raw + (size_t)s * Cfg::STAGE_BYTES;
+        mbar_expect_tx(&bars[s], Cfg::TX_BYTES);
+        tma_load_4d(st + Cfg::OFF_B, &tm_b, 2 * (i0 - Cfg::HX), j0 - 1, z, r0, &bars[s]);
+        tma_load_3d(st + Cfg::OFF_D, &tm_d, 2 * (i0 - Cfg::HX), j0 - 1, z, &bars[s]);
+        tma_load_3d(st + Cfg::OFF_C, &tm_c, 2 * i0, j0, z, &bars[s]);
+        tma_load_4d(st + Cfg::OFF_XC, &tm_xc, 2 * Is, Js, z >> 1, r0, &bars[s]);
+        tma_load_4d(st + Cfg::OFF_XC + Cfg::XC_PLANE, &tm_xc, 2 * Is, Js, (z >> 1) + 1, r0, &bars[s]);
+    };
+    // interpolation geometry: as in k_fine3d_tma_pro (the centre cell of this thread, and one cell of the halo ring for the
+    // first 84*KB threads)
+    auto geom = [&](int fi, int fj, int q, int& coff, int& par) {
+        coff = 0;
+        par = 0;
+        if ((unsigned)fi < (unsigned)n0 && (unsigned)fj < (unsigned)n1) {
+            coff = q * Cfg::CT + ((fj >> 1) - Js) * Cfg::CTX + ((fi >> 1) - Is);
+            par = 4 | (fi & 1) | ((fj & 1) << 1);
+        }
+    };
+    auto interp = [&](const cx<T>* c0, int coff, int par, int ok) -> cx<T> {
+        const int oi = par & 1, oj = (par >> 1) & 1;
+        const cx<T>* p0 = c0 + coff;
+        cx<T> acc = p0[0];
+        if (oi) acc = acc + p0[1];
+        if (oj) {
+            acc = acc + p0[Cfg::CTX];
+            if (oi) acc = acc + p0[Cfg::CTX + 1];
+        }
+        if (ok) {
+            const cx<T>* p1 = p0 + Cfg::XC_PLANE / Cfg::ES;
+            acc = acc + p1[0];
+            if (oi) acc = acc + p1[1];
+            if (oj) {
+                acc = acc + p1[Cfg::CTX];
+                if (oi) acc = acc + p1[Cfg::CTX + 1];
+            }
+        }
+        return (T(1) / T(1 << (oi + oj + ok))) * acc;
+    };
+    const int cidx = (ty + 1) * PX + (tx + Cfg::HX);
+    const int bidx = ty * TX + tx;
+    int ccoff[KB], cpar;  // centre
+    {
+        int par0 = 0;
+#pragma unroll
+        for (int q = 0; q < KB; ++q) geom(i, j, q, ccoff[q], par0);
+        cpar = par0;
+    }
+    int hoff = -1, hdoff = 0, hcoff = 0, hpar = 0;  // halo-ring cell of this thread (if any)
+    if (threadIdx.x < 84 * KB) {
+        const int q = threadIdx.x / 84, t = threadIdx.x - q * 84;
+        constexpr int RW = TX + 2;  // width of the one-node ring rows
+        int row, col;              // col counted from the node i0-1
+        if (t < RW) {
+            row = 0;
+            col = t;
+        } else if (t < 2 * RW) {
+            row = TY + 1;
+            col = t - RW;
+        } else if (t < 2 * RW + TY) {
+            row = 1 + (t - 2 * RW);
+            col = 0;
+        } else {
+            row = 1 + (t - 2 * RW - TY);
+            col = TX + 1;
+        }
+        geom(i0 - 1 + col, j0 - 1 + row, q, hcoff, hpar);
+        if (hpar & 4) {
+            hdoff = row * PX + (col + Cfg::HX - 1);
+            hoff = q * Cfg::XT + hdoff;
+        }
+    }
+    // plane z of stage st: the b tile becomes x' = dinv .* b + P xc; xv / bv / dv = x', b, dinv of this thread's column
+    auto correct_plane = [&](unsigned char* st, int z, cx<T>* xv, cx<T>* bv, cx<T>& dv) {
+        cx<T>* xs = reinterpret_cast<cx<T>*>(st + Cfg::OFF_B);
+        const cx<T>* sd = reinterpret_cast<const cx<T>*>(st + Cfg::OFF_D);
+        const cx<T>* c0 = reinterpret_cast<const cx<T>*>(st + Cfg::OFF_XC);
+        const int ok = z & 1;
+        dv = sd[cidx];
+#pragma unroll
+        for (int q = 0; q < KB; ++q) {
+            const cx<T> bq = xs[q * Cfg::XT + cidx];
+            cx<T> v = dv * bq;
+            if (cpar & 4) v = v + interp(c0, ccoff[q], cpar, ok);
+            xs[q * Cfg::XT + cidx] = v;
+            xv[q] = v;
+            bv[q] = bq;
+        }
+        if (hoff >= 0) xs[hoff] = sd[hdoff] * xs[hoff] + interp(c0, hcoff, hpar, ok);
+        fence_proxy_async();  // these generic stores precede the TMA refill of this stage (after a CTA barrier)
+    };
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < NS; ++s) mbar_init(&bars[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        for (int s = 0; s < NS && z0 + s <= zl; ++s) issue(s, z0 + s);
+    }
+    __syncthreads();
+    const int ic = active ? i : 0, jc = active ? j : 0;
+    const T wxm = fine_w(op, 0, 0, ic, n0), wxp = fine_w(op, 0, 1, ic, n0);
+    const T wym = fine_w(op, 1, 0, jc, n1), wyp = fine_w(op, 1, 1, jc, n1);
+    const int64_t pxy = ic + sy * jc;
+    cx<T> xm[KB], xc[KB], xp[KB], bc[KB], bp[KB];
+    cx<T> dc, dp = mk<T>(T(0), T(0));
+    mbar_wait(&bars[0], 0);
+    correct_plane(smem_raw, z0, xc, bc, dc);
+    __syncthreads();  // once per chunk: plane z0 is used in the first iteration already
+#pragma unroll
+    for (int q = 0; q < KB; ++q) {
+        xm[q] = mk<T>(T(0), T(0));
+        bp[q] = mk<T>(T(0), T(0));
+        if (z0 > 0 && active) {
+            const int r = min(r0 + q, nrhs - 1);
+            const int64_t pm = pxy + (int64_t)(z0 - 1) * sz;
+            xm[q] = op.dinv[pm] * b[(int64_t)r * ld + pm] + prolong_point<T>(xcg + (int64_t)r * ldc, ic, jc, z0 - 1, csy, nc1);
+        }
+    }
+#pragma unroll 1
+    for (int z = z0; z < z1; ++z) {
+        const int s = (z - z0) % NS;
+        const unsigned char* st = smem_raw + (size_t)s * Cfg::STAGE_BYTES;
+        const bool zlast = (z == n2 - 1);
+        if (!zlast) {
+            const int s1 = (z + 1 - z0) % NS;
+            mbar_wait(&bars[s1], (uint32_t)(((z + 1 - z0) / NS) & 1));
+            correct_plane(smem_raw + (size_t)s1 * Cfg::STAGE_BYTES, z + 1, xp, bp, dp);
+        } else {
+#pragma unroll
+            for (int q = 0; q < KB; ++q) xp[q] = mk<T>(T(0), T(0));
+        }
+        if (active) {
+            const cx<T>* sx = reinterpret_cast<const cx<T>*>(st + Cfg::OFF_B);
+            const cx<T> c = reinterpret_cast<const cx<T>*>(st + Cfg::OFF_C)[bidx];
+            const T wzm = fine_wz(op, 0, z), wzp = fine_wz(op, 1, z);
+            const int64_t p = pxy + (int64_t)z * sz;
+#pragma unroll
+            for (int q = 0; q < KB; ++q) {
+                const cx<T>* xt = sx + q * Cfg::XT + cidx;
+                cx<T> a = c * xc[q];
+                rfma(a, -wxm, xt[-1]);
+                rfma(a, -wxp, xt[1]);
+                rfma(a, -wym, xt[-PX]);
+                rfma(a, -wyp, xt[PX]);
+                rfma(a, -wzm, xm[q]);
+                rfma(a, -wzp, xp[q]);
+                if (r0 + q < nrhs) {
+                    const int64_t o = (int64_t)(r0 + q) * ld + p;
+                    out[o] = xc[q] + dc * (bc[q] - a);
+                }
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < KB; ++q) {
+            xm[q] = xc[q];
+            xc[q] = xp[q];
+            bc[q] = bp[q];
+        }
+        dc = dp;
+        __syncthreads();
+        if (threadIdx.x == 0 && z + NS <= zl) issue(s, z + NS);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Fused coarse-grid correction + TWO post-smoothing sweeps on the fine level (3-D, TMA form):
 //   x' = x + P xc ;  x1 = x' + dinv .* (b - A x') ;  out = x1 + dinv .* (b - A x1)
 // Neither x' nor x1 touches HBM: per node and right-hand side the pass reads x, b (and xc/8) and writes x2 --
@@ -1127,7 +1342,7 @@ __global__ void __launch_bounds__(256) k_fine3d_tma_first(FineOp<T> op, const __
                     const int64_t o = (int64_t)(r0 + q) * ld + p;
                     const cx<T> res = bt[0] - a;
                     if (SECOND == 0) {
-                        out[o] = tc[q];
+                        if (out != nullptr) out[o] = tc[q];  // nullptr: x1 is recomputed by k_fine3d_tma_prob
                         out2[o] = res;
                     } else {
                         out[o] = tc[q] + dC * res;

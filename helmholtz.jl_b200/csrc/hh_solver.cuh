@@ -610,8 +610,12 @@ class Solver : public SolverBase {
         skip_last_update = !(sl && sl[0] == '0');
         const char* sf = getenv("HH_SMALL_FUSED");
         small_fused = !(sf && sf[0] == '0');
+        // cycles with one pre-smoothing sweep: x1 = dinv .* b is recomputed by the correction pass instead of being stored
+        // (k_fine3d_tma_prob; default on, HH_FUSE_RECOMPUTE=0 is the A/B)
+        const char* fr = getenv("HH_FUSE_RECOMPUTE");
+        fuse_recompute = !(fr && fr[0] == '0');
         const char* sq = getenv("HH_SCALAR_FAST");  // one warp per reduced quantity + lane-parallel Givens (default on)
-        scalar_fast = sq && sq[0] == '1';  // TODO(verify on B200): default on once the GPU suite has run with it
+        scalar_fast = !(sq && sq[0] == '0');
         use_pitch = sizeof(T) == 4 && pb.dim == 3 && fine_kernel == FK_TMA;
     }
     ~Solver() override {
@@ -1083,7 +1087,7 @@ class Solver : public SolverBase {
     }
     void fine_first_range(int second, const FineOp<T>& op, const C* b, C* out, C* out2, int64_t ld, int nrhs) {
         const double N = (double)pb.n[0] * pb.n[1] * (op.ze - op.zb);
-        const double bytes = (second == 0 ? 3.0 : 2.0) * S * N * nrhs + 2.0 * S * N;
+        const double bytes = ((second == 0 && out != nullptr) ? 3.0 : 2.0) * S * N * nrhs + 2.0 * S * N;
         launch(second == 0 ? T_FINE_FIRST_RESID : T_FINE_FIRST_JACOBI, bytes, [&] {
             if (second == 0) {
                 if (nrhs >= 2) tma3d_first_launch<0, 2>(op, b, out, out2, ld, nrhs);
@@ -1134,6 +1138,44 @@ class Solver : public SolverBase {
         launch(T_FINE_PROLONG_JACOBI, (3.0 * N + 0.125 * N) * S * nrhs + 2.0 * S * N, [&] {
             if (nrhs >= 2) tma3d_pro_launch<2>(op, x, b, Cc, xc, out, ld, nrhs);
             else tma3d_pro_launch<1>(op, x, b, Cc, xc, out, ld, nrhs);
+        });
+    }
+    // the same with x = dinv .* b recomputed on the fly (cycle start with one pre-smoothing sweep); see k_fine3d_tma_prob
+    template <int KB>
+    void tma3d_prob_launch(const FineOp<T>& op, const C* b, const Level& Cc, const C* xc, C* out, int64_t ld, int nrhs) {
+        typedef FineProBCfg<T, KB> Cfg;
+        constexpr int NS = 4;
+        constexpr size_t smem = (size_t)NS * Cfg::STAGE_BYTES + NS * sizeof(uint64_t);
+        static bool attr_set = false;
+        if (!attr_set) {
+            HH_CUDA(cudaFuncSetAttribute(k_fine3d_tma_prob<T, KB, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            attr_set = true;
+        }
+        const int groups = (nrhs + KB - 1) / KB;
+        const int tx = (pb.n[0] + Cfg::TX - 1) / Cfg::TX, ty = (pb.n[1] + Cfg::TY - 1) / Cfg::TY;
+        int zchunk, nzc;
+        zchunks(op.ze - op.zb, tx * ty, groups, 64, zchunk, nzc);
+        dim3 g(tx * groups, ty, nzc);
+        TmaDesc mb = make_tmap_n(b, op.sy, ld, Cfg::PX, Cfg::TY + 2, KB, nrhs);
+        TmaDesc md = make_tmap_n(op.dinv, op.sy, ld, Cfg::PX, Cfg::TY + 2, 1, 0);
+        TmaDesc mc = make_tmap_n(op.cdiag, op.sy, ld, Cfg::TX, Cfg::TY, 1, 0);
+        TmaDesc mxc = make_tmap_g(xc, Cc.n, Cc.p0, Cc.N, Cfg::CTX, Cfg::CTY, KB, nrhs);
+        k_fine3d_tma_prob<T, KB, NS><<<g, 256, smem, stream>>>(op, mb, md, mc, mxc, b, xc, out, ld, Cc.N, Cc.p0, Cc.n[1], nrhs, zchunk, groups);
+    }
+    bool can_fuse_prolong_b(const FineOp<T>& op, const C* b, const Level& Cc, const C* xc, int64_t ld) const {
+        return fuse_recompute && can_fuse_first(op, b, ld) && tma_ok_level(Cc) && ((uintptr_t)xc % 16 == 0);
+    }
+    // b's halo planes were exchanged for the cycle start (fine_first) and b has not changed since: only xc travels
+    void fine_prolong_jacobi_b(const FineOp<T>& op0, const C* b, const Level& Cc, const C* xc, C* out, int64_t ld, int nrhs) {
+        with_halos({{1, xc, 0}}, nrhs, op0.zb, op0.ze, [&](int z0, int z1) {
+            FineOp<T> o = op0;
+            o.zb = z0;
+            o.ze = z1;
+            const double N = (double)pb.n[0] * pb.n[1] * (o.ze - o.zb);
+            launch(T_FINE_PROLONG_JACOBI, (2.0 * N + 0.125 * N) * S * nrhs + 2.0 * S * N, [&] {
+                if (nrhs >= 2) tma3d_prob_launch<2>(o, b, Cc, xc, out, ld, nrhs);
+                else tma3d_prob_launch<1>(o, b, Cc, xc, out, ld, nrhs);
+            });
         });
     }
     // fused coarse-grid correction + two post-smoothing sweeps; see k_fine3d_tma_pro2 (whole grids only: two-node halo)
@@ -1589,7 +1631,7 @@ class Solver : public SolverBase {
         hoH.n2g = L0.n2g;
         const double sw2 = o.shift[0] * pb.w_re * pb.w_re;
         const char* hb = getenv("HH_HO_BUILD");
-        if (hb && !strcmp(hb, "device")) {  // TODO(verify on B200): default once test_gpu_ho*.py have run with it
+        if (!(hb && !strcmp(hb, "host"))) {
             HH_REQUIRE(pb.w_re != 0.0, HH_ERR_ARG, "high-order operator: Re(omega) must be non-zero");
             const HoGeom g = ho_geom(pb.dim, nn, pb.h, pb.w_re, pb.w_im, pb.neumann_top, pb.sommerfeld, ho_beta);
             DevBuf<double> dm, dg;
@@ -2184,12 +2226,16 @@ class Solver : public SolverBase {
         // result to another, and the result must land in the caller's x: the pre-smoothed iterate then lives in the
         // level's scratch vector and the residual (dead after the restriction) borrows x.
         bool post2 = false;
+        // One pre-smoothing sweep from zero: x1 = dinv .* b is cheap to recompute, so the cycle start writes only the
+        // residual and the correction + first post-sweep pass forms x1 from b again (k_fine3d_tma_prob).
+        bool recompute = false;
         if (l == 0 && x_is_zero && opt.relax_type == HH_RELAX_JAC && npre >= 1 && can_fuse_first(mg_fine, b, F.N)) {
             post2 = npost >= 2 && (npost % 2) == 0 && can_fuse_post2(mg_fine, tt, b, Cc, Cc.px, F.N) && ((uintptr_t)xx % 16 == 0);
+            recompute = !post2 && npre == 1 && npost >= 1 && can_fuse_prolong_b(mg_fine, b, Cc, Cc.px, F.N);
             C* itb = post2 ? tt : xx;  // the iterate after pre-smoothing
             C* rsb = post2 ? xx : tt;  // the residual
             if (npre == 1) {
-                fine_first(0, mg_fine, b, itb, rsb, F.N, nrhs);  // x1 and r = b - A x1 in one pass
+                fine_first(0, mg_fine, b, recompute ? nullptr : itb, rsb, F.N, nrhs);  // [x1 and] r = b - A x1 in one pass
             } else {
                 // first two sweeps in one pass, written so that the remaining npre-2 ping-pong sweeps end in itb
                 C* cur = ((npre - 2) % 2 == 0) ? itb : rsb;
@@ -2227,6 +2273,18 @@ class Solver : public SolverBase {
                 std::swap(cur, oth);
             }
             return;  // npost is even: the last sweep wrote the caller's x
+        }
+        if (recompute) {
+            // x' = dinv .* b + P xc and the first post-smoothing sweep in one pass; the residual buffer is free now, and
+            // the first target is chosen so that the last sweep writes the caller's x
+            C* cur = ((npost - 1) % 2 == 0) ? xx : tt;
+            C* oth = (cur == xx) ? tt : xx;
+            fine_prolong_jacobi_b(mg_fine, b, Cc, Cc.px, cur, F.N, nrhs);
+            for (int sw = 1; sw < npost; ++sw) {
+                level_apply(l, MODE_JACOBI, cur, b, oth, nrhs);
+                std::swap(cur, oth);
+            }
+            return;
         }
         if (l == 0 && opt.relax_type == HH_RELAX_JAC && npost >= 1 && can_fuse_prolong(mg_fine, xx, b, Cc, Cc.px, F.N)) {
             // x' = x + P xc and the first post-smoothing sweep in one pass (x' never touches HBM)
@@ -2612,6 +2670,7 @@ class Solver : public SolverBase {
     bool scaled_gmres = true;
     bool tma_restrict = true;            // HH_TMA_RESTRICT=0: the one-thread-per-coarse-node restriction (A/B baseline)
     bool skip_last_update = true;        // HH_SKIP_LAST_UPDATE=0: orthogonalise the last column of a cycle like the others
+    bool fuse_recompute = true;          // HH_FUSE_RECOMPUTE=0: npre == 1 cycles recompute x1 = dinv .* b instead of storing it
     bool scalar_fast = true;             // HH_SCALAR_FAST=0: the one-warp, one-thread forms of the GMRES scalar kernels
     bool small_fused = true;             // HH_SMALL_FUSED=0: two scalar kernels / two reductions per step of a level's GMRES
     bool fuse_post2 = false;             // HH_FUSE_POST2=1: correction + BOTH post-sweeps in one pass (k_fine3d_tma_pro2; slower, see ctor)

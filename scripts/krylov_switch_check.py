@@ -44,9 +44,15 @@ def main():
         for flag in ("1", "0"):
             os.environ["HH_SKIP_LAST_UPDATE"] = flag
             os.environ["HH_SMALL_FUSED"] = flag
+            if os.environ.get("HH_CHECK_ALL"):  # also the other default-on paths of this round against their plain forms
+                os.environ["HH_SCALAR_FAST"] = flag
+                os.environ["HH_FUSE_RECOMPUTE"] = flag
             A = solver(prec, tols[0], **kw)
             pkg.api._ensure_hierarchy(A, 0)
             del os.environ["HH_SKIP_LAST_UPDATE"], os.environ["HH_SMALL_FUSED"]
+            if os.environ.get("HH_CHECK_ALL"):
+                os.environ.pop("HH_SCALAR_FAST", None)
+                os.environ.pop("HH_FUSE_RECOMPUTE", None)
             out = []
             for tol in tols:
                 A.MG.relativeTol = tol

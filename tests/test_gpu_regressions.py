@@ -10,6 +10,29 @@ from conftest import rel_err
 pytestmark = pytest.mark.gpu
 
 
+class _env:
+    """Set environment switches for the creation of a handle (the library reads them in the solver's constructor) and put
+    the previous values back afterwards."""
+
+    def __init__(self, **kw):
+        self.kw = kw
+
+    def __enter__(self):
+        import os
+
+        self.old = {k: os.environ.get(k) for k in self.kw}
+        os.environ.update(self.kw)
+
+    def __exit__(self, *exc):
+        import os
+
+        for k, v in self.old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+
+
 def _problem(pkg, n=17, seed=9):
     cfg = pkg.workloads.config4(n=n, sigma=2.0, seed=seed, pad=3)
     mesh = pkg.getRegularMesh(cfg["domain"], cfg["n_cells"])
@@ -219,17 +242,12 @@ def test_skipped_last_update_and_fused_level_gmres_match_plain_path(gpu_pkg, pre
     B[:, 1] = 0  # a zero right-hand side rides along (frozen column)
     out = {}
     for flag in ("1", "0"):
-        os.environ["HH_SKIP_LAST_UPDATE"] = flag
-        os.environ["HH_SMALL_FUSED"] = flag
-        try:
+        with _env(HH_SKIP_LAST_UPDATE=flag, HH_SMALL_FUSED=flag):
             MG = pkg.getMGparam(prec, pkg.Int64, levels, 1, 40, 1e-6 if prec == np.complex128 else 1e-4, relax, 0.8, pre, post, cyc,
                                 coarse, coarseIters=citers)
             hp = pkg.HelmholtzParam(mesh, gamma, m.ravel(order="F"), w, True, True)
             A = pkg.getShiftedLaplacianMultigridSolver(hp, MG, 0.2, "GMRES", 5)
             hd = pkg.api._ensure_hierarchy(A, 0)
-        finally:
-            del os.environ["HH_SKIP_LAST_UPDATE"]
-            del os.environ["HH_SMALL_FUSED"]
         Z = np.empty_like(B, order="F")
         pkg._lib.check(hd.lib.hh_cycle(hd.h, B.ctypes.data, Z.ctypes.data, nrhs), hd.h)
         X, A = pkg.solveLinearSystem(None, B, A)
@@ -243,3 +261,47 @@ def test_skipped_last_update_and_fused_level_gmres_match_plain_path(gpu_pkg, pre
         assert np.abs(out["1"][2].astype(int) - out["0"][2].astype(int)).max() <= 1
     # both solves stop at the same residual tolerance: they agree to a small multiple of it
     assert rel_err(out["1"][1], out["0"][1]) < (2e-5 if prec == np.complex128 else 5e-3)
+
+
+@pytest.mark.parametrize("prec,tol", [(np.complex128, 1e-13), (np.complex64, 2e-5)])
+@pytest.mark.parametrize("nodes,post,cyc,nrhs", [((33, 33, 33), 2, "W", 2), ((65, 49, 37), 1, "V", 3), ((41, 25, 33), 3, "V", 1),
+                                                  ((97, 17, 21), 2, "W", 5)])
+def test_recomputed_first_sweep_equals_stored_first_sweep(gpu_pkg, prec, tol, nodes, post, cyc, nrhs):
+    """k_fine3d_tma_prob (cycles with ONE pre-smoothing sweep: the cycle start writes only the residual, and the
+    correction + first post-sweep pass recomputes x1 = dinv .* b from b staged with halo) against the path that stores x1
+    and reads it back (HH_FUSE_RECOMPUTE=0), on grids with partial tiles in every direction; also in 3 slabs."""
+    import os
+
+    pkg = gpu_pkg
+    rng = np.random.default_rng(29)
+    n = np.array(nodes)
+    dom = sum([[0.0, 0.1 * (v - 1)] for v in n], [])
+    mesh = pkg.getRegularMesh(dom, list(n - 1))
+    m = 1.0 / (1.5 + 2.0 * rng.random(tuple(n))) ** 2
+    w = 0.8 * pkg.getMaximalFrequency(m, mesh)
+    gamma = 0.02 * w * (1.0 + rng.random(tuple(n))) + pkg.getABL(n, True, [3, 3, 4], w)
+    N = int(np.prod(n))
+    B = np.asfortranarray((rng.standard_normal((N, nrhs)) + 1j * rng.standard_normal((N, nrhs))).astype(prec))
+    out = {}
+    for flag, slabs in (("1", 0), ("0", 0), ("1", 3)):
+        with _env(HH_FUSE_RECOMPUTE=flag):
+            MG = pkg.getMGparam(prec, pkg.Int64, 3, 1, 30, 1e-6 if prec == np.complex128 else 1e-4, "Jac", 0.8, 1, post, cyc, "GMRES",
+                                coarseIters=6)
+            hp = pkg.HelmholtzParam(mesh, gamma, m.ravel(order="F"), w, True, True)
+            A = pkg.getShiftedLaplacianMultigridSolver(hp, MG, 0.2, "GMRES", 5)
+            if slabs:
+                A.slabs = {"mode": "local", "devices": [0] * slabs}
+            hd = pkg.api._ensure_hierarchy(A, 0)
+        Z = None
+        if not slabs:
+            Z = np.empty_like(B, order="F")
+            pkg._lib.check(hd.lib.hh_cycle(hd.h, B.ctypes.data, Z.ctypes.data, nrhs), hd.h)
+        X, A = pkg.solveLinearSystem(None, B, A)
+        out[(flag, slabs)] = (Z, np.reshape(X, (N, nrhs)).copy(), A.iterations.copy())
+        pkg.clear(MG)
+    assert rel_err(out[("1", 0)][0], out[("0", 0)][0]) < tol
+    assert np.array_equal(out[("1", 0)][2], out[("0", 0)][2])
+    assert rel_err(out[("1", 0)][1], out[("0", 0)][1]) < 100 * tol
+    if prec == np.complex128:
+        assert np.array_equal(out[("1", 3)][2], out[("0", 0)][2])
+    assert rel_err(out[("1", 3)][1], out[("0", 0)][1]) < (1e-9 if prec == np.complex128 else 5e-3)
