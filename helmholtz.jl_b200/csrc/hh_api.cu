@@ -973,10 +973,21 @@ static int solve_host(hh_handle_t h, const void* B, const int64_t* idx, const do
                 HH_CUDA(cudaEventRecord(hs.h2d[slot], hs.cs));
             }
         };
+        // HH_HOST_TRACE=1: wall-clock marks of the host pipeline on stderr (where an e2e call spends its time)
+        const char* tr = getenv("HH_HOST_TRACE");
+        const bool trace = tr && tr[0] == '1';
+        const auto tr0 = std::chrono::steady_clock::now();
+        auto mark = [&](const char* what, int64_t a, int64_t b) {
+            if (!trace) return;
+            const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tr0).count();
+            fprintf(stderr, "[hh_solve dev %d] %9.2f ms  %s %lld %lld\n", s->device, ms, what, (long long)a, (long long)b);
+        };
+        mark("begin: columns, kmax", ncols, kmax);
         stage_in(0);
         for (int64_t bidx = 0; bidx < nb; ++bidx) {
             const int slot = (int)(bidx & 1);
             const int64_t c = start[bidx], k = sizes[bidx];
+            mark("sub-batch enqueue: index, size", bidx, k);
             // prefetch the next sub-batch: its B slot was last read by solve(bidx-1), which has returned
             if (bidx + 1 < nb) stage_in(bidx + 1);
             if (!idx) HH_CUDA(cudaStreamWaitEvent(s->stream, hs.h2d[slot], 0));
@@ -984,6 +995,7 @@ static int solve_host(hh_handle_t h, const void* B, const int64_t* idx, const do
             int r = s->solve_device(hs.db[slot].p, hs.dx[slot].p, k, *opts, iters_out ? iters_out + c : nullptr,
                                     relres_out ? relres_out + c : nullptr);
             rcs[i] = std::max(rcs[i], r);
+            mark("sub-batch solved (host returned): index, rc", bidx, r);
             HH_CUDA(cudaEventRecord(hs.solved[slot], s->stream));
             HH_CUDA(cudaStreamWaitEvent(hs.cs, hs.solved[slot], 0));
             HH_CUDA(cudaMemcpyAsync((char*)X + (size_t)c * N * es, hs.dx[slot].p, (size_t)N * k * es, cudaMemcpyDeviceToHost, hs.cs));
@@ -991,6 +1003,7 @@ static int solve_host(hh_handle_t h, const void* B, const int64_t* idx, const do
         }
         HH_CUDA(cudaStreamSynchronize(hs.cs));
         HH_CUDA(cudaStreamSynchronize(s->stream));
+        mark("end: copies drained", nb, 0);
     });
     int rc = HH_OK;
     for (int r : rcs) rc = std::max(rc, r);

@@ -22,7 +22,7 @@ def classify(name):
         return "fine_first_resid" if m.group(1) == "0" else "fine_first_jacobi"
     if "k_fine3d_tma_pro2<" in name:
         return "fine_prolong_jacobi2"
-    if "k_fine3d_tma_pro<" in name:
+    if "k_fine3d_tma_pro<" in name or "k_fine3d_tma_prob<" in name:
         return "fine_prolong_jacobi"
     m = re.search(r"k_fine3d_(?:tma|zmarch)<\w+, (\d)", name)
     if m:
@@ -45,7 +45,7 @@ def classify(name):
         return "prolong"
     if "k_multidot" in name:
         return "krylov_dot"
-    if "k_multiaxpy" in name or "k_bicg_p" in name:
+    if "k_multiaxpy" in name or "k_bicg_p" in name or "k_combine" in name:
         return "krylov_axpy"
     if "k_diag_scale" in name:
         return "coarse_jacobi0"
@@ -57,7 +57,7 @@ def classify(name):
         return "scalar"
     if re.search(r"k_repitch|k_convert|k_point_sources", name):
         return "copy"
-    if re.search(r"k_galerkin|k_coarse_dinv|k_fine_precompute|k_fine_dinv|k_scale_columns|k_band|k_inverse|k_gamma_abl|k_max_partial|k_fine_diag", name):
+    if re.search(r"k_galerkin|k_coarse_dinv|k_fine_precompute|k_fine_dinv|k_scale_columns|k_band|k_inverse|k_gamma_abl|k_max_partial|k_fine_diag|k_ho_stencil", name):
         return "setup"
     return "other"
 

@@ -10,7 +10,7 @@ WANT = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "smsp__pcsamp_warps_issue_stalled_barrier", "smsp__pcsamp_sample_count"]
 # kernel function (+ mode template argument) -> bench.py kernel class
 CLASS = [(r"k_fine3d_tma_first<double, 0", "fine_first_resid"), (r"k_fine3d_tma_first<double, 1", "fine_first_jacobi"),
-         (r"k_fine3d_tma_pro<double", "fine_prolong_jacobi"), (r"k_fine3d_tma<double, 0", "fine_apply"),
+         (r"k_fine3d_tma_pro<double", "fine_prolong_jacobi"), (r"k_fine3d_tma_prob<double", "fine_prolong_jacobi"), (r"k_fine3d_tma<double, 0", "fine_apply"),
          (r"k_fine3d_tma<double, 1", "fine_resid"), (r"k_fine3d_tma<double, 2", "fine_jacobi"),
          (r"k_coarse3d_tma<double, 0", "coarse_apply"), (r"k_coarse3d_tma<double, 1", "coarse_resid"),
          (r"k_coarse3d_tma<double, 2", "coarse_jacobi"), (r"k_restrict", "restrict"), (r"k_prolong_add", "prolong")]
