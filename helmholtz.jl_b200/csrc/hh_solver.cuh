@@ -614,11 +614,23 @@ class Solver : public SolverBase {
         // (k_fine3d_tma_prob; default on, HH_FUSE_RECOMPUTE=0 is the A/B)
         const char* fr = getenv("HH_FUSE_RECOMPUTE");
         fuse_recompute = !(fr && fr[0] == '0');
+        // k_fine3d_tma_prob keeps the in-plane interpolation of a coarse plane in registers (HH_PRO_CACHE=0: recompute it
+        // for every fine plane); levels >= 1 swap their iterate / scratch buffers instead of a copy (HH_LEVEL_SWAP=0)
+        const char* pc = getenv("HH_PRO_CACHE");
+        pro_cache = !(pc && pc[0] == '0');
+        const char* ls = getenv("HH_LEVEL_SWAP");
+        level_swap = !(ls && ls[0] == '0');
+        const char* ms = getenv("HH_MAPPED_STATE");
+        mapped_state = !(ms && ms[0] == '0');
         const char* sq = getenv("HH_SCALAR_FAST");  // one warp per reduced quantity + lane-parallel Givens (default on)
         scalar_fast = !(sq && sq[0] == '0');
         use_pitch = sizeof(T) == 4 && pb.dim == 3 && fine_kernel == FK_TMA;
     }
     ~Solver() override {
+        if (h_state) {
+            cudaSetDevice(device);
+            cudaFreeHost(h_state);
+        }
         if (comm_stream) {
             cudaSetDevice(device);
             cudaStreamDestroy(comm_stream);
@@ -1148,7 +1160,8 @@ class Solver : public SolverBase {
         constexpr size_t smem = (size_t)NS * Cfg::STAGE_BYTES + NS * sizeof(uint64_t);
         static bool attr_set = false;
         if (!attr_set) {
-            HH_CUDA(cudaFuncSetAttribute(k_fine3d_tma_prob<T, KB, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            HH_CUDA(cudaFuncSetAttribute(k_fine3d_tma_prob<T, KB, NS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            HH_CUDA(cudaFuncSetAttribute(k_fine3d_tma_prob<T, KB, NS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             attr_set = true;
         }
         const int groups = (nrhs + KB - 1) / KB;
@@ -1160,7 +1173,10 @@ class Solver : public SolverBase {
         TmaDesc md = make_tmap_n(op.dinv, op.sy, ld, Cfg::PX, Cfg::TY + 2, 1, 0);
         TmaDesc mc = make_tmap_n(op.cdiag, op.sy, ld, Cfg::TX, Cfg::TY, 1, 0);
         TmaDesc mxc = make_tmap_g(xc, Cc.n, Cc.p0, Cc.N, Cfg::CTX, Cfg::CTY, KB, nrhs);
-        k_fine3d_tma_prob<T, KB, NS><<<g, 256, smem, stream>>>(op, mb, md, mc, mxc, b, xc, out, ld, Cc.N, Cc.p0, Cc.n[1], nrhs, zchunk, groups);
+        if (pro_cache)
+            k_fine3d_tma_prob<T, KB, NS, true><<<g, 256, smem, stream>>>(op, mb, md, mc, mxc, b, xc, out, ld, Cc.N, Cc.p0, Cc.n[1], nrhs, zchunk, groups);
+        else
+            k_fine3d_tma_prob<T, KB, NS, false><<<g, 256, smem, stream>>>(op, mb, md, mc, mxc, b, xc, out, ld, Cc.N, Cc.p0, Cc.n[1], nrhs, zchunk, groups);
     }
     bool can_fuse_prolong_b(const FineOp<T>& op, const C* b, const Level& Cc, const C* xc, int64_t ld) const {
         return fuse_recompute && can_fuse_first(op, b, ld) && tma_ok_level(Cc) && ((uintptr_t)xc % 16 == 0);
@@ -2229,6 +2245,9 @@ class Solver : public SolverBase {
         // One pre-smoothing sweep from zero: x1 = dinv .* b is cheap to recompute, so the cycle start writes only the
         // residual and the correction + first post-sweep pass forms x1 from b again (k_fine3d_tma_prob).
         bool recompute = false;
+        // Levels >= 1 own both their iterate and their scratch vector: after an odd number of ping-pong sweeps the two
+        // swap roles (the callers read Level::px after the call) instead of a copy back.
+        const bool swap_ok = level_swap && l >= 1 && x == F.px;
         if (l == 0 && x_is_zero && opt.relax_type == HH_RELAX_JAC && npre >= 1 && can_fuse_first(mg_fine, b, F.N)) {
             post2 = npost >= 2 && (npost % 2) == 0 && can_fuse_post2(mg_fine, tt, b, Cc, Cc.px, F.N) && ((uintptr_t)xx % 16 == 0);
             recompute = !post2 && npre == 1 && npost >= 1 && can_fuse_prolong_b(mg_fine, b, Cc, Cc.px, F.N);
@@ -2249,7 +2268,7 @@ class Solver : public SolverBase {
             }
             if (post2) std::swap(xx, tt);  // from here on: xx = iterate (the scratch vector), tt = residual (the caller's x)
         } else {
-            smooth(l, npre, b, xx, tt, x_is_zero, false, nrhs);
+            smooth(l, npre, b, xx, tt, x_is_zero, swap_ok, nrhs);
             level_apply(l, MODE_RESID, xx, b, tt, nrhs);
         }
         restrict_to(F, Cc, tt, Cc.pb, nrhs);
@@ -2298,7 +2317,11 @@ class Solver : public SolverBase {
             if (cur != xx) copy_vec(cur, xx, F.N, nrhs);
         } else {
             prolong_add(F, Cc, xx, Cc.px, nrhs);
-            smooth(l, npost, b, xx, tt, false, false, nrhs);
+            smooth(l, npost, b, xx, tt, false, swap_ok, nrhs);
+        }
+        if (swap_ok) {  // the iterate may have ended in the scratch vector: the two buffers swap roles
+            F.px = xx;
+            F.pt = tt;
         }
     }
 
@@ -2496,10 +2519,35 @@ class Solver : public SolverBase {
     }
 
     // returns true when every RHS is done; throws on NaN
-    bool fetch_done(const int* d_done, int nrhs) {
-        h_done.resize(nrhs);
-        HH_CUDA(cudaMemcpyAsync(h_done.data(), d_done, nrhs * sizeof(int), cudaMemcpyDeviceToHost, stream));
+    // mapped pinned block [done | nprec | err] the scalar state is published into (k_publish_state)
+    void ensure_state_block(int nrhs) {
+        if (nrhs <= state_cap) return;
+        if (h_state) HH_CUDA(cudaFreeHost(h_state));
+        h_state = nullptr;
+        state_cap = std::max(nrhs, 64);
+        HH_CUDA(cudaHostAlloc((void**)&h_state, (size_t)state_cap * (2 * sizeof(int) + sizeof(double)), cudaHostAllocMapped));
+        HH_CUDA(cudaHostGetDevicePointer((void**)&d_state, h_state, 0));
+    }
+    double* state_err(char* base) const { return reinterpret_cast<double*>(base); }                      // doubles first (alignment)
+    int* state_done(char* base) const { return reinterpret_cast<int*>(base + (size_t)state_cap * sizeof(double)); }
+    int* state_nprec(char* base) const { return state_done(base) + state_cap; }
+    void publish_state(const int* d_done, const int* d_nprec, const double* d_err, int nrhs) {
+        ensure_state_block(nrhs);
+        launch(T_SCALAR, 0, [&] {
+            k_publish_state<<<(nrhs + 127) / 128, 128, 0, stream>>>(d_done, d_nprec, d_err, state_done(d_state), state_nprec(d_state),
+                                                                   state_err(d_state), nrhs);
+        });
         HH_CUDA(cudaStreamSynchronize(stream));
+    }
+    bool fetch_done(const int* d_done, int nrhs) {
+        if (!mapped_state) {  // HH_MAPPED_STATE=0: the copy-engine form (A/B)
+            h_done.resize(nrhs);
+            HH_CUDA(cudaMemcpyAsync(h_done.data(), d_done, nrhs * sizeof(int), cudaMemcpyDeviceToHost, stream));
+            HH_CUDA(cudaStreamSynchronize(stream));
+        } else {
+            publish_state(d_done, nullptr, nullptr, nrhs);
+            h_done.assign(state_done(h_state), state_done(h_state) + nrhs);
+        }
         bool all = true;
         for (int r = 0; r < nrhs; ++r) {
             if (h_done[r] == 2) throw Error(HH_ERR_NAN, "NaN in the residual norm of right-hand side " + std::to_string(r));
@@ -2558,9 +2606,15 @@ class Solver : public SolverBase {
     int finish(const int* d_nprec, const double* d_err, int nrhs, int32_t* iters, double* relres, bool all_done) {
         std::vector<int> np(nrhs);
         std::vector<double> er(nrhs);
-        HH_CUDA(cudaMemcpyAsync(np.data(), d_nprec, nrhs * sizeof(int), cudaMemcpyDeviceToHost, stream));
-        HH_CUDA(cudaMemcpyAsync(er.data(), d_err, nrhs * sizeof(double), cudaMemcpyDeviceToHost, stream));
-        HH_CUDA(cudaStreamSynchronize(stream));
+        if (!mapped_state) {
+            HH_CUDA(cudaMemcpyAsync(np.data(), d_nprec, nrhs * sizeof(int), cudaMemcpyDeviceToHost, stream));
+            HH_CUDA(cudaMemcpyAsync(er.data(), d_err, nrhs * sizeof(double), cudaMemcpyDeviceToHost, stream));
+            HH_CUDA(cudaStreamSynchronize(stream));
+        } else {
+            publish_state(d_nprec /* any int array: the flags are not read here */, d_nprec, d_err, nrhs);
+            np.assign(state_nprec(h_state), state_nprec(h_state) + nrhs);
+            er.assign(state_err(h_state), state_err(h_state) + nrhs);
+        }
         for (int r = 0; r < nrhs; ++r) {
             if (iters) iters[r] = np[r];
             if (relres) relres[r] = er[r];
@@ -2670,6 +2724,8 @@ class Solver : public SolverBase {
     bool scaled_gmres = true;
     bool tma_restrict = true;            // HH_TMA_RESTRICT=0: the one-thread-per-coarse-node restriction (A/B baseline)
     bool skip_last_update = true;        // HH_SKIP_LAST_UPDATE=0: orthogonalise the last column of a cycle like the others
+    bool pro_cache = true;               // HH_PRO_CACHE=0: the interpolation is recomputed for every fine plane
+    bool level_swap = true;              // HH_LEVEL_SWAP=0: copy back after an odd sweep count instead of swapping x / scratch
     bool fuse_recompute = true;          // HH_FUSE_RECOMPUTE=0: npre == 1 cycles recompute x1 = dinv .* b instead of storing it
     bool scalar_fast = true;             // HH_SCALAR_FAST=0: the one-warp, one-thread forms of the GMRES scalar kernels
     bool small_fused = true;             // HH_SMALL_FUSED=0: two scalar kernels / two reductions per step of a level's GMRES
@@ -2678,6 +2734,10 @@ class Solver : public SolverBase {
     int outer_cap = 0;
     BicgMem bicg;
     std::vector<int> h_done;
+    char* h_state = nullptr;             // mapped pinned host block the per-RHS state is published into
+    char* d_state = nullptr;             // its device alias
+    int state_cap = 0;
+    bool mapped_state = true;            // HH_MAPPED_STATE=0: cudaMemcpyAsync of the flags (queues behind bulk D2H copies)
 };
 
 }  // namespace hh

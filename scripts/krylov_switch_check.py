@@ -45,14 +45,14 @@ def main():
             os.environ["HH_SKIP_LAST_UPDATE"] = flag
             os.environ["HH_SMALL_FUSED"] = flag
             if os.environ.get("HH_CHECK_ALL"):  # also the other default-on paths of this round against their plain forms
-                os.environ["HH_SCALAR_FAST"] = flag
-                os.environ["HH_FUSE_RECOMPUTE"] = flag
+                for k in ("HH_SCALAR_FAST", "HH_FUSE_RECOMPUTE", "HH_PRO_CACHE", "HH_FIRST_CONVERT", "HH_LEVEL_SWAP"):
+                    os.environ[k] = flag
             A = solver(prec, tols[0], **kw)
             pkg.api._ensure_hierarchy(A, 0)
             del os.environ["HH_SKIP_LAST_UPDATE"], os.environ["HH_SMALL_FUSED"]
             if os.environ.get("HH_CHECK_ALL"):
-                os.environ.pop("HH_SCALAR_FAST", None)
-                os.environ.pop("HH_FUSE_RECOMPUTE", None)
+                for k in ("HH_SCALAR_FAST", "HH_FUSE_RECOMPUTE", "HH_PRO_CACHE", "HH_FIRST_CONVERT", "HH_LEVEL_SWAP"):
+                    os.environ.pop(k, None)
             out = []
             for tol in tols:
                 A.MG.relativeTol = tol
