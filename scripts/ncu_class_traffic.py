@@ -53,7 +53,7 @@ def classify(name):
         return "fine_jacobi0"
     if "k_dense_apply" in name:
         return "coarsest_dense"
-    if re.search(r"k_gmres_|k_bicg_scalars|k_sum_partials", name):
+    if re.search(r"k_gmres_|k_bicg_scalars|k_sum_partials|k_publish_state", name):
         return "scalar"
     if re.search(r"k_repitch|k_convert|k_point_sources", name):
         return "copy"
