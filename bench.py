@@ -441,8 +441,24 @@ def run_b200(a):
                 ne //= 2
         except Exception:
             pass
-        Bh = torch.zeros((ne, N), dtype=tdt, pin_memory=True)
-        Xh_t = torch.empty((ne, N), dtype=tdt, pin_memory=True)
+        # every rank must end up with the same block: a failed pinned allocation on any rank halves it for all of them
+        while True:
+            try:
+                Bh = torch.zeros((ne, N), dtype=tdt, pin_memory=True)
+                Xh_t = torch.empty((ne, N), dtype=tdt, pin_memory=True)
+                ok = 1
+            except Exception:
+                Bh = Xh_t = None
+                ok = 0
+            flag = torch.tensor([ok], dtype=torch.int32, device="cuda")
+            if world > 1:
+                dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            if int(flag.item()) or ne == 1:
+                break
+            Bh = Xh_t = None
+            ne //= 2
+        if Bh is None:
+            raise SystemExit("bench.py: cannot pin host memory for one right-hand side")
         Bh_np, Xh = Bh.numpy().T, Xh_t.numpy().T  # N x nrhs column-major views of the pinned buffers
         t_e2e, t_ps = [], []
         for k in range(1 + a.e2e_steps):
