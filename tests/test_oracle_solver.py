@@ -84,3 +84,73 @@ def test_solver_goldens_regression(ho):
         assert A.iters == list(G[f"{name}_solve_iters"])
         assert rel_err(xs, G[f"{name}_solve_fgmres5"]) < 1e-10
         assert rel_err(xs, G[f"{name}_direct"]) < 1e-7  # tol 1e-8 solve vs the direct solve
+
+
+def _device_level_gmres(A, b, dinv, nsteps, skip_last=True):
+    """numpy restatement of the algebra the device runs for the fixed-length GMRES of a level
+    (hh_kernels.cuh: k_multidot / k_gmres_hcol / k_multiaxpy / k_gmres_givens / k_gmres_solve_y / k_combine):
+    classical Gram-Schmidt in one pass on a SCALED basis (stored vectors v~_i = d_i v_i, d_0 = ||b||, d_{i+1} ~ 1 from the
+    estimate beta_est), Givens rotations per column, and -- skip_last -- no update pass for the last column: its
+    h_{j+1,j} comes from the dot pass alone, ||w||^2 - sum |<v_i,w>|^2."""
+    V = [b.astype(complex)]
+    d = [np.linalg.norm(b)]
+    m = nsteps
+    H = np.zeros((m + 1, m), dtype=complex)
+    cs, sn = np.zeros(m), np.zeros(m, dtype=complex)
+    s = np.zeros(m + 1, dtype=complex)
+    s[0] = d[0]
+    for j in range(m):
+        w = A @ (dinv * V[j])
+        g = np.array([np.vdot(V[i], w) for i in range(j + 1)])
+        nw2 = np.vdot(w, w).real
+        dd = np.array(d[: j + 1])
+        hcol = g / dd**2
+        H[: j + 1, j] = g / (dd * d[j])
+        sumsq = float(np.sum(np.abs(g) ** 2 / dd**2))
+        be2 = max(nw2 - sumsq, 1e-6 * nw2)
+        scale = 1.0 / np.sqrt(be2)
+        if skip_last and j == m - 1:
+            hn = np.sqrt(max(nw2 - sumsq, 1e-12 * nw2)) / d[j]
+        else:
+            vn = (w - sum(hcol[i] * V[i] for i in range(j + 1))) * scale
+            V.append(vn)
+            d.append(np.linalg.norm(vn))
+            hn = d[j + 1] / (scale * d[j])
+        H[j + 1, j] = hn
+        for k in range(j):
+            t = cs[k] * H[k, j] + sn[k] * H[k + 1, j]
+            H[k + 1, j] = cs[k] * H[k + 1, j] - np.conj(sn[k]) * H[k, j]
+            H[k, j] = t
+        a = H[j, j]
+        aa, den = abs(a), np.hypot(abs(a), hn)
+        cs[j] = aa / den
+        sn[j] = (hn / (den * aa)) * a
+        H[j, j] = cs[j] * a + hn * sn[j]
+        H[j + 1, j] = 0.0
+        s[j + 1] = -np.conj(sn[j]) * s[j]
+        s[j] = cs[j] * s[j]
+    y = np.linalg.solve(np.triu(H[:m, :m]), s[:m]) / np.array(d[:m])
+    return dinv * sum(y[i] * V[i] for i in range(m)), abs(s[m]) / d[0]
+
+
+@pytest.mark.parametrize("nsteps", [1, 2, 5, 10])
+def test_scaled_basis_gmres_with_estimated_last_column_equals_mgs_gmres(ho, nsteps):
+    """The device's formulation of a level's GMRES (scaled basis, one-pass Gram-Schmidt, last column
+    without an update pass) against the oracle's textbook MGS GMRES on the coarsest operator of a small 3-D hierarchy: the
+    same iterate to round-off, with and without the skipped pass, and the Givens residual estimate equal to the true
+    preconditioned residual."""
+    rng = np.random.default_rng(5)
+    n = np.array([9, 9, 9])
+    mesh = ho.getRegularMesh([0.0, 0.8, 0.0, 0.8, 0.0, 0.8], list(n - 1))
+    m = 1.0 / (1.5 + rng.random(tuple(n))) ** 2
+    w = 0.9 * ho.getMaximalFrequency(m, mesh)
+    gamma = 0.05 * w * np.ones(tuple(n))
+    H = ho.GetHelmholtzOperator(mesh, m, w, gamma, True, True) + ho.GetHelmholtzShiftOP(m, w, 0.2)
+    A = H.tocsr()
+    dinv = 0.8 / A.diagonal()
+    b = rng.standard_normal(A.shape[0]) + 1j * rng.standard_normal(A.shape[0])
+    x_ref = ho._gmres_fixed(A, b[:, None], np.zeros((len(b), 1), dtype=complex), dinv, nsteps)[:, 0]
+    for skip in (False, True):
+        x, est = _device_level_gmres(A, b, dinv, nsteps, skip_last=skip)
+        assert rel_err(x, x_ref) < 1e-12, (nsteps, skip)
+        assert abs(est - np.linalg.norm(b - A @ x) / np.linalg.norm(b)) < 1e-12, (nsteps, skip)
